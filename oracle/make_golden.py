@@ -1,0 +1,197 @@
+"""Generate tests/golden/*.npz by running the REFERENCE itself (build container only).
+
+TEST INFRASTRUCTURE.  Usage (from the repo root):  python -m oracle.make_golden
+
+For every case in tests/cases.py it instantiates the reference module (through oracle/ref_shim.py),
+overwrites its parameters with the case's deterministic values, runs `.eval()` forward in fp32 on
+CPU, and stores the outputs.  Inputs/parameters are NOT stored -- tests/cases.py regenerates them.
+An fp64 run of the same reference modules (`.double()`) is stored too (`<case>/f64`), for error
+budgeting of the fp32 CUDA kernels (SURVEY.md section 7 "Tolerance vs arithmetic").
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_shim import load_reference  # noqa: E402
+from tests import cases  # noqa: E402
+
+T = torch.from_numpy
+# fp64 reference runs are stored only where rounding matters (cancellation / long reductions)
+F64_LAYER_KINDS = ('fm', 'cross', 'cin', 'cin_direct', 'ipn', 'afm', 'mlp')
+
+
+def _set(param, value, dtype):
+    with torch.no_grad():
+        param.copy_(T(np.ascontiguousarray(value)).to(dtype).reshape(param.shape))
+
+
+def _load_mlp(dnn, params, dtype, prefix='mlp'):
+    ws, bs = cases.mlp_lists(params, prefix)
+    linears = [m for m in dnn.model._modules.values() if isinstance(m, nn.Linear)]
+    assert len(linears) == len(ws)
+    for lin, w, b in zip(linears, ws, bs):
+        _set(lin.weight, w, dtype)
+        _set(lin.bias, b, dtype)
+
+
+def _load_cin(cin, params, dtype):
+    c = cases.cin_lists(params)
+    for l, block in enumerate(cin.model):
+        _set(block.Conv1d.weight, c['conv_w'][l][:, :, None], dtype)
+        _set(block.Conv1d.bias, c['conv_b'][l], dtype)
+        g, b, m, v, _ = c['bn'][l]
+        _set(block.Batchnorm.weight, g, dtype)
+        _set(block.Batchnorm.bias, b, dtype)
+        block.Batchnorm.running_mean.copy_(T(m).to(dtype))
+        block.Batchnorm.running_var.copy_(T(v).to(dtype))
+    _set(cin.fc.weight, c['fc_w'], dtype)
+    _set(cin.fc.bias, c['fc_b'], dtype)
+
+
+def _load_cross(cross, params, dtype):
+    ws, bs = cases.cross_lists(params)
+    for lin, w, b in zip(cross.model, ws, bs):
+        _set(lin.weight, w, dtype)
+        _set(lin.bias, b, dtype)
+
+
+def run_layer(trs, kind, b, n, e, dtype):
+    L = trs.layers
+    c = cases.layer_case(kind, b, n, e)
+    x = T(c['inputs']['x']).to(dtype)
+    p = c['params']
+    if kind == 'fm':
+        m = L.FMLayer(0.5)
+    elif kind == 'ffm':
+        m = L.FFMLayer(n, dropout_p=0.5)
+    elif kind == 'cross':
+        m = L.CrossNetworkLayer(e, cases.CROSS_LAYERS).to(dtype)
+        _load_cross(m, p, dtype)
+    elif kind in ('cin', 'cin_direct'):
+        m = L.CINLayer(e, n, 3, list(cases.CIN_SIZES), is_direct=(kind == 'cin_direct')).to(dtype)
+        _load_cin(m, p, dtype)
+    elif kind == 'ipn':
+        m = L.InnerProductNetworkLayer(n)
+    elif kind in ('bilinear_all', 'bilinear_each'):
+        m = L.BilinearInteractionLayer(e, n, bilinear_type=kind.split('_')[1]).to(dtype)
+        _set(m.bilinear.weight, p['w'], dtype)
+        _set(m.bilinear.bias, p['b'], dtype)
+    elif kind == 'afm':
+        m = L.AFMLayer(e, n, cases.AFM_ATTN, dropout_p=0.5).to(dtype)
+        _set(m.attention.Linear.weight, p['w1'], dtype)
+        _set(m.attention.Linear.bias, p['b1'], dtype)
+        _set(m.attention.OutProj.weight, p['w2'], dtype)
+        _set(m.attention.OutProj.bias, p['b2'], dtype)
+    elif kind == 'mlp':
+        m = L.DNNLayer(e, 5, list(cases.MLP_SIZES), dropout_p=[0.5] * len(cases.MLP_SIZES)).to(dtype)
+        _load_mlp(m, p, dtype)
+    else:
+        raise KeyError(kind)
+    m.eval()
+    with torch.no_grad():
+        out = m(x)
+    if isinstance(out, tuple):
+        return {'out': out[0].rename(None).numpy(), 'scores': out[1].rename(None).numpy()}
+    return {'out': out.rename(None).numpy()}
+
+
+def run_emb(trs, kind, b, n, e, dtype):
+    I = trs.inputs.base
+    c = cases.emb_case(kind, b, n, e)
+    idx = T(c['inputs']['idx'])
+    p = c['params']
+    if kind == 'emb_single':
+        m = I.SingleIndexEmbedding(e, c['field_sizes'][0])
+        _set(m.embedding.weight, p['w'], torch.float32)
+    elif kind in ('emb_multi', 'emb_multi_flat'):
+        m = I.MultiIndicesEmbedding(e, c['field_sizes'], flatten=(kind == 'emb_multi_flat'))
+        _set(m.embedding.weight, p['w'], torch.float32)
+    else:
+        m = I.MultiIndicesFieldAwareEmbedding(e, c['field_sizes'])
+        for t in range(n):
+            _set(m.embeddings[t].weight, p[f'w{t}'], torch.float32)
+    with torch.no_grad():
+        out = m(idx)
+    return {'out': out.rename(None).numpy()}
+
+
+def run_model(trs, kind, b, n, e, dtype):
+    I, M = trs.inputs, trs.models
+    c = cases.model_case(kind, b, n, e)
+    fs, p = c['field_sizes'], c['params']
+    schema = {}
+    if kind != 'dcn_model':
+        feat = I.base.MultiIndicesEmbedding(1, fs)
+        feat.set_schema(['idx'])
+        _set(feat.embedding.weight, p['w_feat'], torch.float32)
+        schema['feat_inputs'] = feat
+    if kind == 'ffm_model':
+        emb = I.base.MultiIndicesFieldAwareEmbedding(e, fs)
+        for t in range(n):
+            _set(emb.embeddings[t].weight, p[f'w_emb{t}'], torch.float32)
+        emb.set_schema(['idx'])
+        schema['field_emb_inputs'] = emb
+    else:
+        emb = I.base.MultiIndicesEmbedding(e, fs)
+        _set(emb.embedding.weight, p['w_emb'], torch.float32)
+        emb.set_schema(['idx'])
+        schema['emb_inputs'] = emb
+    inputs = I.Inputs(schema)
+    if kind == 'fm_model':
+        model = M.FactorizationMachineModel(use_bias=True, dropout_p=0.5)
+        _set(model.bias, p['bias'], torch.float32)
+    elif kind == 'deepfm_model':
+        model = M.DeepFactorizationMachineModel(e, n, list(cases.MLP_SIZES), fm_dropout_p=0.5)
+        _load_mlp(model.deep, p, torch.float32)
+    elif kind == 'dcn_model':
+        sizes, od = cases.DCN_DEEP
+        model = M.DeepAndCrossNetworkModel(e, n, od, list(sizes), cases.CROSS_LAYERS)
+        _load_mlp(model.deep, p, torch.float32)
+        _load_cross(model.cross, p, torch.float32)
+        _set(model.fc.weight, p['fc_w'], torch.float32)
+        _set(model.fc.bias, p['fc_b'], torch.float32)
+    elif kind == 'xdeepfm_model':
+        model = M.XDeepFactorizationMachineModel(e, n, list(cases.CIN_SIZES), list(cases.MLP_SIZES))
+        _load_mlp(model.deep, p, torch.float32)
+        _load_cin(model.cin, p, torch.float32)
+        _set(model.bias, p['bias'], torch.float32)
+    elif kind == 'ffm_model':
+        model = M.FieldAwareFactorizationMachineModel(n, dropout_p=0.5)
+        _set(model.bias, p['bias'], torch.float32)
+    else:
+        raise KeyError(kind)
+    seq = trs.Sequential(inputs, model).to(dtype).eval()
+    with torch.no_grad():
+        out = seq({'idx': T(c['inputs']['idx'])})
+    return {'out': out.rename(None).numpy()}
+
+
+def main():
+    trs = load_reference()
+    torch.set_num_threads(1)  # fixed reduction order for the stored fp32 outputs
+    out_dir = os.path.join(ROOT, 'tests', 'golden')
+    os.makedirs(out_dir, exist_ok=True)
+    for fname, kinds, fn in (('layers.npz', cases.LAYER_KINDS, run_layer),
+                             ('embeddings.npz', cases.EMB_KINDS, run_emb),
+                             ('models.npz', cases.MODEL_KINDS, run_model)):
+        store = {}
+        for kind in kinds:
+            for (b, n, e) in cases.GRID:
+                cid = cases.case_id(kind, b, n, e)
+                for k, v in fn(trs, kind, b, n, e, torch.float32).items():
+                    store[f'{cid}/{k}'] = v
+                if fn is run_model or (fn is run_layer and kind in F64_LAYER_KINDS):
+                    for k, v in fn(trs, kind, b, n, e, torch.float64).items():
+                        store[f'{cid}/{k}/f64'] = v
+        np.savez_compressed(os.path.join(out_dir, fname), **store)
+        print(fname, len(store), 'arrays', os.path.getsize(os.path.join(out_dir, fname)) // 1024, 'KiB')
+
+
+if __name__ == '__main__':
+    main()

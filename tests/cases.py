@@ -1,0 +1,184 @@
+"""Deterministic test cases for the hot path (inputs + parameters), shared by the golden generator
+(oracle/make_golden.py, runs the reference), the oracle tests (CPU) and the CUDA parity tests (GPU).
+
+Nothing here is random at run time: everything derives from torecsys_b200.synth's counter hash, so
+the fixtures under tests/golden/ only need to store the reference's OUTPUTS.
+
+The grid follows the reference's own test grid `(B,N,E) in {(8,4,128),(16,6,64),(32,12,8)}`
+(reference tests/test_layers.py:16-20 etc.) plus one Criteo-shaped case (39 fields, E=16).
+"""
+import numpy as np
+
+from torecsys_b200 import synth
+
+GRID = [(8, 4, 128), (16, 6, 64), (32, 12, 8), (2, 39, 16)]
+
+LAYER_KINDS = ['fm', 'ffm', 'cross', 'cin', 'cin_direct', 'ipn', 'bilinear_all', 'bilinear_each', 'afm', 'mlp']
+EMB_KINDS = ['emb_single', 'emb_multi', 'emb_multi_flat', 'emb_field_aware']
+MODEL_KINDS = ['fm_model', 'deepfm_model', 'dcn_model', 'xdeepfm_model', 'ffm_model']
+
+CROSS_LAYERS = 3
+CIN_SIZES = [8, 6]
+AFM_ATTN = 8
+MLP_SIZES = [16, 16, 16]
+DCN_DEEP = ([32, 16, 8], 4)  # reference tests/test_models.py:57-66
+
+
+def case_id(kind, b, n, e):
+    return f'{kind}_B{b}_N{n}_E{e}'
+
+
+def field_sizes_for(n):
+    # multiples of 16 (exact through the reference's float32 offset rounding), ragged
+    return [16 * (1 + (3 * i) % 7) for i in range(n)]
+
+
+def _u(shape, tag, scale=1.0, dtype=np.float32):
+    return synth.uniform(shape, tag, -scale, scale, dtype)
+
+
+def _pairs(n):
+    return n * (n - 1) // 2
+
+
+def _mlp_params(cid, in_f, sizes, out_f, prefix='mlp'):
+    p = {}
+    dims = [in_f] + list(sizes)
+    for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+        p[f'{prefix}_w{i}'] = _u((b, a), f'{cid}/{prefix}_w{i}', 1.0 / np.sqrt(a))
+        p[f'{prefix}_b{i}'] = _u((b,), f'{cid}/{prefix}_b{i}', 0.5)
+    p[f'{prefix}_wout'] = _u((out_f, dims[-1]), f'{cid}/{prefix}_wout', 1.0 / np.sqrt(dims[-1]))
+    p[f'{prefix}_bout'] = _u((out_f,), f'{cid}/{prefix}_bout', 0.5)
+    return p
+
+
+def _cin_params(cid, n, e, sizes, direct, out_f=1):
+    p = {}
+    h_prev = n
+    for l, h in enumerate(sizes):
+        c = h if direct else 2 * h
+        k = n * h_prev
+        p[f'cin_w{l}'] = _u((c, k), f'{cid}/cin_w{l}', 1.0 / np.sqrt(k))
+        p[f'cin_b{l}'] = _u((c,), f'{cid}/cin_b{l}', 0.5)
+        p[f'cin_bn_g{l}'] = synth.uniform((c,), f'{cid}/cin_bn_g{l}', 0.5, 1.5)
+        p[f'cin_bn_b{l}'] = _u((c,), f'{cid}/cin_bn_b{l}', 0.5)
+        p[f'cin_bn_m{l}'] = _u((c,), f'{cid}/cin_bn_m{l}', 0.5)
+        p[f'cin_bn_v{l}'] = synth.uniform((c,), f'{cid}/cin_bn_v{l}', 0.5, 2.0)
+        h_prev = h
+    tot = int(sum(sizes))
+    p['cin_fc_w'] = _u((out_f, tot), f'{cid}/cin_fc_w', 1.0 / np.sqrt(tot))
+    p['cin_fc_b'] = _u((out_f,), f'{cid}/cin_fc_b', 0.5)
+    return p
+
+
+def layer_case(kind, b, n, e):
+    """Returns dict(inputs={...}, params={...}) of float32 numpy arrays for one layer case."""
+    cid = case_id(kind, b, n, e)
+    inputs, params = {}, {}
+    if kind == 'ffm':
+        inputs['x'] = _u((b, n * n, e), f'{cid}/x')
+    else:
+        inputs['x'] = _u((b, n, e), f'{cid}/x')
+    if kind == 'cross':
+        for l in range(CROSS_LAYERS):
+            params[f'cross_w{l}'] = _u((e, e), f'{cid}/w{l}', 1.0 / np.sqrt(e))
+            params[f'cross_b{l}'] = _u((e,), f'{cid}/b{l}', 0.5)
+    elif kind in ('cin', 'cin_direct'):
+        params.update(_cin_params(cid, n, e, CIN_SIZES, kind == 'cin_direct', out_f=3))
+    elif kind == 'bilinear_all':
+        params['w'] = _u((e, e), f'{cid}/w', 1.0 / np.sqrt(e))
+        params['b'] = _u((e,), f'{cid}/b', 0.5)
+    elif kind == 'bilinear_each':
+        params['w'] = _u((_pairs(n), e, e), f'{cid}/w', 1.0 / np.sqrt(e))
+        params['b'] = _u((_pairs(n), e), f'{cid}/b', 0.5)
+    elif kind == 'afm':
+        params['w1'] = _u((AFM_ATTN, e), f'{cid}/w1', 1.0 / np.sqrt(e))
+        params['b1'] = _u((AFM_ATTN,), f'{cid}/b1', 0.5)
+        params['w2'] = _u((1, AFM_ATTN), f'{cid}/w2', 1.0)
+        params['b2'] = _u((1,), f'{cid}/b2', 0.5)
+    elif kind == 'mlp':
+        params.update(_mlp_params(cid, e, MLP_SIZES, 5))
+    return dict(inputs=inputs, params=params)
+
+
+def emb_case(kind, b, n, e):
+    cid = case_id(kind, b, n, e)
+    if kind == 'emb_single':
+        rows = 97
+        return dict(field_sizes=[rows], inputs={'idx': synth.integers((b, 1), f'{cid}/idx', rows)},
+                    params={'w': _u((rows, e), f'{cid}/w')})
+    fs = field_sizes_for(n)
+    idx = synth.integers((b, n), f'{cid}/idx', np.asarray(fs)[None, :])
+    # make sure the extreme rows of every field are hit (first and last row)
+    idx[0, :] = 0
+    idx[-1, :] = np.asarray(fs) - 1
+    if kind == 'emb_field_aware':
+        params = {f'w{t}': _u((sum(fs), e), f'{cid}/w{t}') for t in range(n)}
+    else:
+        params = {'w': _u((sum(fs), e), f'{cid}/w')}
+    return dict(field_sizes=fs, inputs={'idx': idx}, params=params)
+
+
+def model_case(kind, b, n, e):
+    cid = case_id(kind, b, n, e)
+    fs = field_sizes_for(n)
+    r = sum(fs)
+    idx = synth.integers((b, n), f'{cid}/idx', np.asarray(fs)[None, :])
+    params = {}
+    if kind != 'dcn_model':
+        params['w_feat'] = _u((r, 1), f'{cid}/w_feat')
+    if kind == 'ffm_model':
+        for t in range(n):
+            params[f'w_emb{t}'] = _u((r, e), f'{cid}/w_emb{t}', 0.5)
+    else:
+        params['w_emb'] = _u((r, e), f'{cid}/w_emb')
+    if kind in ('fm_model', 'ffm_model', 'xdeepfm_model'):
+        params['bias'] = _u((1,), f'{cid}/bias')
+    if kind in ('deepfm_model', 'xdeepfm_model'):
+        params.update(_mlp_params(cid, n * e, MLP_SIZES, 1))
+    if kind == 'xdeepfm_model':
+        params.update(_cin_params(cid, n, e, CIN_SIZES, False, out_f=1))
+    if kind == 'dcn_model':
+        sizes, od = DCN_DEEP
+        params.update(_mlp_params(cid, e, sizes, od))
+        for l in range(CROSS_LAYERS):
+            params[f'cross_w{l}'] = _u((e, e), f'{cid}/cw{l}', 1.0 / np.sqrt(e))
+            params[f'cross_b{l}'] = _u((e,), f'{cid}/cb{l}', 0.5)
+        params['fc_w'] = _u((1, (od + e) * n), f'{cid}/fc_w', 1.0 / np.sqrt((od + e) * n))
+        params['fc_b'] = _u((1,), f'{cid}/fc_b', 0.5)
+    return dict(field_sizes=fs, inputs={'idx': idx}, params=params)
+
+
+def mlp_lists(params, prefix='mlp'):
+    ws, bs = [], []
+    i = 0
+    while f'{prefix}_w{i}' in params:
+        ws.append(params[f'{prefix}_w{i}'])
+        bs.append(params[f'{prefix}_b{i}'])
+        i += 1
+    ws.append(params[f'{prefix}_wout'])
+    bs.append(params[f'{prefix}_bout'])
+    return ws, bs
+
+
+def cin_lists(params):
+    """-> dict(conv_w, conv_b, bn=[(g,b,m,v,eps)], fc_w, fc_b) in oracle.restated.cin_layer's layout."""
+    cw, cb, bn = [], [], []
+    l = 0
+    while f'cin_w{l}' in params:
+        cw.append(params[f'cin_w{l}'])
+        cb.append(params[f'cin_b{l}'])
+        bn.append((params[f'cin_bn_g{l}'], params[f'cin_bn_b{l}'], params[f'cin_bn_m{l}'], params[f'cin_bn_v{l}'],
+                   1e-5))
+        l += 1
+    return dict(conv_w=cw, conv_b=cb, bn=bn, fc_w=params['cin_fc_w'], fc_b=params['cin_fc_b'])
+
+
+def cross_lists(params):
+    ws, bs = [], []
+    l = 0
+    while f'cross_w{l}' in params:
+        ws.append(params[f'cross_w{l}'])
+        bs.append(params[f'cross_b{l}'])
+        l += 1
+    return ws, bs
