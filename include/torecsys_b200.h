@@ -1,0 +1,208 @@
+/*
+ * torecsys_b200 -- C ABI of the B200-native CTR forward hot path.
+ *
+ * The reference (p768lwy3/torecsys) is pure Python on torch ATen and has no FFI of its own; the boundary a
+ * maintainer would bind is therefore "one C entry point per reference forward() on the hot path"
+ * (SURVEY.md section 8a rows a1..a12).  Every entry point below cites the reference forward it replaces.
+ * INTEGRATION.md shows the ctypes stub that goes into the reference module for each of them.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer on the current CUDA device unless the
+ *     parameter name ends in `_host` (then it is a host pointer, pinned or pageable);
+ *   - float tensors are contiguous row-major fp32, indices are contiguous row-major int64 (`idx_bits` = 64) or
+ *     int32 (`idx_bits` = 32; the reference accepts both, multi_indices_emb.py:104 promotes);
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream); calls are asynchronous and
+ *     CUDA-graph capturable (no host synchronisation, no allocation) unless stated otherwise;
+ *   - `status` (may be NULL) points to `TRS_STATUS_WORDS` int32 words in device memory that kernels update when
+ *     they meet an out-of-range row id: word0 += 1 per offending lookup, word1 = flat position (b*N+n) of one
+ *     offender.  An offending lookup reads as a row of zeros, never out of bounds.  The Python layer turns a
+ *     non-zero word0 into IndexError (the reference raises IndexError from nn.Embedding on CPU);
+ *   - return value: TRS_OK (0) or a negative TRS_ERR_* code; `trs_last_error()` gives the message (thread local).
+ *     Argument errors are reported before anything is launched.
+ */
+#ifndef TORECSYS_B200_H_
+#define TORECSYS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRS_OK 0
+#define TRS_ERR_INVALID_ARGUMENT (-1)
+#define TRS_ERR_UNSUPPORTED (-2)
+#define TRS_ERR_CUDA (-3)
+
+#define TRS_STATUS_WORDS 2
+
+/* activation ids (nn.ReLU / None / nn.Sigmoid / nn.Tanh instances of the reference constructors) */
+#define TRS_ACT_NONE 0
+#define TRS_ACT_RELU 1
+#define TRS_ACT_SIGMOID 2
+#define TRS_ACT_TANH 3
+
+/* ---- library ---------------------------------------------------------------------------------------------- */
+const char* trs_version(void);
+const char* trs_last_error(void);
+/* compute capability of the current device as major*10+minor (100 on B200); negative on error */
+int trs_device_arch(void);
+
+/* ---- a1/a2: embedding row gather ----------------------------------------------------------------------------
+ * Replaces SingleIndexEmbedding.forward (torecsys/inputs/base/single_index_emb.py:45-59; offsets = NULL, N = 1)
+ * and MultiIndicesEmbedding.forward (torecsys/inputs/base/multi_indices_emb.py:92-112):
+ *     out[b, n, :] = weight[idx[b, n] + offsets[n], :]            bit-exact copy of fp32 rows
+ * weight (rows, embed) ; idx (batch, fields) ; offsets (fields) int64 or NULL ; out (batch, fields, embed).
+ * `flatten` of the reference is a view of the same bytes and is done by the caller. */
+int trs_embedding_gather(const float* weight, int64_t rows, int embed,
+                         const void* idx, int idx_bits, const int64_t* offsets,
+                         int64_t batch, int fields, float* out, int32_t* status, void* stream);
+
+/* ---- a3: field-aware gather -----------------------------------------------------------------------------------
+ * Replaces MultiIndicesFieldAwareEmbedding.forward (torecsys/inputs/base/multi_indices_field_aware_emb.py:90-111):
+ *     out[b, t*N + f, :] = tables[t][idx[b, f] + offsets[f], :]   for t, f in [0, N)
+ * tables: device array of N device pointers, each (rows, embed); out (batch, N*N, embed). */
+int trs_embedding_gather_field_aware(const float* const* tables, int64_t rows, int embed,
+                                     const void* idx, int idx_bits, const int64_t* offsets,
+                                     int64_t batch, int fields, float* out, int32_t* status, void* stream);
+
+/* ---- a5: FM second order ----------------------------------------------------------------------------------------
+ * Replaces FactorizationMachineLayer.forward (torecsys/layers/ctr/factorization_machine.py:46-81), eval mode:
+ *     out[b, e] = 0.5 * ((sum_n x[b,n,e])^2 - sum_n x[b,n,e]^2)      x (batch, fields, embed) -> out (batch, embed) */
+int trs_fm_forward(const float* x, int64_t batch, int fields, int embed, float* out, void* stream);
+
+/* ---- a6: field-aware FM ------------------------------------------------------------------------------------------
+ * Replaces FieldAwareFactorizationMachineLayer.forward
+ * (torecsys/layers/ctr/field_aware_factorization_machine.py:50-94), eval mode:
+ *     out[b, p, :] = v[b, i*N + j, :] * v[b, j*N + i, :]   for pairs p = (i<j) in lexicographic order
+ * v (batch, N*N, embed) -> out (batch, N(N-1)/2, embed). */
+int trs_ffm_forward(const float* v, int64_t batch, int fields, int embed, float* out, void* stream);
+
+/* ---- a9: inner product network -----------------------------------------------------------------------------------
+ * Replaces InnerProductNetworkLayer.forward (torecsys/layers/ctr/inner_product_network.py:54-79):
+ *     out[b, p] = sum_e x[b,i,e] * x[b,j,e]        x (batch, fields, embed) -> out (batch, N(N-1)/2) */
+int trs_ipn_forward(const float* x, int64_t batch, int fields, int embed, float* out, void* stream);
+
+/* ---- a10: bilinear interaction -----------------------------------------------------------------------------------
+ * Replaces BilinearInteractionLayer.forward (torecsys/layers/ctr/bilinear_interaction.py:230-255) with
+ * FieldAllTypeBilinear.forward (:72-76; each_type = 0, weight (E,E), bias (E)) or
+ * FieldEachTypeBilinear.forward (:144-149; each_type = 1, weight (P,E,E), bias (P,E)):
+ *     out[b, p, :] = (x[b,i,:] @ W_(p)) * x[b,j,:] + bias_(p)       bias may be NULL
+ * x (batch, fields, embed) -> out (batch, P, embed). */
+int trs_bilinear_forward(const float* x, const float* weight, const float* bias, int each_type,
+                         int64_t batch, int fields, int embed, float* out, void* stream);
+
+/* ---- a11: attentional FM -----------------------------------------------------------------------------------------
+ * Replaces AttentionalFactorizationMachineLayer.forward
+ * (torecsys/layers/ctr/attentional_factorization_machine.py:86-120), eval mode (dropouts are identity):
+ *     prod_p = x_i * x_j ; s = softmax_p( w2 . relu(W1 prod_p + b1) + b2 ) ; out[b,:] = sum_p s_p prod_p
+ * W1 (attn, embed), b1 (attn), w2 (attn) [= OutProj.weight (1, attn)], b2 (1).
+ * out (batch, embed), scores (batch, P) [= the reference's (B, P, 1)]. */
+int trs_afm_forward(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                    int64_t batch, int fields, int embed, int attn, float* out, float* scores, void* stream);
+
+/* ---- a7: cross network -------------------------------------------------------------------------------------------
+ * Replaces CrossNetworkLayer.forward (torecsys/layers/ctr/cross_network.py:52-87):
+ *     h_0 = x ; h_{l+1} = x * (h_l @ W_l^T + b_l) + x    per (b, n) row, W_l (E, E), b_l (E)
+ * weights (layers, E, E), biases (layers, E) packed contiguously; x (rows, embed) with rows = batch*fields. */
+int trs_cross_forward(const float* x, const float* weights, const float* biases, int layers,
+                      int64_t rows, int embed, float* out, void* stream);
+
+/* ---- a8: compress interaction network ------------------------------------------------------------------------------
+ * Replaces CompressInteractionNetworkLayer.forward (torecsys/layers/ctr/compress_interaction_network.py:85-184), eval:
+ *     per layer l:  z[b, xf*H + y, e] = x[b,xf,e] * h[b,y,e]
+ *                   o = act( scale_l * (conv_w_l z) + shift_l )      (Conv1d bias and eval-BatchNorm folded by the
+ *                                                                     caller into a per-channel scale/shift)
+ *                   direct: d = h = o ; else: d = o[:, :H_l], h = o[:, H_l:]   (every layer)
+ *     out = fc_w . ( sum_e cat_l d ) + fc_b
+ * conv_w[l] (C_l, N*H_{l-1}), scale[l]/shift[l] (C_l) are HOST arrays of DEVICE pointers (length `layers`);
+ * layer_sizes (HOST) = H_1..H_L; C_l = H_l if is_direct else 2*H_l.
+ * workspace: device scratch of at least trs_cin_workspace_bytes(...) bytes.
+ * x (batch, fields, embed) -> out (batch, out_features). */
+int64_t trs_cin_workspace_bytes(int64_t batch, int fields, int embed, const int* layer_sizes, int layers,
+                                int is_direct);
+int trs_cin_forward(const float* x, const float* const* conv_w, const float* const* scale,
+                    const float* const* shift, const int* layer_sizes, int layers, int is_direct, int activation,
+                    const float* fc_w, const float* fc_b, int out_features,
+                    int64_t batch, int fields, int embed, float* out, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+
+/* ---- MLP (adjacent; used inside the fused model entry points and by DNNLayer) ---------------------------------------
+ * Replaces MultilayerPerceptionLayer.forward (torecsys/layers/ctr/multilayer_perceptron.py:63-84), eval mode:
+ *     h = act(h @ W_i^T + b_i) for the hidden Linears, then LinearOutput without activation, on the last dim.
+ * The parameter pack used by every entry point that embeds an MLP:
+ *   dims (HOST, int[layers+1]) = in, hidden..., out ; weights[i] (dims[i+1], dims[i]), biases[i] (dims[i+1]) are HOST
+ *   arrays of DEVICE pointers of length `layers` (the last one is LinearOutput). */
+int trs_mlp_forward(const float* x, int64_t rows, const int* dims, int layers,
+                    const float* const* weights, const float* const* biases, int activation,
+                    float* out, void* stream);
+
+/* ---- a12: fused model forwards, indices -> logits (the L2 boundary: Sequential.forward,
+ *      torecsys/models/sequential.py:31-44 = Inputs.forward (torecsys/inputs/inputs.py:56-89) + model.forward) -------
+ * Common arguments: idx (batch, fields); offsets (fields) int64; w_feat (rows, 1) = the first-order
+ * MultiIndicesEmbedding(embed_size=1) table; w_emb (rows, embed); logits (batch, 1).
+ */
+
+/* FactorizationMachineModel.forward (torecsys/models/ctr/factorization_machine.py:42-71):
+ *     logit = sum_n w_feat[r_n] + sum_e FM(emb)[e] (+ bias[0] when bias != NULL) */
+int trs_fm_model_forward(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                         const float* w_feat, const float* w_emb, int64_t rows, int embed,
+                         const float* bias, float* logits, int32_t* status, void* stream);
+
+/* DeepFactorizationMachineModel.forward (torecsys/models/ctr/deep_fm.py:55-110):
+ *     logit = MLP(flatten(emb)) + sum_e FM(emb)[e] + sum_n w_feat[r_n]           (MLP in = fields*embed, out = 1) */
+int trs_deepfm_forward(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                       const float* w_feat, const float* w_emb, int64_t rows, int embed,
+                       const int* mlp_dims, int mlp_layers, const float* const* mlp_w, const float* const* mlp_b,
+                       int activation, float* logits, int32_t* status, void* stream);
+
+/* DeepAndCrossNetworkModel.forward (torecsys/models/ctr/deep_and_cross_network.py:58-98):
+ *     logit = fc( flatten( cat[ Cross(emb) (B,N,E), MLP_per_field(emb) (B,N,Od) ], dim=-1 ) )
+ * cross_w (cross_layers, E, E), cross_b (cross_layers, E); MLP in = embed, out = Od; fc_w (1, N*(E+Od)), fc_b (1). */
+int trs_dcn_forward(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                    const float* w_emb, int64_t rows, int embed,
+                    const float* cross_w, const float* cross_b, int cross_layers,
+                    const int* mlp_dims, int mlp_layers, const float* const* mlp_w, const float* const* mlp_b,
+                    int activation, const float* fc_w, const float* fc_b,
+                    float* logits, int32_t* status, void* stream);
+
+/* XDeepFactorizationMachineModel.forward (torecsys/models/ctr/xdeep_fm.py:82-124):
+ *     logit = sum_n w_feat[r_n] + CIN(emb)[0] + MLP(flatten(emb)) + bias[0]
+ * CIN arguments as in trs_cin_forward with out_features = 1. */
+int64_t trs_xdeepfm_workspace_bytes(int64_t batch, int fields, int embed, const int* cin_layer_sizes, int cin_layers,
+                                    int cin_is_direct);
+int trs_xdeepfm_forward(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                        const float* w_feat, const float* w_emb, int64_t rows, int embed,
+                        const float* const* cin_w, const float* const* cin_scale, const float* const* cin_shift,
+                        const int* cin_layer_sizes, int cin_layers, int cin_is_direct, int cin_activation,
+                        const float* cin_fc_w, const float* cin_fc_b,
+                        const int* mlp_dims, int mlp_layers, const float* const* mlp_w, const float* const* mlp_b,
+                        int mlp_activation, const float* bias,
+                        float* logits, void* workspace, int64_t workspace_bytes, int32_t* status, void* stream);
+
+/* FieldAwareFactorizationMachineModel.forward (torecsys/models/ctr/field_aware_factorization_machine.py:39-81):
+ *     logit = sum_{i<j} < tables[i][r_j], tables[j][r_i] > + sum_n w_feat[r_n] + bias[0]
+ * (= sum over p,e of FFM(field_emb)[b,p,e] with field_emb[b, t*N+f] = tables[t][r_f]; the 39 diagonal rows the
+ * reference gathers and never uses are not read).  tables: device array of N device pointers. */
+int trs_ffm_model_forward(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                          const float* w_feat, const float* const* tables, int64_t rows, int embed,
+                          const float* bias, float* logits, int32_t* status, void* stream);
+
+/* ---- host-buffer entry point (the e2e path: pageable/pinned host indices in, host logits out) -----------------------
+ * A session owns pinned staging buffers, device buffers and two streams; `trs_session_deepfm_forward_host` splits
+ * the batch into chunks and overlaps H2D(idx) / kernel / D2H(logits).  It synchronises before returning and
+ * returns the status word0 (out-of-range count) through *oob_count when oob_count != NULL. */
+typedef struct trs_session trs_session;
+int trs_session_create(int64_t max_batch, int fields, int chunks, trs_session** out_session);
+int trs_session_destroy(trs_session* session);
+int trs_session_deepfm_forward_host(trs_session* session, const void* idx_host, int idx_bits,
+                                    const int64_t* offsets, int64_t batch, int fields,
+                                    const float* w_feat, const float* w_emb, int64_t rows, int embed,
+                                    const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                                    const float* const* mlp_b, int activation,
+                                    float* logits_host, int64_t* oob_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TORECSYS_B200_H_ */

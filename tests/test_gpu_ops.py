@@ -1,0 +1,198 @@
+"""CUDA parity tests at the C-ABI level (through torecsys_b200.ops -> ctypes -> libtorecsys_b200.so).
+
+Every case of tests/cases.py is run on the B200 and compared with (i) the oracle on the same inputs and
+(ii) the committed golden outputs of the reference itself.  Bars (BASELINE.json north_star / SURVEY 8d):
+gathers bit-exact; floating point |a-b| <= 1e-5 * (|b| + mean|b|) ("1e-5 rel", normwise).
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import cases
+from tests.oracle_run import normwise_err, oracle_emb, oracle_layer, oracle_model
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+GRID = cases.GRID
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.cuda()
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from torecsys_b200 import ops as _ops
+    _ops.set_index_check('sync')
+    return _ops
+
+
+def run_layer_cuda(ops, kind, b, n, e):
+    c = cases.layer_case(kind, b, n, e)
+    x = dev(c['inputs']['x'])
+    p = {k: dev(v) for k, v in c['params'].items()}
+    if kind == 'fm':
+        return {'out': ops.fm(x)}
+    if kind == 'ffm':
+        return {'out': ops.ffm(x, n)}
+    if kind == 'ipn':
+        return {'out': ops.ipn(x)}
+    if kind == 'cross':
+        ws, bs = cases.cross_lists(p)
+        return {'out': ops.cross(x, torch.stack(ws), torch.stack(bs))}
+    if kind in ('bilinear_all', 'bilinear_each'):
+        return {'out': ops.bilinear(x, p['w'], p['b'], kind.endswith('each'))}
+    if kind == 'afm':
+        o, s = ops.afm(x, p['w1'], p['b1'], p['w2'], p['b2'])
+        return {'out': o, 'scores': s}
+    if kind == 'mlp':
+        ws, bs = cases.mlp_lists(p)
+        return {'out': ops.mlp(x, ops.MlpPack(ws, bs, ops.activation_id('relu')))}
+    if kind in ('cin', 'cin_direct'):
+        return {'out': ops.cin(x, cin_pack(ops, p, kind == 'cin_direct'), 3)}
+    raise KeyError(kind)
+
+
+def cin_pack(ops, p, direct):
+    a = cases.cin_lists(p)
+    scale, shift = [], []
+    for l, (g, beta, mean, var, eps) in enumerate(a['bn']):
+        sc = g / torch.sqrt(var + eps)
+        scale.append(sc.contiguous())
+        shift.append(((a['conv_b'][l] - mean) * sc + beta).contiguous())
+    return ops.CinPack([w.contiguous() for w in a['conv_w']], scale, shift, cases.CIN_SIZES, direct,
+                       ops.activation_id('relu'), a['fc_w'], a['fc_b'])
+
+
+@pytest.mark.parametrize('kind', cases.LAYER_KINDS)
+@pytest.mark.parametrize('b,n,e', GRID)
+def test_layer_parity(ops, golden, kind, b, n, e):
+    cid = cases.case_id(kind, b, n, e)
+    got = run_layer_cuda(ops, kind, b, n, e)
+    want = oracle_layer(kind, b, n, e, torch.float32)
+    for k in want:
+        g = got[k].cpu().numpy()
+        assert g.shape == tuple(want[k].shape), (cid, k)
+        assert normwise_err(g, want[k].numpy()) <= TOL, (cid, k, 'vs oracle')
+        assert normwise_err(g, golden[f'{cid}/{k}']) <= TOL, (cid, k, 'vs reference golden')
+
+
+@pytest.mark.parametrize('kind', cases.EMB_KINDS)
+@pytest.mark.parametrize('b,n,e', GRID)
+@pytest.mark.parametrize('idx_dtype', [torch.int64, torch.int32])
+def test_embedding_bit_exact(ops, golden, kind, b, n, e, idx_dtype):
+    from oracle.restated import field_offsets
+    cid = cases.case_id(kind, b, n, e)
+    c = cases.emb_case(kind, b, n, e)
+    idx = dev(c['inputs']['idx']).to(idx_dtype)
+    if kind == 'emb_single':
+        got = ops.embedding_gather(dev(c['params']['w']), idx, None)
+    else:
+        off = field_offsets(c['field_sizes']).cuda()
+        if kind == 'emb_field_aware':
+            got = ops.embedding_gather_field_aware([dev(c['params'][f'w{t}']) for t in range(n)], idx, off)
+        else:
+            got = ops.embedding_gather(dev(c['params']['w']), idx, off)
+            if kind == 'emb_multi_flat':
+                got = got.reshape(b, 1, n * e)
+    ref = golden[f'{cid}/out']
+    g = got.cpu().numpy()
+    assert g.shape == ref.shape
+    assert np.array_equal(g.view(np.uint32), ref.view(np.uint32)), cid
+    assert np.array_equal(g, oracle_emb(kind, b, n, e)['out'].numpy())
+
+
+def run_model_cuda(ops, kind, b, n, e, idx_dtype=torch.int64):
+    from oracle.restated import field_offsets
+    c = cases.model_case(kind, b, n, e)
+    p = {k: dev(v) for k, v in c['params'].items()}
+    idx = dev(c['inputs']['idx']).to(idx_dtype)
+    off = field_offsets(c['field_sizes']).cuda()
+    relu = ops.activation_id('relu')
+    if kind == 'fm_model':
+        return ops.fm_model(idx, off, p['w_feat'], p['w_emb'], p['bias'])
+    if kind == 'deepfm_model':
+        ws, bs = cases.mlp_lists(p)
+        return ops.deepfm(idx, off, p['w_feat'], p['w_emb'], ops.MlpPack(ws, bs, relu))
+    if kind == 'dcn_model':
+        ws, bs = cases.mlp_lists(p)
+        cw, cb = cases.cross_lists(p)
+        return ops.dcn(idx, off, p['w_emb'], torch.stack(cw), torch.stack(cb), ops.MlpPack(ws, bs, relu), p['fc_w'],
+                       p['fc_b'])
+    if kind == 'xdeepfm_model':
+        ws, bs = cases.mlp_lists(p)
+        return ops.xdeepfm(idx, off, p['w_feat'], p['w_emb'], cin_pack(ops, p, False), ops.MlpPack(ws, bs, relu),
+                           p['bias'])
+    if kind == 'ffm_model':
+        return ops.ffm_model(idx, off, p['w_feat'], [p[f'w_emb{t}'] for t in range(n)], p['bias'])
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize('kind', cases.MODEL_KINDS)
+@pytest.mark.parametrize('b,n,e', GRID)
+@pytest.mark.parametrize('idx_dtype', [torch.int64, torch.int32])
+def test_fused_model_parity(ops, golden, kind, b, n, e, idx_dtype):
+    cid = cases.case_id(kind, b, n, e)
+    got = run_model_cuda(ops, kind, b, n, e, idx_dtype).cpu().numpy()
+    want = oracle_model(kind, b, n, e, torch.float32)['out'].numpy()
+    assert got.shape == (b, 1)
+    assert normwise_err(got, want) <= TOL, (cid, 'vs oracle')
+    assert normwise_err(got, golden[f'{cid}/out']) <= TOL, (cid, 'vs reference golden')
+    # error budget: our fp32 result is as close to the fp64 reference as the reference's own fp32 run (x4 slack)
+    f64 = golden[f'{cid}/out/f64']
+    assert normwise_err(got, f64) <= max(4 * normwise_err(golden[f'{cid}/out'], f64), 2e-6), cid
+
+
+def test_deepfm_fast_path_matches_generic_and_oracle(ops, monkeypatch):
+    """Criteo shape (39 fields, E=16, MLP 16-16-16) goes through deepfm_fast.cu (3xTF32 mma.sync); ragged batch
+    sizes exercise the 16-sample warp tiles and the tail masking."""
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    n, e = 39, 16
+    fs = [16 * (3 + i % 5) for i in range(n)]
+    rows = sum(fs)
+    off = R.field_offsets(fs)
+    w_feat = torch.from_numpy(synth.uniform((rows, 1), 'fast/wf'))
+    w_emb = torch.from_numpy(synth.uniform((rows, e), 'fast/we'))
+    dims = [n * e, 16, 16, 16, 1]
+    ws = [torch.from_numpy(synth.uniform((dims[i + 1], dims[i]), f'fast/w{i}', -1 / np.sqrt(dims[i]),
+                                         1 / np.sqrt(dims[i]))) for i in range(4)]
+    bs = [torch.from_numpy(synth.uniform((dims[i + 1],), f'fast/b{i}', -0.5, 0.5)) for i in range(4)]
+    pack = ops.MlpPack([w.cuda() for w in ws], [b.cuda() for b in bs], ops.activation_id('relu'))
+    for batch in (1, 15, 16, 17, 129, 1000, 4099):
+        idx = torch.from_numpy(synth.integers((batch, n), f'fast/idx{batch}', np.asarray(fs)[None, :]))
+        want = R.deepfm_from_indices(idx, off, w_feat, w_emb, ws, bs).numpy()
+        want64 = R.deepfm_from_indices(idx, off, w_feat.double(), w_emb.double(), [w.double() for w in ws],
+                                       [b.double() for b in bs]).numpy()
+        for dt in (torch.int64, torch.int32):
+            got = ops.deepfm(idx.cuda().to(dt), off.cuda(), w_feat.cuda(), w_emb.cuda(), pack).cpu().numpy()
+            assert normwise_err(got, want) <= TOL, batch
+            assert normwise_err(got, want64) <= max(4 * normwise_err(want, want64), 2e-6), batch
+
+
+def test_out_of_range_index_raises(ops):
+    w = torch.randn(10, 4, device='cuda')
+    idx = torch.tensor([[3], [10]], device='cuda')
+    with pytest.raises(IndexError):
+        ops.embedding_gather(w, idx, None)
+    idx = torch.tensor([[-1], [2]], device='cuda')
+    with pytest.raises(IndexError):
+        ops.embedding_gather(w, idx, None)
+    # and the library is usable afterwards
+    out = ops.embedding_gather(w, torch.tensor([[9]], device='cuda'), None)
+    assert torch.equal(out[0, 0], w[9])
+
+
+def test_cpu_tensor_is_rejected(ops):
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ops.fm(torch.randn(2, 3, 4))
+
+
+def test_empty_batch(ops):
+    x = torch.empty(0, 5, 8, device='cuda')
+    assert ops.fm(x).shape == (0, 8)
+    assert ops.ipn(x).shape == (0, 10)
+    w = torch.randn(7, 8, device='cuda')
+    assert ops.embedding_gather(w, torch.empty(0, 3, dtype=torch.long, device='cuda'), None).shape == (0, 3, 8)

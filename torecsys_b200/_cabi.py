@@ -1,0 +1,111 @@
+"""ctypes binding of libtorecsys_b200.so (include/torecsys_b200.h).
+
+The library is the product; this module only loads it and declares prototypes.  There is NO fallback: if the
+shared library is missing (`python -m torecsys_b200.build` not run) or a tensor is not on a CUDA device, the
+callers raise -- they never route to torch/CPU code (see DESIGN.md "no CPU fallback").
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+LIB_NAME = 'libtorecsys_b200.so'
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+
+TRS_OK = 0
+TRS_ERR_INVALID_ARGUMENT = -1
+TRS_ERR_UNSUPPORTED = -2
+TRS_ERR_CUDA = -3
+TRS_STATUS_WORDS = 2
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
+
+_P = c_void_p            # device / host data pointer
+_PP = POINTER(c_void_p)  # host array of device pointers
+_IP = POINTER(c_int)     # host int array
+
+# name -> (restype, argtypes): exactly the declarations of include/torecsys_b200.h
+PROTOTYPES = {
+    'trs_version': (c_char_p, []),
+    'trs_last_error': (c_char_p, []),
+    'trs_device_arch': (c_int, []),
+    'trs_embedding_gather': (c_int, [_P, c_int64, c_int, _P, c_int, _P, c_int64, c_int, _P, _P, _P]),
+    'trs_embedding_gather_field_aware': (c_int, [_P, c_int64, c_int, _P, c_int, _P, c_int64, c_int, _P, _P, _P]),
+    'trs_fm_forward': (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
+    'trs_ffm_forward': (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
+    'trs_ipn_forward': (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
+    'trs_bilinear_forward': (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int, _P, _P]),
+    'trs_afm_forward': (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
+    'trs_cross_forward': (c_int, [_P, _P, _P, c_int, c_int64, c_int, _P, _P]),
+    'trs_cin_workspace_bytes': (c_int64, [c_int64, c_int, c_int, _IP, c_int, c_int]),
+    'trs_cin_forward': (c_int, [_P, _PP, _PP, _PP, _IP, c_int, c_int, c_int, _P, _P, c_int, c_int64, c_int, c_int,
+                                _P, _P, c_int64, _P]),
+    'trs_mlp_forward': (c_int, [_P, c_int64, _IP, c_int, _PP, _PP, c_int, _P, _P]),
+    'trs_fm_model_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _P, _P, _P, _P]),
+    'trs_deepfm_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _IP, c_int, _PP, _PP,
+                                   c_int, _P, _P, _P]),
+    'trs_dcn_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, c_int, _P, _P, c_int, _IP, c_int, _PP,
+                                _PP, c_int, _P, _P, _P, _P, _P]),
+    'trs_xdeepfm_workspace_bytes': (c_int64, [c_int64, c_int, c_int, _IP, c_int, c_int]),
+    'trs_xdeepfm_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _PP, _PP, _PP, _IP, c_int,
+                                    c_int, c_int, _P, _P, _IP, c_int, _PP, _PP, c_int, _P, _P, _P, c_int64, _P, _P]),
+    'trs_ffm_model_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _P, _P, _P, _P]),
+    'trs_session_create': (c_int, [c_int64, c_int, c_int, POINTER(c_void_p)]),
+    'trs_session_destroy': (c_int, [c_void_p]),
+    'trs_session_deepfm_forward_host': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _IP,
+                                                c_int, _PP, _PP, c_int, _P, POINTER(c_int64)]),
+}
+
+_lib = None
+
+
+class LibraryNotBuiltError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (once).  Raises LibraryNotBuiltError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryNotBuiltError(
+            f'{LIB_PATH} is missing: build it with `python -m torecsys_b200.build` (nvcc, sm_100a). '
+            'torecsys_b200 has no CPU or PyTorch fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().trs_last_error().decode()
+
+
+def check(rc: int, what: str):
+    """Maps a TRS_* return code to the Python exception the reference user would see."""
+    if rc == TRS_OK:
+        return
+    msg = f'{what}: {last_error()}'
+    if rc == TRS_ERR_INVALID_ARGUMENT:
+        raise ValueError(msg)
+    if rc == TRS_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(msg)
+
+
+def ptr_array(ptrs):
+    """Host array of device pointers (ctypes keeps it alive as long as the returned object lives)."""
+    arr = (c_void_p * max(len(ptrs), 1))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr
+
+
+def int_array(vals):
+    arr = (c_int * max(len(vals), 1))()
+    for i, v in enumerate(vals):
+        arr[i] = int(v)
+    return arr

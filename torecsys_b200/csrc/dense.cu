@@ -1,0 +1,119 @@
+// MLP (DNNLayer, adjacent to the hot path) and a7 Cross network as L1 ops on materialised rows.
+//
+// Both treat the input as a (rows, width) matrix, stage a tile of rows in shared memory and run the small dense
+// layers on it in plain fp32 FFMA (parity bar 1e-5: no TF32/bf16).
+#include "tile_ops.cuh"
+
+namespace trs {
+namespace {
+
+__global__ void __launch_bounds__(256) mlp_kernel(const float* __restrict__ x, int64_t rows, MlpParams mp, int ts,
+                                                  int in_pitch, int hpitch, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  float* in = smem;
+  float* buf0 = in + (size_t)ts * in_pitch;
+  float* buf1 = buf0 + (size_t)ts * hpitch;
+  const int k = mp.dims[0];
+  const int o_dim = mp.dims[mp.layers];
+  for (int64_t r0 = (int64_t)blockIdx.x * ts; r0 < rows; r0 += (int64_t)gridDim.x * ts) {
+    const int n = static_cast<int>(rows - r0 < ts ? rows - r0 : ts);
+    __syncthreads();
+    for (int t = threadIdx.x; t < ts * k; t += blockDim.x) {
+      const int s = t / k, c = t - s * k;
+      in[s * in_pitch + c] = (s < n) ? ldg_stream_f1(x + (r0 + s) * k + c) : 0.f;
+    }
+    __syncthreads();
+    const float* res = mlp_tile(mp, in, in_pitch, ts, buf0, buf1, hpitch);
+    for (int t = threadIdx.x; t < n * o_dim; t += blockDim.x) {
+      const int s = t / o_dim, o = t - s * o_dim;
+      out[(r0 + s) * o_dim + o] = res[s * hpitch + o];
+    }
+  }
+}
+
+// h_{l+1} = x * (W_l h_l + b_l) + x on a tile of rows; x stays in shared memory, h ping-pongs.
+__global__ void __launch_bounds__(256) cross_kernel(const float* __restrict__ x, const float* __restrict__ weights,
+                                                    const float* __restrict__ biases, int layers, int64_t rows,
+                                                    int embed, int ts, int pitch, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;
+  float* h0 = xs + (size_t)ts * pitch;
+  float* h1 = h0 + (size_t)ts * pitch;
+  for (int64_t r0 = (int64_t)blockIdx.x * ts; r0 < rows; r0 += (int64_t)gridDim.x * ts) {
+    const int n = static_cast<int>(rows - r0 < ts ? rows - r0 : ts);
+    __syncthreads();
+    for (int t = threadIdx.x; t < ts * embed; t += blockDim.x) {
+      const int s = t / embed, c = t - s * embed;
+      xs[s * pitch + c] = (s < n) ? ldg_stream_f1(x + (r0 + s) * embed + c) : 0.f;
+    }
+    __syncthreads();
+    const float* cur = xs;
+    float* dst = h0;
+    for (int l = 0; l < layers; ++l) {
+      float* d = dst;
+      dense_layer_tile(cur, pitch, embed, weights + (int64_t)l * embed * embed, biases + (int64_t)l * embed, embed,
+                       ts, [=](int s, int o, float v) {
+                         const float x0 = xs[s * pitch + o];
+                         d[s * pitch + o] = fmaf(x0, v, x0);  // x0 * v + x0
+                       });
+      __syncthreads();
+      cur = dst;
+      dst = (dst == h0) ? h1 : h0;
+    }
+    for (int t = threadIdx.x; t < n * embed; t += blockDim.x) {
+      const int s = t / embed, c = t - s * embed;
+      out[(r0 + s) * embed + c] = cur[s * pitch + c];
+    }
+  }
+}
+
+}  // namespace
+}  // namespace trs
+
+using namespace trs;
+
+extern "C" int trs_mlp_forward(const float* x, int64_t rows, const int* dims, int layers,
+                               const float* const* weights, const float* const* biases, int activation, float* out,
+                               void* stream) {
+  TRS_REQUIRE(x && out && dims && weights, "trs_mlp_forward: null pointer");
+  TRS_REQUIRE(rows >= 0 && layers >= 1, "trs_mlp_forward: bad sizes");
+  MlpParams mp;
+  TRS_REQUIRE(fill_mlp_params(mp, dims, layers, weights, biases, activation) == 0,
+              "trs_mlp_forward: bad layer description (at most %d layers)", MlpParams::kMaxLayers);
+  if (rows == 0) return TRS_OK;
+  const int in_pitch = tile_pitch(dims[0]);
+  const int hpitch = tile_pitch(mlp_max_hidden(dims, layers));
+  int ts = 64;
+  size_t smem;
+  for (;; ts >>= 1) {
+    smem = ((size_t)ts * in_pitch + 2 * (size_t)ts * hpitch) * sizeof(float);
+    if (smem <= (size_t)kMaxDynSmem - 1024 || ts == 1) break;
+  }
+  TRS_UNSUPPORTED(smem > (size_t)kMaxDynSmem - 1024, "trs_mlp_forward: layer widths do not fit shared memory");
+  TRS_SMEM_OPT_IN(mlp_kernel);
+  const int64_t tiles = (rows + ts - 1) / ts;
+  const int grid = static_cast<int>(tiles < kNumSMs * 2 ? tiles : kNumSMs * 2);
+  mlp_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, rows, mp, ts, in_pitch, hpitch, out);
+  return check_launch("mlp_kernel");
+}
+
+extern "C" int trs_cross_forward(const float* x, const float* weights, const float* biases, int layers, int64_t rows,
+                                 int embed, float* out, void* stream) {
+  TRS_REQUIRE(x && out && (layers == 0 || (weights && biases)), "trs_cross_forward: null pointer");
+  TRS_REQUIRE(rows >= 0 && embed > 0 && layers >= 0, "trs_cross_forward: bad sizes");
+  if (rows == 0) return TRS_OK;
+  const int pitch = tile_pitch(embed);
+  int ts = 128;
+  size_t smem;
+  for (;; ts >>= 1) {
+    smem = 3 * (size_t)ts * pitch * sizeof(float);
+    if (smem <= 96 * 1024 || ts == 1) break;
+  }
+  TRS_UNSUPPORTED(smem > (size_t)kMaxDynSmem - 1024, "trs_cross_forward: embed too large");
+  TRS_SMEM_OPT_IN(cross_kernel);
+  const int64_t tiles = (rows + ts - 1) / ts;
+  const int grid = static_cast<int>(tiles < kNumSMs * 2 ? tiles : kNumSMs * 2);
+  cross_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, weights, biases, layers, rows, embed, ts,
+                                                                        pitch, out);
+  return check_launch("cross_kernel");
+}

@@ -1,0 +1,404 @@
+"""Functional layer over the C ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+PyTorch is plumbing here (device memory, current stream); every function below launches hand-written sm_100a
+kernels from libtorecsys_b200.so through ctypes.  CPU tensors are rejected loudly -- there is no fallback.
+"""
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import check, int_array, ptr_array
+
+_ACT_IDS = {'none': _cabi.ACT_NONE, 'relu': _cabi.ACT_RELU, 'sigmoid': _cabi.ACT_SIGMOID, 'tanh': _cabi.ACT_TANH}
+
+_status = {}          # device index -> int32[2] status tensor
+_index_check = 'deferred'
+
+
+def activation_id(act) -> int:
+    """Maps the reference's activation argument (an nn.Module instance or None) to a TRS_ACT_* id."""
+    import torch.nn as nn
+    if act is None:
+        return _cabi.ACT_NONE
+    if isinstance(act, str):
+        return _ACT_IDS[act]
+    if isinstance(act, nn.ReLU):
+        return _cabi.ACT_RELU
+    if isinstance(act, nn.Sigmoid):
+        return _cabi.ACT_SIGMOID
+    if isinstance(act, nn.Tanh):
+        return _cabi.ACT_TANH
+    if isinstance(act, nn.Identity):
+        return _cabi.ACT_NONE
+    raise NotImplementedError(f'activation {type(act).__name__} has no sm_100a kernel epilogue '
+                              '(supported: None, ReLU, Sigmoid, Tanh)')
+
+
+def set_index_check(mode: str):
+    """'sync': every lookup synchronises and raises IndexError at once (like the reference on CPU);
+    'deferred' (default): out-of-range lookups are counted on the device and raised by `check_index_errors()`."""
+    global _index_check
+    if mode not in ('sync', 'deferred'):
+        raise ValueError(mode)
+    _index_check = mode
+
+
+def _status_tensor(device: torch.device) -> torch.Tensor:
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _status.get(key)
+    if st is None:
+        st = torch.zeros(_cabi.TRS_STATUS_WORDS, dtype=torch.int32, device=device)
+        _status[key] = st
+    return st
+
+
+def check_index_errors(device=None):
+    """Synchronises and raises IndexError if any lookup since the last call was out of range."""
+    for key, st in list(_status.items()):
+        if device is not None and torch.device(device).index not in (None, key):
+            continue
+        host = st.cpu()
+        if int(host[0]) != 0:
+            st.zero_()
+            raise IndexError(f'index out of range in self ({int(host[0])} lookups; one offender at flat position '
+                             f'{int(host[1])} of the (batch, fields) index tensor)')
+
+
+def _after_lookup(device):
+    if _index_check == 'sync':
+        check_index_errors(device)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(name: str, *tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f'{name}: expected a tensor, got {type(t).__name__}')
+        if not t.is_cuda:
+            raise RuntimeError(f'{name}: torecsys_b200 runs on CUDA (sm_100a) only and has no CPU fallback; '
+                               f'got a tensor on {t.device}')
+
+
+def _f32(name: str, t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f'{name}: expected float32, got {t.dtype}')
+    t = t.rename(None) if t.has_names() else t
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _index(name: str, t: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    t = t.rename(None) if t.has_names() else t
+    if t.dtype == torch.int64:
+        bits = 64
+    elif t.dtype == torch.int32:
+        bits = 32
+    else:  # the reference promotes through `inputs + offsets` / `.long()`
+        t = t.long()
+        bits = 64
+    return (t if t.is_contiguous() else t.contiguous()), bits
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------- embeddings
+def embedding_gather(weight: torch.Tensor, idx: torch.Tensor, offsets: Optional[torch.Tensor]) -> torch.Tensor:
+    """out[b,n,:] = weight[idx[b,n] + offsets[n]]  (trs_embedding_gather)."""
+    _need_cuda('embedding_gather', weight, idx, offsets)
+    lib = _cabi.load()
+    w = _f32('embedding_gather', weight)
+    ix, bits = _index('embedding_gather', idx)
+    if ix.dim() != 2:
+        raise ValueError(f'embedding_gather: indices must be (B, N), got {tuple(ix.shape)}')
+    b, n = ix.shape
+    off = None
+    if offsets is not None:
+        off = offsets.rename(None).reshape(-1).to(device=w.device, dtype=torch.int64).contiguous()
+        if off.numel() != n:
+            raise ValueError(f'embedding_gather: {n} index columns but {off.numel()} offsets')
+    out = torch.empty((b, n, w.shape[1]), dtype=torch.float32, device=w.device)
+    st = _status_tensor(w.device)
+    check(lib.trs_embedding_gather(_ptr(w), w.shape[0], w.shape[1], _ptr(ix), bits, _ptr(off), b, n, _ptr(out),
+                                   _ptr(st), _stream()), 'trs_embedding_gather')
+    _after_lookup(w.device)
+    return out
+
+
+class TablePointers:
+    """Device array of table base pointers for the field-aware entry points (rebuilt when a table moves)."""
+
+    def __init__(self):
+        self._key = None
+        self._dev = None
+
+    def get(self, tables: Sequence[torch.Tensor]) -> torch.Tensor:
+        key = tuple(t.data_ptr() for t in tables)
+        if key != self._key:
+            self._dev = torch.tensor(key, dtype=torch.int64, device=tables[0].device)
+            self._key = key
+        return self._dev
+
+
+def embedding_gather_field_aware(tables: Sequence[torch.Tensor], idx: torch.Tensor, offsets: torch.Tensor,
+                                 table_ptrs: Optional[TablePointers] = None) -> torch.Tensor:
+    """out[b, t*N+f, :] = tables[t][idx[b,f] + offsets[f]]  (trs_embedding_gather_field_aware)."""
+    _need_cuda('embedding_gather_field_aware', idx, offsets, *tables)
+    lib = _cabi.load()
+    ws = [_f32('embedding_gather_field_aware', t) for t in tables]
+    ix, bits = _index('embedding_gather_field_aware', idx)
+    b, n = ix.shape
+    if len(ws) != n:
+        raise ValueError(f'embedding_gather_field_aware: {n} index columns but {len(ws)} tables')
+    rows, e = ws[0].shape
+    for w in ws:
+        if tuple(w.shape) != (rows, e):
+            raise ValueError('embedding_gather_field_aware: tables must share one shape')
+    off = offsets.rename(None).reshape(-1).to(device=ws[0].device, dtype=torch.int64).contiguous()
+    tp = (table_ptrs or TablePointers()).get(ws)
+    out = torch.empty((b, n * n, e), dtype=torch.float32, device=ws[0].device)
+    st = _status_tensor(ws[0].device)
+    check(lib.trs_embedding_gather_field_aware(_ptr(tp), rows, e, _ptr(ix), bits, _ptr(off), b, n, _ptr(out),
+                                               _ptr(st), _stream()), 'trs_embedding_gather_field_aware')
+    _after_lookup(ws[0].device)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------- layers
+def _bne(name: str, x: torch.Tensor) -> Tuple[torch.Tensor, int, int, int]:
+    _need_cuda(name, x)
+    x = _f32(name, x)
+    if x.dim() != 3:
+        raise ValueError(f'{name}: expected (B, N, E), got {tuple(x.shape)}')
+    return (x,) + tuple(x.shape)
+
+
+def fm(x: torch.Tensor) -> torch.Tensor:
+    x, b, n, e = _bne('fm', x)
+    out = torch.empty((b, e), dtype=torch.float32, device=x.device)
+    check(_cabi.load().trs_fm_forward(_ptr(x), b, n, e, _ptr(out), _stream()), 'trs_fm_forward')
+    return out
+
+
+def ffm(v: torch.Tensor, num_fields: int) -> torch.Tensor:
+    v, b, nn_, e = _bne('ffm', v)
+    if nn_ != num_fields * num_fields:
+        raise ValueError(f'ffm: expected (B, {num_fields * num_fields}, E), got {tuple(v.shape)}')
+    pairs = num_fields * (num_fields - 1) // 2
+    out = torch.empty((b, pairs, e), dtype=torch.float32, device=v.device)
+    check(_cabi.load().trs_ffm_forward(_ptr(v), b, num_fields, e, _ptr(out), _stream()), 'trs_ffm_forward')
+    return out
+
+
+def ipn(x: torch.Tensor) -> torch.Tensor:
+    x, b, n, e = _bne('ipn', x)
+    out = torch.empty((b, n * (n - 1) // 2), dtype=torch.float32, device=x.device)
+    check(_cabi.load().trs_ipn_forward(_ptr(x), b, n, e, _ptr(out), _stream()), 'trs_ipn_forward')
+    return out
+
+
+def bilinear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], each_type: bool) -> torch.Tensor:
+    x, b, n, e = _bne('bilinear', x)
+    _need_cuda('bilinear', weight, bias)
+    w = _f32('bilinear', weight)
+    bs = _f32('bilinear', bias) if bias is not None else None
+    pairs = n * (n - 1) // 2
+    want = (pairs, e, e) if each_type else (e, e)
+    if tuple(w.shape) != want:
+        raise ValueError(f'bilinear: weight must be {want}, got {tuple(w.shape)}')
+    out = torch.empty((b, pairs, e), dtype=torch.float32, device=x.device)
+    check(_cabi.load().trs_bilinear_forward(_ptr(x), _ptr(w), _ptr(bs), int(each_type), b, n, e, _ptr(out),
+                                            _stream()), 'trs_bilinear_forward')
+    return out
+
+
+def afm(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor
+        ) -> Tuple[torch.Tensor, torch.Tensor]:
+    x, b, n, e = _bne('afm', x)
+    _need_cuda('afm', w1, b1, w2, b2)
+    w1, b1, w2, b2 = (_f32('afm', t) for t in (w1, b1, w2, b2))
+    attn = w1.shape[0]
+    if tuple(w1.shape) != (attn, e) or w2.numel() != attn:
+        raise ValueError('afm: attention weights do not match (attn, embed)')
+    pairs = n * (n - 1) // 2
+    out = torch.empty((b, e), dtype=torch.float32, device=x.device)
+    scores = torch.empty((b, pairs, 1), dtype=torch.float32, device=x.device)
+    check(_cabi.load().trs_afm_forward(_ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), b, n, e, attn, _ptr(out),
+                                       _ptr(scores), _stream()), 'trs_afm_forward')
+    return out, scores
+
+
+def cross(x: torch.Tensor, weights: torch.Tensor, biases: torch.Tensor) -> torch.Tensor:
+    """x (..., E); weights (L, E, E); biases (L, E)."""
+    _need_cuda('cross', x, weights, biases)
+    x = _f32('cross', x)
+    w, bs = _f32('cross', weights), _f32('cross', biases)
+    e = x.shape[-1]
+    layers = w.shape[0]
+    if tuple(w.shape) != (layers, e, e) or tuple(bs.shape) != (layers, e):
+        raise ValueError('cross: weights must be (L, E, E) and biases (L, E)')
+    rows = x.numel() // e
+    out = torch.empty_like(x)
+    check(_cabi.load().trs_cross_forward(_ptr(x), _ptr(w), _ptr(bs), layers, rows, e, _ptr(out), _stream()),
+          'trs_cross_forward')
+    return out
+
+
+class CinPack:
+    """Host-side argument pack of a CIN stack (device pointers of the folded per-layer parameters)."""
+
+    def __init__(self, conv_w: List[torch.Tensor], scale: List[torch.Tensor], shift: List[torch.Tensor],
+                 layer_sizes: Sequence[int], is_direct: bool, act_id: int, fc_w: torch.Tensor, fc_b: torch.Tensor):
+        self.keep = (conv_w, scale, shift, fc_w, fc_b)
+        self.w = ptr_array([t.data_ptr() for t in conv_w])
+        self.scale = ptr_array([t.data_ptr() for t in scale])
+        self.shift = ptr_array([t.data_ptr() for t in shift])
+        self.sizes = int_array(layer_sizes)
+        self.layers = len(layer_sizes)
+        self.is_direct = int(is_direct)
+        self.act = act_id
+        self.fc_w, self.fc_b = fc_w, fc_b
+
+
+def cin(x: torch.Tensor, pack: CinPack, out_features: int) -> torch.Tensor:
+    x, b, n, e = _bne('cin', x)
+    lib = _cabi.load()
+    ws_bytes = lib.trs_cin_workspace_bytes(b, n, e, pack.sizes, pack.layers, pack.is_direct)
+    if ws_bytes < 0:
+        raise ValueError('cin: bad layer description')
+    ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=x.device)
+    out = torch.empty((b, out_features), dtype=torch.float32, device=x.device)
+    check(lib.trs_cin_forward(_ptr(x), pack.w, pack.scale, pack.shift, pack.sizes, pack.layers, pack.is_direct,
+                              pack.act, _ptr(pack.fc_w), _ptr(pack.fc_b), out_features, b, n, e, _ptr(out), _ptr(ws),
+                              ws.numel(), _stream()), 'trs_cin_forward')
+    return out
+
+
+class MlpPack:
+    """Host-side argument pack of an MLP: dims, device pointers of weights/biases."""
+
+    def __init__(self, weights: List[torch.Tensor], biases: List[torch.Tensor], act_id: int):
+        self.keep = (weights, biases)
+        self.dims_list = [weights[0].shape[1]] + [w.shape[0] for w in weights]
+        self.dims = int_array(self.dims_list)
+        self.layers = len(weights)
+        self.w = ptr_array([w.data_ptr() for w in weights])
+        self.b = ptr_array([b.data_ptr() for b in biases])
+        self.act = act_id
+
+
+def mlp(x: torch.Tensor, pack: MlpPack) -> torch.Tensor:
+    _need_cuda('mlp', x)
+    x = _f32('mlp', x)
+    k = pack.dims_list[0]
+    if x.shape[-1] != k:
+        raise ValueError(f'mlp: last dim {x.shape[-1]} != {k}')
+    rows = x.numel() // k
+    out = torch.empty(x.shape[:-1] + (pack.dims_list[-1],), dtype=torch.float32, device=x.device)
+    check(_cabi.load().trs_mlp_forward(_ptr(x), rows, pack.dims, pack.layers, pack.w, pack.b, pack.act, _ptr(out),
+                                       _stream()), 'trs_mlp_forward')
+    return out
+
+
+# ------------------------------------------------------------------------------------------------- fused models
+def _fused_common(name, idx, offsets, *tensors):
+    _need_cuda(name, idx, offsets, *tensors)
+    ix, bits = _index(name, idx)
+    if ix.dim() != 2:
+        raise ValueError(f'{name}: indices must be (B, N), got {tuple(ix.shape)}')
+    off = offsets.rename(None).reshape(-1).to(device=ix.device, dtype=torch.int64).contiguous()
+    if off.numel() != ix.shape[1]:
+        raise ValueError(f'{name}: {ix.shape[1]} index columns but {off.numel()} offsets')
+    return ix, bits, off
+
+
+def fm_model(idx, offsets, w_feat, w_emb, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None):
+    ix, bits, off = _fused_common('fm_model', idx, offsets, w_feat, w_emb, bias)
+    wf, we = _f32('fm_model', w_feat), _f32('fm_model', w_emb)
+    bs = _f32('fm_model', bias).reshape(-1) if bias is not None else None
+    b, n = ix.shape
+    out = out if out is not None else torch.empty((b, 1), dtype=torch.float32, device=we.device)
+    st = _status_tensor(we.device)
+    check(_cabi.load().trs_fm_model_forward(_ptr(ix), bits, _ptr(off), b, n, _ptr(wf), _ptr(we), we.shape[0],
+                                            we.shape[1], _ptr(bs), _ptr(out), _ptr(st), _stream()),
+          'trs_fm_model_forward')
+    _after_lookup(we.device)
+    return out
+
+
+def deepfm(idx, offsets, w_feat, w_emb, pack: MlpPack, out: Optional[torch.Tensor] = None):
+    ix, bits, off = _fused_common('deepfm', idx, offsets, w_feat, w_emb)
+    wf, we = _f32('deepfm', w_feat), _f32('deepfm', w_emb)
+    b, n = ix.shape
+    out = out if out is not None else torch.empty((b, 1), dtype=torch.float32, device=we.device)
+    st = _status_tensor(we.device)
+    check(_cabi.load().trs_deepfm_forward(_ptr(ix), bits, _ptr(off), b, n, _ptr(wf), _ptr(we), we.shape[0],
+                                          we.shape[1], pack.dims, pack.layers, pack.w, pack.b, pack.act, _ptr(out),
+                                          _ptr(st), _stream()), 'trs_deepfm_forward')
+    _after_lookup(we.device)
+    return out
+
+
+def dcn(idx, offsets, w_emb, cross_w, cross_b, pack: MlpPack, fc_w, fc_b, out: Optional[torch.Tensor] = None):
+    ix, bits, off = _fused_common('dcn', idx, offsets, w_emb, cross_w, cross_b, fc_w, fc_b)
+    we = _f32('dcn', w_emb)
+    cw, cb, fw, fb = (_f32('dcn', t) for t in (cross_w, cross_b, fc_w, fc_b))
+    b, n = ix.shape
+    if fw.shape[0] != 1:
+        raise NotImplementedError('dcn: the fused kernel emits one logit (output_size = 1)')
+    out = out if out is not None else torch.empty((b, 1), dtype=torch.float32, device=we.device)
+    st = _status_tensor(we.device)
+    check(_cabi.load().trs_dcn_forward(_ptr(ix), bits, _ptr(off), b, n, _ptr(we), we.shape[0], we.shape[1], _ptr(cw),
+                                       _ptr(cb), cw.shape[0], pack.dims, pack.layers, pack.w, pack.b, pack.act,
+                                       _ptr(fw), _ptr(fb), _ptr(out), _ptr(st), _stream()), 'trs_dcn_forward')
+    _after_lookup(we.device)
+    return out
+
+
+def xdeepfm(idx, offsets, w_feat, w_emb, cin_pack: CinPack, mlp_pack: MlpPack, bias,
+            out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    ix, bits, off = _fused_common('xdeepfm', idx, offsets, w_feat, w_emb, bias)
+    wf, we = _f32('xdeepfm', w_feat), _f32('xdeepfm', w_emb)
+    bs = _f32('xdeepfm', bias).reshape(-1)
+    b, n = ix.shape
+    lib = _cabi.load()
+    need = lib.trs_xdeepfm_workspace_bytes(b, n, we.shape[1], cin_pack.sizes, cin_pack.layers, cin_pack.is_direct)
+    if need < 0:
+        raise ValueError('xdeepfm: bad CIN description')
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(int(need), dtype=torch.uint8, device=we.device)
+    out = out if out is not None else torch.empty((b, 1), dtype=torch.float32, device=we.device)
+    st = _status_tensor(we.device)
+    check(lib.trs_xdeepfm_forward(_ptr(ix), bits, _ptr(off), b, n, _ptr(wf), _ptr(we), we.shape[0], we.shape[1],
+                                  cin_pack.w, cin_pack.scale, cin_pack.shift, cin_pack.sizes, cin_pack.layers,
+                                  cin_pack.is_direct, cin_pack.act, _ptr(cin_pack.fc_w), _ptr(cin_pack.fc_b),
+                                  mlp_pack.dims, mlp_pack.layers, mlp_pack.w, mlp_pack.b, mlp_pack.act, _ptr(bs),
+                                  _ptr(out), _ptr(workspace), workspace.numel(), _ptr(st), _stream()),
+          'trs_xdeepfm_forward')
+    _after_lookup(we.device)
+    return out
+
+
+def ffm_model(idx, offsets, w_feat, tables: Sequence[torch.Tensor], bias, table_ptrs: Optional[TablePointers] = None,
+              out: Optional[torch.Tensor] = None):
+    ix, bits, off = _fused_common('ffm_model', idx, offsets, w_feat, bias, *tables)
+    wf = _f32('ffm_model', w_feat)
+    ws = [_f32('ffm_model', t) for t in tables]
+    bs = _f32('ffm_model', bias).reshape(-1) if bias is not None else None
+    b, n = ix.shape
+    if len(ws) != n:
+        raise ValueError(f'ffm_model: {n} index columns but {len(ws)} tables')
+    rows, e = ws[0].shape
+    tp = (table_ptrs or TablePointers()).get(ws)
+    out = out if out is not None else torch.empty((b, 1), dtype=torch.float32, device=ws[0].device)
+    st = _status_tensor(ws[0].device)
+    check(_cabi.load().trs_ffm_model_forward(_ptr(ix), bits, _ptr(off), b, n, _ptr(wf), _ptr(tp), rows, e, _ptr(bs),
+                                             _ptr(out), _ptr(st), _stream()), 'trs_ffm_model_forward')
+    _after_lookup(ws[0].device)
+    return out
