@@ -156,6 +156,21 @@ int trs_deepfm_forward(const void* idx, int idx_bits, const int64_t* offsets, in
                        const int* mlp_dims, int mlp_layers, const float* const* mlp_w, const float* const* mlp_b,
                        int activation, float* logits, int32_t* status, void* stream);
 
+/* Packed-table variant of the DeepFM forward (embed_size = 16 only): the B200-first memory layout of this path.
+ * A random row read costs one 128-byte DRAM transaction whatever its size (measured), so the two
+ * lookups per field of the reference (MultiIndicesEmbedding(16) and MultiIndicesEmbedding(1) on the same row id,
+ * torecsys/inputs/inputs.py:69-87) are served from ONE 128-byte aligned shadow row:
+ *     packed[r] = [ w_emb[r][0..15] | w_feat[r] | 15 x 0 ]        packed (rows, 32) fp32, 128-byte aligned
+ * trs_fm_pack_table builds it from the two registered tables (run again whenever they change);
+ * trs_deepfm_forward_packed computes exactly what trs_deepfm_forward computes.
+ * Restrictions: hidden widths 16, ReLU, fields <= 40, rows < 2^31 (TRS_ERR_UNSUPPORTED otherwise). */
+int trs_fm_pack_table(const float* w_emb, const float* w_feat, int64_t rows, int embed, float* packed, void* stream);
+int trs_deepfm_forward_packed(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                              const float* packed, int64_t rows,
+                              const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                              const float* const* mlp_b, int activation, float* logits, int32_t* status,
+                              void* stream);
+
 /* DeepAndCrossNetworkModel.forward (torecsys/models/ctr/deep_and_cross_network.py:58-98):
  *     logit = fc( flatten( cat[ Cross(emb) (B,N,E), MLP_per_field(emb) (B,N,Od) ], dim=-1 ) )
  * cross_w (cross_layers, E, E), cross_b (cross_layers, E); MLP in = embed, out = Od; fc_w (1, N*(E+Od)), fc_b (1). */
@@ -201,6 +216,12 @@ int trs_session_deepfm_forward_host(trs_session* session, const void* idx_host, 
                                     const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
                                     const float* const* mlp_b, int activation,
                                     float* logits_host, int64_t* oob_count);
+int trs_session_deepfm_forward_host_packed(trs_session* session, const void* idx_host, int idx_bits,
+                                           const int64_t* offsets, int64_t batch, int fields,
+                                           const float* packed, int64_t rows,
+                                           const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                                           const float* const* mlp_b, int activation,
+                                           float* logits_host, int64_t* oob_count);
 
 #ifdef __cplusplus
 }

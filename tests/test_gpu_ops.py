@@ -172,6 +172,52 @@ def test_deepfm_fast_path_matches_generic_and_oracle(ops, monkeypatch):
             assert normwise_err(got, want64) <= max(4 * normwise_err(want, want64), 2e-6), batch
 
 
+@pytest.mark.parametrize('n', [1, 7, 8, 9, 16, 17, 24, 26, 32, 39, 40])
+def test_deepfm_packed_table_path(ops, n):
+    """deepfm_packed.cu: 128-byte shadow rows + cp.async ring + field-split warps.  Must equal the oracle (and hence
+    the split-table path) for every fields-per-warp instantiation, ragged batches, int32/int64 indices."""
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    e = 16
+    fs = [16 * (3 + i % 5) for i in range(n)]
+    rows = sum(fs)
+    off = R.field_offsets(fs)
+    w_feat = torch.from_numpy(synth.uniform((rows, 1), f'pk{n}/wf'))
+    w_emb = torch.from_numpy(synth.uniform((rows, e), f'pk{n}/we'))
+    dims = [n * e, 16, 16, 16, 1]
+    ws = [torch.from_numpy(synth.uniform((dims[i + 1], dims[i]), f'pk{n}/w{i}', -1 / np.sqrt(dims[i]),
+                                         1 / np.sqrt(dims[i]))) for i in range(4)]
+    bs = [torch.from_numpy(synth.uniform((dims[i + 1],), f'pk{n}/b{i}', -0.5, 0.5)) for i in range(4)]
+    pack = ops.MlpPack([w.cuda() for w in ws], [b.cuda() for b in bs], ops.activation_id('relu'))
+    packed = ops.fm_pack_table(w_emb.cuda(), w_feat.cuda())
+    assert packed.shape == (rows, 32)
+    assert torch.equal(packed[:, :16].cpu(), w_emb) and torch.equal(packed[:, 16].cpu(), w_feat[:, 0])
+    assert not packed[:, 17:].any()
+    for batch in (1, 16, 33, 2500, 16 * 148 * 5 + 3):
+        idx = torch.from_numpy(synth.integers((batch, n), f'pk{n}/idx{batch}', np.asarray(fs)[None, :]))
+        want = R.deepfm_from_indices(idx, off, w_feat, w_emb, ws, bs).numpy()
+        want64 = R.deepfm_from_indices(idx, off, w_feat.double(), w_emb.double(), [w.double() for w in ws],
+                                       [b.double() for b in bs]).numpy()
+        for dt in (torch.int64, torch.int32):
+            got = ops.deepfm_packed(idx.cuda().to(dt), off.cuda(), packed, pack).cpu().numpy()
+            assert normwise_err(got, want) <= TOL, (n, batch)
+            assert normwise_err(got, want64) <= max(4 * normwise_err(want, want64), 2e-6), (n, batch)
+
+
+def test_deepfm_packed_out_of_range(ops):
+    from torecsys_b200 import synth
+    n, rows = 39, 39 * 16
+    packed = ops.fm_pack_table(torch.randn(rows, 16, device='cuda'), torch.randn(rows, 1, device='cuda'))
+    dims = [n * 16, 16, 16, 16, 1]
+    pack = ops.MlpPack([torch.randn(dims[i + 1], dims[i], device='cuda') for i in range(4)],
+                       [torch.randn(dims[i + 1], device='cuda') for i in range(4)], ops.activation_id('relu'))
+    off = (torch.arange(n) * 16).cuda()
+    idx = torch.zeros(20, n, dtype=torch.long, device='cuda')
+    idx[7, 38] = 16   # one past the last row of the table
+    with pytest.raises(IndexError):
+        ops.deepfm_packed(idx, off, packed, pack)
+
+
 def test_out_of_range_index_raises(ops):
     w = torch.randn(10, 4, device='cuda')
     idx = torch.tensor([[3], [10]], device='cuda')

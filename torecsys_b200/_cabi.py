@@ -43,6 +43,9 @@ PROTOTYPES = {
     'trs_fm_model_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _P, _P, _P, _P]),
     'trs_deepfm_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _IP, c_int, _PP, _PP,
                                    c_int, _P, _P, _P]),
+    'trs_fm_pack_table': (c_int, [_P, _P, c_int64, c_int, _P, _P]),
+    'trs_deepfm_forward_packed': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, _IP, c_int, _PP, _PP, c_int,
+                                          _P, _P, _P]),
     'trs_dcn_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, c_int, _P, _P, c_int, _IP, c_int, _PP,
                                 _PP, c_int, _P, _P, _P, _P, _P]),
     'trs_xdeepfm_workspace_bytes': (c_int64, [c_int64, c_int, c_int, _IP, c_int, c_int]),
@@ -53,6 +56,8 @@ PROTOTYPES = {
     'trs_session_destroy': (c_int, [c_void_p]),
     'trs_session_deepfm_forward_host': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _IP,
                                                 c_int, _PP, _PP, c_int, _P, POINTER(c_int64)]),
+    'trs_session_deepfm_forward_host_packed': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, c_int64, _IP,
+                                                       c_int, _PP, _PP, c_int, _P, POINTER(c_int64)]),
 }
 
 _lib = None

@@ -75,12 +75,10 @@ extern "C" int trs_session_destroy(trs_session* s) {
   return TRS_OK;
 }
 
-extern "C" int trs_session_deepfm_forward_host(trs_session* s, const void* idx_host, int idx_bits,
-                                               const int64_t* offsets, int64_t batch, int fields,
-                                               const float* w_feat, const float* w_emb, int64_t rows, int embed,
-                                               const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
-                                               const float* const* mlp_b, int activation, float* logits_host,
-                                               int64_t* oob_count) {
+static int session_run(trs_session* s, const void* idx_host, int idx_bits, const int64_t* offsets, int64_t batch,
+                       int fields, const float* w_feat, const float* w_emb, const float* packed, int64_t rows,
+                       int embed, const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                       const float* const* mlp_b, int activation, float* logits_host, int64_t* oob_count) {
   TRS_REQUIRE(s && idx_host && logits_host, "trs_session_deepfm_forward_host: null pointer");
   TRS_REQUIRE(idx_bits == 32 || idx_bits == 64, "trs_session_deepfm_forward_host: idx_bits must be 32 or 64");
   TRS_REQUIRE(batch >= 0 && batch <= s->max_batch && fields == s->fields,
@@ -99,7 +97,7 @@ extern "C" int trs_session_deepfm_forward_host(trs_session* s, const void* idx_h
   TRS_CUDA(cudaEventRecord(ready, s->streams[0]));
   TRS_CUDA(cudaStreamWaitEvent(s->streams[1], ready, 0));
   const int chunks = (int)(batch < s->chunks ? batch : s->chunks);
-  const int64_t per = (batch + chunks - 1) / chunks;
+  const int64_t per = (((batch + chunks - 1) / chunks + 15) / 16) * 16;  // slices start on 16-byte aligned indices
   int rc = TRS_OK;
   for (int c = 0; c < chunks && rc == TRS_OK; ++c) {
     const int64_t b0 = c * per;
@@ -113,9 +111,14 @@ extern "C" int trs_session_deepfm_forward_host(trs_session* s, const void* idx_h
       src = static_cast<const char*>(s->idx_pinned) + off;
     }
     TRS_CUDA(cudaMemcpyAsync(static_cast<char*>(s->idx_dev) + off, src, bytes, cudaMemcpyHostToDevice, st));
-    rc = trs_deepfm_forward(static_cast<char*>(s->idx_dev) + off, idx_bits, offsets, nb, fields, w_feat, w_emb, rows,
-                            embed, mlp_dims, mlp_layers, mlp_w, mlp_b, activation, s->logits_dev + b0, s->status_dev,
-                            st);
+    if (packed != nullptr)
+      rc = trs_deepfm_forward_packed(static_cast<char*>(s->idx_dev) + off, idx_bits, offsets, nb, fields, packed, rows,
+                                     mlp_dims, mlp_layers, mlp_w, mlp_b, activation, s->logits_dev + b0,
+                                     s->status_dev, st);
+    else
+      rc = trs_deepfm_forward(static_cast<char*>(s->idx_dev) + off, idx_bits, offsets, nb, fields, w_feat, w_emb,
+                              rows, embed, mlp_dims, mlp_layers, mlp_w, mlp_b, activation, s->logits_dev + b0,
+                              s->status_dev, st);
     if (rc != TRS_OK) break;
     float* dst = dst_pinned ? logits_host + b0 : s->logits_pinned + b0;
     TRS_CUDA(cudaMemcpyAsync(dst, s->logits_dev + b0, (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -136,4 +139,25 @@ extern "C" int trs_session_deepfm_forward_host(trs_session* s, const void* idx_h
   if (!dst_pinned) memcpy(logits_host, s->logits_pinned, (size_t)batch * sizeof(float));
   if (oob_count) *oob_count = s->status_pinned[0];
   return TRS_OK;
+}
+
+extern "C" int trs_session_deepfm_forward_host(trs_session* s, const void* idx_host, int idx_bits,
+                                               const int64_t* offsets, int64_t batch, int fields,
+                                               const float* w_feat, const float* w_emb, int64_t rows, int embed,
+                                               const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                                               const float* const* mlp_b, int activation, float* logits_host,
+                                               int64_t* oob_count) {
+  return session_run(s, idx_host, idx_bits, offsets, batch, fields, w_feat, w_emb, nullptr, rows, embed, mlp_dims,
+                     mlp_layers, mlp_w, mlp_b, activation, logits_host, oob_count);
+}
+
+extern "C" int trs_session_deepfm_forward_host_packed(trs_session* s, const void* idx_host, int idx_bits,
+                                                      const int64_t* offsets, int64_t batch, int fields,
+                                                      const float* packed, int64_t rows, const int* mlp_dims,
+                                                      int mlp_layers, const float* const* mlp_w,
+                                                      const float* const* mlp_b, int activation,
+                                                      float* logits_host, int64_t* oob_count) {
+  TRS_REQUIRE(packed, "trs_session_deepfm_forward_host_packed: null packed table");
+  return session_run(s, idx_host, idx_bits, offsets, batch, fields, nullptr, nullptr, packed, rows, 16, mlp_dims,
+                     mlp_layers, mlp_w, mlp_b, activation, logits_host, oob_count);
 }

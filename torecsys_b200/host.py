@@ -34,6 +34,24 @@ class DeepFMSession:
             raise IndexError(f'index out of range in self ({oob.value} lookups)')
         return logits_host
 
+    def forward_host_packed(self, idx_host: torch.Tensor, offsets: torch.Tensor, packed: torch.Tensor, pack: MlpPack,
+                            logits_host: torch.Tensor) -> torch.Tensor:
+        """Same as forward_host on the packed [v|w] shadow table (ops.fm_pack_table)."""
+        if idx_host.is_cuda or logits_host.is_cuda:
+            raise RuntimeError('forward_host_packed takes HOST index/logit buffers')
+        if not (packed.is_cuda and offsets.is_cuda):
+            raise RuntimeError('forward_host_packed: table and offsets live on the CUDA device (no CPU fallback)')
+        bits = {torch.int64: 64, torch.int32: 32}[idx_host.dtype]
+        b, n = idx_host.shape
+        oob = ctypes.c_int64(0)
+        check(self._lib.trs_session_deepfm_forward_host_packed(
+            self._h, idx_host.data_ptr(), bits, offsets.data_ptr(), b, n, packed.data_ptr(), packed.shape[0],
+            pack.dims, pack.layers, pack.w, pack.b, pack.act, logits_host.data_ptr(), ctypes.byref(oob)),
+            'trs_session_deepfm_forward_host_packed')
+        if oob.value:
+            raise IndexError(f'index out of range in self ({oob.value} lookups)')
+        return logits_host
+
     def close(self):
         if self._h:
             self._lib.trs_session_destroy(self._h)

@@ -105,7 +105,11 @@ def _index(name: str, t: torch.Tensor) -> Tuple[torch.Tensor, int]:
 
 
 def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else t.data_ptr()
+    if t is None:
+        return None
+    # torch gives empty tensors a null data pointer; the C ABI treats null as "argument missing", so hand it the
+    # (never dereferenced) status word instead
+    return t.data_ptr() or _status_tensor(t.device).data_ptr()
 
 
 # ------------------------------------------------------------------------------------------------- embeddings
@@ -342,6 +346,34 @@ def deepfm(idx, offsets, w_feat, w_emb, pack: MlpPack, out: Optional[torch.Tenso
                                           we.shape[1], pack.dims, pack.layers, pack.w, pack.b, pack.act, _ptr(out),
                                           _ptr(st), _stream()), 'trs_deepfm_forward')
     _after_lookup(we.device)
+    return out
+
+
+def fm_pack_table(w_emb: torch.Tensor, w_feat: torch.Tensor) -> torch.Tensor:
+    """Builds the 128-byte-row shadow table [v(16) | w | pad] (trs_fm_pack_table); (R, 32) fp32."""
+    _need_cuda('fm_pack_table', w_emb, w_feat)
+    we, wf = _f32('fm_pack_table', w_emb), _f32('fm_pack_table', w_feat)
+    rows, e = we.shape
+    if wf.numel() != rows:
+        raise ValueError('fm_pack_table: the two tables must have the same number of rows')
+    packed = torch.empty((rows, 32), dtype=torch.float32, device=we.device)
+    check(_cabi.load().trs_fm_pack_table(_ptr(we), _ptr(wf), rows, e, _ptr(packed), _stream()), 'trs_fm_pack_table')
+    return packed
+
+
+def deepfm_packed(idx, offsets, packed: torch.Tensor, pack: MlpPack, out: Optional[torch.Tensor] = None):
+    ix, bits, off = _fused_common('deepfm_packed', idx, offsets, packed)
+    if packed.dtype != torch.float32 or packed.dim() != 2 or packed.shape[1] != 32 or not packed.is_contiguous():
+        raise ValueError('deepfm_packed: packed table must be a contiguous (rows, 32) float32 tensor')
+    b, n = ix.shape
+    if ix.data_ptr() % 16:   # a view into a larger tensor: the kernel copies index tiles with 16-byte cp.async
+        ix = ix.clone()
+    out = out if out is not None else torch.empty((b, 1), dtype=torch.float32, device=packed.device)
+    st = _status_tensor(packed.device)
+    check(_cabi.load().trs_deepfm_forward_packed(_ptr(ix), bits, _ptr(off), b, n, _ptr(packed), packed.shape[0],
+                                                 pack.dims, pack.layers, pack.w, pack.b, pack.act, _ptr(out),
+                                                 _ptr(st), _stream()), 'trs_deepfm_forward_packed')
+    _after_lookup(packed.device)
     return out
 
 
