@@ -1,23 +1,28 @@
 // DeepFM forward on a PACKED table (embed = 16, hidden widths = 16): the B200-first layout of the hot path.
 //
-// Measured on B200 (tools/gather_microbench.cu, profiles/r01_gather_microbench_ncu.csv): a random row read costs one
-// 128-byte DRAM transaction whatever its size <= 128 B, and the chip sustains ~38 G such transactions/s.  The
-// reference's two tables (emb (R,16) and first-order (R,1), same row ids) therefore cost 78 transactions per sample;
-// packing them as one 128-byte-aligned row  [ v0..v15 | w | pad ]  (trs_fm_pack_table) makes it 39, the floor for
-// this model.  The packed table is a shadow of the registered parameters (rebuilt by the host layer when their
-// version changes), 25.6 GB for 200 M rows.
+// Measured on B200 (tools/gather_microbench.cu, profiles/r01_gather_microbench_ncu.csv): random row reads are bound
+// by the number of memory REQUESTS, not by bytes -- the chip sustains ~32-38 G random requests/s whatever the row
+// size up to 128 B, DRAM always moves the whole 128-byte line, and a second request to the same line from another
+// instruction costs almost as much as the first (64 B + a separate 4 B read of the same line: 69 -> 121 us).
+// The reference's two tables (emb (R,16) and first-order (R,1), same row ids) therefore cost 78 requests per sample;
+// packing them as one 128-byte-aligned row  [ v0..v15 | w | pad ]  (trs_fm_pack_table) and reading [v|w] with ONE
+// warp instruction makes it 39, the floor for this model.  The packed table is a shadow of the registered
+// parameters (rebuilt by the host layer when their version changes), 25.6 GB for 200 M rows.
 //
 // Kernel shape (one persistent CTA of 8 warps per SM, grid = 148):
 //   * a tile = 16 samples; warp w owns fields [w*FPW, (w+1)*FPW) of EVERY tile, so its slice of W1 (B fragments of
 //     mma.sync.m16n8k8 TF32, pre-split hi/lo) lives in its registers -- no shared memory, no L2 traffic for W1;
 //   * rows travel global -> shared with cp.async (LDGSTS) into a per-warp ring of kStages tiles, so in-flight loads
 //     cost no registers (8 warps x 2 stages x 16 x FPW rows = 1 248 rows in flight per SM); eight lanes per row copy
-//     [v|w] as ONE 80-byte request; the (16 x fields) index tiles have their own, deeper cp.async ring;
-//     lane (g,t) then reads chunk t of the rows of samples g and g+8 = exactly its A-fragment elements;
-//   * per tile each warp produces partial layer-1 accumulators, partial FM sums and first-order sums for its fields;
-//     one bar.sync per tile, then warp (tile % 8) reduces the 8 partials and runs the tiny 16x16 layers + output
-//     while the other warps already work on the next tile.
-// FP32 accuracy on the tensor pipe through the 3xTF32 split; the roofline is the HBM transaction rate.
+//     [v|w] as ONE 80-byte request; each lane resolves (index + offset, range check) at most three rows of the
+//     warp's 16 x FPW and the copy loop gets the row ids by shuffle; the (16 x fields) index tiles have their own,
+//     deeper cp.async ring because the loaded memory latency (several microseconds) exceeds one tile iteration;
+//   * lane (g,t) reads chunk t of the rows of samples g and g+8 = exactly its mma A-fragment elements; per tile each
+//     warp publishes partial layer-1 accumulators, partial FM sums and first-order sums for its fields; after ONE
+//     bar.sync per tile every warp finishes two of the 16 samples (reduce the 8 partials, bias + ReLU, the 16x16
+//     hidden layers and the output layer in plain FP32 FFMA with shuffles, FM, logit).
+// Layer 1 (9 984 MACs/sample) runs on the tensor pipe, FP32-accurate through the 3xTF32 split; the roofline of the
+// kernel is the HBM request rate, not the tensor pipe.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -27,12 +32,24 @@ namespace {
 
 constexpr int kWarps = 8;
 constexpr int kTile = 16;
-constexpr int kStages = 3;      // row ring depth (kStages-1 tiles of rows in flight)
+constexpr int kStages = 3;                  // row ring depth (kStages-1 tiles of rows in flight)
 constexpr int kIdxAhead = 2 * kStages - 1;  // index tiles are requested this many tiles ahead of their use ...
-constexpr int kIdxSlots = kIdxAhead + 1;    // ... into a ring of this many slots
+constexpr int kIdxSlots = kIdxAhead;        // ... into a ring of this many slots
 constexpr int kMaxHidden = 4;
-constexpr int kRowFloats = 32;   // packed row pitch: 128 B
-constexpr int kPartial = 18;     // floats per lane per warp per tile: 8 acc + 8 S + 2 c
+constexpr int kRowFloats = 32;              // packed row pitch: 128 B
+
+// Row staging layout of one (warp, stage): [field f][sample pair k = s/2][40 floats]:
+//   floats  0..15 = v of sample 2k, 16..31 = v of sample 2k+1, 32..35 / 36..39 = the 16-byte chunk holding w of each.
+// The two rows of a pair fill the 32 banks exactly once, so the consumers' LDS.128 (quarter-warp = two samples x four
+// chunks) are conflict-free, and every cp.async destination is 16-byte aligned.
+constexpr int kPairFloats = 40;
+constexpr int kFieldFloats = 8 * kPairFloats;  // 16 samples of one field
+
+// Partial exchange buffer of one (parity, warp): H[16 samples][24] layer-1 partials, S[16][16] FM sums,
+// C[16][4] = first-order - 0.5 * sum of squares (per t lane).  Pitches chosen for conflict-free publishing stores.
+constexpr int kHPitch = 24;
+constexpr int kPartialFloats = 16 * kHPitch + 16 * 16 + 16 * 4;  // 704
+constexpr int kHidPitch = 17;
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
   uint32_t r;
@@ -61,13 +78,9 @@ __device__ __forceinline__ void mma_3x(float (&d)[4], const uint32_t (&ah)[4], c
   mma_tf32(d, ah, bl0, bl1);
   mma_tf32(d, ah, bh0, bh1);
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zeros
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, bool valid) {
-  const int sz = valid ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  // src_bytes < 16 => the remaining destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -91,34 +104,32 @@ struct PackedArgs {
   int fields, hidden_layers;
 };
 
-// Row staging layout of one (warp, stage): [field f][sample pair k = s/2][40 floats]:
-//   floats  0..15 = v of sample 2k, 16..31 = v of sample 2k+1, 32..35 / 36..39 = the 16-byte chunk holding w of each.
-// The two rows of a pair fill the 32 banks exactly once, so the consumers' LDS.128 (quarter-warp = two samples x four
-// chunks) are conflict-free, and every cp.async destination is 16-byte aligned.
-constexpr int kPairFloats = 40;
-constexpr int kFieldFloats = 8 * kPairFloats;   // 16 samples of one field
-
 template <int FPW>
 struct Smem {
   static constexpr size_t v_bytes = (size_t)kWarps * kStages * FPW * kFieldFloats * sizeof(float);
-  static constexpr size_t w_bytes = 0;
-  static constexpr size_t p_bytes = (size_t)2 * kWarps * kPartial * 32 * sizeof(float);
-  static constexpr size_t h_bytes = (size_t)kMaxHidden * 8 * 32 * sizeof(float2);
+  static constexpr size_t p_bytes = (size_t)2 * kWarps * kPartialFloats * sizeof(float);
+  static constexpr size_t h_bytes = (size_t)kMaxHidden * 16 * kHidPitch * sizeof(float);
   static constexpr size_t b_bytes = ((1 + kMaxHidden) * 16 + 16 + 4) * sizeof(float);
-  static constexpr size_t fixed = v_bytes + w_bytes + p_bytes + h_bytes + b_bytes;
-  // + index ring: kIdxSlots x (16 samples x fields x idx bytes), sized at launch
-  static size_t total(int fields, int idx_bits) { return fixed + (size_t)kIdxSlots * kTile * fields * (idx_bits / 8); }
+  static constexpr size_t fixed = v_bytes + p_bytes + h_bytes + b_bytes;
+  // + field offsets (int64 per field, padded to 16 B) + index ring (kIdxSlots x 16 samples x fields x idx bytes)
+  __host__ __device__ static size_t off_bytes(int fields) { return (((size_t)fields * 8 + 15) / 16) * 16; }
+  static size_t total(int fields, int idx_bits) {
+    return fixed + off_bytes(fields) + (size_t)kIdxSlots * kTile * fields * (idx_bits / 8);
+  }
 };
 
 template <int IdxBits, int FPW>
 __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArgs a) {
   using S = Smem<FPW>;
+  constexpr int kRowsPerWarp = 16 * FPW;                 // rows of one tile copied by one warp
+  constexpr int kResolve = (kRowsPerWarp + 31) / 32;     // rows resolved per lane
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* vbuf = reinterpret_cast<float*>(smem_raw);
-  float* pbuf = reinterpret_cast<float*>(smem_raw + S::v_bytes + S::w_bytes);
-  float2* whs = reinterpret_cast<float2*>(smem_raw + S::v_bytes + S::w_bytes + S::p_bytes);
-  float* bias_s = reinterpret_cast<float*>(smem_raw + S::v_bytes + S::w_bytes + S::p_bytes + S::h_bytes);
-  unsigned char* idx_ring = smem_raw + S::fixed;   // [kIdxSlots][16 * fields] indices, 16-byte aligned slots
+  float* pbuf = reinterpret_cast<float*>(smem_raw + S::v_bytes);
+  float* hid_s = reinterpret_cast<float*>(smem_raw + S::v_bytes + S::p_bytes);   // [layer][16][17]
+  float* bias_s = reinterpret_cast<float*>(smem_raw + S::v_bytes + S::p_bytes + S::h_bytes);
+  long long* off_s = reinterpret_cast<long long*>(smem_raw + S::fixed);
+  unsigned char* idx_ring = smem_raw + S::fixed + S::off_bytes(a.fields);   // [kIdxSlots][16 * fields] indices
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -126,7 +137,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
   const int kdim = 16 * n_fields;
   const int f0 = warp * FPW;  // first field of this warp
 
-  // ---- one-time: this warp's W1 B-fragments into registers (hi/lo), hidden-layer fragments + biases to smem ----
+  // ---- one-time: this warp's W1 B-fragments into registers (hi/lo); hidden layers, biases, offsets to smem ----------
   float4 w1h[FPW][2], w1l[FPW][2];
 #pragma unroll
   for (int f = 0; f < FPW; ++f) {
@@ -144,14 +155,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
       w1l[f][j] = make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3]));
     }
   }
-  for (int i = threadIdx.x; i < a.hidden_layers * 4 * 32; i += blockDim.x) {
-    const int l = i & 31, jk = (i >> 5) & 1, jn = (i >> 6) & 1, layer = i >> 7;
-    const float* w = a.wh[layer] + (8 * jn + (l >> 2)) * 16 + 8 * jk + 2 * (l & 3);
-    uint32_t h0, l0, h1, l1;
-    split_rna(__ldg(w), h0, l0);
-    split_rna(__ldg(w + 1), h1, l1);
-    whs[(((layer * 2 + jn) * 2 + jk) * 2 + 0) * 32 + l] = make_float2(__uint_as_float(h0), __uint_as_float(h1));
-    whs[(((layer * 2 + jn) * 2 + jk) * 2 + 1) * 32 + l] = make_float2(__uint_as_float(l0), __uint_as_float(l1));
+  for (int i = threadIdx.x; i < a.hidden_layers * 256; i += blockDim.x) {
+    const int layer = i >> 8, o = (i >> 4) & 15, k = i & 15;
+    hid_s[(layer * 16 + o) * kHidPitch + k] = __ldg(a.wh[layer] + o * 16 + k);
   }
   for (int i = threadIdx.x; i < 16; i += blockDim.x) {
     bias_s[i] = __ldg(a.b1 + i);
@@ -159,60 +165,61 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
     bias_s[(1 + kMaxHidden) * 16 + i] = __ldg(a.w_out + i);
   }
   if (threadIdx.x == 0) bias_s[(1 + kMaxHidden) * 16 + 16] = __ldg(a.b_out);
-  __syncthreads();
+  for (int i = threadIdx.x; i < n_fields; i += blockDim.x) off_s[i] = __ldg(a.offsets + i);
 
   const int64_t tiles = (a.batch + kTile - 1) / kTile;
   const int64_t my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
   float* my_v = vbuf + (size_t)warp * kStages * FPW * kFieldFloats;   // + stage * FPW * kFieldFloats
 
   // Index tiles: the (16 x fields) indices of a tile are contiguous in global memory; the CTA copies them with
-  // cp.async into slot (tile % kIdxSlots) kIdxAhead tiles before `resolve` reads them.  (With ~1 300 rows in flight
-  // per SM the loaded memory latency is several microseconds -- longer than one tile iteration -- so a register
-  // prefetch one iteration ahead still stalls; profiles/r01_deepfm_packed_notes.md.)
+  // cp.async into slot (it % kIdxSlots) kIdxAhead tiles before the row copies read them.
   constexpr int kIdxBytes = IdxBits / 8;
   const int tile_idx_bytes = kTile * n_fields * kIdxBytes;   // multiple of 16
   const int64_t total_idx_bytes = a.batch * n_fields * kIdxBytes;
   auto issue_idx = [&](int64_t it) {
     if (it >= my_tiles) return;
-    const int64_t tile = blockIdx.x + it * (int64_t)gridDim.x;
-    const int64_t g0 = tile * tile_idx_bytes;
+    const int64_t g0 = (blockIdx.x + it * (int64_t)gridDim.x) * tile_idx_bytes;
     const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(idx_ring + (size_t)(it % kIdxSlots) * tile_idx_bytes));
     for (int c = threadIdx.x * 16; c < tile_idx_bytes; c += blockDim.x * 16) {
       const int64_t remain = total_idx_bytes - (g0 + c);
       const int sz = remain >= 16 ? 16 : (remain > 0 ? static_cast<int>(remain) : 0);   // zero-fill past the batch
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + c),
-                   "l"(static_cast<const unsigned char*>(a.idx) + (sz > 0 ? g0 + c : 0)), "r"(sz) : "memory");
+      cp_async16(dst + c, static_cast<const unsigned char*>(a.idx) + (sz > 0 ? g0 + c : 0), sz);
     }
   };
-  int64_t foff[FPW];
-#pragma unroll
-  for (int f = 0; f < FPW; ++f) foff[f] = (f0 + f < n_fields) ? __ldg(a.offsets + f0 + f) : 0;
-  // Row copies of tile `it` into `stage`.  EIGHT lanes per row, five active: chunks 0..3 = v, chunk 4 = the 16 bytes
-  // holding w, so that [v|w] of a row is ONE 80-byte request of one warp instruction.  (A separate 4-byte read of w
-  // from the same 128-byte line costs almost a full extra transaction: tools/gather_microbench.cu, 69 -> 121 us.)
-  // Instruction i of the warp covers rows rho = 4i + (lane>>3), rho = f*16 + s  =>  f = i>>2, s = 4(i&3) + (lane>>3).
+
+  // Row copies of tile `it` into `stage`.
+  //   phase 1: lane resolves rows rho = lane + 32k (rho = f*16 + s): index + field offset, range check -> row id / -1;
+  //   phase 2: EIGHT lanes per row, five active (chunks 0..3 = v, chunk 4 = the 16 bytes holding w): instruction i of
+  //            the warp covers rows rho = 4i + (lane>>3); the row id comes from lane (rho & 31), register rho >> 5.
   const int sub = lane & 7, rsel = lane >> 3;
+  const int lane_dst = (rsel >> 1) * kPairFloats + (sub < 4 ? (rsel & 1) * 16 + 4 * sub : 32 + (rsel & 1) * 4);
   auto issue = [&](int64_t it, int stage) {
     const int64_t b0 = (blockIdx.x + it * (int64_t)gridDim.x) * kTile;
     const bool tile_ok = it < my_tiles;
     const unsigned char* slot = idx_ring + (size_t)(it % kIdxSlots) * tile_idx_bytes;
-    const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(my_v + (size_t)stage * FPW * kFieldFloats));
+    int rid[kResolve];
 #pragma unroll
-    for (int i = 0; i < FPW * 4; ++i) {
-      const int f = i >> 2, s = 4 * (i & 3) + rsel;
-      const bool live = tile_ok && f0 + f < n_fields && b0 + s < a.batch;
-      int64_t ix = 0;
+    for (int k = 0; k < kResolve; ++k) {
+      const int rho = lane + 32 * k;
+      const int f = rho >> 4, s = rho & 15;
+      const bool live = tile_ok && rho < kRowsPerWarp && f0 + f < n_fields && b0 + s < a.batch;
+      rid[k] = -1;
       if (live) {
+        int64_t ix;
         if (IdxBits == 64) ix = reinterpret_cast<const long long*>(slot)[s * n_fields + f0 + f];
         else ix = reinterpret_cast<const int*>(slot)[s * n_fields + f0 + f];
+        const int64_t r = ix + off_s[f0 + f];
+        if (r >= 0 && r < a.rows) rid[k] = static_cast<int>(r);
+        else report_oob(a.status, (b0 + s) * n_fields + f0 + f);
       }
-      const int64_t r = ix + foff[f];
-      const bool in = live && r >= 0 && r < a.rows;
-      if (live && !in && sub == 0) report_oob(a.status, (b0 + s) * n_fields + f0 + f);
-      const float* src = a.packed + (in ? r * kRowFloats : 0) + 4 * sub;
-      const int dst_f = f * kFieldFloats + (s >> 1) * kPairFloats + (sub < 4 ? (s & 1) * 16 + 4 * sub : 32 + (s & 1) * 4);
-      if (sub < 5) cp_async16(base + dst_f * 4, src, in);
+    }
+    const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(my_v + (size_t)stage * FPW * kFieldFloats + lane_dst));
+    const float* src0 = a.packed + 4 * sub;
+#pragma unroll
+    for (int i = 0; i < FPW * 4; ++i) {
+      const int r = __shfl_sync(0xffffffffu, rid[i >> 3], 4 * (i & 7) + rsel);
+      const int dst_f = (i >> 2) * kFieldFloats + 2 * (i & 3) * kPairFloats;   // + lane_dst (folded into base)
+      if (sub < 5) cp_async16(base + dst_f * 4, src0 + (r >= 0 ? (int64_t)r * kRowFloats : 0), r >= 0 ? 16 : 0);
     }
   };
 
@@ -226,6 +233,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
     issue(s, s);
     cp_async_commit();
   }
+
+  // finisher role of this lane: sample 2*warp + (lane>>4) of every tile, output / FM component (lane & 15)
+  const int fs = 2 * warp + (lane >> 4), fo = lane & 15;
 
   for (int64_t it = 0; it < my_tiles; ++it) {
     const int stage = static_cast<int>(it % kStages);
@@ -272,82 +282,48 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
         cb += sw[f * kFieldFloats + 4 * kPairFloats];
       }
     }
-    // ---- publish partials -------------------------------------------------------------------------------------------
-    float* pw = pbuf + ((size_t)(it & 1) * kWarps + warp) * kPartial * 32 + lane;
-    pw[0 * 32] = acc[0][0]; pw[1 * 32] = acc[0][1]; pw[2 * 32] = acc[0][2]; pw[3 * 32] = acc[0][3];
-    pw[4 * 32] = acc[1][0]; pw[5 * 32] = acc[1][1]; pw[6 * 32] = acc[1][2]; pw[7 * 32] = acc[1][3];
-    pw[8 * 32] = sa.x; pw[9 * 32] = sa.y; pw[10 * 32] = sa.z; pw[11 * 32] = sa.w;
-    pw[12 * 32] = sb.x; pw[13 * 32] = sb.y; pw[14 * 32] = sb.z; pw[15 * 32] = sb.w;
-    pw[16 * 32] = ca; pw[17 * 32] = cb;
+    // ---- publish partials: acc[j] = {(g, 8j+2t), (g, 8j+2t+1), (g+8, 8j+2t), (g+8, 8j+2t+1)} ---------------------------
+    float* pw = pbuf + ((size_t)(it & 1) * kWarps + warp) * kPartialFloats;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      *reinterpret_cast<float2*>(pw + g * kHPitch + 8 * j + 2 * t) = make_float2(acc[j][0], acc[j][1]);
+      *reinterpret_cast<float2*>(pw + (g + 8) * kHPitch + 8 * j + 2 * t) = make_float2(acc[j][2], acc[j][3]);
+    }
+    *reinterpret_cast<float4*>(pw + 16 * kHPitch + g * 16 + 4 * t) = sa;
+    *reinterpret_cast<float4*>(pw + 16 * kHPitch + (g + 8) * 16 + 4 * t) = sb;
+    pw[16 * kHPitch + 256 + g * 4 + t] = ca;
+    pw[16 * kHPitch + 256 + (g + 8) * 4 + t] = cb;
     __syncthreads();
 
-    if (warp == static_cast<int>(it % kWarps)) {
-      // ---- finisher: reduce the 8 partials, FM, MLP tail, store 16 logits -------------------------------------------
-      float r[kPartial];
+    // ---- finish two samples per warp: lane = (sample fs, output / component fo) -------------------------------------
+    const float* pr = pbuf + (size_t)(it & 1) * kWarps * kPartialFloats;
+    float h = bias_s[fo], sx = 0.f, c = 0.f;
 #pragma unroll
-      for (int k = 0; k < kPartial; ++k) r[k] = 0.f;
-      const float* pr = pbuf + (size_t)(it & 1) * kWarps * kPartial * 32 + lane;
+    for (int w = 0; w < kWarps; ++w) {
+      h += pr[w * kPartialFloats + fs * kHPitch + fo];
+      sx += pr[w * kPartialFloats + 16 * kHPitch + fs * 16 + fo];
+    }
+    // the 32 C partials of the sample (8 warps x 4 t), two per lane
+    c = pr[(fo >> 1) * kPartialFloats + 16 * kHPitch + 256 + fs * 4 + 2 * (fo & 1)] +
+        pr[(fo >> 1) * kPartialFloats + 16 * kHPitch + 256 + fs * 4 + 2 * (fo & 1) + 1];
+    h = fmaxf(h, 0.f);
+    const int src_base = lane & 16;
+    for (int layer = 0; layer < a.hidden_layers; ++layer) {
+      float o = bias_s[(1 + layer) * 16 + fo];
+      const float* wr = hid_s + (layer * 16 + fo) * kHidPitch;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w)
-#pragma unroll
-        for (int k = 0; k < kPartial; ++k) r[k] += pr[(w * kPartial + k) * 32];
-      float side_a = 0.5f * (r[8] * r[8] + r[9] * r[9] + r[10] * r[10] + r[11] * r[11]) + r[16];
-      float side_b = 0.5f * (r[12] * r[12] + r[13] * r[13] + r[14] * r[14] + r[15] * r[15]) + r[17];
-      float h[2][4];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const float b0v = bias_s[8 * j + 2 * t], b1v = bias_s[8 * j + 2 * t + 1];
-        h[j][0] = fmaxf(r[4 * j + 0] + b0v, 0.f);
-        h[j][1] = fmaxf(r[4 * j + 1] + b1v, 0.f);
-        h[j][2] = fmaxf(r[4 * j + 2] + b0v, 0.f);
-        h[j][3] = fmaxf(r[4 * j + 3] + b1v, 0.f);
-      }
-      for (int layer = 0; layer < a.hidden_layers; ++layer) {
-        float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-        for (int jk = 0; jk < 2; ++jk) {
-          uint32_t ah[4], al[4];
-          split_rna(h[jk][0], ah[0], al[0]);
-          split_rna(h[jk][2], ah[1], al[1]);
-          split_rna(h[jk][1], ah[2], al[2]);
-          split_rna(h[jk][3], ah[3], al[3]);
-#pragma unroll
-          for (int jn = 0; jn < 2; ++jn) {
-            const float2 wh = whs[(((layer * 2 + jn) * 2 + jk) * 2 + 0) * 32 + lane];
-            const float2 wl = whs[(((layer * 2 + jn) * 2 + jk) * 2 + 1) * 32 + lane];
-            mma_3x(o[jn], ah, al, __float_as_uint(wh.x), __float_as_uint(wh.y), __float_as_uint(wl.x),
-                   __float_as_uint(wl.y));
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float b0v = bias_s[(1 + layer) * 16 + 8 * j + 2 * t];
-          const float b1v = bias_s[(1 + layer) * 16 + 8 * j + 2 * t + 1];
-          h[j][0] = fmaxf(o[j][0] + b0v, 0.f);
-          h[j][1] = fmaxf(o[j][1] + b1v, 0.f);
-          h[j][2] = fmaxf(o[j][2] + b0v, 0.f);
-          h[j][3] = fmaxf(o[j][3] + b1v, 0.f);
-        }
-      }
-      const float* wo = bias_s + (1 + kMaxHidden) * 16;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const float w0 = wo[8 * j + 2 * t], w1v = wo[8 * j + 2 * t + 1];
-        side_a = fmaf(h[j][0], w0, side_a);
-        side_a = fmaf(h[j][1], w1v, side_a);
-        side_b = fmaf(h[j][2], w0, side_b);
-        side_b = fmaf(h[j][3], w1v, side_b);
-      }
-      side_a += __shfl_xor_sync(0xffffffffu, side_a, 1);
-      side_b += __shfl_xor_sync(0xffffffffu, side_b, 1);
-      side_a += __shfl_xor_sync(0xffffffffu, side_a, 2);
-      side_b += __shfl_xor_sync(0xffffffffu, side_b, 2);
-      if (t == 0) {
-        const int64_t b0 = (blockIdx.x + it * (int64_t)gridDim.x) * kTile;
-        const float bo = wo[16];
-        if (b0 + g < a.batch) a.logits[b0 + g] = side_a + bo;
-        if (b0 + g + 8 < a.batch) a.logits[b0 + g + 8] = side_b + bo;
-      }
+      for (int k = 0; k < 16; ++k) o = fmaf(wr[k], __shfl_sync(0xffffffffu, h, src_base + k), o);
+      h = fmaxf(o, 0.f);
+    }
+    float side = fmaf(0.5f * sx, sx, c);
+    side = fmaf(h, bias_s[(1 + kMaxHidden) * 16 + fo], side);
+    side += __shfl_xor_sync(0xffffffffu, side, 8);
+    side += __shfl_xor_sync(0xffffffffu, side, 4);
+    side += __shfl_xor_sync(0xffffffffu, side, 2);
+    side += __shfl_xor_sync(0xffffffffu, side, 1);
+    if (fo == 0) {
+      const int64_t b = (blockIdx.x + it * (int64_t)gridDim.x) * kTile + fs;
+      if (b < a.batch) a.logits[b] = side + bias_s[(1 + kMaxHidden) * 16 + 16];
     }
   }
   cp_async_wait<0>();
@@ -383,6 +359,7 @@ int deepfm_packed_supported(int fields, int embed, const int* mlp_dims, int mlp_
 template <int IdxBits, int FPW>
 static int launch_packed(const PackedArgs& a, cudaStream_t s) {
   const size_t smem = Smem<FPW>::total(a.fields, IdxBits);
+  TRS_REQUIRE(smem <= (size_t)kMaxDynSmem, "trs_deepfm_forward_packed: shared memory budget exceeded (%zu B)", smem);
   TRS_SMEM_OPT_IN((deepfm_packed_kernel<IdxBits, FPW>));
   const int64_t tiles = (a.batch + kTile - 1) / kTile;
   const int grid = static_cast<int>(tiles < kNumSMs ? tiles : kNumSMs);
