@@ -1,0 +1,23 @@
+"""torecsys_b200 -- the CTR forward hot path of p768lwy3/torecsys (multi-field embedding lookup feeding the
+feature-interaction layers) as hand-written sm_100a CUDA behind the reference's own nn.Module API.
+
+    csrc/ + include/torecsys_b200.h   the product: CUDA kernels behind a C ABI (libtorecsys_b200.so)
+    _cabi / ops / host                ctypes binding, tensor-level wrappers, host-buffer session
+    inputs / layers / models          drop-in modules: same constructors, state_dict keys, output names
+    patch                             patch_torecsys() / convert() for an existing torecsys code base
+
+CUDA only: there is no CPU or PyTorch fallback; CPU tensors and a missing library raise.
+"""
+from . import inputs, layers, models, ops  # noqa: F401
+from .inputs import Inputs, MultiIndicesEmbedding, MultiIndicesFieldAwareEmbedding, SingleIndexEmbedding  # noqa: F401
+from .layers import (AFMLayer, AttentionalFactorizationMachineLayer, BilinearInteractionLayer, CINLayer,  # noqa: F401
+                     CompressInteractionNetworkLayer, CrossNetworkLayer, DNNLayer,
+                     FactorizationMachineLayer, FFMLayer, FieldAwareFactorizationMachineLayer, FMLayer,
+                     InnerProductNetworkLayer, MultilayerPerceptionLayer)
+from .models import (DeepAndCrossNetworkModel, DeepFactorizationMachineModel,  # noqa: F401
+                     FactorizationMachineModel, FieldAwareFactorizationMachineModel, Sequential,
+                     XDeepFactorizationMachineModel)
+from .ops import check_index_errors, set_index_check  # noqa: F401
+from .patch import convert, patch_torecsys, unpatch_torecsys  # noqa: F401
+
+__version__ = '0.1.0'

@@ -72,11 +72,14 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void mma_3x(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
-                                       uint32_t bh1, uint32_t bl0, uint32_t bl1) {
-  mma_tf32(d, al, bh0, bh1);
-  mma_tf32(d, ah, bl0, bl1);
-  mma_tf32(d, ah, bh0, bh1);
+// d0 += A_lo*B_hi, d1 += A_hi*B_lo, d2 += A_hi*B_hi: three independent accumulator chains (summed once per tile)
+// instead of one 3x longer dependent chain -- with two warps per scheduler the MMA latency is otherwise exposed
+__device__ __forceinline__ void mma_3x(float (&d0)[4], float (&d1)[4], float (&d2)[4], const uint32_t (&ah)[4],
+                                       const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1, uint32_t bl0,
+                                       uint32_t bl1) {
+  mma_tf32(d0, al, bh0, bh1);
+  mma_tf32(d1, ah, bl0, bl1);
+  mma_tf32(d2, ah, bh0, bh1);
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
   // src_bytes < 16 => the remaining destination bytes are zero-filled
@@ -252,6 +255,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
     float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
     float qsa = 0.f, qsb = 0.f;
     float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float acl[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // A_lo * B_hi terms
+    float acm[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // A_hi * B_lo terms
 #pragma unroll
     for (int f = 0; f < FPW; ++f) {
       const float4 va = *reinterpret_cast<const float4*>(sv + f * kFieldFloats);                    // sample g
@@ -268,12 +273,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const float4 wh = w1h[f][j], wl = w1l[f][j];
-        mma_3x(acc[j], ah0, al0, __float_as_uint(wh.x), __float_as_uint(wh.y), __float_as_uint(wl.x),
-               __float_as_uint(wl.y));
-        mma_3x(acc[j], ah1, al1, __float_as_uint(wh.z), __float_as_uint(wh.w), __float_as_uint(wl.z),
-               __float_as_uint(wl.w));
+        mma_3x(acl[j], acm[j], acc[j], ah0, al0, __float_as_uint(wh.x), __float_as_uint(wh.y),
+               __float_as_uint(wl.x), __float_as_uint(wl.y));
+        mma_3x(acl[j], acm[j], acc[j], ah1, al1, __float_as_uint(wh.z), __float_as_uint(wh.w),
+               __float_as_uint(wl.z), __float_as_uint(wl.w));
       }
     }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[j][k] += acl[j][k] + acm[j][k];
     float ca = -0.5f * qsa, cb = -0.5f * qsb;
 #pragma unroll
     for (int f = 0; f < FPW; ++f) {
