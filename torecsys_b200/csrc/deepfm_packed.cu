@@ -140,6 +140,29 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
   const int kdim = 16 * n_fields;
   const int f0 = warp * FPW;  // first field of this warp
 
+  const int64_t tiles = (a.batch + kTile - 1) / kTile;
+  const int64_t my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  // Index tiles: the (16 x fields) indices of a tile are contiguous in global memory; the CTA copies them with
+  // cp.async into slot (it % kIdxSlots) kIdxAhead tiles before the row copies read them.
+  constexpr int kIdxBytes = IdxBits / 8;
+  const int tile_idx_bytes = kTile * n_fields * kIdxBytes;   // multiple of 16
+  const int64_t total_idx_bytes = a.batch * n_fields * kIdxBytes;
+  auto issue_idx = [&](int64_t it) {
+    if (it >= my_tiles) return;
+    const int64_t g0 = (blockIdx.x + it * (int64_t)gridDim.x) * tile_idx_bytes;
+    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(idx_ring + (size_t)(it % kIdxSlots) * tile_idx_bytes));
+    for (int c = threadIdx.x * 16; c < tile_idx_bytes; c += blockDim.x * 16) {
+      const int64_t remain = total_idx_bytes - (g0 + c);
+      const int sz = remain >= 16 ? 16 : (remain > 0 ? static_cast<int>(remain) : 0);   // zero-fill past the batch
+      cp_async16(dst + c, static_cast<const unsigned char*>(a.idx) + (sz > 0 ? g0 + c : 0), sz);
+    }
+  };
+
+  // the first index tiles are requested before anything else so that they fly during the weight set-up below
+  for (int s = 0; s < kIdxAhead; ++s) issue_idx(s);
+  cp_async_commit();
+
   // ---- one-time: this warp's W1 B-fragments into registers (hi/lo); hidden layers, biases, offsets to smem ----------
   float4 w1h[FPW][2], w1l[FPW][2];
 #pragma unroll
@@ -170,25 +193,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
   if (threadIdx.x == 0) bias_s[(1 + kMaxHidden) * 16 + 16] = __ldg(a.b_out);
   for (int i = threadIdx.x; i < n_fields; i += blockDim.x) off_s[i] = __ldg(a.offsets + i);
 
-  const int64_t tiles = (a.batch + kTile - 1) / kTile;
-  const int64_t my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   float* my_v = vbuf + (size_t)warp * kStages * FPW * kFieldFloats;   // + stage * FPW * kFieldFloats
-
-  // Index tiles: the (16 x fields) indices of a tile are contiguous in global memory; the CTA copies them with
-  // cp.async into slot (it % kIdxSlots) kIdxAhead tiles before the row copies read them.
-  constexpr int kIdxBytes = IdxBits / 8;
-  const int tile_idx_bytes = kTile * n_fields * kIdxBytes;   // multiple of 16
-  const int64_t total_idx_bytes = a.batch * n_fields * kIdxBytes;
-  auto issue_idx = [&](int64_t it) {
-    if (it >= my_tiles) return;
-    const int64_t g0 = (blockIdx.x + it * (int64_t)gridDim.x) * tile_idx_bytes;
-    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(idx_ring + (size_t)(it % kIdxSlots) * tile_idx_bytes));
-    for (int c = threadIdx.x * 16; c < tile_idx_bytes; c += blockDim.x * 16) {
-      const int64_t remain = total_idx_bytes - (g0 + c);
-      const int sz = remain >= 16 ? 16 : (remain > 0 ? static_cast<int>(remain) : 0);   // zero-fill past the batch
-      cp_async16(dst + c, static_cast<const unsigned char*>(a.idx) + (sz > 0 ? g0 + c : 0), sz);
-    }
-  };
 
   // Row copies of tile `it` into `stage`.
   //   phase 1: lane resolves rows rho = lane + 32k (rho = f*16 + s): index + field offset, range check -> row id / -1;
@@ -226,9 +231,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
     }
   };
 
-  // ---- prologue: index tiles 0..kIdxAhead-1, then rows of tiles 0..kStages-2 ---------------------------------------
-  for (int s = 0; s < kIdxAhead; ++s) issue_idx(s);
-  cp_async_commit();
+  // ---- prologue: index tiles 0..kIdxAhead-1 (requested at kernel entry), then rows of tiles 0..kStages-2 ----------
   cp_async_wait<0>();
   __syncthreads();
 #pragma unroll
