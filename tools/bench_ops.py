@@ -1,0 +1,206 @@
+#!/usr/bin/env python
+"""Per-kernel measurements at the BASELINE.json shapes: every L1 op and every fused model forward,
+timed with CUDA events over back-to-back launches on rotating inputs, reported as samples/s and achieved algorithmic
+GB/s (or TFLOP/s) against MEASURED_PEAKS.json.  Not the bench contract (bench.py is); this is the per-row evidence.
+
+    python tools/bench_ops.py [--rows-per-field N] [--only name,name] [--json out.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from torecsys_b200 import ops  # noqa: E402
+
+N = 39
+PAIRS = N * (N - 1) // 2
+
+
+def timeit(fn, reps=20, warmup=3):
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
+def lin(o, k, dev):
+    b = k ** -0.5
+    return (torch.rand(o, k, device=dev) * 2 - 1) * b, (torch.rand(o, device=dev) * 2 - 1) * b
+
+
+def mlp_pack(dims, dev):
+    ws, bs = zip(*[lin(dims[i + 1], dims[i], dev) for i in range(len(dims) - 1)])
+    return ops.MlpPack(list(ws), list(bs), ops.activation_id('relu'))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--rows-per-field', type=int, default=5_128_192)
+    ap.add_argument('--only', default='')
+    ap.add_argument('--json', default='')
+    args = ap.parse_args()
+    only = set(x for x in args.only.split(',') if x)
+    dev = torch.device('cuda', 0)
+    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(
+        os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {'hbm_gbs': 6650.0}
+    hbm = peaks['hbm_gbs']
+    rpf = args.rows_per_field
+    rows = N * rpf
+    off = (torch.arange(N, dtype=torch.int64) * rpf).to(dev)
+    results = []
+
+    def report(name, batch, secs, bytes_per_sample=None, flops_per_sample=None, note=''):
+        r = {'op': name, 'batch': batch, 'us': secs * 1e6, 'samples_per_s': batch / secs, 'note': note}
+        if bytes_per_sample:
+            r['algorithmic_GBps'] = bytes_per_sample * batch / secs / 1e9
+            r['frac_of_hbm_peak'] = r['algorithmic_GBps'] / hbm
+        if flops_per_sample:
+            r['algorithmic_TFLOPs'] = flops_per_sample * batch / secs / 1e12
+        results.append(r)
+        print(json.dumps(r), flush=True)
+
+    def want(name):
+        return not only or name in only
+
+    def idx_ring(batch, n=4):
+        return [torch.randint(0, rpf, (batch, N), device=dev) for _ in range(n)]
+
+    # ---------------------------------------------------------------- E = 16 tables (cfg 2)
+    B = 65536
+    if any(want(x) for x in ('gather16', 'gather1', 'fm_layer', 'deepfm_packed', 'deepfm_split', 'fm_model',
+                             'deepfm_generic_mlp400', 'ipn', 'bilinear_all', 'bilinear_each', 'afm', 'xdeepfm',
+                             'cin_layer')):
+        w16 = torch.randn(rows, 16, device=dev)
+        w1 = torch.randn(rows, 1, device=dev)
+        ring = idx_ring(B)
+        x = ops.embedding_gather(w16, ring[0], off)
+        if want('gather16'):
+            t = timeit(lambda i: ops.embedding_gather(w16, ring[i % 4], off))
+            report('gather16 (a2, E=16)', B, t, N * (8 + 64 + 64))
+        if want('gather1'):
+            t = timeit(lambda i: ops.embedding_gather(w1, ring[i % 4], off))
+            report('gather1 (a2, E=1 first-order)', B, t, N * (8 + 4 + 4))
+        if want('fm_layer'):
+            xs = [ops.embedding_gather(w16, ring[i], off) for i in range(4)]
+            t = timeit(lambda i: ops.fm(xs[i % 4]))
+            report('fm_layer (a5)', B, t, N * 64 + 64)
+            del xs
+        pack = mlp_pack([N * 16, 16, 16, 16, 1], dev)
+        if want('deepfm_packed'):
+            packed = ops.fm_pack_table(w16, w1)
+            t = timeit(lambda i: ops.deepfm_packed(ring[i % 4], off, packed, pack), reps=50)
+            report('deepfm fused, packed table (a12, cfg2)', B, t, 2968)
+            del packed
+        if want('deepfm_split'):
+            t = timeit(lambda i: ops.deepfm(ring[i % 4], off, w1, w16, pack), reps=50)
+            report('deepfm fused, split tables (a12, cfg2)', B, t, 2968)
+        if want('fm_model'):
+            bias = torch.rand(1, device=dev)
+            t = timeit(lambda i: ops.fm_model(ring[i % 4], off, w1, w16, bias))
+            report('fm model fused (a12)', B, t, 2968)
+        if want('deepfm_generic_mlp400'):
+            big = mlp_pack([N * 16, 400, 400, 400, 1], dev)
+            t = timeit(lambda i: ops.deepfm(ring[i % 4], off, w1, w16, big), reps=5)
+            report('deepfm fused, MLP [400,400,400] (generic FFMA)', B, t, 2968, 2 * (624 * 400 + 2 * 400 * 400 + 400))
+        if want('ipn'):
+            t = timeit(lambda i: ops.ipn(x))
+            report('ipn (a9)', B, t, N * 64 + PAIRS * 4, 2 * PAIRS * 16)
+        if want('bilinear_all'):
+            w, b = lin(16, 16, dev)
+            xb = x[:16384].contiguous()
+            t = timeit(lambda i: ops.bilinear(xb, w, b, False))
+            report('bilinear all (a10)', 16384, t, N * 64 + PAIRS * 64, 2 * (N * 256 + PAIRS * 16))
+        if want('bilinear_each'):
+            w = torch.randn(PAIRS, 16, 16, device=dev) * 0.25
+            b = torch.randn(PAIRS, 16, device=dev)
+            xb = x[:16384].contiguous()
+            t = timeit(lambda i: ops.bilinear(xb, w, b, True), reps=5)
+            report('bilinear each (a10)', 16384, t, N * 64 + PAIRS * 64, 2 * PAIRS * (256 + 16))
+        if want('afm'):
+            w1a, b1a = lin(16, 16, dev)
+            w2a, b2a = lin(1, 16, dev)
+            xb = x[:16384].contiguous()
+            t = timeit(lambda i: ops.afm(xb, w1a, b1a, w2a, b2a), reps=5)
+            report('afm (a11, attn 16)', 16384, t, N * 64 + 64 + PAIRS * 4, 2 * PAIRS * (16 * 16 + 16 + 16 + 16))
+        if want('cin_layer') or want('xdeepfm'):
+            sizes = [128, 128]
+            conv_w, scale, shift = [], [], []
+            hp = N
+            for h in sizes:
+                conv_w.append(torch.randn(2 * h, N * hp, device=dev) * (N * hp) ** -0.5)
+                scale.append(torch.rand(2 * h, device=dev) + 0.5)
+                shift.append(torch.randn(2 * h, device=dev) * 0.1)
+                hp = h
+            fw, fb = lin(1, sum(sizes), dev)
+            cpack = ops.CinPack(conv_w, scale, shift, sizes, False, ops.activation_id('relu'), fw, fb)
+            flops = 2 * 16 * (N * N * 256 + N * 128 * 128)
+            if want('cin_layer'):
+                xb = x[:8192].contiguous()
+                t = timeit(lambda i: ops.cin(xb, cpack, 1), reps=3, warmup=1)
+                report('cin layer [128,128] (a8, FFMA path)', 8192, t, None, flops)
+            if want('xdeepfm'):
+                bias = torch.rand(1, device=dev)
+                rb = [r[:8192].contiguous() for r in ring]
+                t = timeit(lambda i: ops.xdeepfm(rb[i % 4], off, w1, w16, cpack, pack, bias), reps=3, warmup=1)
+                report('xdeepfm fused (a12, cfg4 at B=8192)', 8192, t, 2968, flops + 2 * (624 * 16 + 512 + 16))
+        del w16, w1, x, ring
+        torch.cuda.empty_cache()
+
+    # ---------------------------------------------------------------- E = 32 (cfg 3: DCN)
+    if any(want(x) for x in ('dcn', 'cross_layer')):
+        B3 = 131072
+        w32 = torch.randn(rows, 32, device=dev)
+        ring = idx_ring(B3, 2)
+        cw = torch.stack([lin(32, 32, dev)[0] for _ in range(6)])
+        cb = torch.stack([lin(32, 32, dev)[1] for _ in range(6)])
+        if want('cross_layer'):
+            x = ops.embedding_gather(w32, ring[0][:32768].contiguous(), off)
+            t = timeit(lambda i: ops.cross(x, cw, cb), reps=5)
+            report('cross layer (a7, E=32, L=6)', 32768, t, 2 * N * 128, 6 * N * (2 * 32 * 32 + 3 * 32))
+            del x
+        if want('dcn'):
+            pack = mlp_pack([32, 32, 16, 8, 4], dev)
+            fw, fb = lin(1, N * 36, dev)
+            t = timeit(lambda i: ops.dcn(ring[i % 2], off, w32, cw, cb, pack, fw, fb), reps=5, warmup=2)
+            report('dcn fused (a12, cfg3)', B3, t, 5308, 636.8e3)
+        del w32, ring
+        torch.cuda.empty_cache()
+
+    # ---------------------------------------------------------------- field-aware (cfg 5, one GPU's share)
+    if any(want(x) for x in ('ffm_model', 'ffm_layer', 'gather_fa')):
+        rfa = 39 * 65_744          # rows per table: 39 tables x 2.56 M rows x 64 B = 6.4 GB (the 1/10 scale of cfg 5)
+        fs_off = (torch.arange(N, dtype=torch.int64) * 65_744).to(dev)
+        tables = [torch.randn(rfa, 16, device=dev) * 0.1 for _ in range(N)]
+        wf = torch.randn(rfa, 1, device=dev)
+        bias = torch.rand(1, device=dev)
+        B5 = 32768
+        ring = [torch.randint(0, 65_744, (B5, N), device=dev) for _ in range(4)]
+        tp = ops.TablePointers()
+        if want('ffm_model'):
+            t = timeit(lambda i: ops.ffm_model(ring[i % 4], fs_off, wf, tables, bias, tp), reps=10)
+            report('ffm model fused (a12, cfg5 per-GPU batch, tables at 1/10 scale)', B5, t, 95320, 2 * PAIRS * 16)
+        if want('gather_fa') or want('ffm_layer'):
+            small = ring[0][:4096].contiguous()
+            t = timeit(lambda i: ops.embedding_gather_field_aware(tables, small, fs_off, tp), reps=5)
+            report('field-aware gather (a3)', 4096, t, N * 8 + 2 * N * N * 64)
+            v = ops.embedding_gather_field_aware(tables, small, fs_off, tp)
+            t = timeit(lambda i: ops.ffm(v, N), reps=5)
+            report('ffm layer (a6)', 4096, t, 2 * PAIRS * 64 + PAIRS * 64)
+    ops.check_index_errors()
+    if args.json:
+        with open(args.json, 'w') as f:
+            json.dump(results, f, indent=1)
+
+
+if __name__ == '__main__':
+    main()
