@@ -1,0 +1,54 @@
+"""gloo world_size-2 CPU worker: the host-side logic of the sharded path (plan consistency across ranks, batch
+sharding covers the batch exactly once, pointer tables agree once base addresses are exchanged)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from torecsys_b200.sharded import TableShardPlan, shard_batch
+    dist.init_process_group('gloo')
+    rank, world = dist.get_rank(), dist.get_world_size()
+    plan = TableShardPlan(39, world)
+    mine = plan.tables_of(rank)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    flat = sorted(t for part in gathered for t in part)
+    assert flat == list(range(39)), flat                      # every table owned exactly once
+    assert all(plan.owner(t) == r for r, part in enumerate(gathered) for t in part)
+    assert max(len(p) for p in gathered) == plan.slots_per_rank
+    # fake "buffer base addresses": each rank publishes one, everybody must derive the same global pointer table
+    base = [None] * world
+    dist.all_gather_object(base, 0x10000000 * (rank + 1))
+    table_bytes = 4096
+    ptrs = plan.pointer_table(base, table_bytes)
+    all_ptrs = [None] * world
+    dist.all_gather_object(all_ptrs, ptrs)
+    assert all(p == all_ptrs[0] for p in all_ptrs)
+    assert len(set(ptrs)) == 39
+    for t in range(39):
+        assert ptrs[t] == base[t % world] + (t // world) * table_bytes
+    # batch sharding: slices tile the batch exactly
+    for batch in (0, 1, 7, 262144, 262145):
+        sl = [None] * world
+        dist.all_gather_object(sl, shard_batch(batch, rank, world))
+        covered = sum(hi - lo for lo, hi in sl)
+        assert covered == batch and sl[0][0] == 0 and sl[-1][1] == batch
+        assert all(sl[i][1] == sl[i + 1][0] for i in range(world - 1))
+    # reduced scalar agrees (the only "collective" bench.py uses: max over ranks of a time)
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert t.item() == world
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print('GLOO_PLAN_OK')
+
+
+if __name__ == '__main__':
+    main()

@@ -417,6 +417,25 @@ def xdeepfm(idx, offsets, w_feat, w_emb, cin_pack: CinPack, mlp_pack: MlpPack, b
     return out
 
 
+def ffm_model_from_pointers(idx, offsets, w_feat, table_ptrs: torch.Tensor, rows: int, embed: int, bias,
+                            out: Optional[torch.Tensor] = None):
+    """trs_ffm_model_forward on an explicit device array of table base addresses (int64[N]); the addresses may be
+    peer-mapped memory of other GPUs (torecsys_b200.sharded) -- the kernel only sees pointers."""
+    ix, bits, off = _fused_common('ffm_model', idx, offsets, w_feat, bias, table_ptrs)
+    wf = _f32('ffm_model', w_feat)
+    bs = _f32('ffm_model', bias).reshape(-1) if bias is not None else None
+    b, n = ix.shape
+    if table_ptrs.dtype != torch.int64 or table_ptrs.numel() != n:
+        raise ValueError(f'ffm_model_from_pointers: need int64[{n}] table addresses')
+    out = out if out is not None else torch.empty((b, 1), dtype=torch.float32, device=ix.device)
+    st = _status_tensor(ix.device)
+    check(_cabi.load().trs_ffm_model_forward(_ptr(ix), bits, _ptr(off), b, n, _ptr(wf), _ptr(table_ptrs), rows,
+                                             embed, _ptr(bs), _ptr(out), _ptr(st), _stream()),
+          'trs_ffm_model_forward')
+    _after_lookup(ix.device)
+    return out
+
+
 def ffm_model(idx, offsets, w_feat, tables: Sequence[torch.Tensor], bias, table_ptrs: Optional[TablePointers] = None,
               out: Optional[torch.Tensor] = None):
     ix, bits, off = _fused_common('ffm_model', idx, offsets, w_feat, bias, *tables)

@@ -1,0 +1,114 @@
+"""Row-sharded field-aware tables across the GPUs of one NVSwitch box (BASELINE.json configs[4]).
+
+The reference has no multi-device code; its FFM keeps N full tables `embeddings.{t}.weight (R, E)` on one device
+(multi_indices_field_aware_emb.py:49-54).  When their sum exceeds one GPU's HBM they are partitioned here TABLE-WISE:
+rank `t % world` owns table t entirely.  Every rank keeps its own slice of the batch and runs the SAME fused kernel as
+on one GPU (`ffm_model_kernel`: pair-parallel dot products straight from gathered rows); the table-pointer array it
+receives simply mixes local HBM pointers with peer pointers mapped over NVLink (torch symmetric memory =
+cuMem fabric handles).  The exchange of looked-up vectors therefore happens INSIDE the kernel as 128-bit peer loads,
+row by row, overlapped with the dot products -- there is no separate all-to-all, no staging buffer and no second
+kernel.  Volume: (world-1)/world of the 1 482 rows x 64 B per sample cross NVLink (83 KB/sample at world 8).
+
+Host logic (`TableShardPlan`) is pure Python and is what the CPU/gloo tests cover; `ShardedFieldAwareTables` needs
+CUDA + NCCL.
+"""
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .inputs import _reference_offsets
+
+
+class TableShardPlan:
+    """Which rank owns which table, and where it sits in the owner's buffer."""
+
+    def __init__(self, num_tables: int, world_size: int):
+        if num_tables <= 0 or world_size <= 0:
+            raise ValueError('num_tables and world_size must be positive')
+        self.num_tables = num_tables
+        self.world_size = world_size
+        self.slots_per_rank = (num_tables + world_size - 1) // world_size
+
+    def owner(self, table: int) -> int:
+        return table % self.world_size
+
+    def slot(self, table: int) -> int:
+        return table // self.world_size
+
+    def tables_of(self, rank: int) -> List[int]:
+        return list(range(rank, self.num_tables, self.world_size))
+
+    def pointer_table(self, base_ptrs: Sequence[int], table_bytes: int) -> List[int]:
+        """Address of every table given the base address of each rank's buffer (as mapped in THIS process)."""
+        if len(base_ptrs) != self.world_size:
+            raise ValueError('one base pointer per rank expected')
+        return [base_ptrs[self.owner(t)] + self.slot(t) * table_bytes for t in range(self.num_tables)]
+
+    def remote_fraction(self) -> float:
+        """Fraction of the row reads of a rank that cross NVLink (uniform over tables)."""
+        return 1.0 - len(self.tables_of(0)) / self.num_tables if self.world_size > 1 else 0.0
+
+
+def shard_batch(batch: int, rank: int, world_size: int):
+    """Contiguous batch slice of `rank` (the forward has no cross-sample dependency)."""
+    per = (batch + world_size - 1) // world_size
+    lo = min(rank * per, batch)
+    return lo, min(lo + per, batch)
+
+
+class ShardedFieldAwareTables:
+    """N field-aware tables (rows x embed) spread table-wise over the ranks of `group`, peer-mapped everywhere."""
+
+    def __init__(self, embed_size: int, field_sizes: Sequence[int], group: Optional[dist.ProcessGroup] = None,
+                 device: Optional[torch.device] = None):
+        import torch.distributed._symmetric_memory as symm_mem
+        if not dist.is_initialized():
+            raise RuntimeError('ShardedFieldAwareTables needs torch.distributed (NCCL) to be initialised')
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.device = device if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.num_fields = len(field_sizes)
+        self.rows = int(sum(field_sizes))
+        self.embed_size = embed_size
+        self.plan = TableShardPlan(self.num_fields, self.world)
+        self.offsets = _reference_offsets(field_sizes).rename(None).reshape(-1).to(self.device)
+        # every rank allocates the same shape (symmetric); unused slots of the last ranks stay empty
+        self.local = symm_mem.empty((self.plan.slots_per_rank, self.rows, embed_size), dtype=torch.float32,
+                                    device=self.device)
+        self._handle = symm_mem.rendezvous(self.local, self.group)
+        table_bytes = self.rows * embed_size * 4
+        ptrs = self.plan.pointer_table([int(p) for p in self._handle.buffer_ptrs], table_bytes)
+        self.table_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+
+    def local_table(self, table: int) -> torch.Tensor:
+        if self.plan.owner(table) != self.rank:
+            raise ValueError(f'table {table} lives on rank {self.plan.owner(table)}')
+        return self.local[self.plan.slot(table)]
+
+    def init_(self, fn):
+        """fn(table_index, tensor) initialises each locally owned table in place; collective (ends with a barrier)."""
+        for t in self.plan.tables_of(self.rank):
+            fn(t, self.local_table(t))
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+        return self
+
+
+class ShardedFFM:
+    """FieldAwareFactorizationMachineModel.forward (field_aware_factorization_machine.py:39-81) on sharded tables:
+    logits of THIS rank's samples = sum_{i<j} <T_i[r_j], T_j[r_i]> + sum_n w[r_n] + bias."""
+
+    def __init__(self, tables: ShardedFieldAwareTables, w_feat: torch.Tensor, bias: torch.Tensor):
+        self.tables = tables
+        self.w_feat = w_feat      # (rows, 1), replicated: 4 B per row
+        self.bias = bias
+
+    def forward(self, idx_local: torch.Tensor) -> torch.Tensor:
+        t = self.tables
+        return ops.ffm_model_from_pointers(idx_local, t.offsets, self.w_feat, t.table_ptrs, t.rows, t.embed_size,
+                                           self.bias)
+
+    __call__ = forward
