@@ -168,6 +168,20 @@ __global__ void __launch_bounds__(256) cin_fc_kernel(const float* __restrict__ p
 
 }  // namespace
 
+int cin_tc_supported(int fields, int embed, const int* sizes, int layers, int is_direct);
+int64_t cin_tc_workspace_bytes(int64_t batch, int fields, int embed, const int* sizes, int layers, int is_direct);
+int cin_tc_run(const float* x, const float* const* conv_w, const float* const* scale, const float* const* shift,
+               const int* sizes, int layers, int is_direct, int activation, const float* fc_w, const float* fc_b,
+               int out_features, int64_t batch, int fields, int embed, float* out, int accumulate, void* workspace,
+               int64_t workspace_bytes, cudaStream_t s);
+
+int cin_fc_launch(const float* pooled, int pooled_width, const float* fc_w, const float* fc_b, int out_features,
+                  int64_t batch, float* out, int accumulate, cudaStream_t s) {
+  const int grid = grid_for(batch * out_features, 256, 8);
+  cin_fc_kernel<<<grid, 256, 0, s>>>(pooled, pooled_width, fc_w, fc_b, out_features, batch, out, accumulate);
+  return check_launch("cin_fc_kernel");
+}
+
 struct CinPlan {
   int64_t pooled_floats, h_floats;
   int pooled_width, h_max;
@@ -193,6 +207,10 @@ int cin_run(const float* x, const float* const* conv_w, const float* const* scal
   TRS_REQUIRE(layers >= 1 && batch >= 0 && fields > 0 && embed > 0 && out_features > 0, "cin: bad sizes");
   TRS_UNSUPPORTED(embed % 4 != 0, "cin: embed_size must be a multiple of 4 (got %d)", embed);
   if (batch == 0) return TRS_OK;
+  // dense GEMM -> tensor cores (tcgen05 / TMEM, 3xTF32) whenever the shape allows; FP32 FFMA tiles otherwise
+  if (cin_tc_supported(fields, embed, layer_sizes, layers, is_direct) && aligned16(x))
+    return cin_tc_run(x, conv_w, scale, shift, layer_sizes, layers, is_direct, activation, fc_w, fc_b, out_features,
+                      batch, fields, embed, out, accumulate, workspace, workspace_bytes, s);
   const CinPlan plan = cin_plan(batch, embed, layer_sizes, layers);
   const int64_t need = (plan.pooled_floats + 2 * plan.h_floats) * (int64_t)sizeof(float);
   TRS_REQUIRE(workspace_bytes >= need, "cin: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes,
@@ -239,9 +257,7 @@ int cin_run(const float* x, const float* const* conv_w, const float* const* scal
     h_prev = hl;
     pool_off += hl;
   }
-  const int grid = grid_for(batch * out_features, 256, 8);
-  cin_fc_kernel<<<grid, 256, 0, s>>>(pooled, plan.pooled_width, fc_w, fc_b, out_features, batch, out, accumulate);
-  return check_launch("cin_fc_kernel");
+  return cin_fc_launch(pooled, plan.pooled_width, fc_w, fc_b, out_features, batch, out, accumulate, s);
 }
 
 }  // namespace trs
@@ -250,11 +266,14 @@ using namespace trs;
 
 extern "C" int64_t trs_cin_workspace_bytes(int64_t batch, int fields, int embed, const int* layer_sizes, int layers,
                                            int is_direct) {
-  (void)fields;
-  (void)is_direct;
   if (!layer_sizes || layers < 1 || batch < 0 || embed <= 0) return -1;
   const CinPlan plan = cin_plan(batch, embed, layer_sizes, layers);
-  return (plan.pooled_floats + 2 * plan.h_floats) * (int64_t)sizeof(float) + 256;
+  int64_t need = (plan.pooled_floats + 2 * plan.h_floats) * (int64_t)sizeof(float) + 256;
+  if (cin_tc_supported(fields, embed, layer_sizes, layers, is_direct)) {
+    const int64_t tc = cin_tc_workspace_bytes(batch, fields, embed, layer_sizes, layers, is_direct);
+    if (tc > need) need = tc;
+  }
+  return need;
 }
 
 extern "C" int trs_cin_forward(const float* x, const float* const* conv_w, const float* const* scale,

@@ -1,0 +1,484 @@
+// a8 on the 5th-generation tensor cores: Compress Interaction Network with tcgen05.mma (kind::tf32), accumulators in
+// TMEM, FP32-accurate through the 3xTF32 split (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, fp32 accumulate).
+//
+// GEMM view per layer: D[(b,e), c] = sum_{x,y} x0[(b,e), x] * h[(b,e), y] * W[c, x*H + y].
+//   * rows (b,e) are independent, so activations are kept ROW-major between layers: x0T [(b,e)][Hp0] (one transpose of
+//     the (B,N,E) input) and h_l [(b,e)][Hp_l] -- which is exactly the accumulator layout (TMEM lane = row, column =
+//     channel), so the epilogue writes full 128-byte lines and the next layer reads contiguous rows;
+//   * the K index is re-ordered y-chunk-major: k' = (yc*N + x)*16 + (y%16).  A producer thread owns one row, keeps
+//     the 16 h values of the current y-chunk in registers across the N chunks that share it, and per chunk emits
+//     z = x0[x] * h[y] split into TF32 hi/lo straight into the UMMA canonical (K-major, no swizzle) smem layout;
+//     the A operand never exists in HBM.  The weights are pre-split and pre-permuted once per call into the same
+//     chunked layout (cin_tc_prep_weights) and stream from L2 with one cp.async.bulk per chunk;
+//   * CTA tile = 256 rows x Npad channels (two M=128 accumulators = up to 512 TMEM columns), BK = 16 per stage;
+//     per chunk 2 halves x 2 k-steps x 3 split terms = 12 tcgen05.mma; tcgen05.commit frees the stage / signals
+//     the epilogue; roles: warps 0-7 = A producers then epilogue (tcgen05.ld -> folded Conv-bias + eval-BN + act ->
+//     hidden half stored row-major, direct half summed over e with shuffles -> pooled), warp 8 = MMA issuer,
+//     warp 9 = weight loader;
+//   * the dead hidden half of the last layer (computed and discarded by the reference) is not computed.
+// Shapes outside (E in {8,16,32}, channels <= 256 per layer) use the FFMA path in cin.cu.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace trs {
+namespace {
+
+constexpr int kTileM = 256;          // rows per CTA tile (2 x UMMA_M 128)
+constexpr int kBK = 16;              // K per stage = 4 sixteen-byte chunks = 2 UMMA k-steps
+constexpr int kProducerThreads = 256;
+constexpr int kThreads = kProducerThreads + 64;   // + MMA warp + weight-loader warp
+constexpr int kAStages = 2;          // operand-A ring (32 KB per stage; generation is cheap, two stages suffice)
+constexpr int kMaxBStages = 8;       // weight ring: deep, the L2 -> smem stream is latency-bound
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, M = 128
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+// core matrix = 8 rows x 16 bytes; SBO = byte distance between 8-row groups, LBO = between 16-byte chunks along K.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= static_cast<uint64_t>(1) << 46;   // descriptor version 1 (Blackwell)
+  return d;                               // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, TF32 x TF32, K-major A and B, M = 128
+__host__ __device__ inline uint32_t umma_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// ---- preparation kernels ------------------------------------------------------------------------------------------------
+// x (B, N, E) -> xt [(b,e)][hp0] row-major with zero padding (layer-0 "h" and the x0 operand of every layer)
+__global__ void __launch_bounds__(256) cin_tc_transpose_kernel(const float* __restrict__ x, int64_t batch, int fields,
+                                                               int embed, int hp0, float* __restrict__ xt) {
+  const int64_t items = batch * embed * hp0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / hp0;
+    const int n = static_cast<int>(i - m * hp0);
+    const int64_t b = m / embed;
+    const int e = static_cast<int>(m - b * embed);
+    xt[i] = n < fields ? __ldg(x + (b * fields + n) * embed + e) : 0.f;
+  }
+}
+
+// W (C, N*H) -> wp[q = yc*N + x][hi|lo][kc 0..3][n 0..npad-1][4 floats]  with k' = q*16 + kc*4 + j,  y = yc*16 + kc*4 + j
+__global__ void __launch_bounds__(256) cin_tc_prep_weights_kernel(const float* __restrict__ w, int c_eff, int fields,
+                                                                  int h_prev, int hp, int npad,
+                                                                  float* __restrict__ wp) {
+  const int chunks = (hp / 16) * fields;
+  const int64_t items = (int64_t)chunks * 4 * npad * 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = static_cast<int>(i & 3);
+    const int n = static_cast<int>((i >> 2) % npad);
+    const int kc = static_cast<int>(((i >> 2) / npad) & 3);
+    const int q = static_cast<int>((i >> 2) / npad / 4);
+    const int yc = q / fields, xf = q - yc * fields;
+    const int y = yc * 16 + kc * 4 + j;
+    float v = 0.f;
+    if (n < c_eff && y < h_prev) v = __ldg(w + (int64_t)n * fields * h_prev + xf * h_prev + y);
+    const uint32_t hi = tf32_rna(v);
+    const uint32_t lo = tf32_rna(v - __uint_as_float(hi));
+    const int64_t base = (int64_t)q * (2 * 4 * npad * 4);
+    wp[base + ((0 * 4 + kc) * npad + n) * 4 + j] = __uint_as_float(hi);
+    wp[base + ((1 * 4 + kc) * npad + n) * 4 + j] = __uint_as_float(lo);
+  }
+}
+
+struct CinTcArgs {
+  const float* xt;       // [(b,e)][hp0]  (x0 operand; also layer-0 h)
+  const float* h;        // [(b,e)][hp]   input activations of this layer
+  const float* wp;       // prepared weights
+  const float* scale;    // (c_eff)
+  const float* shift;    // (c_eff)
+  float* h_next;         // [(b,e)][hp_next] or null
+  float* pooled;         // (B, pooled_width)
+  int64_t m_rows;        // B * E
+  int fields, embed, hp0, hp, npad, c_eff;
+  int n_direct, hid_begin, hid_count, hp_next;
+  int pool_off, pooled_width, act, b_stages;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int npad = a.npad;
+  const uint32_t a_stage_bytes = 2 * 4 * kTileM * 16;          // hi/lo x 4 chunks x 256 rows x 16 B = 32 KB
+  const uint32_t b_stage_bytes = 2 * 4 * npad * 16;            // hi/lo x 4 chunks x npad rows x 16 B
+  unsigned char* a_smem = smem_raw;
+  unsigned char* b_smem = a_smem + (size_t)kAStages * a_stage_bytes;
+  float* x0_s = reinterpret_cast<float*>(b_smem + (size_t)a.b_stages * b_stage_bytes);   // [fields][256]
+  float* ss_s = x0_s + (size_t)a.fields * kTileM;                                        // scale[npad], shift[npad]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ss_s + 2 * npad);
+  // barriers: full_a[kAStages], empty_a[kAStages], full_b[kMaxBStages], empty_b[kMaxBStages], acc_full, acc_empty
+  constexpr int kNumBars = 2 * kAStages + 2 * kMaxBStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_a = [&](int s) { return bar0 + 8u * s; };
+  auto empty_a = [&](int s) { return bar0 + 8u * (kAStages + s); };
+  auto full_b = [&](int s) { return bar0 + 8u * (2 * kAStages + s); };
+  auto empty_b = [&](int s) { return bar0 + 8u * (2 * kAStages + kMaxBStages + s); };
+  const uint32_t acc_full = bar0 + 8u * (2 * kAStages + 2 * kMaxBStages), acc_empty = acc_full + 8u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(full_a(s), kProducerThreads / 32);   // one arrive per producer warp
+      mbar_init(empty_a(s), 1);
+    }
+    for (int s = 0; s < a.b_stages; ++s) {
+      mbar_init(full_b(s), 1);
+      mbar_init(empty_b(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, kProducerThreads / 32);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+    ss_s[i] = i < a.c_eff ? __ldg(a.scale + i) : 0.f;
+    ss_s[npad + i] = i < a.c_eff ? __ldg(a.shift + i) : 0.f;
+  }
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t tiles = (a.m_rows + kTileM - 1) / kTileM;
+  const int ychunks = a.hp / 16;
+  const int chunks = ychunks * a.fields;   // K' / 16
+
+  if (warp < 8) {
+    // =========================== A producers, then epilogue =====================================================
+    const int r = threadIdx.x;   // row within the tile
+    int sa = 0;                  // A ring position and phase
+    uint32_t pa = 0;
+    uint32_t tile_n = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_n) {
+      const int64_t m = tile * kTileM + r;
+      const bool row_ok = m < a.m_rows;
+      for (int xf = 0; xf < a.fields; ++xf) x0_s[xf * kTileM + r] = row_ok ? __ldg(a.xt + m * a.hp0 + xf) : 0.f;
+      for (int yc = 0; yc < ychunks; ++yc) {
+        float hreg[16];
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok) v = __ldg(reinterpret_cast<const float4*>(a.h + m * a.hp + yc * 16) + v4);
+          hreg[4 * v4 + 0] = v.x; hreg[4 * v4 + 1] = v.y; hreg[4 * v4 + 2] = v.z; hreg[4 * v4 + 3] = v.w;
+        }
+        for (int xf = 0; xf < a.fields; ++xf) {
+          mbar_wait(empty_a(sa), pa ^ 1);   // stage free (first pass: passes immediately)
+          const float xv = x0_s[xf * kTileM + r];
+          unsigned char* dst = a_smem + (size_t)sa * a_stage_bytes + r * 16;
+#pragma unroll
+          for (int kc = 0; kc < 4; ++kc) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float z = xv * hreg[4 * kc + j];
+              hi[j] = (__float_as_uint(z) + 0x1000u) & 0xffffe000u;   // round to TF32 (full-rate ALU)
+              // exact remainder, itself rounded to TF32 (the MMA would otherwise truncate it: 2^-21 -> 2^-22 |z|)
+              lo[j] = (__float_as_uint(z - __uint_as_float(hi[j])) + 0x1000u) & 0xffffe000u;
+            }
+            *reinterpret_cast<uint4*>(dst + (0 * 4 + kc) * (kTileM * 16)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(dst + (1 * 4 + kc) * (kTileM * 16)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          fence_proxy_async();   // make the generic-proxy stores visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_a(sa));
+          if (++sa == kAStages) { sa = 0; pa ^= 1; }
+        }
+      }
+      // ---- epilogue of this tile: warps 0-3 -> accumulator half 0 (rows 0..127), warps 4-7 -> half 1 ------------
+      mbar_wait(acc_full, tile_n & 1);
+      tc_fence_after();
+      const int half = warp >> 2;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + half * npad;
+      const int64_t b = row_ok ? m / a.embed : 0;
+      const int e = row_ok ? static_cast<int>(m - b * a.embed) : 0;
+      for (int c0 = 0; c0 < npad; c0 += 32) {
+        uint32_t raw[32];
+        tmem_ld32(taddr + c0, raw);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          v[j] = apply_act(fmaf(__uint_as_float(raw[j]), ss_s[c0 + j], ss_s[npad + c0 + j]), a.act);
+        // hidden half -> next layer's activations, row-major
+        if (a.h_next != nullptr) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const int c = c0 + 4 * j4;
+            if (row_ok && c >= a.hid_begin && c + 3 < a.hid_begin + a.hid_count)
+              *reinterpret_cast<float4*>(a.h_next + m * a.hp_next + (c - a.hid_begin)) =
+                  make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+            else if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (c + j >= a.hid_begin && c + j < a.hid_begin + a.hid_count)
+                  a.h_next[m * a.hp_next + (c + j - a.hid_begin)] = v[4 * j4 + j];
+            }
+          }
+        }
+        // direct half -> sum over the `embed` rows of each sample (consecutive lanes), one writer per (b, c)
+        if (c0 < a.n_direct) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float sum = row_ok ? v[j] : 0.f;
+            for (int o = a.embed >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (row_ok && e == 0 && c0 + j < a.n_direct) a.pooled[b * a.pooled_width + a.pool_off + c0 + j] = sum;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+  } else if (warp == 8) {
+    // =========================== MMA issuer ===============================================================================
+    const uint32_t idesc = umma_idesc_tf32(npad);
+    const uint32_t a_lbo = kTileM * 16, b_lbo = npad * 16;
+    uint32_t tile_n = 0, pa = 0, pb = 0;
+    int sa = 0, sb = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_n) {
+      mbar_wait(acc_empty, (tile_n & 1) ^ 1);   // epilogue of the previous tile has drained TMEM
+      tc_fence_after();
+      for (int q = 0; q < chunks; ++q) {
+        mbar_wait(full_a(sa), pa);
+        mbar_wait(full_b(sb), pb);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_base = smem_u32(a_smem + (size_t)sa * a_stage_bytes);
+          const uint32_t b_base = smem_u32(b_smem + (size_t)sb * b_stage_bytes);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint32_t a_hi = a_base + (0 * 4 + 2 * ks) * a_lbo + half * 128 * 16;
+              const uint32_t a_lo = a_base + (1 * 4 + 2 * ks) * a_lbo + half * 128 * 16;
+              const uint32_t b_hi = b_base + (0 * 4 + 2 * ks) * b_lbo;
+              const uint32_t b_lo = b_base + (1 * 4 + 2 * ks) * b_lbo;
+              const uint32_t d = tmem_base + half * npad;
+              const uint32_t acc = (q > 0 || ks > 0) ? 1u : 0u;
+              umma_tf32(d, umma_desc(a_lo, a_lbo, 128), umma_desc(b_hi, b_lbo, 128), idesc, acc);
+              umma_tf32(d, umma_desc(a_hi, a_lbo, 128), umma_desc(b_lo, b_lbo, 128), idesc, 1u);
+              umma_tf32(d, umma_desc(a_hi, a_lbo, 128), umma_desc(b_hi, b_lbo, 128), idesc, 1u);
+            }
+          }
+          umma_commit(empty_a(sa));                     // stages reusable once these MMAs have read them
+          umma_commit(empty_b(sb));
+          if (q == chunks - 1) umma_commit(acc_full);   // accumulators complete -> epilogue
+        }
+        __syncwarp();
+        if (++sa == kAStages) { sa = 0; pa ^= 1; }
+        if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
+      }
+    }
+  } else {
+    // =========================== weight loader (bulk copies L2 -> smem) ======================================================
+    int sb = 0;
+    uint32_t pb = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (int q = 0; q < chunks; ++q) {
+        mbar_wait(empty_b(sb), pb ^ 1);
+        if (lane == 0) {
+          mbar_expect_tx(full_b(sb), b_stage_bytes);
+          bulk_g2s(smem_u32(b_smem + (size_t)sb * b_stage_bytes),
+                   reinterpret_cast<const unsigned char*>(a.wp) + (size_t)q * b_stage_bytes, b_stage_bytes,
+                   full_b(sb));
+        }
+        __syncwarp();
+        if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct CinTcPlan {
+  int hp0, hp_max, pooled_width;
+  int64_t xt_floats, h_floats, pooled_floats, w_floats;
+};
+
+static CinTcPlan cin_tc_plan(int64_t batch, int fields, int embed, const int* sizes, int layers, int is_direct) {
+  CinTcPlan p{};
+  p.hp0 = round_up(fields, 16);
+  int hp = p.hp0;
+  for (int l = 0; l < layers; ++l) {
+    const bool last = l == layers - 1;
+    const int c_eff = (is_direct || last) ? sizes[l] : 2 * sizes[l];
+    const int npad = round_up(c_eff, 32);
+    p.w_floats += (int64_t)(hp / 16) * fields * 2 * 4 * npad * 4;
+    p.pooled_width += sizes[l];
+    hp = round_up(sizes[l], 16);
+    if (!last && hp > p.hp_max) p.hp_max = hp;
+  }
+  const int64_t m = batch * embed;
+  p.xt_floats = (m * p.hp0 + 63) / 64 * 64;
+  p.h_floats = (m * p.hp_max + 63) / 64 * 64;
+  p.pooled_floats = (batch * p.pooled_width + 63) / 64 * 64;
+  p.w_floats = (p.w_floats + 63) / 64 * 64;
+  return p;
+}
+
+int cin_tc_supported(int fields, int embed, const int* sizes, int layers, int is_direct) {
+  static const bool disabled = getenv("TRS_DISABLE_TC") != nullptr;
+  if (disabled) return 0;
+  if (!(embed == 8 || embed == 16 || embed == 32) || fields < 1 || fields > 64 || layers < 1) return 0;
+  for (int l = 0; l < layers; ++l) {
+    const int c_eff = (is_direct || l == layers - 1) ? sizes[l] : 2 * sizes[l];
+    if (sizes[l] < 1 || c_eff > 256) return 0;
+    if (!is_direct && l < layers - 1 && sizes[l] % 4 != 0) return 0;   // hidden half must start 16-byte aligned
+  }
+  return 1;
+}
+
+int64_t cin_tc_workspace_bytes(int64_t batch, int fields, int embed, const int* sizes, int layers, int is_direct) {
+  const CinTcPlan p = cin_tc_plan(batch, fields, embed, sizes, layers, is_direct);
+  return (p.xt_floats + 2 * p.h_floats + p.pooled_floats + p.w_floats) * (int64_t)sizeof(float) + 1024;
+}
+
+// out (+)= fc( pooled );  implemented in cin.cu
+int cin_fc_launch(const float* pooled, int pooled_width, const float* fc_w, const float* fc_b, int out_features,
+                  int64_t batch, float* out, int accumulate, cudaStream_t s);
+
+int cin_tc_run(const float* x, const float* const* conv_w, const float* const* scale, const float* const* shift,
+               const int* sizes, int layers, int is_direct, int activation, const float* fc_w, const float* fc_b,
+               int out_features, int64_t batch, int fields, int embed, float* out, int accumulate, void* workspace,
+               int64_t workspace_bytes, cudaStream_t s) {
+  const CinTcPlan p = cin_tc_plan(batch, fields, embed, sizes, layers, is_direct);
+  TRS_REQUIRE(workspace_bytes >= cin_tc_workspace_bytes(batch, fields, embed, sizes, layers, is_direct),
+              "cin: workspace too small for the tensor-core path");
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  ws += (128 - (reinterpret_cast<uintptr_t>(ws) & 127)) & 127;
+  float* xt = reinterpret_cast<float*>(ws);
+  float* hbuf[2] = {xt + p.xt_floats, xt + p.xt_floats + p.h_floats};
+  float* pooled = hbuf[1] + p.h_floats;
+  float* wprep = pooled + p.pooled_floats;
+  const int64_t m_rows = batch * embed;
+
+  cin_tc_transpose_kernel<<<grid_for(m_rows * p.hp0, 256, 8), 256, 0, s>>>(x, batch, fields, embed, p.hp0, xt);
+  int rc = check_launch("cin_tc_transpose_kernel");
+  if (rc != TRS_OK) return rc;
+  TRS_SMEM_OPT_IN(cin_tc_layer_kernel);
+
+  const float* h = xt;
+  int hp = p.hp0, h_prev = fields, pool_off = 0;
+  float* wp = wprep;
+  for (int l = 0; l < layers; ++l) {
+    const bool last = l == layers - 1;
+    const int hl = sizes[l];
+    const int c_eff = (is_direct || last) ? hl : 2 * hl;
+    const int npad = round_up(c_eff, 32);
+    const int64_t w_items = (int64_t)(hp / 16) * fields * 2 * 4 * npad * 4;
+    cin_tc_prep_weights_kernel<<<grid_for(w_items / 2, 256, 8), 256, 0, s>>>(conv_w[l], c_eff, fields, h_prev, hp,
+                                                                             npad, wp);
+    rc = check_launch("cin_tc_prep_weights_kernel");
+    if (rc != TRS_OK) return rc;
+    CinTcArgs a{};
+    a.xt = xt; a.h = h; a.wp = wp; a.scale = scale[l]; a.shift = shift[l];
+    a.h_next = last ? nullptr : hbuf[l & 1];
+    a.pooled = pooled;
+    a.m_rows = m_rows; a.fields = fields; a.embed = embed; a.hp0 = p.hp0; a.hp = hp; a.npad = npad; a.c_eff = c_eff;
+    a.n_direct = hl;
+    a.hid_begin = is_direct ? 0 : hl;
+    a.hid_count = last ? 0 : hl;
+    a.hp_next = round_up(hl, 16);
+    a.pool_off = pool_off; a.pooled_width = p.pooled_width; a.act = activation;
+    const size_t a_stage = 2 * 4 * kTileM * 16, b_stage = (size_t)2 * 4 * npad * 16;
+    const size_t fixed = kAStages * a_stage + (size_t)fields * kTileM * 4 + 2 * npad * 4 +
+                         (2 * kAStages + 2 * kMaxBStages + 2) * 8 + 16 + 128;
+    int b_stages = kMaxBStages;
+    while (b_stages > 2 && b_stages * b_stage + fixed > (size_t)kMaxDynSmem) --b_stages;
+    const size_t smem = b_stages * b_stage + fixed;
+    TRS_UNSUPPORTED(smem > (size_t)kMaxDynSmem, "cin: tensor-core tile does not fit shared memory");
+    a.b_stages = b_stages;
+    if (a.h_next != nullptr && a.hp_next != hl)   // zero the padding columns the next layer will read
+      TRS_CUDA(cudaMemsetAsync(a.h_next, 0, (size_t)m_rows * a.hp_next * sizeof(float), s));
+    const int64_t tiles = (m_rows + kTileM - 1) / kTileM;
+    const int grid = static_cast<int>(tiles < kNumSMs ? tiles : kNumSMs);
+    cin_tc_layer_kernel<<<grid, kThreads, smem, s>>>(a);
+    rc = check_launch("cin_tc_layer_kernel");
+    if (rc != TRS_OK) return rc;
+    h = a.h_next;
+    hp = a.hp_next;
+    h_prev = hl;
+    pool_off += hl;
+    wp += w_items;
+  }
+  return cin_fc_launch(pooled, p.pooled_width, fc_w, fc_b, out_features, batch, out, accumulate, s);
+}
+
+}  // namespace trs
