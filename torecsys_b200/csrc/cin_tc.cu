@@ -304,6 +304,15 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
     // =========================== MMA issuer ===============================================================================
     const uint32_t idesc = umma_idesc_tf32(npad);
     const uint32_t a_lbo = kTileM * 16, b_lbo = npad * 16;
+    // descriptors differ only in their 14-bit start-address field (16-byte units, shared memory < 256 KB): build the
+    // two base descriptors once and add offsets, so that issuing an MMA costs a few integer adds in the one issuing
+    // thread (with N = 128 an MMA lasts only ~64 cycles; descriptor arithmetic was the limiter)
+    const uint64_t a_desc0 = umma_desc(smem_u32(a_smem), a_lbo, 128);
+    const uint64_t b_desc0 = umma_desc(smem_u32(b_smem), b_lbo, 128);
+    const uint32_t a_stage_u = a_stage_bytes >> 4, b_stage_u = b_stage_bytes >> 4;
+    const uint32_t a_ks_u = (2 * a_lbo) >> 4, b_ks_u = (2 * b_lbo) >> 4;      // next k-step = two 16-byte chunks on
+    const uint32_t a_lo_u = (4 * a_lbo) >> 4, b_lo_u = (4 * b_lbo) >> 4;      // hi -> lo plane
+    const uint32_t a_half_u = (128 * 16) >> 4;                                // rows 128..255
     uint32_t tile_n = 0, pa = 0, pb = 0;
     int sa = 0, sb = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_n) {
@@ -314,21 +323,19 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
         mbar_wait(full_b(sb), pb);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_base = smem_u32(a_smem + (size_t)sa * a_stage_bytes);
-          const uint32_t b_base = smem_u32(b_smem + (size_t)sb * b_stage_bytes);
+          const uint64_t ad = a_desc0 + sa * a_stage_u;
+          const uint64_t bd = b_desc0 + sb * b_stage_u;
+          const uint32_t acc0 = q > 0 ? 1u : 0u;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
+            const uint32_t d = tmem_base + half * npad;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              const uint32_t a_hi = a_base + (0 * 4 + 2 * ks) * a_lbo + half * 128 * 16;
-              const uint32_t a_lo = a_base + (1 * 4 + 2 * ks) * a_lbo + half * 128 * 16;
-              const uint32_t b_hi = b_base + (0 * 4 + 2 * ks) * b_lbo;
-              const uint32_t b_lo = b_base + (1 * 4 + 2 * ks) * b_lbo;
-              const uint32_t d = tmem_base + half * npad;
-              const uint32_t acc = (q > 0 || ks > 0) ? 1u : 0u;
-              umma_tf32(d, umma_desc(a_lo, a_lbo, 128), umma_desc(b_hi, b_lbo, 128), idesc, acc);
-              umma_tf32(d, umma_desc(a_hi, a_lbo, 128), umma_desc(b_lo, b_lbo, 128), idesc, 1u);
-              umma_tf32(d, umma_desc(a_hi, a_lbo, 128), umma_desc(b_hi, b_lbo, 128), idesc, 1u);
+              const uint64_t a_hi = ad + ks * a_ks_u + half * a_half_u, a_lo = a_hi + a_lo_u;
+              const uint64_t b_hi = bd + ks * b_ks_u, b_lo = b_hi + b_lo_u;
+              umma_tf32(d, a_lo, b_hi, idesc, ks > 0 ? 1u : acc0);
+              umma_tf32(d, a_hi, b_lo, idesc, 1u);
+              umma_tf32(d, a_hi, b_hi, idesc, 1u);
             }
           }
           umma_commit(empty_a(sa));                     // stages reusable once these MMAs have read them
