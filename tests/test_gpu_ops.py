@@ -207,6 +207,37 @@ def test_deepfm_packed_table_path(ops, n):
             assert normwise_err(got, want64) <= max(4 * normwise_err(want, want64), 2e-6), (n, batch)
 
 
+@pytest.mark.parametrize('n,e,cross_layers,deep,od', [(39, 32, 6, [32, 16, 8], 4), (7, 32, 1, [32], 1),
+                                                      (13, 16, 3, [24, 10], 3), (5, 64, 2, [64, 32], 8),
+                                                      (26, 8, 4, [32, 16, 8], 4)])
+def test_dcn_tensor_core_path(ops, n, e, cross_layers, deep, od):
+    """dcn_tc.cu (3xTF32 mma.sync chains in registers) at the BASELINE configs[2] shape and odd variants: padded
+    layer widths, ragged batches around the 16-sample CTA groups, int32/int64 indices."""
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    tag = f'dcn{n}_{e}'
+    fs = [16 * (2 + i % 5) for i in range(n)]
+    rows = sum(fs)
+    off = R.field_offsets(fs)
+    w_emb = torch.from_numpy(synth.uniform((rows, e), f'{tag}/we'))
+    dims = [e] + deep + [od]
+    ws = [torch.from_numpy(synth.uniform((dims[i + 1], dims[i]), f'{tag}/w{i}', -dims[i] ** -0.5, dims[i] ** -0.5))
+          for i in range(len(dims) - 1)]
+    bs = [torch.from_numpy(synth.uniform((dims[i + 1],), f'{tag}/b{i}', -0.5, 0.5)) for i in range(len(dims) - 1)]
+    cw = [torch.from_numpy(synth.uniform((e, e), f'{tag}/cw{l}', -e ** -0.5, e ** -0.5)) for l in range(cross_layers)]
+    cb = [torch.from_numpy(synth.uniform((e,), f'{tag}/cb{l}', -0.5, 0.5)) for l in range(cross_layers)]
+    fc_w = torch.from_numpy(synth.uniform((1, n * (e + od)), f'{tag}/fcw', -0.1, 0.1))
+    fc_b = torch.from_numpy(synth.uniform((1,), f'{tag}/fcb'))
+    pack = ops.MlpPack([w.cuda() for w in ws], [b.cuda() for b in bs], ops.activation_id('relu'))
+    for batch in (1, 16, 17, 300, 16 * 296 + 5):
+        idx = torch.from_numpy(synth.integers((batch, n), f'{tag}/idx{batch}', np.asarray(fs)[None, :]))
+        want = R.dcn_from_indices(idx, off, w_emb, cw, cb, ws, bs, fc_w, fc_b).numpy()
+        for dt in (torch.int64, torch.int32):
+            got = ops.dcn(idx.cuda().to(dt), off.cuda(), w_emb.cuda(), torch.stack(cw).cuda(), torch.stack(cb).cuda(),
+                          pack, fc_w.cuda(), fc_b.cuda()).cpu().numpy()
+            assert normwise_err(got, want) <= TOL, (n, e, batch)
+
+
 def test_deepfm_packed_out_of_range(ops):
     from torecsys_b200 import synth
     n, rows = 39, 39 * 16

@@ -21,6 +21,12 @@ int deepfm_fast_launch(const void* idx, int idx_bits, const int64_t* offsets, in
                        const float* w_feat, const float* w_emb, int64_t rows, const float* const* mlp_w,
                        const float* const* mlp_b, int mlp_layers, float* logits, int32_t* status, cudaStream_t s);
 
+int dcn_tc_supported(int embed, int cross_layers, const int* mlp_dims, int mlp_layers, int activation);
+int dcn_tc_launch(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                  const float* w_emb, int64_t rows, int embed, const float* cross_w, const float* cross_b,
+                  int cross_layers, const MlpParams& mp, const float* fc_w, const float* fc_b, float* logits,
+                  int32_t* status, cudaStream_t s);
+
 namespace {
 
 struct FmFamilyArgs {
@@ -360,6 +366,10 @@ extern "C" int trs_dcn_forward(const void* idx, int idx_bits, const int64_t* off
               "trs_dcn_forward: bad MLP description (at most %d layers)", MlpParams::kMaxLayers);
   TRS_REQUIRE(mlp_dims[0] == embed, "trs_dcn_forward: the per-field MLP input size must be embed");
   if (batch == 0) return TRS_OK;
+  // the per-row dense chains on the tensor pipe (3xTF32 mma.sync, dcn_tc.cu) whenever the shape allows
+  if (dcn_tc_supported(embed, cross_layers, mlp_dims, mlp_layers, activation) && (fields * 16) % 16 == 0)
+    return dcn_tc_launch(idx, idx_bits, offsets, batch, fields, w_emb, rows, embed, cross_w, cross_b, cross_layers,
+                         a.mp, fc_w, fc_b, logits, status, static_cast<cudaStream_t>(stream));
   a.idx = idx; a.offsets = offsets; a.w_emb = w_emb; a.cross_w = cross_w; a.cross_b = cross_b; a.fc_w = fc_w;
   a.fc_b = fc_b; a.logits = logits; a.status = status; a.batch = batch; a.rows = rows; a.fields = fields;
   a.embed = embed; a.cross_layers = cross_layers;
