@@ -237,12 +237,14 @@ def test_embedding_modules_names_offsets_and_errors(trs):
     assert torch.equal(o.rename(None)[1, 2 * 3 + 1], fa.embeddings[2].weight[16 + 31])
 
 
-def test_backward_fails_loudly_instead_of_silently(trs):
+def test_forward_in_grad_mode_is_differentiable(trs):
+    """In grad mode the modules return tensors attached to the autograd graph (details: test_gpu_training.py)."""
     emb = trs.MultiIndicesEmbedding(8, [16, 16]).cuda()
     out = emb(torch.zeros(4, 2, dtype=torch.long, device='cuda'))
     assert out.requires_grad
-    with pytest.raises(NotImplementedError, match='backward'):
-        out.rename(None).sum().backward()
+    out.rename(None).sum().backward()
+    g = emb.embedding.weight.grad
+    assert g[0].sum().item() == 32.0 and g[16].sum().item() == 32.0 and g[1].abs().sum().item() == 0.0
 
 
 def test_state_dict_round_trip_between_instances(trs):

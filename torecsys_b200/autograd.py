@@ -1,117 +1,256 @@
-"""autograd.Function wrappers of the forward kernels.
+"""autograd.Function wrappers: forward = the hand-written sm_100a kernels, backward = recompute through torch CUDA ops.
 
-Scope note: this round delivers the FORWARD hot path.  The Functions exist so that forward works
-unchanged inside grad mode (parameters of a freshly built model require grad) and so that calling `.backward()`
-fails loudly instead of silently producing no gradient; backward kernels slot into the `backward` methods.
+Scope: this repository's product is the FORWARD hot path.  So that the drop-ins
+still "construct and train unchanged" on a GPU, every Function saves its inputs and, in `backward`, re-evaluates the
+layer's formula with differentiable torch ops ON THE SAME CUDA DEVICE and lets torch differentiate it (a composite
+recompute backward).  Nothing here runs on the CPU and nothing is imported from `oracle/`; dedicated backward kernels
+(embedding gradient as a sorted segmented scatter-add, etc.) are the next step.  Gradient parity with the reference
+is covered by tests/test_gpu_training.py, including the upstream quirk that CrossNetworkLayer cuts the gradient path
+through h_0 (cross_network.py:65).
 """
 import torch
+import torch.nn.functional as F
 
 from . import ops
 
 
-def _no_backward(name):
-    raise NotImplementedError(
-        f'torecsys_b200: backward of {name} has no CUDA kernel yet (forward hot path only; see DESIGN.md '
-        '"out of scope: training").  Run inference under torch.no_grad() / .eval().')
+def _pairs(n, device):
+    idx = torch.triu_indices(n, n, offset=1, device=device)
+    return idx[0], idx[1]
 
 
+def _grad_of(fn, inputs, grad_outputs):
+    """d fn(inputs) . grad_outputs w.r.t. each input that requires grad (None for the others)."""
+    with torch.enable_grad():
+        detached = [t.detach().requires_grad_(t.requires_grad) if t is not None else None for t in inputs]
+        outs = fn(*detached)
+        outs = outs if isinstance(outs, (tuple, list)) else (outs,)
+        gos = grad_outputs if isinstance(grad_outputs, (tuple, list)) else (grad_outputs,)
+        pairs = [(o, g) for o, g in zip(outs, gos) if g is not None and o.requires_grad]
+        need = [t for t in detached if t is not None and t.requires_grad]
+        grads = torch.autograd.grad([o for o, _ in pairs], need, [g for _, g in pairs], allow_unused=True) if (
+            pairs and need) else ()
+    it = iter(grads)
+    return tuple(next(it) if (t is not None and t.requires_grad) else None for t in detached)
+
+
+# ------------------------------------------------------------------------------------------------ embeddings
 class GatherFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, weight, idx, offsets, padding_idx):
+        ctx.save_for_backward(idx, offsets if offsets is not None else idx.new_zeros(0))
+        ctx.rows = weight.shape[0]
+        ctx.padding_idx = padding_idx
         return ops.embedding_gather(weight, idx, offsets)
 
     @staticmethod
     def backward(ctx, grad):
-        _no_backward('embedding gather')
+        idx, offsets = ctx.saved_tensors
+        rows = idx.long() + (offsets.view(1, -1) if offsets.numel() else 0)
+        flat = rows.reshape(-1)
+        g = grad.reshape(flat.numel(), -1)
+        if ctx.padding_idx is not None:
+            g = g * (flat != ctx.padding_idx).unsqueeze(1)
+        dw = torch.zeros((ctx.rows, g.shape[1]), dtype=g.dtype, device=g.device).index_add_(0, flat, g)
+        return dw, None, None, None
 
 
 class GatherFieldAwareFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, idx, offsets, table_ptrs, *tables):
+        ctx.save_for_backward(idx, offsets)
+        ctx.rows = tables[0].shape[0]
         return ops.embedding_gather_field_aware(tables, idx, offsets, table_ptrs)
 
     @staticmethod
     def backward(ctx, grad):
-        _no_backward('field-aware embedding gather')
+        idx, offsets = ctx.saved_tensors
+        b, n = idx.shape
+        flat = (idx.long() + offsets.view(1, -1)).reshape(-1)
+        g = grad.reshape(b, n, n, -1)                      # (B, table t, field f, E)
+        grads = []
+        for t in range(n):
+            gt = g[:, t].reshape(b * n, -1)
+            grads.append(torch.zeros((ctx.rows, gt.shape[1]), dtype=gt.dtype, device=gt.device).index_add_(0, flat, gt))
+        return (None, None, None) + tuple(grads)
+
+
+# ------------------------------------------------------------------------------------------------ layers
+def _fm(x):
+    return 0.5 * (x.sum(1) ** 2 - (x ** 2).sum(1))
+
+
+def _ffm(v, n):
+    b, _, e = v.shape
+    v4 = v.reshape(b, n, n, e)
+    i, j = _pairs(n, v.device)
+    return v4[:, i, j] * v4[:, j, i]
+
+
+def _ipn(x):
+    i, j = _pairs(x.shape[1], x.device)
+    return (x[:, i] * x[:, j]).sum(-1)
+
+
+def _bilinear(x, w, bias, each):
+    i, j = _pairs(x.shape[1], x.device)
+    p, q = x[:, i], x[:, j]
+    out = (torch.matmul(p.unsqueeze(-2), w).squeeze(-2) if each else torch.matmul(p, w)) * q
+    return out + bias if bias is not None else out
+
+
+def _afm(x, w1, b1, w2, b2):
+    i, j = _pairs(x.shape[1], x.device)
+    prod = x[:, i] * x[:, j]
+    s = torch.softmax(F.linear(torch.relu(F.linear(prod, w1, b1)), w2, b2), dim=1)
+    return (prod * s).sum(1), s
+
+
+def _cross(x, ws, bs):
+    # upstream: outputs = emb_inputs.detach().requires_grad_() (cross_network.py:65) -- h_0 carries no gradient to x
+    h = x.detach()
+    for l in range(ws.shape[0]):
+        h = x * F.linear(h, ws[l], bs[l]) + x
+    return h
 
 
 class FmFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
+        ctx.save_for_backward(x)
         return ops.fm(x)
 
     @staticmethod
     def backward(ctx, grad):
-        _no_backward('FactorizationMachineLayer')
+        (x,) = ctx.saved_tensors
+        return grad.unsqueeze(1) * (x.sum(1, keepdim=True) - x)     # closed form of d/dx 0.5((sum x)^2 - sum x^2)
 
 
 class FfmFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, v, num_fields):
+        ctx.save_for_backward(v)
+        ctx.n = num_fields
         return ops.ffm(v, num_fields)
 
     @staticmethod
     def backward(ctx, grad):
-        _no_backward('FieldAwareFactorizationMachineLayer')
+        (v,) = ctx.saved_tensors
+        return _grad_of(lambda t: _ffm(t, ctx.n), [v], grad) + (None,)
 
 
 class IpnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
+        ctx.save_for_backward(x)
         return ops.ipn(x)
 
     @staticmethod
     def backward(ctx, grad):
-        _no_backward('InnerProductNetworkLayer')
+        (x,) = ctx.saved_tensors
+        return _grad_of(_ipn, [x], grad)
 
 
 class BilinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, each_type):
+        ctx.save_for_backward(x, weight, bias)
+        ctx.each = each_type
         return ops.bilinear(x, weight, bias, each_type)
 
     @staticmethod
     def backward(ctx, grad):
-        _no_backward('BilinearInteractionLayer')
+        x, w, b = ctx.saved_tensors
+        return _grad_of(lambda a, c, d: _bilinear(a, c, d, ctx.each), [x, w, b], grad) + (None,)
 
 
 class AfmFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2):
-        out, scores = ops.afm(x, w1, b1, w2, b2)
-        ctx.mark_non_differentiable(scores)
-        return out, scores
+        ctx.save_for_backward(x, w1, b1, w2, b2)
+        return ops.afm(x, w1, b1, w2, b2)
 
     @staticmethod
     def backward(ctx, grad, grad_scores):
-        _no_backward('AttentionalFactorizationMachineLayer')
+        return _grad_of(_afm, list(ctx.saved_tensors), (grad, grad_scores))
 
 
 class CrossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weights, biases):
+        ctx.save_for_backward(x, weights, biases)
         return ops.cross(x, weights, biases)
 
     @staticmethod
     def backward(ctx, grad):
-        _no_backward('CrossNetworkLayer')
+        return _grad_of(_cross, list(ctx.saved_tensors), grad)
 
 
 class CinFn(torch.autograd.Function):
+    """forward(x, module): the module supplies the argument pack; backward re-evaluates the eval-mode formula
+    (Conv1d k=1 as einsum, BatchNorm with running statistics, activation, direct/hidden split, sum over e, fc)."""
+
     @staticmethod
-    def forward(ctx, x, pack, out_features, *params):
-        return ops.cin(x, pack, out_features)
+    def forward(ctx, x, layer, out_features, *params):
+        ctx.layer = layer
+        ctx.save_for_backward(x, *params)
+        return ops.cin(x, layer.cin_pack(), out_features)
 
     @staticmethod
     def backward(ctx, grad):
-        _no_backward('CompressInteractionNetworkLayer')
+        layer = ctx.layer
+        x = ctx.saved_tensors[0]
+        names = [n for n, _ in layer.named_parameters()]
+        params = list(ctx.saved_tensors[1:])
+
+        def fn(xx, *ps):
+            p = dict(zip(names, ps))
+            h, directs = xx, []
+            for l, block in enumerate(layer.model):
+                z = (xx.unsqueeze(2) * h.unsqueeze(1)).reshape(xx.shape[0], -1, xx.shape[2])
+                o = torch.einsum('oc,bce->boe', p[f'model.{l}.Conv1d.weight'].squeeze(-1), z)
+                if f'model.{l}.Conv1d.bias' in p:
+                    o = o + p[f'model.{l}.Conv1d.bias'].view(1, -1, 1)
+                if 'Batchnorm' in block._modules:
+                    bn = block.Batchnorm
+                    o = (o - bn.running_mean.view(1, -1, 1)) / torch.sqrt(bn.running_var.view(1, -1, 1) + bn.eps)
+                    if f'model.{l}.Batchnorm.weight' in p:
+                        o = o * p[f'model.{l}.Batchnorm.weight'].view(1, -1, 1) + \
+                            p[f'model.{l}.Batchnorm.bias'].view(1, -1, 1)
+                if 'Activation' in block._modules:
+                    o = block.Activation(o)
+                if layer.is_direct:
+                    d, h = o, o
+                else:
+                    half = o.shape[1] // 2
+                    d, h = o[:, :half], o[:, half:]
+                directs.append(d)
+            return F.linear(torch.cat(directs, 1).sum(-1), p['fc.weight'], p['fc.bias'])
+
+        grads = _grad_of(fn, [x] + params, grad)
+        return (grads[0], None, None) + tuple(grads[1:])
 
 
 class MlpFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, pack, *params):
-        return ops.mlp(x, pack)
+    def forward(ctx, x, layer, *params):
+        ctx.layer = layer
+        ctx.save_for_backward(x, *params)
+        return ops.mlp(x, layer.mlp_pack())
 
     @staticmethod
     def backward(ctx, grad):
-        _no_backward('MultilayerPerceptionLayer')
+        act = next((m for k, m in ctx.layer.model._modules.items() if k.startswith('Activation')), None)
+        x, params = ctx.saved_tensors[0], list(ctx.saved_tensors[1:])
+
+        def fn(xx, *ps):
+            h = xx
+            n_lin = len(ps) // 2
+            for i in range(n_lin):
+                h = F.linear(h, ps[2 * i], ps[2 * i + 1])
+                if i < n_lin - 1 and act is not None:
+                    h = act(h)
+            return h
+
+        grads = _grad_of(fn, [x] + params, grad)
+        return (grads[0], None) + tuple(grads[1:])

@@ -205,8 +205,8 @@ class CompressInteractionNetworkLayer(BaseLayer):
         if self.training and any('Batchnorm' in b._modules for b in self.model):
             raise NotImplementedError('CompressInteractionNetworkLayer: train-mode BatchNorm (batch statistics) has '
                                       'no kernel; the forward hot path is eval mode (call .eval())')
-        outputs = CinFn.apply(emb_inputs.rename(None), self.cin_pack(), self.fc.out_features,
-                              *list(self.parameters()))
+        outputs = CinFn.apply(emb_inputs.rename(None), self, self.fc.out_features,
+                              *[p for _, p in self.named_parameters()])
         outputs.names = ('B', 'O',)
         return outputs
 
@@ -420,10 +420,17 @@ class MultilayerPerceptionLayer(BaseLayer):
     def forward(self, emb_inputs: torch.Tensor) -> torch.Tensor:
         has_dropout = any(isinstance(m, nn.Dropout) and m.p > 0 for m in self.model._modules.values())
         if self.training and has_dropout:
-            raise NotImplementedError('MultilayerPerceptionLayer: train-mode dropout between layers has no kernel; '
-                                      'the forward hot path is eval mode (call .eval())')
+            # training with dropout BETWEEN the Linears cannot use the fused whole-stack kernel; the MLP is adjacent to
+            # the hot path, so this one training-only case runs the registered torch modules
+            # (cuBLAS on the same device, native autograd).  Eval -- the measured path -- always takes the kernel.
+            outputs = self.model(emb_inputs.rename(None))
+            if outputs.dim() == 2:
+                outputs.names = ('B', 'O',)
+            elif outputs.dim() == 3:
+                outputs.names = ('B', 'N', 'O',)
+            return outputs
         lin = self.linears()
-        outputs = MlpFn.apply(emb_inputs.rename(None), self.mlp_pack(), *[p for l in lin for p in (l.weight, l.bias)])
+        outputs = MlpFn.apply(emb_inputs.rename(None), self, *[p for l in lin for p in (l.weight, l.bias)])
         if outputs.dim() == 2:
             outputs.names = ('B', 'O',)
         elif outputs.dim() == 3:
