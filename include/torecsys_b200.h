@@ -165,6 +165,10 @@ int trs_deepfm_forward(const void* idx, int idx_bits, const int64_t* offsets, in
  * trs_deepfm_forward_packed computes exactly what trs_deepfm_forward computes.
  * Restrictions: hidden widths 16, ReLU, fields <= 40, rows < 2^31 (TRS_ERR_UNSUPPORTED otherwise). */
 int trs_fm_pack_table(const float* w_emb, const float* w_feat, int64_t rows, int embed, float* packed, void* stream);
+/* FactorizationMachineModel.forward on the packed table (same result as trs_fm_model_forward; bias may be NULL) */
+int trs_fm_model_forward_packed(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                                const float* packed, int64_t rows, const float* bias, float* logits,
+                                int32_t* status, void* stream);
 int trs_deepfm_forward_packed(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
                               const float* packed, int64_t rows,
                               const int* mlp_dims, int mlp_layers, const float* const* mlp_w,

@@ -238,6 +238,26 @@ def test_dcn_tensor_core_path(ops, n, e, cross_layers, deep, od):
             assert normwise_err(got, want) <= TOL, (n, e, batch)
 
 
+@pytest.mark.parametrize('n', [3, 39])
+def test_fm_model_on_packed_table(ops, n):
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    fs = [16 * (3 + i % 5) for i in range(n)]
+    rows = sum(fs)
+    off = R.field_offsets(fs)
+    w_feat = torch.from_numpy(synth.uniform((rows, 1), f'fmp{n}/wf'))
+    w_emb = torch.from_numpy(synth.uniform((rows, 16), f'fmp{n}/we'))
+    bias = torch.from_numpy(synth.uniform((1,), f'fmp{n}/b'))
+    packed = ops.fm_pack_table(w_emb.cuda(), w_feat.cuda())
+    for batch in (1, 100, 5000):
+        idx = torch.from_numpy(synth.integers((batch, n), f'fmp{n}/idx{batch}', np.asarray(fs)[None, :]))
+        want = R.fm_from_indices(idx, off, w_feat, w_emb, bias).numpy()
+        got = ops.fm_model_packed(idx.cuda(), off.cuda(), packed, bias.cuda()).cpu().numpy()
+        assert normwise_err(got, want) <= TOL, (n, batch)
+        got0 = ops.fm_model_packed(idx.cuda(), off.cuda(), packed, None).cpu().numpy()
+        assert normwise_err(got0, want - bias.numpy()) <= TOL, (n, batch)
+
+
 def test_deepfm_packed_out_of_range(ops):
     from torecsys_b200 import synth
     n, rows = 39, 39 * 16

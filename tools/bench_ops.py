@@ -107,7 +107,11 @@ def main():
         if want('fm_model'):
             bias = torch.rand(1, device=dev)
             t = timeit(lambda i: ops.fm_model(ring[i % 4], off, w1, w16, bias))
-            report('fm model fused (a12)', B, t, 2968)
+            report('fm model fused, split tables (a12, cfg1 shape at scale)', B, t, 2968)
+            packed = ops.fm_pack_table(w16, w1)
+            t = timeit(lambda i: ops.fm_model_packed(ring[i % 4], off, packed, bias), reps=50)
+            report('fm model fused, packed table (a12)', B, t, 2968)
+            del packed
         if want('deepfm_generic_mlp400'):
             big = mlp_pack([N * 16, 400, 400, 400, 1], dev)
             t = timeit(lambda i: ops.deepfm(ring[i % 4], off, w1, w16, big), reps=5)

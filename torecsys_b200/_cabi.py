@@ -44,6 +44,7 @@ PROTOTYPES = {
     'trs_deepfm_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _IP, c_int, _PP, _PP,
                                    c_int, _P, _P, _P]),
     'trs_fm_pack_table': (c_int, [_P, _P, c_int64, c_int, _P, _P]),
+    'trs_fm_model_forward_packed': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, _P, _P, _P, _P]),
     'trs_deepfm_forward_packed': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, _IP, c_int, _PP, _PP, c_int,
                                           _P, _P, _P]),
     'trs_dcn_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, c_int, _P, _P, c_int, _IP, c_int, _PP,

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (f0 + f < n_fields)
+      if (f0 + f < n_fields && a.w1 != nullptr)   // w1 == null: no deep part (FactorizationMachineModel)
         w = __ldg(reinterpret_cast<const float4*>(a.w1 + (size_t)(8 * j + g) * kdim + 16 * (f0 + f) + 4 * t));
       uint32_t h[4], l[4];
       split_rna(w.x, h[0], l[0]);
@@ -186,11 +186,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
     hid_s[(layer * 16 + o) * kHidPitch + k] = __ldg(a.wh[layer] + o * 16 + k);
   }
   for (int i = threadIdx.x; i < 16; i += blockDim.x) {
-    bias_s[i] = __ldg(a.b1 + i);
+    bias_s[i] = a.b1 ? __ldg(a.b1 + i) : 0.f;
     for (int l = 0; l < a.hidden_layers; ++l) bias_s[(1 + l) * 16 + i] = __ldg(a.bh[l] + i);
-    bias_s[(1 + kMaxHidden) * 16 + i] = __ldg(a.w_out + i);
+    bias_s[(1 + kMaxHidden) * 16 + i] = a.w_out ? __ldg(a.w_out + i) : 0.f;
   }
-  if (threadIdx.x == 0) bias_s[(1 + kMaxHidden) * 16 + 16] = __ldg(a.b_out);
+  if (threadIdx.x == 0) bias_s[(1 + kMaxHidden) * 16 + 16] = a.b_out ? __ldg(a.b_out) : 0.f;
   for (int i = threadIdx.x; i < n_fields; i += blockDim.x) off_s[i] = __ldg(a.offsets + i);
 
   float* my_v = vbuf + (size_t)warp * kStages * FPW * kFieldFloats;   // + stage * FPW * kFieldFloats
@@ -395,6 +395,35 @@ extern "C" int trs_fm_pack_table(const float* w_emb, const float* w_feat, int64_
                                                                          w_feat, rows,
                                                                          reinterpret_cast<float4*>(packed));
   return check_launch("pack_table_kernel");
+}
+
+// FactorizationMachineModel on the packed table = the DeepFM kernel with no deep part: logit = FM + first-order + bias
+extern "C" int trs_fm_model_forward_packed(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch,
+                                           int fields, const float* packed, int64_t rows, const float* bias,
+                                           float* logits, int32_t* status, void* stream) {
+  TRS_REQUIRE(idx && offsets && packed && logits, "trs_fm_model_forward_packed: null pointer");
+  TRS_REQUIRE(idx_bits == 32 || idx_bits == 64, "trs_fm_model_forward_packed: idx_bits must be 32 or 64");
+  TRS_REQUIRE(batch >= 0 && fields > 0 && rows > 0, "trs_fm_model_forward_packed: bad sizes");
+  TRS_UNSUPPORTED(fields > 5 * kWarps || rows >= (int64_t(1) << 31),
+                  "trs_fm_model_forward_packed: needs <= 40 fields and < 2^31 rows");
+  TRS_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127u) == 0 && aligned16(idx),
+              "trs_fm_model_forward_packed: packed table must be 128-byte aligned, idx 16-byte aligned");
+  if (batch == 0) return TRS_OK;
+  PackedArgs a{};
+  a.idx = idx; a.offsets = offsets; a.packed = packed; a.logits = logits; a.status = status;
+  a.batch = batch; a.rows = rows; a.fields = fields;
+  a.hidden_layers = 0;
+  a.b_out = bias;   // w1, b1, w_out stay null: zero deep part
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch ((fields + kWarps - 1) / kWarps) {
+    case 1: return idx_bits == 64 ? launch_packed<64, 1>(a, s) : launch_packed<32, 1>(a, s);
+    case 2: return idx_bits == 64 ? launch_packed<64, 2>(a, s) : launch_packed<32, 2>(a, s);
+    case 3: return idx_bits == 64 ? launch_packed<64, 3>(a, s) : launch_packed<32, 3>(a, s);
+    case 4: return idx_bits == 64 ? launch_packed<64, 4>(a, s) : launch_packed<32, 4>(a, s);
+    case 5: return idx_bits == 64 ? launch_packed<64, 5>(a, s) : launch_packed<32, 5>(a, s);
+  }
+  set_error("trs_fm_model_forward_packed: unsupported field count %d", fields);
+  return TRS_ERR_UNSUPPORTED;
 }
 
 extern "C" int trs_deepfm_forward_packed(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch,

@@ -61,6 +61,17 @@ def _canonical(inputs_module, keys: List[str], kinds: List[type]) -> bool:
     return True
 
 
+def _packed_table(owner: nn.Module, feat: MultiIndicesEmbedding, emb: MultiIndicesEmbedding) -> torch.Tensor:
+    """The 128-byte-row shadow [v|w] of the (first-order, embedding) table pair (embed_size 16), cached on `owner` and
+    rebuilt when either table was modified in place (`_version`) or moved.  Costs rows x 128 B of HBM."""
+    wf, we = feat.embedding.weight, emb.embedding.weight
+    key = (wf.data_ptr(), wf._version, we.data_ptr(), we._version)
+    if getattr(owner, '_packed_key', None) != key:
+        owner._packed = ops.fm_pack_table(we.detach(), wf.detach())
+        owner._packed_key = key
+    return owner._packed
+
+
 class FactorizationMachineModel(CtrBaseModel):
     """factorization_machine.py:10-71: logit = sum_n feat + sum_e FM(emb) (+ bias (1,1))."""
 
@@ -92,7 +103,11 @@ class FactorizationMachineModel(CtrBaseModel):
         idx = _index_batch(inputs_module, 'emb_inputs', batch)
         w = emb.embedding.weight
         bias = self.bias.rename(None) if self.use_bias else None
-        return ops.fm_model(idx, emb._offsets_on(w.device), feat.embedding.weight, w, bias)
+        off = emb._offsets_on(w.device)
+        if w.shape[1] == 16 and idx.shape[1] <= 40 and w.shape[0] < 2 ** 31 and getattr(self, 'use_packed_table', True):
+            packed = _packed_table(self, feat, emb)
+            return ops.fm_model_packed(idx, off, packed, bias)
+        return ops.fm_model(idx, off, feat.embedding.weight, w, bias)
 
 
 class DeepFactorizationMachineModel(CtrBaseModel):
@@ -129,11 +144,7 @@ class DeepFactorizationMachineModel(CtrBaseModel):
         wf, we = feat.embedding.weight, emb.embedding.weight
         if not getattr(self, 'use_packed_table', True) or we.shape[1] != 16:
             return None
-        key = (wf.data_ptr(), wf._version, we.data_ptr(), we._version)
-        if key != self._packed_key:
-            self._packed = ops.fm_pack_table(we.detach(), wf.detach())
-            self._packed_key = key
-        return self._packed
+        return _packed_table(self, feat, emb)
 
     def fused_forward(self, inputs_module, batch) -> torch.Tensor:
         feat, emb = inputs_module.schema['feat_inputs'], inputs_module.schema['emb_inputs']

@@ -361,6 +361,25 @@ def fm_pack_table(w_emb: torch.Tensor, w_feat: torch.Tensor) -> torch.Tensor:
     return packed
 
 
+def fm_model_packed(idx, offsets, packed: torch.Tensor, bias: Optional[torch.Tensor],
+                    out: Optional[torch.Tensor] = None):
+    """FactorizationMachineModel forward on the packed [v|w] table (trs_fm_model_forward_packed)."""
+    ix, bits, off = _fused_common('fm_model_packed', idx, offsets, packed, bias)
+    if packed.dtype != torch.float32 or packed.dim() != 2 or packed.shape[1] != 32 or not packed.is_contiguous():
+        raise ValueError('fm_model_packed: packed table must be a contiguous (rows, 32) float32 tensor')
+    bs = _f32('fm_model_packed', bias).reshape(-1) if bias is not None else None
+    b, n = ix.shape
+    if ix.data_ptr() % 16:
+        ix = ix.clone()
+    out = out if out is not None else torch.empty((b, 1), dtype=torch.float32, device=packed.device)
+    st = _status_tensor(packed.device)
+    check(_cabi.load().trs_fm_model_forward_packed(_ptr(ix), bits, _ptr(off), b, n, _ptr(packed), packed.shape[0],
+                                                   _ptr(bs), _ptr(out), _ptr(st), _stream()),
+          'trs_fm_model_forward_packed')
+    _after_lookup(packed.device)
+    return out
+
+
 def deepfm_packed(idx, offsets, packed: torch.Tensor, pack: MlpPack, out: Optional[torch.Tensor] = None):
     ix, bits, off = _fused_common('deepfm_packed', idx, offsets, packed)
     if packed.dtype != torch.float32 or packed.dim() != 2 or packed.shape[1] != 32 or not packed.is_contiguous():
