@@ -238,6 +238,41 @@ def test_dcn_tensor_core_path(ops, n, e, cross_layers, deep, od):
             assert normwise_err(got, want) <= TOL, (n, e, batch)
 
 
+@pytest.mark.parametrize('n,e,sizes,direct', [(7, 16, [128, 40], False), (39, 16, [64, 64], False),
+                                              (5, 8, [200, 12], True), (9, 32, [24, 128, 8], False)])
+def test_cin_tensor_core_wide_layers(ops, n, e, sizes, direct):
+    """cin_tc.cu at realistic widths: 2*128 = 256 channels (A operand in shared memory, all 512 TMEM columns are
+    accumulators), <= 128 channels (A operand in tensor memory), padded channel counts, direct mode, three layers,
+    ragged batches around the 256-row tiles."""
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    tag = f'cinw{n}_{e}_{sizes[0]}'
+    conv_w, conv_b, bn, scale, shift = [], [], [], [], []
+    hp = n
+    for l, h in enumerate(sizes):
+        c = h if direct else 2 * h
+        k = n * hp
+        w = torch.from_numpy(synth.uniform((c, k), f'{tag}/w{l}', -k ** -0.5, k ** -0.5))
+        b = torch.from_numpy(synth.uniform((c,), f'{tag}/b{l}', -0.5, 0.5))
+        g = torch.from_numpy(synth.uniform((c,), f'{tag}/g{l}', 0.5, 1.5))
+        beta = torch.from_numpy(synth.uniform((c,), f'{tag}/be{l}', -0.5, 0.5))
+        mean = torch.from_numpy(synth.uniform((c,), f'{tag}/m{l}', -0.5, 0.5))
+        var = torch.from_numpy(synth.uniform((c,), f'{tag}/v{l}', 0.5, 2.0))
+        conv_w.append(w); conv_b.append(b); bn.append((g, beta, mean, var, 1e-5))
+        sc = g / torch.sqrt(var + 1e-5)
+        scale.append(sc.cuda().contiguous()); shift.append(((b - mean) * sc + beta).cuda().contiguous())
+        hp = h
+    fc_w = torch.from_numpy(synth.uniform((3, sum(sizes)), f'{tag}/fw', -0.2, 0.2))
+    fc_b = torch.from_numpy(synth.uniform((3,), f'{tag}/fb'))
+    pack = ops.CinPack([w.cuda() for w in conv_w], scale, shift, sizes, direct, ops.activation_id('relu'), fc_w.cuda(),
+                       fc_b.cuda())
+    for batch in (1, 16, 37, 300):
+        x = torch.from_numpy(synth.uniform((batch, n, e), f'{tag}/x{batch}'))
+        want = R.cin_layer(x, conv_w, conv_b, bn, fc_w, fc_b, is_direct=direct).numpy()
+        got = ops.cin(x.cuda(), pack, 3).cpu().numpy()
+        assert normwise_err(got, want) <= TOL, (n, e, sizes, batch)
+
+
 @pytest.mark.parametrize('n', [3, 39])
 def test_fm_model_on_packed_table(ops, n):
     from oracle import restated as R

@@ -28,7 +28,8 @@ constexpr int kTileM = 256;          // rows per CTA tile (2 x UMMA_M 128)
 constexpr int kBK = 16;              // K per stage = 4 sixteen-byte chunks = 2 UMMA k-steps
 constexpr int kProducerThreads = 256;
 constexpr int kThreads = kProducerThreads + 64;   // + MMA warp + weight-loader warp
-constexpr int kAStages = 2;          // operand-A ring (32 KB per stage; generation is cheap, two stages suffice)
+constexpr int kAStages = 2;          // operand-A ring in smem (32 KB per stage; generation is cheap, two stages suffice)
+constexpr int kMaxAStages = 4;       // (four 64-column stages when the A ring lives in tensor memory)
 constexpr int kMaxBStages = 8;       // weight ring: deep, the L2 -> smem stream is latency-bound
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
@@ -82,6 +83,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with the A operand in tensor memory (lane = row, one 32-bit column per k): only B streams from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// registers -> tensor memory: thread i of the warp writes 16 consecutive columns of lane (warp % 4) * 32 + i
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -167,29 +188,36 @@ struct CinTcArgs {
   int pool_off, pooled_width, act, b_stages;
 };
 
+// kATmem = true (npad <= 128): the generated A operand goes to TENSOR MEMORY (columns 256..511, four 64-column stages:
+//   per half hi[16] | lo[16]) with tcgen05.st, the accumulators use columns 0..255, and only the weights stream from
+//   shared memory -- the SS form with both operands in shared memory is smem-port bound for N = 128
+//   (profiles/r01_cin_tcgen05_notes.md).  kATmem = false (npad = 256): accumulators need all 512 columns, A in smem.
+template <bool kATmem>
 __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int kAS = kATmem ? 4 : kAStages;                   // A ring depth
   const int npad = a.npad;
-  const uint32_t a_stage_bytes = 2 * 4 * kTileM * 16;          // hi/lo x 4 chunks x 256 rows x 16 B = 32 KB
+  const int dstride = kATmem ? 128 : npad;                     // TMEM columns between the two accumulator halves
+  const uint32_t a_stage_bytes = kATmem ? 0 : 2 * 4 * kTileM * 16;   // hi/lo x 4 chunks x 256 rows x 16 B = 32 KB
   const uint32_t b_stage_bytes = 2 * 4 * npad * 16;            // hi/lo x 4 chunks x npad rows x 16 B
   unsigned char* a_smem = smem_raw;
-  unsigned char* b_smem = a_smem + (size_t)kAStages * a_stage_bytes;
+  unsigned char* b_smem = a_smem + (size_t)kAS * a_stage_bytes;
   float* x0_s = reinterpret_cast<float*>(b_smem + (size_t)a.b_stages * b_stage_bytes);   // [fields][256]
   float* ss_s = x0_s + (size_t)a.fields * kTileM;                                        // scale[npad], shift[npad]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ss_s + 2 * npad);
-  // barriers: full_a[kAStages], empty_a[kAStages], full_b[kMaxBStages], empty_b[kMaxBStages], acc_full, acc_empty
-  constexpr int kNumBars = 2 * kAStages + 2 * kMaxBStages + 2;
+  // barriers: full_a[kMaxAStages], empty_a[kMaxAStages], full_b[kMaxBStages], empty_b[kMaxBStages], acc_full, acc_empty
+  constexpr int kNumBars = 2 * kMaxAStages + 2 * kMaxBStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   const uint32_t bar0 = smem_u32(bars);
   auto full_a = [&](int s) { return bar0 + 8u * s; };
-  auto empty_a = [&](int s) { return bar0 + 8u * (kAStages + s); };
-  auto full_b = [&](int s) { return bar0 + 8u * (2 * kAStages + s); };
-  auto empty_b = [&](int s) { return bar0 + 8u * (2 * kAStages + kMaxBStages + s); };
-  const uint32_t acc_full = bar0 + 8u * (2 * kAStages + 2 * kMaxBStages), acc_empty = acc_full + 8u;
+  auto empty_a = [&](int s) { return bar0 + 8u * (kMaxAStages + s); };
+  auto full_b = [&](int s) { return bar0 + 8u * (2 * kMaxAStages + s); };
+  auto empty_b = [&](int s) { return bar0 + 8u * (2 * kMaxAStages + kMaxBStages + s); };
+  const uint32_t acc_full = bar0 + 8u * (2 * kMaxAStages + 2 * kMaxBStages), acc_empty = acc_full + 8u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kAStages; ++s) {
+    for (int s = 0; s < kAS; ++s) {
       mbar_init(full_a(s), kProducerThreads / 32);   // one arrive per producer warp
       mbar_init(empty_a(s), 1);
     }
@@ -214,6 +242,9 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
   const int64_t tiles = (a.m_rows + kTileM - 1) / kTileM;
   const int ychunks = a.hp / 16;
   const int chunks = ychunks * a.fields;   // K' / 16
+  // Every CTA walks the K loop from its own starting point (the sum is order independent): otherwise all 148 CTAs
+  // stream the SAME weight chunk from L2 at the same moment and hot-spot a few L2 slices.
+  const int yc_rot = blockIdx.x % ychunks, x_rot = (blockIdx.x * 5) % a.fields;
 
   if (warp < 8) {
     // =========================== A producers, then epilogue =====================================================
@@ -225,7 +256,8 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
       const int64_t m = tile * kTileM + r;
       const bool row_ok = m < a.m_rows;
       for (int xf = 0; xf < a.fields; ++xf) x0_s[xf * kTileM + r] = row_ok ? __ldg(a.xt + m * a.hp0 + xf) : 0.f;
-      for (int yc = 0; yc < ychunks; ++yc) {
+      for (int yci = 0; yci < ychunks; ++yci) {
+        const int yc = yci + yc_rot < ychunks ? yci + yc_rot : yci + yc_rot - ychunks;
         float hreg[16];
 #pragma unroll
         for (int v4 = 0; v4 < 4; ++v4) {
@@ -233,9 +265,26 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
           if (row_ok) v = __ldg(reinterpret_cast<const float4*>(a.h + m * a.hp + yc * 16) + v4);
           hreg[4 * v4 + 0] = v.x; hreg[4 * v4 + 1] = v.y; hreg[4 * v4 + 2] = v.z; hreg[4 * v4 + 3] = v.w;
         }
-        for (int xf = 0; xf < a.fields; ++xf) {
+        for (int xi = 0; xi < a.fields; ++xi) {
+          const int xf = xi + x_rot < a.fields ? xi + x_rot : xi + x_rot - a.fields;
           mbar_wait(empty_a(sa), pa ^ 1);   // stage free (first pass: passes immediately)
           const float xv = x0_s[xf * kTileM + r];
+          if (kATmem) {
+            // 16 z values of this row -> TMEM columns [hi 0..15 | lo 16..31] of this half's slot in stage sa
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float z = xv * hreg[j];
+              hi[j] = (__float_as_uint(z) + 0x1000u) & 0xffffe000u;
+              lo[j] = (__float_as_uint(z - __uint_as_float(hi[j])) + 0x1000u) & 0xffffe000u;
+            }
+            const uint32_t ta = tmem_base + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + 256 + sa * 64 +
+                                (warp >> 2) * 32;
+            tmem_st16(ta, hi);
+            tmem_st16(ta + 16, lo);
+            tmem_st_wait();
+            tc_fence_before();
+          } else {
           unsigned char* dst = a_smem + (size_t)sa * a_stage_bytes + r * 16;
 #pragma unroll
           for (int kc = 0; kc < 4; ++kc) {
@@ -251,16 +300,17 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
             *reinterpret_cast<uint4*>(dst + (1 * 4 + kc) * (kTileM * 16)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
           fence_proxy_async();   // make the generic-proxy stores visible to the tensor core (async proxy)
+          }
           __syncwarp();
           if (lane == 0) mbar_arrive(full_a(sa));
-          if (++sa == kAStages) { sa = 0; pa ^= 1; }
+          if (++sa == kAS) { sa = 0; pa ^= 1; }
         }
       }
       // ---- epilogue of this tile: warps 0-3 -> accumulator half 0 (rows 0..127), warps 4-7 -> half 1 ------------
       mbar_wait(acc_full, tile_n & 1);
       tc_fence_after();
       const int half = warp >> 2;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + half * npad;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + half * dstride;
       const int64_t b = row_ok ? m / a.embed : 0;
       const int e = row_ok ? static_cast<int>(m - b * a.embed) : 0;
       for (int c0 = 0; c0 < npad; c0 += 32) {
@@ -326,16 +376,26 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
           const uint64_t ad = a_desc0 + sa * a_stage_u;
           const uint64_t bd = b_desc0 + sb * b_stage_u;
           const uint32_t acc0 = q > 0 ? 1u : 0u;
+          // issue order alternates between the two accumulator halves: consecutive MMAs into the SAME TMEM tile
+          // serialise on the accumulator (measured ~50 cycles per MMA), the halves are independent
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const uint32_t d = tmem_base + half * npad;
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t b_hi = bd + ks * b_ks_u, b_lo = b_hi + b_lo_u;
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t a_hi = ad + ks * a_ks_u + half * a_half_u, a_lo = a_hi + a_lo_u;
-              const uint64_t b_hi = bd + ks * b_ks_u, b_lo = b_hi + b_lo_u;
-              umma_tf32(d, a_lo, b_hi, idesc, ks > 0 ? 1u : acc0);
-              umma_tf32(d, a_hi, b_lo, idesc, 1u);
-              umma_tf32(d, a_hi, b_hi, idesc, 1u);
+            for (int term = 0; term < 3; ++term) {   // 0: A_lo*B_hi, 1: A_hi*B_lo, 2: A_hi*B_hi
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const uint32_t d = tmem_base + half * dstride;
+                const uint32_t accf = (ks > 0 || term > 0) ? 1u : acc0;
+                const uint64_t bsel = term == 1 ? b_lo : b_hi;
+                if (kATmem) {
+                  const uint32_t ta_hi = tmem_base + 256 + sa * 64 + half * 32 + 8 * ks;
+                  umma_tf32_ts(d, term == 0 ? ta_hi + 16 : ta_hi, bsel, idesc, accf);
+                } else {
+                  const uint64_t a_hi = ad + ks * a_ks_u + half * a_half_u;
+                  umma_tf32(d, term == 0 ? a_hi + a_lo_u : a_hi, bsel, idesc, accf);
+                }
+              }
             }
           }
           umma_commit(empty_a(sa));                     // stages reusable once these MMAs have read them
@@ -343,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
           if (q == chunks - 1) umma_commit(acc_full);   // accumulators complete -> epilogue
         }
         __syncwarp();
-        if (++sa == kAStages) { sa = 0; pa ^= 1; }
+        if (++sa == kAS) { sa = 0; pa ^= 1; }
         if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
       }
     }
@@ -352,7 +412,11 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
     int sb = 0;
     uint32_t pb = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      for (int q = 0; q < chunks; ++q) {
+      for (int i = 0; i < chunks; ++i) {
+        const int yci = i / a.fields, xi = i - yci * a.fields;   // same walk as the producers
+        const int yc = yci + yc_rot < ychunks ? yci + yc_rot : yci + yc_rot - ychunks;
+        const int xf = xi + x_rot < a.fields ? xi + x_rot : xi + x_rot - a.fields;
+        const int q = yc * a.fields + xf;
         mbar_wait(empty_b(sb), pb ^ 1);
         if (lane == 0) {
           mbar_expect_tx(full_b(sb), b_stage_bytes);
@@ -439,7 +503,8 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
   cin_tc_transpose_kernel<<<grid_for(m_rows * p.hp0, 256, 8), 256, 0, s>>>(x, batch, fields, embed, p.hp0, xt);
   int rc = check_launch("cin_tc_transpose_kernel");
   if (rc != TRS_OK) return rc;
-  TRS_SMEM_OPT_IN(cin_tc_layer_kernel);
+  TRS_SMEM_OPT_IN(cin_tc_layer_kernel<true>);
+  TRS_SMEM_OPT_IN(cin_tc_layer_kernel<false>);
 
   const float* h = xt;
   int hp = p.hp0, h_prev = fields, pool_off = 0;
@@ -464,9 +529,10 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
     a.hid_count = last ? 0 : hl;
     a.hp_next = round_up(hl, 16);
     a.pool_off = pool_off; a.pooled_width = p.pooled_width; a.act = activation;
+    const bool a_tmem = npad <= 128;   // accumulators leave 256 TMEM columns free: A operand goes to tensor memory
     const size_t a_stage = 2 * 4 * kTileM * 16, b_stage = (size_t)2 * 4 * npad * 16;
-    const size_t fixed = kAStages * a_stage + (size_t)fields * kTileM * 4 + 2 * npad * 4 +
-                         (2 * kAStages + 2 * kMaxBStages + 2) * 8 + 16 + 128;
+    const size_t fixed = (a_tmem ? 0 : kAStages * a_stage) + (size_t)fields * kTileM * 4 + 2 * npad * 4 +
+                         (2 * kMaxAStages + 2 * kMaxBStages + 2) * 8 + 16 + 128;
     int b_stages = kMaxBStages;
     while (b_stages > 2 && b_stages * b_stage + fixed > (size_t)kMaxDynSmem) --b_stages;
     const size_t smem = b_stages * b_stage + fixed;
@@ -476,7 +542,8 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
       TRS_CUDA(cudaMemsetAsync(a.h_next, 0, (size_t)m_rows * a.hp_next * sizeof(float), s));
     const int64_t tiles = (m_rows + kTileM - 1) / kTileM;
     const int grid = static_cast<int>(tiles < kNumSMs ? tiles : kNumSMs);
-    cin_tc_layer_kernel<<<grid, kThreads, smem, s>>>(a);
+    if (a_tmem) cin_tc_layer_kernel<true><<<grid, kThreads, smem, s>>>(a);
+    else cin_tc_layer_kernel<false><<<grid, kThreads, smem, s>>>(a);
     rc = check_launch("cin_tc_layer_kernel");
     if (rc != TRS_OK) return rc;
     h = a.h_next;
