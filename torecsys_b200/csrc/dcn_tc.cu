@@ -296,6 +296,126 @@ __global__ void __launch_bounds__(kWarps * 32, E <= 32 ? 2 : 1) dcn_tc_kernel(Dc
   }
 }
 
+// ---- a7 as an L1 op: CrossNetworkLayer on materialised rows (rows, E) -> (rows, E), same register-resident chain ----
+struct CrossTcArgs {
+  const float* x;
+  const float* w;   // (L, E, E)
+  const float* b;   // (L, E)
+  float* out;
+  int64_t rows;
+  int layers;
+};
+
+template <int E>
+__global__ void __launch_bounds__(kWarps * 32, E <= 32 ? 2 : 1) cross_tc_kernel(CrossTcArgs a) {
+  using C = Cfg<E>;
+  constexpr int KE = E / 8, kPitch = C::kPitch;
+  constexpr int kChunks = E / 4, kCopies = 16 * kChunks / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* frags = reinterpret_cast<float2*>(smem_raw);                       // [L][KE][KE][hi|lo][32]
+  float* bias_s = reinterpret_cast<float*>(frags + (size_t)a.layers * KE * KE * 2 * 32);   // [L][E]
+  float* stage_all = bias_s + ((a.layers * E + 3) & ~3);                      // [warps][2][16][kPitch]
+  for (int i = threadIdx.x; i < a.layers * KE * KE * 32; i += blockDim.x) {
+    const int ln = i & 31, j = (i >> 5) % KE, k = ((i >> 5) / KE) % KE, l = (i >> 5) / (KE * KE);
+    const float* w = a.w + (size_t)l * E * E + (size_t)(8 * j + (ln >> 2)) * E + 8 * k + 2 * (ln & 3);
+    const float w0 = __ldg(w), w1 = __ldg(w + 1);
+    const uint32_t h0 = tf32_rna(w0), h1 = tf32_rna(w1);
+    const uint32_t l0 = tf32_rna(w0 - __uint_as_float(h0)), l1 = tf32_rna(w1 - __uint_as_float(h1));
+    frags[(((l * KE + k) * KE + j) * 2 + 0) * 32 + ln] = make_float2(__uint_as_float(h0), __uint_as_float(h1));
+    frags[(((l * KE + k) * KE + j) * 2 + 1) * 32 + ln] = make_float2(__uint_as_float(l0), __uint_as_float(l1));
+  }
+  for (int i = threadIdx.x; i < a.layers * E; i += blockDim.x) bias_s[i] = __ldg(a.b + i);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  float* stage = stage_all + warp * 2 * 16 * kPitch;
+  const int64_t tiles = (a.rows + 15) / 16;
+  const int64_t wstride = (int64_t)gridDim.x * kWarps;
+  auto issue_tile = [&](int64_t tile, int buf) {
+    const uint32_t dst0 = static_cast<uint32_t>(__cvta_generic_to_shared(stage + buf * 16 * kPitch));
+#pragma unroll
+    for (int k = 0; k < kCopies; ++k) {
+      const int c = lane + 32 * k;
+      const int r = c / kChunks, ch = c - r * kChunks;
+      const int64_t row = tile * 16 + r;
+      const bool ok = row < a.rows;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (r * kPitch + 4 * ch) * 4),
+                   "l"(a.x + (ok ? row * E + 4 * ch : 0)), "r"(ok ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  int64_t tile = (int64_t)blockIdx.x * kWarps + warp;
+  if (tile < tiles) issue_tile(tile, 0);
+  for (; tile < tiles; tile += wstride) {
+    if (tile + wstride < tiles) {
+      issue_tile(tile + wstride, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    float* sx = stage + buf * 16 * kPitch;
+    float x[KE][4], h[KE][4], acc[KE][4];
+#pragma unroll
+    for (int j = 0; j < KE; ++j) {
+      const float2 lo = *reinterpret_cast<const float2*>(sx + g * kPitch + 8 * j + 2 * t);
+      const float2 hi = *reinterpret_cast<const float2*>(sx + (g + 8) * kPitch + 8 * j + 2 * t);
+      x[j][0] = lo.x; x[j][1] = lo.y; x[j][2] = hi.x; x[j][3] = hi.y;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) h[j][q] = x[j][q];
+    }
+    for (int l = 0; l < a.layers; ++l) {
+      dense_mma<KE>(h, KE, KE, frags + (size_t)l * KE * KE * 2 * 32, lane, acc);
+#pragma unroll
+      for (int j = 0; j < KE; ++j) {
+        const float bb0 = bias_s[l * E + 8 * j + 2 * t], bb1 = bias_s[l * E + 8 * j + 2 * t + 1];
+        h[j][0] = fmaf(x[j][0], acc[j][0] + bb0, x[j][0]);
+        h[j][1] = fmaf(x[j][1], acc[j][1] + bb1, x[j][1]);
+        h[j][2] = fmaf(x[j][2], acc[j][2] + bb0, x[j][2]);
+        h[j][3] = fmaf(x[j][3], acc[j][3] + bb1, x[j][3]);
+      }
+    }
+    // back through the staging buffer so that the global stores are whole 16-byte chunks of contiguous rows
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < KE; ++j) {
+      *reinterpret_cast<float2*>(sx + g * kPitch + 8 * j + 2 * t) = make_float2(h[j][0], h[j][1]);
+      *reinterpret_cast<float2*>(sx + (g + 8) * kPitch + 8 * j + 2 * t) = make_float2(h[j][2], h[j][3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kCopies; ++k) {
+      const int c = lane + 32 * k;
+      const int r = c / kChunks, ch = c - r * kChunks;
+      const int64_t row = tile * 16 + r;
+      if (row < a.rows)
+        *reinterpret_cast<float4*>(a.out + row * E + 4 * ch) = *reinterpret_cast<const float4*>(sx + r * kPitch + 4 * ch);
+    }
+    __syncwarp();
+    buf ^= 1;
+  }
+}
+
+template <int E>
+int cross_tc_dispatch(const CrossTcArgs& a, cudaStream_t s) {
+  constexpr int KE = E / 8;
+  const size_t smem = (size_t)a.layers * KE * KE * 2 * 32 * sizeof(float2) + (size_t)((a.layers * E + 3) & ~3) * 4 +
+                      (size_t)kWarps * 2 * 16 * Cfg<E>::kPitch * sizeof(float);
+  if (smem > (size_t)kMaxDynSmem) return TRS_ERR_UNSUPPORTED;
+  static size_t configured = 0;
+  if (smem > configured) {
+    TRS_CUDA(cudaFuncSetAttribute(cross_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int64_t tiles = (a.rows + 15) / 16;
+  const int64_t ctas = (tiles + kWarps - 1) / kWarps;
+  const int grid = static_cast<int>(ctas < 2 * kNumSMs ? ctas : 2 * kNumSMs);
+  cross_tc_kernel<E><<<grid, kWarps * 32, smem, s>>>(a);
+  return check_launch("cross_tc_kernel");
+}
+
 template <int E>
 size_t dcn_tc_smem(const DcnTcArgs& a) {
   size_t frag = 0, bias = 0;
@@ -337,6 +457,21 @@ int dcn_tc_dispatch(const DcnTcArgs& a, int idx_bits, cudaStream_t s) {
 }
 
 }  // namespace
+
+// CrossNetworkLayer (L1) on the tensor pipe; returns TRS_ERR_UNSUPPORTED when the shape is not covered
+int cross_tc_launch(const float* x, const float* w, const float* b, int layers, int64_t rows, int embed, float* out,
+                    cudaStream_t s) {
+  static const bool disabled = getenv("TRS_DISABLE_TC") != nullptr;
+  if (disabled || layers < 1 || !aligned16(x) || !aligned16(out)) return TRS_ERR_UNSUPPORTED;
+  CrossTcArgs a{x, w, b, out, rows, layers};
+  switch (embed) {
+    case 8: return cross_tc_dispatch<8>(a, s);
+    case 16: return cross_tc_dispatch<16>(a, s);
+    case 32: return cross_tc_dispatch<32>(a, s);
+    case 64: return cross_tc_dispatch<64>(a, s);
+  }
+  return TRS_ERR_UNSUPPORTED;
+}
 
 int dcn_tc_supported(int embed, int cross_layers, const int* mlp_dims, int mlp_layers, int activation) {
   static const bool disabled = getenv("TRS_DISABLE_TC") != nullptr;

@@ -5,6 +5,10 @@
 #include "tile_ops.cuh"
 
 namespace trs {
+
+int cross_tc_launch(const float* x, const float* w, const float* b, int layers, int64_t rows, int embed, float* out,
+                    cudaStream_t s);
+
 namespace {
 
 __global__ void __launch_bounds__(256) mlp_kernel(const float* __restrict__ x, int64_t rows, MlpParams mp, int ts,
@@ -102,6 +106,11 @@ extern "C" int trs_cross_forward(const float* x, const float* weights, const flo
   TRS_REQUIRE(x && out && (layers == 0 || (weights && biases)), "trs_cross_forward: null pointer");
   TRS_REQUIRE(rows >= 0 && embed > 0 && layers >= 0, "trs_cross_forward: bad sizes");
   if (rows == 0) return TRS_OK;
+  // E in {8,16,32,64}: register-resident 3xTF32 mma.sync chain (dcn_tc.cu); FP32 FFMA tiles otherwise
+  {
+    const int rc = cross_tc_launch(x, weights, biases, layers, rows, embed, out, static_cast<cudaStream_t>(stream));
+    if (rc != TRS_ERR_UNSUPPORTED) return rc;
+  }
   const int pitch = tile_pitch(embed);
   int ts = 128;
   size_t smem;
