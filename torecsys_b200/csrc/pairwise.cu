@@ -6,6 +6,10 @@
 #include "common.cuh"
 
 namespace trs {
+
+int afm_tc_launch(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, int64_t batch,
+                  int fields, int embed, int attn, float* out, float* scores, cudaStream_t s);
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------ FM (a5)
@@ -407,6 +411,10 @@ extern "C" int trs_afm_forward(const float* x, const float* w1, const float* b1,
   TRS_REQUIRE(batch >= 0 && fields > 1 && embed > 0 && attn > 0, "trs_afm_forward: bad sizes");
   if (batch == 0) return TRS_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {  // the pair x embed x attn contraction on the tensor pipe (afm_tc.cu) when the shape allows
+    const int rc = afm_tc_launch(x, w1, b1, w2, b2, batch, fields, embed, attn, out, scores, s);
+    if (rc != TRS_ERR_UNSUPPORTED) return rc;
+  }
   const int pairs = fields * (fields - 1) / 2;
   const int threads = 256;
   const size_t smem = ((size_t)fields * (embed | 1) + (size_t)attn * embed + 2 * attn + pairs + threads + pairs) *
