@@ -254,7 +254,7 @@ def run_ours(args):
                 'algorithmic_bytes_per_launch': ALGO_BYTES_PER_SAMPLE * batch}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            _, _, _, cpu = cpu_reference_run(60, 1, batch, budget_s=15.0)
+            _, _, _, cpu = cpu_reference_run(600, 2, batch, budget_s=12.0)   # ~12 s of CPU work, bounded
         print(json.dumps({
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',

@@ -7,6 +7,7 @@
 
 namespace trs {
 
+int ipn_tc_launch(const float* x, int64_t batch, int fields, int embed, float* out, cudaStream_t s);
 int afm_tc_launch(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, int64_t batch,
                   int fields, int embed, int attn, float* out, float* scores, cudaStream_t s);
 
@@ -359,6 +360,10 @@ extern "C" int trs_ipn_forward(const float* x, int64_t batch, int fields, int em
   TRS_REQUIRE(batch >= 0 && fields > 1 && embed > 0, "trs_ipn_forward: bad sizes");
   if (batch == 0) return TRS_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {  // Gram matrix on the tensor pipe (ipn_tc.cu) when the shape allows
+    const int rc = ipn_tc_launch(x, batch, fields, embed, out, s);
+    if (rc != TRS_ERR_UNSUPPORTED) return rc;
+  }
   const int pairs = fields * (fields - 1) / 2;
   const int pitch = fields | 1;
   int warps = 8;

@@ -161,46 +161,55 @@ class MultiIndicesFieldAwareEmbedding(BaseInput):
         return out
 
 
+_DICT_FED = ('ConcatInput', 'StackedInput')        # composite inputs take the whole batch dict (inputs.py:70)
+_LENGTH_FED = ('SequenceIndexEmbedding',)            # the (misspelt) name upstream tests for (inputs.py:84)
+
+
+def _as_column(v: torch.Tensor) -> torch.Tensor:
+    return v.unsqueeze(-1) if v.dim() == 1 else v
+
+
 class Inputs(BaseInput):
-    """torecsys/inputs/inputs.py:9-132: dict-of-modules router; same class-name dispatch as upstream (:70,:84)."""
+    """Dict-of-modules router of torecsys/inputs/inputs.py:9-132: for every schema entry, collect the batch columns the
+    entry's module asked for (`module.schema.inputs`), concatenate them on dim 1 and call the module; returns a dict
+    keyed like the schema.  Dispatch is on the class NAME, as upstream, so reference composite inputs keep working
+    with drop-in children."""
 
     def __init__(self, schema: Union[Dict[str, nn.Module], None]):
         super().__init__()
-        self.schema = schema if schema is not None else {}
-        for k, emb_fn in self.schema.items():
-            self.add_module(k, emb_fn)
+        self.schema = {} if schema is None else schema
+        for key, module in self.schema.items():
+            self.add_module(key, module)
         self.length = None
 
+    def _arguments(self, module: nn.Module, batch: Dict[str, torch.Tensor]) -> list:
+        kind = type(module).__name__
+        wanted = module.schema.inputs
+        if kind in _DICT_FED:
+            return [{name: batch[name] for name in wanted}]
+        columns = [_as_column(batch[name]) for name in wanted]
+        args = [columns[0] if len(columns) == 1 else torch.cat(columns, dim=1)]
+        if kind in _LENGTH_FED:
+            args.append(batch[module.schema.lengths])
+        return args
+
     def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-        outputs = {}
-        for k, emb_fn in self.schema.items():
-            if emb_fn.__class__.__name__ in ['ConcatInput', 'StackedInput']:
-                inp_args = [{i: inputs[i] for i in emb_fn.schema.inputs}]
-            else:
-                cols = []
-                for emb_k in emb_fn.schema.inputs:
-                    v = inputs[emb_k]
-                    cols.append(v.unsqueeze(-1) if v.dim() == 1 else v)
-                inp_args = [cols[0] if len(cols) == 1 else torch.cat(cols, dim=1)]
-                if emb_fn.__class__.__name__ == 'SequenceIndexEmbedding':
-                    inp_args.append(inputs[emb_fn.schema.lengths])
-            outputs[k] = emb_fn(*inp_args)
-        return outputs
+        return {key: module(*self._arguments(module, inputs)) for key, module in self.schema.items()}
 
     def add_inputs(self, name: Optional[str] = None, model: Optional[nn.Module] = None,
                    schema: Optional[Dict[str, nn.Module]] = None):
+        """Registers one (name, module) pair, or every pair of `schema`; same exceptions as upstream (:91-132)."""
         if schema is not None:
             if not isinstance(schema, dict):
                 raise TypeError(f'type of schema is not allowed, given {type(schema).__name__}')
-            for name, model in schema.items():
-                self.add_inputs(name=name, model=model)
-        else:
-            if not isinstance(name, str):
-                raise TypeError(f'type of name is not allowed, given {type(name).__name__}')
-            if name in self.schema:
-                raise AssertionError(f'Given {name} is defined in the schema.')
-            if not isinstance(model, nn.Module):
-                raise TypeError(f'type of model is not not allowed, given {type(model).__name__}')
-            self.schema.update([(name, model)])
-            self.add_module(name, model)
+            for key, module in schema.items():
+                self.add_inputs(name=key, model=module)
+            return self
+        for what, value, kind in (('name', name, str), ('model', model, nn.Module)):
+            if not isinstance(value, kind):
+                raise TypeError(f'type of {what} is not allowed, given {type(value).__name__}')
+        if name in self.schema:
+            raise AssertionError(f'Given {name} is defined in the schema.')
+        self.schema[name] = model
+        self.add_module(name, model)
         return self
