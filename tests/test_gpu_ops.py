@@ -273,6 +273,59 @@ def test_cin_tensor_core_wide_layers(ops, n, e, sizes, direct):
         assert normwise_err(got, want) <= TOL, (n, e, sizes, batch)
 
 
+def _wide_mlp(tag, dims):
+    from torecsys_b200 import synth
+    ws = [torch.from_numpy(synth.uniform((dims[i + 1], dims[i]), f'{tag}/w{i}', -dims[i] ** -0.5, dims[i] ** -0.5))
+          for i in range(len(dims) - 1)]
+    bs = [torch.from_numpy(synth.uniform((dims[i + 1],), f'{tag}/b{i}', -0.5, 0.5)) for i in range(len(dims) - 1)]
+    return ws, bs
+
+
+@pytest.mark.parametrize('dims', [[624, 400, 400, 400, 1], [312, 256, 128, 40], [64, 64, 64], [100, 300, 36, 5],
+                                  [128, 1024, 16]])
+def test_mlp_tensor_core_chain(ops, dims):
+    """Wide DNNLayer stacks run layer by layer on tcgen05 (cin_tc.cu dense mode: one field, x0 = 1): channel blocks
+    over blockIdx.y (400 -> 2 x 224, 1024 -> 4 x 256), the TMEM-operand form (<= 128 channels), input widths that
+    are not a multiple of 16, narrow layers in between / at the end, ragged row counts around the 256-row tiles."""
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    tag = 'mlpw' + '_'.join(map(str, dims))
+    ws, bs = _wide_mlp(tag, dims)
+    pack = ops.MlpPack([w.cuda() for w in ws], [b.cuda() for b in bs], ops.activation_id('relu'))
+    for rows in (1024, 1500, 40000):
+        x = torch.from_numpy(synth.uniform((rows, dims[0]), f'{tag}/x{rows}', -1.0, 1.0))
+        want = R.mlp_layer(x, ws, bs).numpy()
+        want64 = R.mlp_layer(x.double(), [w.double() for w in ws], [b.double() for b in bs]).numpy()
+        got = ops.mlp(x.cuda(), pack).cpu().numpy()
+        assert normwise_err(got, want) <= TOL, (dims, rows)
+        # the tensor core accumulates with truncation, not round-to-nearest: over K = 624 (234 chained MMAs) and three
+        # layers the distance to the fp64 truth is 8e-6 where cuBLAS fp32 SGEMM has 5e-7 (tools/mlp_chain_probe.py).
+        # The bar here is the path's stated tolerance measured against the TRUTH, not a multiple of fp32's own error.
+        assert normwise_err(got, want64) <= TOL, (dims, rows)
+
+
+@pytest.mark.parametrize('n,e,deep', [(39, 16, [400, 400, 400]), (26, 8, [256, 64]), (10, 10, [96, 96])])
+def test_deepfm_wide_mlp(ops, n, e, deep):
+    """DeepFM with a production-size deep branch: gather + first-order + FM in one kernel, the MLP as a chain of
+    tensor-core layers accumulating into the logits.  Also the small-batch route (one-kernel FFMA tile MLP)."""
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    tag = f'dfw{n}_{e}'
+    fs = [16 * (3 + i % 5) for i in range(n)]
+    rows = sum(fs)
+    off = R.field_offsets(fs)
+    w_feat = torch.from_numpy(synth.uniform((rows, 1), f'{tag}/wf'))
+    w_emb = torch.from_numpy(synth.uniform((rows, e), f'{tag}/we'))
+    ws, bs = _wide_mlp(tag, [n * e] + deep + [1])
+    pack = ops.MlpPack([w.cuda() for w in ws], [b.cuda() for b in bs], ops.activation_id('relu'))
+    for batch in (100, 1024, 4100):
+        idx = torch.from_numpy(synth.integers((batch, n), f'{tag}/idx{batch}', np.asarray(fs)[None, :]))
+        want = R.deepfm_from_indices(idx, off, w_feat, w_emb, ws, bs).numpy()
+        for dt in (torch.int64, torch.int32):
+            got = ops.deepfm(idx.cuda().to(dt), off.cuda(), w_feat.cuda(), w_emb.cuda(), pack).cpu().numpy()
+            assert normwise_err(got, want) <= TOL, (n, e, batch)
+
+
 @pytest.mark.parametrize('n', [3, 39])
 def test_fm_model_on_packed_table(ops, n):
     from oracle import restated as R

@@ -115,7 +115,11 @@ def main():
         if want('deepfm_generic_mlp400'):
             big = mlp_pack([N * 16, 400, 400, 400, 1], dev)
             t = timeit(lambda i: ops.deepfm(ring[i % 4], off, w1, w16, big), reps=5)
-            report('deepfm fused, MLP [400,400,400] (generic FFMA)', B, t, 2968, 2 * (624 * 400 + 2 * 400 * 400 + 400))
+            report('deepfm fused, MLP [400,400,400] (gather+FM kernel, tcgen05 MLP chain)', B, t, 2968, 2 * (624 * 400 + 2 * 400 * 400 + 400))
+            xf = x.reshape(B, N * 16)
+            t = timeit(lambda i: ops.mlp(xf, big), reps=5)
+            report('mlp [624,400,400,400,1] (DNNLayer, tcgen05 chain)', B, t, 624 * 4 + 4,
+                   2 * (624 * 400 + 2 * 400 * 400 + 400))
         if want('ipn'):
             t = timeit(lambda i: ops.ipn(x))
             report('ipn (a9)', B, t, N * 64 + PAIRS * 4, 2 * PAIRS * 16)
@@ -151,7 +155,7 @@ def main():
             if want('cin_layer'):
                 xb = x[:8192].contiguous()
                 t = timeit(lambda i: ops.cin(xb, cpack, 1), reps=3, warmup=1)
-                report('cin layer [128,128] (a8, FFMA path)', 8192, t, None, flops)
+                report('cin layer [128,128] (a8, tcgen05)', 8192, t, None, flops)
             if want('xdeepfm'):
                 bias = torch.rand(1, device=dev)
                 rb = [r[:8192].contiguous() for r in ring]

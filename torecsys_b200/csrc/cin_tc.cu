@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) cin_tc_transpose_kernel(const float* __re
 }
 
 // W (C, N*H) -> wp[q = yc*N + x][hi|lo][kc 0..3][n 0..npad-1][4 floats]  with k' = q*16 + kc*4 + j,  y = yc*16 + kc*4 + j
-__global__ void __launch_bounds__(256) cin_tc_prep_weights_kernel(const float* __restrict__ w, int c_eff, int fields,
+__global__ void __launch_bounds__(256) cin_tc_prep_weights_kernel(const float* __restrict__ w, int c_begin, int c_eff, int fields,
                                                                   int h_prev, int hp, int npad,
                                                                   float* __restrict__ wp) {
   const int chunks = (hp / 16) * fields;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) cin_tc_prep_weights_kernel(const float* _
     const int yc = q / fields, xf = q - yc * fields;
     const int y = yc * 16 + kc * 4 + j;
     float v = 0.f;
-    if (n < c_eff && y < h_prev) v = __ldg(w + (int64_t)n * fields * h_prev + xf * h_prev + y);
+    if (n < c_eff && y < h_prev) v = __ldg(w + (int64_t)(c_begin + n) * fields * h_prev + xf * h_prev + y);
     const uint32_t hi = tf32_rna(v);
     const uint32_t lo = tf32_rna(v - __uint_as_float(hi));
     const int64_t base = (int64_t)q * (2 * 4 * npad * 4);
@@ -178,14 +178,19 @@ struct CinTcArgs {
   const float* xt;       // [(b,e)][hp0]  (x0 operand; also layer-0 h)
   const float* h;        // [(b,e)][hp]   input activations of this layer
   const float* wp;       // prepared weights
-  const float* scale;    // (c_eff)
-  const float* shift;    // (c_eff)
+  const float* scale;    // per channel (indexed c_begin + c), null = 1
+  const float* shift;    // per channel, null = 0
   float* h_next;         // [(b,e)][hp_next] or null
   float* pooled;         // (B, pooled_width)
   int64_t m_rows;        // B * E
-  int fields, embed, hp0, hp, npad, c_eff;
+  int fields, embed, hp0, hp, npad, c_eff;   // c_eff = channels computed by this pass
+  int c_begin;                                // first channel of this pass (channel blocks of a wide layer)
   int n_direct, hid_begin, hid_count, hp_next;
   int pool_off, pooled_width, act, b_stages;
+  int h_pitch, k_valid;    // row pitch of h in floats and its valid columns (loads beyond read as zero); CIN: both = hp
+  int c_total;             // gridDim.y > 1: channel blocks of `c_block` over c_total channels, one block per blockIdx.y
+  int c_block;
+  int64_t wp_pass_stride;  // floats between the prepared weights of consecutive channel blocks
 };
 
 // kATmem = true (npad <= 128): the generated A operand goes to TENSOR MEMORY (columns 256..511, four 64-column stages:
@@ -195,6 +200,12 @@ struct CinTcArgs {
 template <bool kATmem>
 __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (gridDim.y > 1) {   // wide dense layer: this CTA column owns one channel block
+    a.c_begin = blockIdx.y * a.c_block;
+    a.c_eff = a.c_total - a.c_begin < a.c_block ? a.c_total - a.c_begin : a.c_block;
+    a.npad = (a.c_eff + 31) & ~31;
+    a.wp += blockIdx.y * a.wp_pass_stride;
+  }
   constexpr int kAS = kATmem ? 4 : kAStages;                   // A ring depth
   const int npad = a.npad;
   const int dstride = kATmem ? 128 : npad;                     // TMEM columns between the two accumulator halves
@@ -230,8 +241,8 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-    ss_s[i] = i < a.c_eff ? __ldg(a.scale + i) : 0.f;
-    ss_s[npad + i] = i < a.c_eff ? __ldg(a.shift + i) : 0.f;
+    ss_s[i] = i < a.c_eff ? (a.scale ? __ldg(a.scale + a.c_begin + i) : 1.f) : 0.f;
+    ss_s[npad + i] = (i < a.c_eff && a.shift) ? __ldg(a.shift + a.c_begin + i) : 0.f;
   }
   if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
@@ -255,16 +266,31 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_n) {
       const int64_t m = tile * kTileM + r;
       const bool row_ok = m < a.m_rows;
-      for (int xf = 0; xf < a.fields; ++xf) x0_s[xf * kTileM + r] = row_ok ? __ldg(a.xt + m * a.hp0 + xf) : 0.f;
-      for (int yci = 0; yci < ychunks; ++yci) {
+      for (int xf = 0; xf < a.fields; ++xf) x0_s[xf * kTileM + r] = row_ok ? (a.xt ? __ldg(a.xt + m * a.hp0 + xf) : 1.f) : 0.f;   // xt == null: x0 = 1 (plain dense layer)
+      // kPF y-chunks of this row's h are in flight in registers: with few fields (one, for a plain dense layer) a chunk
+      // lasts less than a global-load latency, so the loads run that many chunks ahead of their use
+      constexpr int kPF = kATmem ? 3 : 4;   // (register budget: the TMEM form also holds hi[16] / lo[16])
+      float hbuf[kPF][16];
+      auto load_h = [&](float (&dst)[16], int yci) {
         const int yc = yci + yc_rot < ychunks ? yci + yc_rot : yci + yc_rot - ychunks;
-        float hreg[16];
 #pragma unroll
         for (int v4 = 0; v4 < 4; ++v4) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row_ok) v = __ldg(reinterpret_cast<const float4*>(a.h + m * a.hp + yc * 16) + v4);
-          hreg[4 * v4 + 0] = v.x; hreg[4 * v4 + 1] = v.y; hreg[4 * v4 + 2] = v.z; hreg[4 * v4 + 3] = v.w;
+          if (row_ok && yci < ychunks && yc * 16 + 4 * v4 < a.k_valid)
+            v = __ldg(reinterpret_cast<const float4*>(a.h + m * a.h_pitch + yc * 16) + v4);
+          dst[4 * v4 + 0] = v.x; dst[4 * v4 + 1] = v.y; dst[4 * v4 + 2] = v.z; dst[4 * v4 + 3] = v.w;
         }
+      };
+#pragma unroll
+      for (int p = 0; p < kPF; ++p) load_h(hbuf[p], p);
+      for (int y0 = 0; y0 < ychunks; y0 += kPF) {
+#pragma unroll
+      for (int p = 0; p < kPF; ++p) {
+        if (y0 + p >= ychunks) break;
+        float hreg[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hreg[j] = hbuf[p][j];
+        load_h(hbuf[p], y0 + p + kPF);
         for (int xi = 0; xi < a.fields; ++xi) {
           const int xf = xi + x_rot < a.fields ? xi + x_rot : xi + x_rot - a.fields;
           mbar_wait(empty_a(sa), pa ^ 1);   // stage free (first pass: passes immediately)
@@ -306,6 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
           if (++sa == kAS) { sa = 0; pa ^= 1; }
         }
       }
+      }
       // ---- epilogue of this tile: warps 0-3 -> accumulator half 0 (rows 0..127), warps 4-7 -> half 1 ------------
       mbar_wait(acc_full, tile_n & 1);
       tc_fence_after();
@@ -324,25 +351,27 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
         if (a.h_next != nullptr) {
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const int c = c0 + 4 * j4;
-            if (row_ok && c >= a.hid_begin && c + 3 < a.hid_begin + a.hid_count)
+            const int c = a.c_begin + c0 + 4 * j4;   // global channel
+            if (row_ok && c >= a.hid_begin && c + 3 < a.hid_begin + a.hid_count && c0 + 4 * j4 + 3 < a.c_eff &&
+                (a.hp_next & 3) == 0)
               *reinterpret_cast<float4*>(a.h_next + m * a.hp_next + (c - a.hid_begin)) =
                   make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
             else if (row_ok) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                if (c + j >= a.hid_begin && c + j < a.hid_begin + a.hid_count)
+                if (c + j >= a.hid_begin && c + j < a.hid_begin + a.hid_count && c0 + 4 * j4 + j < a.c_eff)
                   a.h_next[m * a.hp_next + (c + j - a.hid_begin)] = v[4 * j4 + j];
             }
           }
         }
         // direct half -> sum over the `embed` rows of each sample (consecutive lanes), one writer per (b, c)
-        if (c0 < a.n_direct) {
+        if (a.c_begin + c0 < a.n_direct) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float sum = row_ok ? v[j] : 0.f;
             for (int o = a.embed >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (row_ok && e == 0 && c0 + j < a.n_direct) a.pooled[b * a.pooled_width + a.pool_off + c0 + j] = sum;
+            if (row_ok && e == 0 && a.c_begin + c0 + j < a.n_direct && c0 + j < a.c_eff)
+              a.pooled[b * a.pooled_width + a.pool_off + a.c_begin + c0 + j] = sum;
           }
         }
       }
@@ -515,7 +544,7 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
     const int c_eff = (is_direct || last) ? hl : 2 * hl;
     const int npad = round_up(c_eff, 32);
     const int64_t w_items = (int64_t)(hp / 16) * fields * 2 * 4 * npad * 4;
-    cin_tc_prep_weights_kernel<<<grid_for(w_items / 2, 256, 8), 256, 0, s>>>(conv_w[l], c_eff, fields, h_prev, hp,
+    cin_tc_prep_weights_kernel<<<grid_for(w_items / 2, 256, 8), 256, 0, s>>>(conv_w[l], 0, c_eff, fields, h_prev, hp,
                                                                              npad, wp);
     rc = check_launch("cin_tc_prep_weights_kernel");
     if (rc != TRS_OK) return rc;
@@ -529,6 +558,7 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
     a.hid_count = last ? 0 : hl;
     a.hp_next = round_up(hl, 16);
     a.pool_off = pool_off; a.pooled_width = p.pooled_width; a.act = activation;
+    a.h_pitch = hp; a.k_valid = hp;
     const bool a_tmem = npad <= 128;   // accumulators leave 256 TMEM columns free: A operand goes to tensor memory
     const size_t a_stage = 2 * 4 * kTileM * 16, b_stage = (size_t)2 * 4 * npad * 16;
     const size_t fixed = (a_tmem ? 0 : kAStages * a_stage) + (size_t)fields * kTileM * 4 + 2 * npad * 4 +
@@ -553,6 +583,68 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
     wp += w_items;
   }
   return cin_fc_launch(pooled, p.pooled_width, fc_w, fc_b, out_features, batch, out, accumulate, s);
+}
+
+
+// ---- a plain dense layer out = act(x W^T + b) on the same kernel: a CIN layer with ONE field and x0 = 1 ----------------
+// x (rows, K) row-major with K % 4 == 0, W (C, K), out (rows, C).  C <= 128 runs the TMEM-operand form; wider layers are
+// cut into equal channel blocks of at most 256 (one block per blockIdx.y, the SMs divided between the blocks), each CTA
+// streaming only its block of the weights.  Scratch for the pre-split weights comes from the stream-ordered pool.
+int dense_tc_supported(int k_dim, int c_dim, const void* x, const void* out) {
+  static const bool disabled = getenv("TRS_DISABLE_TC") != nullptr;
+  return !disabled && k_dim % 4 == 0 && k_dim >= 16 && c_dim >= 16 && aligned16(x) && aligned16(out);
+}
+
+int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const float* bias, int c_dim, int activation,
+                 float* out, cudaStream_t s) {
+  if (rows == 0) return TRS_OK;
+  const int kp = round_up(k_dim, 16);
+  const int passes = (c_dim + 255) / 256;
+  const int block = round_up((c_dim + passes - 1) / passes, 32);
+  const bool a_tmem = block <= 128;
+  const size_t w_floats = (size_t)(kp / 16) * 2 * 4 * block * 4;   // upper bound per channel block
+  float* wp = nullptr;
+  TRS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&wp), w_floats * sizeof(float) * passes, s));
+  int rc = TRS_OK;
+  for (int pass = 0; pass < passes && rc == TRS_OK; ++pass) {
+    const int c0 = pass * block;
+    const int c_cnt = c_dim - c0 < block ? c_dim - c0 : block;
+    const int npad = round_up(c_cnt, 32);
+    const int64_t w_items = (int64_t)(kp / 16) * 2 * 4 * npad * 4;
+    cin_tc_prep_weights_kernel<<<grid_for(w_items / 2, 256, 8), 256, 0, s>>>(w, c0, c_cnt, 1, k_dim, kp, npad,
+                                                                             wp + (size_t)pass * w_floats);
+    rc = check_launch("cin_tc_prep_weights_kernel");
+  }
+  if (rc == TRS_OK) {
+    CinTcArgs a{};
+    a.xt = nullptr; a.h = x; a.wp = wp; a.scale = nullptr; a.shift = bias;
+    a.h_next = out; a.pooled = nullptr;
+    a.m_rows = rows; a.fields = 1; a.embed = 1; a.hp0 = 0; a.hp = kp; a.h_pitch = k_dim; a.k_valid = k_dim;
+    a.c_begin = 0; a.c_eff = c_dim < block ? c_dim : block; a.npad = round_up(a.c_eff, 32);
+    a.c_total = c_dim; a.c_block = block; a.wp_pass_stride = (int64_t)w_floats;
+    a.n_direct = 0; a.hid_begin = 0; a.hid_count = c_dim; a.hp_next = c_dim;
+    a.pool_off = 0; a.pooled_width = 0; a.act = activation;
+    const size_t a_stage = 2 * 4 * kTileM * 16, b_stage = (size_t)2 * 4 * a.npad * 16;
+    const size_t fixed = (a_tmem ? 0 : kAStages * a_stage) + (size_t)kTileM * 4 + 2 * a.npad * 4 +
+                         (2 * kMaxAStages + 2 * kMaxBStages + 2) * 8 + 16 + 128;
+    int b_stages = kMaxBStages;
+    while (b_stages > 2 && b_stages * b_stage + fixed > (size_t)kMaxDynSmem) --b_stages;
+    a.b_stages = b_stages;
+    const size_t smem = b_stages * b_stage + fixed;
+    const int64_t tiles = (rows + kTileM - 1) / kTileM;
+    const int per_pass = kNumSMs / passes > 0 ? kNumSMs / passes : 1;
+    const dim3 grid(static_cast<unsigned>(tiles < per_pass ? tiles : per_pass), passes);
+    if (a_tmem) {
+      TRS_SMEM_OPT_IN(cin_tc_layer_kernel<true>);
+      cin_tc_layer_kernel<true><<<grid, kThreads, smem, s>>>(a);
+    } else {
+      TRS_SMEM_OPT_IN(cin_tc_layer_kernel<false>);
+      cin_tc_layer_kernel<false><<<grid, kThreads, smem, s>>>(a);
+    }
+    rc = check_launch("cin_tc_layer_kernel(dense)");
+  }
+  cudaFreeAsync(wp, s);
+  return rc;
 }
 
 }  // namespace trs

@@ -2,14 +2,52 @@
 //
 // Both treat the input as a (rows, width) matrix, stage a tile of rows in shared memory and run the small dense
 // layers on it in plain fp32 FFMA (parity bar 1e-5: no TF32/bf16).
+#include <stdlib.h>
+
 #include "tile_ops.cuh"
 
 namespace trs {
 
 int cross_tc_launch(const float* x, const float* w, const float* b, int layers, int64_t rows, int embed, float* out,
                     cudaStream_t s);
+int dense_tc_supported(int k_dim, int c_dim, const void* x, const void* out);
+int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const float* bias, int c_dim, int activation,
+                 float* out, cudaStream_t s);
 
 namespace {
+
+// Narrow output layers (the logit layer of every model): out[r, o] (+)= act(b[o] + <x[r, :], w[o, :]>), one warp per row.
+__global__ void __launch_bounds__(256) narrow_dense_kernel(const float* __restrict__ x, int64_t rows, int k,
+                                                           const float* __restrict__ w, const float* __restrict__ b,
+                                                           int c, int act, float* __restrict__ out, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool vec = (k & 3) == 0 && aligned16(x) && aligned16(w);
+  for (int64_t r = warp0; r < rows; r += warps) {
+    const float* xr = x + r * k;
+    for (int o = 0; o < c; ++o) {
+      const float* wr = w + (int64_t)o * k;
+      float acc = 0.f;
+      if (vec) {
+        for (int i = lane; i < (k >> 2); i += 32) {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(xr) + i);
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(wr) + i);
+          acc = fmaf(xv.x, wv.x, acc); acc = fmaf(xv.y, wv.y, acc);
+          acc = fmaf(xv.z, wv.z, acc); acc = fmaf(xv.w, wv.w, acc);
+        }
+      } else {
+        for (int i = lane; i < k; i += 32) acc = fmaf(__ldg(xr + i), __ldg(wr + i), acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        const float v = apply_act(acc + (b ? __ldg(b + o) : 0.f), act);
+        if (accumulate) out[r * c + o] += v;
+        else out[r * c + o] = v;
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(256) mlp_kernel(const float* __restrict__ x, int64_t rows, MlpParams mp, int ts,
                                                   int in_pitch, int hpitch, float* __restrict__ out) {
@@ -72,6 +110,50 @@ __global__ void __launch_bounds__(256) cross_kernel(const float* __restrict__ x,
 }
 
 }  // namespace
+
+// The MLP as a chain of kernels for WIDE layers: every layer with >= 32 outputs runs on tcgen05 (cin_tc.cu, 3xTF32,
+// fp32-accurate), narrower ones (the logit layer) one warp per row; activations ping-pong through stream-ordered
+// scratch.  Taken when some layer is at least 64 x 64 -- below that the one-kernel shared-memory tile MLP wins.
+// `accumulate` adds the last layer's output onto `out` (the deep branch of DeepFM / xDeepFM joining the other terms).
+int mlp_chain_supported(const int* dims, int layers, int64_t rows, const void* x, const void* out, int accumulate) {
+  static const bool disabled = getenv("TRS_DISABLE_TC") != nullptr;
+  if (disabled || rows < 1024 || !aligned16(x) || !aligned16(out)) return 0;
+  if (accumulate && dims[layers] >= 32) return 0;
+  bool wide = false;
+  for (int l = 0; l < layers; ++l) {
+    if (dims[l + 1] < 32) continue;
+    if (!dense_tc_supported(dims[l], dims[l + 1], x, out)) return 0;
+    if (dims[l] >= 64 && dims[l + 1] >= 64) wide = true;
+  }
+  return wide ? 1 : 0;
+}
+
+int mlp_chain_run(const float* x, int64_t rows, const MlpParams& mp, float* out, int accumulate, cudaStream_t s) {
+  int hmax = 0;
+  for (int l = 1; l < mp.layers; ++l) hmax = mp.dims[l] > hmax ? mp.dims[l] : hmax;
+  const size_t half = ((size_t)rows * hmax + 63) / 64 * 64;
+  float* buf = nullptr;
+  if (mp.layers > 1) TRS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&buf), 2 * half * sizeof(float), s));
+  const float* cur = x;
+  int rc = TRS_OK;
+  for (int l = 0; l < mp.layers && rc == TRS_OK; ++l) {
+    const bool last = l == mp.layers - 1;
+    float* dst = last ? out : buf + (l & 1) * half;
+    const int act = last ? TRS_ACT_NONE : mp.act;
+    if (mp.dims[l + 1] >= 32) {
+      rc = dense_tc_run(cur, rows, mp.dims[l], mp.w[l], mp.b[l], mp.dims[l + 1], act, dst, s);
+    } else {
+      narrow_dense_kernel<<<grid_for(rows * 32, 256, 8), 256, 0, s>>>(cur, rows, mp.dims[l], mp.w[l], mp.b[l],
+                                                                      mp.dims[l + 1], act, dst,
+                                                                      last && accumulate ? 1 : 0);
+      rc = check_launch("narrow_dense_kernel");
+    }
+    cur = dst;
+  }
+  if (buf) cudaFreeAsync(buf, s);
+  return rc;
+}
+
 }  // namespace trs
 
 using namespace trs;
@@ -85,6 +167,8 @@ extern "C" int trs_mlp_forward(const float* x, int64_t rows, const int* dims, in
   TRS_REQUIRE(fill_mlp_params(mp, dims, layers, weights, biases, activation) == 0,
               "trs_mlp_forward: bad layer description (at most %d layers)", MlpParams::kMaxLayers);
   if (rows == 0) return TRS_OK;
+  if (mlp_chain_supported(dims, layers, rows, x, out, 0))
+    return mlp_chain_run(x, rows, mp, out, 0, static_cast<cudaStream_t>(stream));
   const int in_pitch = tile_pitch(dims[0]);
   const int hpitch = tile_pitch(mlp_max_hidden(dims, layers));
   int ts = 64;

@@ -21,6 +21,8 @@ int deepfm_fast_launch(const void* idx, int idx_bits, const int64_t* offsets, in
                        const float* w_feat, const float* w_emb, int64_t rows, const float* const* mlp_w,
                        const float* const* mlp_b, int mlp_layers, float* logits, int32_t* status, cudaStream_t s);
 
+int mlp_chain_supported(const int* dims, int layers, int64_t rows, const void* x, const void* out, int accumulate);
+int mlp_chain_run(const float* x, int64_t rows, const MlpParams& mp, float* out, int accumulate, cudaStream_t s);
 int dcn_tc_supported(int embed, int cross_layers, const int* mlp_dims, int mlp_layers, int activation);
 int dcn_tc_launch(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
                   const float* w_emb, int64_t rows, int embed, const float* cross_w, const float* cross_b,
@@ -297,6 +299,20 @@ int launch_fm_family(const void* idx, int idx_bits, const int64_t* offsets, int6
   a.idx = idx; a.offsets = offsets; a.w_feat = w_feat; a.w_emb = w_emb; a.bias = bias; a.x_out = x_out;
   a.logits = logits; a.status = status; a.batch = batch; a.rows = rows; a.fields = fields; a.embed = embed;
   a.use_fm = use_fm;
+  // wide deep branch: gather + first-order + FM in this kernel (rows written out once), then the MLP as a chain of
+  // tensor-core layers (dense.cu / cin_tc.cu) accumulating into the logits
+  const MlpParams chain = a.mp;
+  float* x_scratch = nullptr;
+  bool chained = false;
+  if (mlp_layers > 0 && mlp_chain_supported(mlp_dims, mlp_layers, batch, logits, logits, 1)) {
+    chained = true;
+    a.mp.layers = 0;
+    mlp_layers = 0;
+    if (a.x_out == nullptr) {
+      TRS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&x_scratch), (size_t)batch * fields * embed * sizeof(float), s));
+      a.x_out = x_scratch;
+    }
+  }
   a.pitch = tile_pitch(fields * embed);
   a.hpitch = mlp_layers > 0 ? tile_pitch(mlp_max_hidden(mlp_dims, mlp_layers)) : 4;
   int ts = 64;
@@ -316,7 +332,12 @@ int launch_fm_family(const void* idx, int idx_bits, const int64_t* offsets, int6
     TRS_SMEM_OPT_IN(fm_family_kernel<32>);
     fm_family_kernel<32><<<grid, 256, smem, s>>>(a);
   }
-  return check_launch("fm_family_kernel");
+  int rc = check_launch("fm_family_kernel");
+  if (chained) {
+    if (rc == TRS_OK) rc = mlp_chain_run(a.x_out, batch, chain, logits, 1, s);
+    if (x_scratch) cudaFreeAsync(x_scratch, s);
+  }
+  return rc;
 }
 
 }  // namespace
