@@ -244,6 +244,19 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * batch * e2e_steps / float(t.item())
     sess.close()
+    # what the host link gives a bare pinned copy of one step's indices (the e2e number is bound by this transfer)
+    dev_idx = torch.empty_like(host_idx[0], device=device)
+    for i in range(3):
+        dev_idx.copy_(host_idx[i % RING], non_blocking=True)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for i in range(20):
+        dev_idx.copy_(host_idx[i % RING], non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 20 * batch * NUM_FIELDS * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    e2e_link_gbs = batch * NUM_FIELDS * 8 * e2e_steps / float(t.item()) / 1e9
+    del dev_idx
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -268,7 +281,8 @@ def run_ours(args):
                                        'the two reference tables as they are (emb (R,16), first-order (R,1))'},
             'roofline': roof, 'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': batch * NUM_FIELDS * 8,
-                    'd2h_bytes_per_step': batch * 4, 'steps': e2e_steps, 'chunks': args.e2e_chunks},
+                    'd2h_bytes_per_step': batch * 4, 'steps': e2e_steps, 'chunks': args.e2e_chunks,
+                    'h2d_gbs_in_e2e': e2e_link_gbs, 'h2d_gbs_bare_pinned_copy': h2d_gbs},
             'gpu_launches': args.steps, 'clocks': clocks,
         }))
     if world > 1:

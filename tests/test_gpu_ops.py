@@ -273,6 +273,27 @@ def test_cin_tensor_core_wide_layers(ops, n, e, sizes, direct):
         assert normwise_err(got, want) <= TOL, (n, e, sizes, batch)
 
 
+@pytest.mark.parametrize('each', [False, True])
+@pytest.mark.parametrize('n,e', [(39, 16), (7, 32), (5, 8), (12, 16), (2, 8)])
+def test_bilinear_tensor_core(ops, n, e, each):
+    """bilinear_tc.cu: 32-sample CTA tiles, a contiguous pair range per warp, 3xTF32 mma.sync -- both weight types,
+    with and without bias, ragged batches around the tile, pair counts that do not divide by the 8 warps."""
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    tag = f'bil{n}_{e}_{int(each)}'
+    pairs = n * (n - 1) // 2
+    wshape, bshape = ((pairs, e, e), (pairs, e)) if each else ((e, e), (e,))
+    w = torch.from_numpy(synth.uniform(wshape, f'{tag}/w', -e ** -0.5, e ** -0.5))
+    b = torch.from_numpy(synth.uniform(bshape, f'{tag}/b', -0.5, 0.5))
+    for batch in (1, 31, 32, 33, 700):
+        x = torch.from_numpy(synth.uniform((batch, n, e), f'{tag}/x{batch}', -1.0, 1.0))
+        for bias in (b, None):
+            want = R.bilinear_layer(x, w, bias, 'each' if each else 'all').numpy()
+            got = ops.bilinear(x.cuda(), w.cuda(), None if bias is None else bias.cuda(), each).cpu().numpy()
+            assert got.shape == want.shape
+            assert normwise_err(got, want) <= TOL, (n, e, each, batch, bias is None)
+
+
 def _wide_mlp(tag, dims):
     from torecsys_b200 import synth
     ws = [torch.from_numpy(synth.uniform((dims[i + 1], dims[i]), f'{tag}/w{i}', -dims[i] ** -0.5, dims[i] ** -0.5))

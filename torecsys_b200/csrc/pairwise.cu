@@ -8,6 +8,8 @@
 namespace trs {
 
 int ipn_tc_launch(const float* x, int64_t batch, int fields, int embed, float* out, cudaStream_t s);
+int bilinear_tc_launch(const float* x, const float* w, const float* bias, int each_type, int64_t batch, int fields,
+                       int embed, float* out, cudaStream_t s);
 int afm_tc_launch(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, int64_t batch,
                   int fields, int embed, int attn, float* out, float* scores, cudaStream_t s);
 
@@ -386,6 +388,10 @@ extern "C" int trs_bilinear_forward(const float* x, const float* weight, const f
   if (batch == 0) return TRS_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int pairs = fields * (fields - 1) / 2;
+  {   // tensor-pipe kernel (bilinear_tc.cu) for embed 8 / 16 / 32; anything else takes the generic kernels below
+    const int rc = bilinear_tc_launch(x, weight, bias, each_type, batch, fields, embed, out, s);
+    if (rc != TRS_ERR_UNSUPPORTED) return rc;
+  }
   if (!each_type) {
     int warps = 8;
     size_t smem;
