@@ -191,7 +191,9 @@ def run_ours(args):
 
     def step(i):
         if packed is not None:
-            ops.deepfm_packed(dev_idx[i % RING], offsets, packed, pack, out=out)
+            # back-to-back batches that are already resident: TRS_LAUNCH_OVERLAP_PREVIOUS lets batch k+1 start on
+            # the SMs batch k has left (its inputs are never written by a kernel; its logits stay ordered)
+            ops.deepfm_packed(dev_idx[i % RING], offsets, packed, pack, out=out, overlap_previous=args.overlap)
         else:
             ops.deepfm(dev_idx[i % RING], offsets, w_feat, w_emb, pack, out=out)
 
@@ -278,7 +280,10 @@ def run_ours(args):
                              f'distinct index batches ({RING * batch * NUM_FIELDS * 8 / 1e6:.0f} MB)',
                        'table_layout': ('packed 128-byte rows [v16|w|pad] built once from the two reference tables '
                                         '(trs_fm_pack_table)') if packed is not None else
-                                       'the two reference tables as they are (emb (R,16), first-order (R,1))'},
+                                       'the two reference tables as they are (emb (R,16), first-order (R,1))',
+                       'launch': ('back-to-back launches with programmatic dependent launch '
+                                  '(TRS_LAUNCH_OVERLAP_PREVIOUS)') if (packed is not None and args.overlap)
+                                 else 'back-to-back fully ordered launches'},
             'roofline': roof, 'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': batch * NUM_FIELDS * 8,
                     'd2h_bytes_per_step': batch * 4, 'steps': e2e_steps, 'chunks': args.e2e_chunks,
@@ -299,6 +304,8 @@ def main():
     ap.add_argument('--rows-per-field', type=int, default=ROWS_PER_FIELD)
     ap.add_argument('--e2e-chunks', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-overlap', dest='overlap', action='store_false',
+                    help='launch the timed kernels fully ordered (no programmatic dependent launch)')
     ap.add_argument('--layout', default='packed', choices=['packed', 'split'],
                     help='packed: one 128-byte shadow row per table row (default); split: the two reference tables')
     ap.add_argument('--traffic', type=float, default=None,

@@ -174,6 +174,20 @@ int trs_deepfm_forward_packed(const void* idx, int idx_bits, const int64_t* offs
                               const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
                               const float* const* mlp_b, int activation, float* logits, int32_t* status,
                               void* stream);
+/* Same computation with launch flags.  TRS_LAUNCH_OVERLAP_PREVIOUS launches the kernel with programmatic stream
+ * serialisation (Hopper/Blackwell "programmatic dependent launch"): its CTAs start on every SM the previous kernel
+ * of the stream has already left and READ their inputs at once, but write nothing (logits, status) before that
+ * previous kernel has completed and its writes are visible.  The drain of batch k then overlaps the start of batch
+ * k+1 -- back-to-back Sequential.forward calls (torecsys/models/sequential.py:31-44) on batches that are already
+ * resident.  Contract of the flag: no kernel still running on `stream` writes idx, offsets, packed or the MLP
+ * parameters of this call (work enqueued as copies/memsets is ordered as usual).  flags = 0 is exactly
+ * trs_deepfm_forward_packed. */
+#define TRS_LAUNCH_OVERLAP_PREVIOUS 1u
+int trs_deepfm_forward_packed_ex(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                                 const float* packed, int64_t rows,
+                                 const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                                 const float* const* mlp_b, int activation, float* logits, int32_t* status,
+                                 unsigned flags, void* stream);
 
 /* DeepAndCrossNetworkModel.forward (torecsys/models/ctr/deep_and_cross_network.py:58-98):
  *     logit = fc( flatten( cat[ Cross(emb) (B,N,E), MLP_per_field(emb) (B,N,Od) ], dim=-1 ) )

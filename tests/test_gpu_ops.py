@@ -207,6 +207,55 @@ def test_deepfm_packed_table_path(ops, n):
             assert normwise_err(got, want64) <= max(4 * normwise_err(want, want64), 2e-6), (n, batch)
 
 
+def test_deepfm_packed_overlapped_launches(ops):
+    """TRS_LAUNCH_OVERLAP_PREVIOUS (programmatic dependent launch): a train of back-to-back launches, each reading
+    its own index batch, must give the same logits as ordered launches -- both into separate outputs and into ONE
+    reused output buffer (the last launch must win: writes stay ordered behind the previous grid)."""
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    n, e = 39, 16
+    fs = [16 * (3 + i % 5) for i in range(n)]
+    rows = sum(fs)
+    off = R.field_offsets(fs)
+    w_feat = torch.from_numpy(synth.uniform((rows, 1), 'pdl/wf'))
+    w_emb = torch.from_numpy(synth.uniform((rows, e), 'pdl/we'))
+    dims = [n * e, 16, 16, 16, 1]
+    ws = [torch.from_numpy(synth.uniform((dims[i + 1], dims[i]), f'pdl/w{i}', -1 / np.sqrt(dims[i]),
+                                         1 / np.sqrt(dims[i]))) for i in range(4)]
+    bs = [torch.from_numpy(synth.uniform((dims[i + 1],), f'pdl/b{i}', -0.5, 0.5)) for i in range(4)]
+    pack = ops.MlpPack([w.cuda() for w in ws], [b.cuda() for b in bs], ops.activation_id('relu'))
+    packed = ops.fm_pack_table(w_emb.cuda(), w_feat.cuda())
+    batch, trains = 16 * 148 * 3 + 5, 12
+    idx = [torch.from_numpy(synth.integers((batch, n), f'pdl/idx{k}', np.asarray(fs)[None, :])).cuda()
+           for k in range(trains)]
+    ordered = [ops.deepfm_packed(ix, off.cuda(), packed, pack) for ix in idx]
+    want_last = R.deepfm_from_indices(idx[-1].cpu(), off, w_feat, w_emb, ws, bs).numpy()
+    assert normwise_err(ordered[-1].cpu().numpy(), want_last) <= TOL
+    off_d = off.cuda()
+    ops.set_index_check('deferred')   # 'sync' would put a host synchronisation between the launches
+    try:
+        for _ in range(5):
+            outs = [torch.empty(batch, 1, device='cuda') for _ in range(trains)]
+            shared = torch.empty(batch, 1, device='cuda')
+            torch.cuda.synchronize()
+            for k, ix in enumerate(idx):
+                ops.deepfm_packed(ix, off_d, packed, pack, out=outs[k], overlap_previous=True)
+            for ix in idx:
+                ops.deepfm_packed(ix, off_d, packed, pack, out=shared, overlap_previous=True)
+            torch.cuda.synchronize()
+            for k in range(trains):
+                assert torch.equal(outs[k], ordered[k]), k
+            assert torch.equal(shared, ordered[-1])
+        ops.check_index_errors()
+    finally:
+        ops.set_index_check('sync')
+    # out-of-range lookups are still reported from an overlapped launch
+    bad = idx[0].clone()
+    bad[7, 3] = 10 ** 9
+    with pytest.raises(IndexError):
+        ops.deepfm_packed(bad, off.cuda(), packed, pack, overlap_previous=True)
+
+
 @pytest.mark.parametrize('n,e,cross_layers,deep,od', [(39, 32, 6, [32, 16, 8], 4), (7, 32, 1, [32], 1),
                                                       (13, 16, 3, [24, 10], 3), (5, 64, 2, [64, 32], 8),
                                                       (26, 8, 4, [32, 16, 8], 4)])

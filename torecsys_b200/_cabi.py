@@ -16,6 +16,7 @@ TRS_ERR_INVALID_ARGUMENT = -1
 TRS_ERR_UNSUPPORTED = -2
 TRS_ERR_CUDA = -3
 TRS_STATUS_WORDS = 2
+TRS_LAUNCH_OVERLAP_PREVIOUS = 1
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
 
@@ -47,6 +48,8 @@ PROTOTYPES = {
     'trs_fm_model_forward_packed': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, _P, _P, _P, _P]),
     'trs_deepfm_forward_packed': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, _IP, c_int, _PP, _PP, c_int,
                                           _P, _P, _P]),
+    'trs_deepfm_forward_packed_ex': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, _IP, c_int, _PP, _PP, c_int,
+                                             _P, _P, ctypes.c_uint, _P]),
     'trs_dcn_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, c_int, _P, _P, c_int, _IP, c_int, _PP,
                                 _PP, c_int, _P, _P, _P, _P, _P]),
     'trs_xdeepfm_workspace_bytes': (c_int64, [c_int64, c_int, c_int, _IP, c_int, c_int]),

@@ -91,6 +91,13 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Programmatic dependent launch (TRS_LAUNCH_OVERLAP_PREVIOUS): every CTA lets the NEXT grid on the stream be scheduled
+// as soon as SMs free up (launch_dependents at entry), and a grid launched that way only READS its inputs until the
+// previous grid has completed and flushed (wait before the first global write).  Without the launch attribute both
+// instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct PackedArgs {
   const void* idx;
   const int64_t* offsets;
@@ -134,6 +141,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
   long long* off_s = reinterpret_cast<long long*>(smem_raw + S::fixed);
   unsigned char* idx_ring = smem_raw + S::fixed + S::off_bytes(a.fields);   // [kIdxSlots][16 * fields] indices
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int n_fields = a.fields;
@@ -218,7 +226,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
         else ix = reinterpret_cast<const int*>(slot)[s * n_fields + f0 + f];
         const int64_t r = ix + off_s[f0 + f];
         if (r >= 0 && r < a.rows) rid[k] = static_cast<int>(r);
-        else report_oob(a.status, (b0 + s) * n_fields + f0 + f);
+        else {
+          pdl_wait();   // status may still be written (or cleared) by the work this launch overlaps
+          report_oob(a.status, (b0 + s) * n_fields + f0 + f);
+        }
       }
     }
     const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(my_v + (size_t)stage * FPW * kFieldFloats + lane_dst));
@@ -305,6 +316,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
     *reinterpret_cast<float4*>(pw + 16 * kHPitch + (g + 8) * 16 + 4 * t) = sb;
     pw[16 * kHPitch + 256 + g * 4 + t] = ca;
     pw[16 * kHPitch + 256 + (g + 8) * 4 + t] = cb;
+    if (it == 0) pdl_wait();   // first global write (logits) below: the overlapped previous grid must be complete
     __syncthreads();
 
     // ---- finish two samples per warp: lane = (sample fs, output / component fo) -------------------------------------
@@ -369,12 +381,31 @@ int deepfm_packed_supported(int fields, int embed, const int* mlp_dims, int mlp_
 }
 
 template <int IdxBits, int FPW>
-static int launch_packed(const PackedArgs& a, cudaStream_t s) {
+static int launch_packed(const PackedArgs& a, cudaStream_t s, unsigned flags = 0) {
   const size_t smem = Smem<FPW>::total(a.fields, IdxBits);
   TRS_REQUIRE(smem <= (size_t)kMaxDynSmem, "trs_deepfm_forward_packed: shared memory budget exceeded (%zu B)", smem);
   TRS_SMEM_OPT_IN((deepfm_packed_kernel<IdxBits, FPW>));
   const int64_t tiles = (a.batch + kTile - 1) / kTile;
   const int grid = static_cast<int>(tiles < kNumSMs ? tiles : kNumSMs);
+  if (flags & TRS_LAUNCH_OVERLAP_PREVIOUS) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kWarps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, deepfm_packed_kernel<IdxBits, FPW>, a);
+    if (e != cudaSuccess) {
+      set_error("launch of deepfm_packed_kernel (overlapped) failed: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return TRS_ERR_CUDA;
+    }
+    return TRS_OK;
+  }
   deepfm_packed_kernel<IdxBits, FPW><<<grid, kWarps * 32, smem, s>>>(a);
   return check_launch("deepfm_packed_kernel");
 }
@@ -430,6 +461,16 @@ extern "C" int trs_deepfm_forward_packed(const void* idx, int idx_bits, const in
                                          int fields, const float* packed, int64_t rows, const int* mlp_dims,
                                          int mlp_layers, const float* const* mlp_w, const float* const* mlp_b,
                                          int activation, float* logits, int32_t* status, void* stream) {
+  return trs_deepfm_forward_packed_ex(idx, idx_bits, offsets, batch, fields, packed, rows, mlp_dims, mlp_layers, mlp_w,
+                                      mlp_b, activation, logits, status, 0u, stream);
+}
+
+extern "C" int trs_deepfm_forward_packed_ex(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch,
+                                            int fields, const float* packed, int64_t rows, const int* mlp_dims,
+                                            int mlp_layers, const float* const* mlp_w, const float* const* mlp_b,
+                                            int activation, float* logits, int32_t* status, unsigned flags,
+                                            void* stream) {
+  TRS_REQUIRE((flags & ~TRS_LAUNCH_OVERLAP_PREVIOUS) == 0, "trs_deepfm_forward_packed_ex: unknown flags 0x%x", flags);
   TRS_REQUIRE(idx && offsets && packed && logits && mlp_dims && mlp_w && mlp_b,
               "trs_deepfm_forward_packed: null pointer");
   TRS_REQUIRE(idx_bits == 32 || idx_bits == 64, "trs_deepfm_forward_packed: idx_bits must be 32 or 64");
@@ -456,7 +497,7 @@ extern "C" int trs_deepfm_forward_packed(const void* idx, int idx_bits, const in
   const int fpw = (fields + kWarps - 1) / kWarps;
 #define DISPATCH(FPW)                                                        \
   case FPW:                                                                  \
-    return idx_bits == 64 ? launch_packed<64, FPW>(a, s) : launch_packed<32, FPW>(a, s);
+    return idx_bits == 64 ? launch_packed<64, FPW>(a, s, flags) : launch_packed<32, FPW>(a, s, flags);
   switch (fpw) {
     DISPATCH(1)
     DISPATCH(2)

@@ -380,7 +380,11 @@ def fm_model_packed(idx, offsets, packed: torch.Tensor, bias: Optional[torch.Ten
     return out
 
 
-def deepfm_packed(idx, offsets, packed: torch.Tensor, pack: MlpPack, out: Optional[torch.Tensor] = None):
+def deepfm_packed(idx, offsets, packed: torch.Tensor, pack: MlpPack, out: Optional[torch.Tensor] = None,
+                  overlap_previous: bool = False):
+    """DeepFM forward on the packed table.  `overlap_previous=True` = TRS_LAUNCH_OVERLAP_PREVIOUS (programmatic
+    dependent launch): the caller promises that no kernel still running on the current stream writes this call's
+    inputs, so the kernel may read them while the previous kernel drains (outputs are still ordered)."""
     ix, bits, off = _fused_common('deepfm_packed', idx, offsets, packed)
     if packed.dtype != torch.float32 or packed.dim() != 2 or packed.shape[1] != 32 or not packed.is_contiguous():
         raise ValueError('deepfm_packed: packed table must be a contiguous (rows, 32) float32 tensor')
@@ -389,9 +393,10 @@ def deepfm_packed(idx, offsets, packed: torch.Tensor, pack: MlpPack, out: Option
         ix = ix.clone()
     out = out if out is not None else torch.empty((b, 1), dtype=torch.float32, device=packed.device)
     st = _status_tensor(packed.device)
-    check(_cabi.load().trs_deepfm_forward_packed(_ptr(ix), bits, _ptr(off), b, n, _ptr(packed), packed.shape[0],
-                                                 pack.dims, pack.layers, pack.w, pack.b, pack.act, _ptr(out),
-                                                 _ptr(st), _stream()), 'trs_deepfm_forward_packed')
+    flags = _cabi.TRS_LAUNCH_OVERLAP_PREVIOUS if overlap_previous else 0
+    check(_cabi.load().trs_deepfm_forward_packed_ex(_ptr(ix), bits, _ptr(off), b, n, _ptr(packed), packed.shape[0],
+                                                    pack.dims, pack.layers, pack.w, pack.b, pack.act, _ptr(out),
+                                                    _ptr(st), flags, _stream()), 'trs_deepfm_forward_packed')
     _after_lookup(packed.device)
     return out
 
