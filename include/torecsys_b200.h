@@ -221,13 +221,36 @@ int trs_ffm_model_forward(const void* idx, int idx_bits, const int64_t* offsets,
                           const float* w_feat, const float* const* tables, int64_t rows, int embed,
                           const float* bias, float* logits, int32_t* status, void* stream);
 
-/* ---- host-buffer entry point (the e2e path: pageable/pinned host indices in, host logits out) -----------------------
- * A session owns pinned staging buffers, device buffers and two streams; `trs_session_deepfm_forward_host` splits
- * the batch into chunks and overlaps H2D(idx) / kernel / D2H(logits).  It synchronises before returning and
- * returns the status word0 (out-of-range count) through *oob_count when oob_count != NULL. */
+/* ---- host-buffer entry points (the e2e path: pageable/pinned host indices in, host logits out) ----------------------
+ * This is the step BEFORE the hot path in the reference: the DataLoader's collate function hands Sequential.forward a
+ * host (B, N) int64 tensor (torecsys/data/dataloader/collate_fn.py:82, torecsys/models/sequential.py:31-44) and the
+ * caller reads the (B, 1) prediction back.  A session owns trs_session_depth() independent slots (pinned staging,
+ * device buffers, two streams each).  A submitted batch is split into `chunks` slices whose H2D(idx) / kernel /
+ * D2H(logits) overlap; batches in different slots overlap each other, so a caller that keeps two or more batches in
+ * flight keeps the host->device link busy all the time.
+ *   trs_session_submit_*   enqueue one batch and return a ticket; no host synchronisation.  idx_host and logits_host
+ *                          must stay valid until the ticket has been waited for.  TRS_ERR_INVALID_ARGUMENT when
+ *                          every slot is in flight.
+ *   trs_session_wait       block until the batch of `ticket` is complete: its logits are in logits_host and
+ *                          *oob_count (when not NULL) = number of out-of-range lookups (status word0).
+ *   trs_session_deepfm_forward_host[_packed] = submit + wait. */
 typedef struct trs_session trs_session;
 int trs_session_create(int64_t max_batch, int fields, int chunks, trs_session** out_session);
 int trs_session_destroy(trs_session* session);
+int trs_session_depth(void);
+int trs_session_submit_deepfm(trs_session* session, const void* idx_host, int idx_bits,
+                              const int64_t* offsets, int64_t batch, int fields,
+                              const float* w_feat, const float* w_emb, int64_t rows, int embed,
+                              const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                              const float* const* mlp_b, int activation,
+                              float* logits_host, int64_t* ticket);
+int trs_session_submit_deepfm_packed(trs_session* session, const void* idx_host, int idx_bits,
+                                     const int64_t* offsets, int64_t batch, int fields,
+                                     const float* packed, int64_t rows,
+                                     const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                                     const float* const* mlp_b, int activation,
+                                     float* logits_host, int64_t* ticket);
+int trs_session_wait(trs_session* session, int64_t ticket, int64_t* oob_count);
 int trs_session_deepfm_forward_host(trs_session* session, const void* idx_host, int idx_bits,
                                     const int64_t* offsets, int64_t batch, int fields,
                                     const float* w_feat, const float* w_emb, int64_t rows, int embed,

@@ -1,0 +1,133 @@
+"""Host-buffer entry points (csrc/session.cu): host indices in -> host logits out, synchronous and pipelined.
+
+The logits must be bit-identical to the device-resident entry points on the same inputs (same kernels, only the
+copies differ) and within 1e-5 of the oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.oracle_run import normwise_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def setup():
+    from oracle import restated as R
+    from torecsys_b200 import ops, synth
+    ops.set_index_check('sync')
+    n, e = 39, 16
+    fs = [16 * (3 + i % 5) for i in range(n)]
+    rows = sum(fs)
+    off = R.field_offsets(fs)
+    w_feat = torch.from_numpy(synth.uniform((rows, 1), 'sess/wf'))
+    w_emb = torch.from_numpy(synth.uniform((rows, e), 'sess/we'))
+    dims = [n * e, 16, 16, 16, 1]
+    ws = [torch.from_numpy(synth.uniform((dims[i + 1], dims[i]), f'sess/w{i}', -1 / np.sqrt(dims[i]),
+                                         1 / np.sqrt(dims[i]))) for i in range(4)]
+    bs = [torch.from_numpy(synth.uniform((dims[i + 1],), f'sess/b{i}', -0.5, 0.5)) for i in range(4)]
+    pack = ops.MlpPack([w.cuda() for w in ws], [b.cuda() for b in bs], ops.activation_id('relu'))
+    packed = ops.fm_pack_table(w_emb.cuda(), w_feat.cuda())
+    return dict(ops=ops, synth=synth, R=R, n=n, fs=fs, off=off, off_d=off.cuda(), w_feat=w_feat, w_emb=w_emb, ws=ws,
+                bs=bs, pack=pack, packed=packed, w_feat_d=w_feat.cuda(), w_emb_d=w_emb.cuda())
+
+
+def _idx(s, batch, tag):
+    return torch.from_numpy(s['synth'].integers((batch, s['n']), f'sess/idx{tag}', np.asarray(s['fs'])[None, :]))
+
+
+@pytest.mark.parametrize('batch', [1, 17, 1000, 5003])
+@pytest.mark.parametrize('pinned', [False, True])
+@pytest.mark.parametrize('idx_dtype', [torch.int64, torch.int32])
+def test_session_sync_matches_device_path_and_oracle(setup, batch, pinned, idx_dtype):
+    from torecsys_b200.host import DeepFMSession
+    s = setup
+    idx = _idx(s, batch, batch).to(idx_dtype)
+    want = s['R'].deepfm_from_indices(idx.long(), s['off'], s['w_feat'], s['w_emb'], s['ws'], s['bs']).numpy()
+    dev_packed = s['ops'].deepfm_packed(idx.cuda(), s['off_d'], s['packed'], s['pack']).cpu()
+    dev_split = s['ops'].deepfm(idx.cuda(), s['off_d'], s['w_feat_d'], s['w_emb_d'], s['pack']).cpu()
+    sess = DeepFMSession(8192, s['n'], chunks=4)
+    try:
+        src = idx.pin_memory() if pinned else idx
+        out = torch.empty(batch, 1)
+        out = out.pin_memory() if pinned else out
+        sess.forward_host_packed(src, s['off_d'], s['packed'], s['pack'], out)
+        assert torch.equal(out, dev_packed)
+        assert normwise_err(out.numpy(), want) <= TOL
+        out.zero_()
+        sess.forward_host(src, s['off_d'], s['w_feat_d'], s['w_emb_d'], s['pack'], out)
+        assert torch.equal(out, dev_split)
+        assert normwise_err(out.numpy(), want) <= TOL
+    finally:
+        sess.close()
+
+
+def test_session_pipelined_batches(setup):
+    """submit/wait with every slot in flight: results land in the right buffers, in any wait order."""
+    from torecsys_b200.host import DeepFMSession
+    s = setup
+    sess = DeepFMSession(4096, s['n'], chunks=3)
+    try:
+        depth = sess.depth
+        assert depth >= 2
+        batches = [4096, 33, 2500, 4096, 1, 777, 4000]
+        idxs = [_idx(s, b, f'p{k}').pin_memory() for k, b in enumerate(batches)]
+        want = [s['ops'].deepfm_packed(ix.cuda(), s['off_d'], s['packed'], s['pack']).cpu() for ix in idxs]
+        outs = [torch.full((b, 1), float('nan')).pin_memory() for b in batches]
+        for rounds in range(3):
+            for o in outs:
+                o.fill_(float('nan'))
+            inflight = []
+            for k, ix in enumerate(idxs):
+                if len(inflight) == depth:
+                    # alternate between waiting for the oldest and the newest ticket
+                    t, j = inflight.pop(0 if (k + rounds) % 2 == 0 else -1)
+                    sess.wait(t)
+                    assert torch.equal(outs[j], want[j]), j
+                inflight.append((sess.submit(ix, s['off_d'], s['pack'], outs[k], packed=s['packed']), k))
+            for t, j in inflight:
+                sess.wait(t)
+                assert torch.equal(outs[j], want[j]), j
+        # pageable buffers go through the slot's staging memory
+        o = torch.empty(batches[2], 1)
+        t = sess.submit(idxs[2].clone(), s['off_d'], s['pack'], o, w_feat=s['w_feat_d'], w_emb=s['w_emb_d'])
+        sess.wait(t)
+        assert normwise_err(o.numpy(), want[2].numpy()) <= TOL
+    finally:
+        sess.close()
+
+
+def test_session_errors(setup):
+    from torecsys_b200.host import DeepFMSession
+    s = setup
+    sess = DeepFMSession(256, s['n'], chunks=2)
+    try:
+        idx = _idx(s, 256, 'err').pin_memory()
+        outs = [torch.empty(256, 1).pin_memory() for _ in range(sess.depth + 1)]
+        tickets = [sess.submit(idx, s['off_d'], s['pack'], outs[k], packed=s['packed']) for k in range(sess.depth)]
+        with pytest.raises(ValueError):      # every slot in flight
+            sess.submit(idx, s['off_d'], s['pack'], outs[-1], packed=s['packed'])
+        for t in tickets:
+            sess.wait(t)
+        with pytest.raises(ValueError):      # a ticket can be waited for once
+            sess.wait(tickets[0])
+        with pytest.raises(ValueError):      # batch larger than the session
+            sess.submit(_idx(s, 300, 'big'), s['off_d'], s['pack'], torch.empty(300, 1), packed=s['packed'])
+        bad = idx.clone()
+        bad[5, 2] = 1 << 40
+        with pytest.raises(IndexError):
+            sess.forward_host_packed(bad, s['off_d'], s['packed'], s['pack'], outs[0])
+        t = sess.submit(bad, s['off_d'], s['pack'], outs[0], packed=s['packed'])
+        with pytest.raises(IndexError):
+            sess.wait(t)
+        # the session is still usable afterwards
+        sess.forward_host_packed(idx, s['off_d'], s['packed'], s['pack'], outs[0])
+        want = s['ops'].deepfm_packed(idx.cuda(), s['off_d'], s['packed'], s['pack']).cpu()
+        assert torch.equal(outs[0], want)
+        with pytest.raises(RuntimeError):    # no CPU path
+            sess.forward_host_packed(idx, s['off_d'].cpu(), s['packed'].cpu(), s['pack'], outs[0])
+    finally:
+        sess.close()

@@ -58,6 +58,12 @@ PROTOTYPES = {
     'trs_ffm_model_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _P, _P, _P, _P]),
     'trs_session_create': (c_int, [c_int64, c_int, c_int, POINTER(c_void_p)]),
     'trs_session_destroy': (c_int, [c_void_p]),
+    'trs_session_depth': (c_int, []),
+    'trs_session_submit_deepfm': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _IP,
+                                          c_int, _PP, _PP, c_int, _P, POINTER(c_int64)]),
+    'trs_session_submit_deepfm_packed': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, c_int64, _IP,
+                                                 c_int, _PP, _PP, c_int, _P, POINTER(c_int64)]),
+    'trs_session_wait': (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
     'trs_session_deepfm_forward_host': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _IP,
                                                 c_int, _PP, _PP, c_int, _P, POINTER(c_int64)]),
     'trs_session_deepfm_forward_host_packed': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, c_int64, _IP,
