@@ -269,7 +269,12 @@ def run_ours(args):
         return world * batch * e2e_steps / float(dt.item())
 
     e2e_sync_value = time_e2e(e2e_sync, host_idx)
-    e2e_value = time_e2e(e2e_pipelined, host_idx)
+    e2e_plain_value = time_e2e(e2e_pipelined, host_idx)
+    # int64 host indices narrowed to int32 by the session's host threads before they cross the link
+    narrow_threads = sess.set_index_narrowing(args.narrow_threads) if args.narrow_threads != 0 else 0
+    e2e_narrow_value = time_e2e(e2e_pipelined, host_idx) if narrow_threads > 0 else None
+    sess.set_index_narrowing(0)
+    e2e_value = max(e2e_plain_value, e2e_narrow_value or 0.0)
     # same call with the loader handing over int32 indices (the reference accepts them, multi_indices_emb.py:104)
     host_idx32 = [h.to(torch.int32).pin_memory() for h in host_idx]
     e2e_int32_value = time_e2e(e2e_pipelined, host_idx32)
@@ -319,6 +324,8 @@ def run_ours(args):
                     'mode': f'pipelined, {depth} batches in flight (trs_session_submit_deepfm_packed / '
                             'trs_session_wait), int64 host indices',
                     'sync_call_value': e2e_sync_value, 'int32_indices_value': e2e_int32_value,
+                    'pipelined_plain_value': e2e_plain_value, 'pipelined_host_narrowing_value': e2e_narrow_value,
+                    'host_narrowing_threads': narrow_threads,
                     'h2d_gbs_in_e2e': e2e_link_gbs, 'h2d_gbs_bare_pinned_copy': h2d_gbs},
             'gpu_launches': args.steps, 'clocks': clocks,
         }))
@@ -335,6 +342,8 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--rows-per-field', type=int, default=ROWS_PER_FIELD)
     ap.add_argument('--e2e-chunks', type=int, default=4)
+    ap.add_argument('--narrow-threads', type=int, default=-1,
+                    help='host threads narrowing int64 indices to int32 in the e2e path (0 = off, -1 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-overlap', dest='overlap', action='store_false',
                     help='launch the timed kernels fully ordered (no programmatic dependent launch)')

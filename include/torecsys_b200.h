@@ -238,6 +238,12 @@ typedef struct trs_session trs_session;
 int trs_session_create(int64_t max_batch, int fields, int chunks, trs_session** out_session);
 int trs_session_destroy(trs_session* session);
 int trs_session_depth(void);
+/* Host-side index narrowing (off by default).  With `threads` > 0 the session converts int64 host indices to int32 in
+ * its pinned staging memory with that many host threads (the submitting thread included) before they cross the
+ * link, halving the bytes of the link-bound path; the result is identical, values that do not fit int32 are
+ * reported as out-of-range lookups exactly as in the int64 path.  threads = 0 turns it off, -1 picks
+ * min(8, usable CPUs / 2).  Returns the thread count in use (>= 0) or a negative TRS_ERR_* code. */
+int trs_session_set_index_narrowing(trs_session* session, int threads);
 int trs_session_submit_deepfm(trs_session* session, const void* idx_host, int idx_bits,
                               const int64_t* offsets, int64_t batch, int fields,
                               const float* w_feat, const float* w_emb, int64_t rows, int embed,

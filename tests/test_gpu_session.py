@@ -131,3 +131,49 @@ def test_session_errors(setup):
             sess.forward_host_packed(idx, s['off_d'].cpu(), s['packed'].cpu(), s['pack'], outs[0])
     finally:
         sess.close()
+
+
+@pytest.mark.parametrize('threads', [1, 3, -1])
+def test_session_host_narrowing_is_transparent(setup, threads):
+    """int64 host indices narrowed to int32 by the session's host threads: identical logits, same error reports."""
+    from torecsys_b200.host import DeepFMSession
+    s = setup
+    sess = DeepFMSession(40000, s['n'], chunks=4)
+    try:
+        used = sess.set_index_narrowing(threads)
+        assert used >= 1
+        for batch in (105, 4096, 39999):        # 105 * 39 < 4096 elements: below the narrowing threshold
+            idx = _idx(s, batch, f'nw{batch}')
+            want = s['ops'].deepfm_packed(idx.cuda(), s['off_d'], s['packed'], s['pack']).cpu()
+            for src in (idx, idx.pin_memory()):
+                out = torch.empty(batch, 1).pin_memory()
+                sess.forward_host_packed(src, s['off_d'], s['packed'], s['pack'], out)
+                assert torch.equal(out, want), batch
+        # pipelined, every slot in flight, repeated (exercises the pool's job hand-over)
+        idxs = [_idx(s, 20000 + 16 * k, f'nwp{k}').pin_memory() for k in range(5)]
+        want = [s['ops'].deepfm_packed(ix.cuda(), s['off_d'], s['packed'], s['pack']).cpu() for ix in idxs]
+        outs = [torch.empty(ix.shape[0], 1).pin_memory() for ix in idxs]
+        for _ in range(4):
+            inflight = []
+            for k, ix in enumerate(idxs):
+                if len(inflight) == sess.depth:
+                    t, j = inflight.pop(0)
+                    sess.wait(t)
+                    assert torch.equal(outs[j], want[j])
+                inflight.append((sess.submit(ix, s['off_d'], s['pack'], outs[k], packed=s['packed']), k))
+            for t, j in inflight:
+                sess.wait(t)
+                assert torch.equal(outs[j], want[j])
+        # values outside int32 (and negative ones) are reported, not wrapped into range
+        base = _idx(s, 4096, 'nwbad')
+        for bad_value in (1 << 40, (1 << 32) + 5, -(1 << 33), -(1 << 31) - 1, (1 << 31), -1 - 10 ** 6):
+            bad = base.clone()
+            bad[4000, 0] = bad_value
+            with pytest.raises(IndexError):
+                sess.forward_host_packed(bad, s['off_d'], s['packed'], s['pack'], torch.empty(4096, 1))
+        assert sess.set_index_narrowing(0) == 0
+        out = torch.empty(4096, 1)
+        sess.forward_host_packed(base, s['off_d'], s['packed'], s['pack'], out)
+        assert torch.equal(out, s['ops'].deepfm_packed(base.cuda(), s['off_d'], s['packed'], s['pack']).cpu())
+    finally:
+        sess.close()

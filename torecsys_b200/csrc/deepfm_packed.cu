@@ -49,7 +49,7 @@ constexpr int kFieldFloats = 8 * kPairFloats;  // 16 samples of one field
 // C[16][4] = first-order - 0.5 * sum of squares (per t lane).  Pitches chosen for conflict-free publishing stores.
 constexpr int kHPitch = 24;
 constexpr int kPartialFloats = 16 * kHPitch + 16 * 16 + 16 * 4;  // 704
-constexpr int kHidPitch = 17;
+constexpr int kHidPitch = 20;   // 16-byte aligned rows; 8 consecutive rows cover the 32 banks once (LDS.128)
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
   uint32_t r;
@@ -149,21 +149,27 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
   const int f0 = warp * FPW;  // first field of this warp
 
   const int64_t tiles = (a.batch + kTile - 1) / kTile;
-  const int64_t my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int my_tiles = blockIdx.x < tiles ? static_cast<int>((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
   // Index tiles: the (16 x fields) indices of a tile are contiguous in global memory; the CTA copies them with
   // cp.async into slot (it % kIdxSlots) kIdxAhead tiles before the row copies read them.
   constexpr int kIdxBytes = IdxBits / 8;
   const int tile_idx_bytes = kTile * n_fields * kIdxBytes;   // multiple of 16
   const int64_t total_idx_bytes = a.batch * n_fields * kIdxBytes;
-  auto issue_idx = [&](int64_t it) {
+  const uint32_t idx_ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(idx_ring));
+  auto issue_idx = [&](int it) {
     if (it >= my_tiles) return;
     const int64_t g0 = (blockIdx.x + it * (int64_t)gridDim.x) * tile_idx_bytes;
-    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(idx_ring + (size_t)(it % kIdxSlots) * tile_idx_bytes));
-    for (int c = threadIdx.x * 16; c < tile_idx_bytes; c += blockDim.x * 16) {
-      const int64_t remain = total_idx_bytes - (g0 + c);
-      const int sz = remain >= 16 ? 16 : (remain > 0 ? static_cast<int>(remain) : 0);   // zero-fill past the batch
-      cp_async16(dst + c, static_cast<const unsigned char*>(a.idx) + (sz > 0 ? g0 + c : 0), sz);
+    const unsigned char* src = static_cast<const unsigned char*>(a.idx) + g0;
+    const uint32_t dst = idx_ring_s + (it % kIdxSlots) * tile_idx_bytes;
+    if (g0 + tile_idx_bytes <= total_idx_bytes) {   // a whole tile (all but the last one of the batch)
+      for (int c = threadIdx.x * 16; c < tile_idx_bytes; c += kWarps * 32 * 16) cp_async16(dst + c, src + c, 16);
+    } else {
+      for (int c = threadIdx.x * 16; c < tile_idx_bytes; c += kWarps * 32 * 16) {
+        const int64_t remain = total_idx_bytes - (g0 + c);
+        const int sz = remain >= 16 ? 16 : (remain > 0 ? static_cast<int>(remain) : 0);   // zero-fill past the batch
+        cp_async16(dst + c, sz > 0 ? src + c : static_cast<const unsigned char*>(a.idx), sz);
+      }
     }
   };
 
@@ -202,6 +208,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
   for (int i = threadIdx.x; i < n_fields; i += blockDim.x) off_s[i] = __ldg(a.offsets + i);
 
   float* my_v = vbuf + (size_t)warp * kStages * FPW * kFieldFloats;   // + stage * FPW * kFieldFloats
+  const uint32_t my_v_s = static_cast<uint32_t>(__cvta_generic_to_shared(my_v));
 
   // Row copies of tile `it` into `stage`.
   //   phase 1: lane resolves rows rho = lane + 32k (rho = f*16 + s): index + field offset, range check -> row id / -1;
@@ -209,10 +216,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
   //            the warp covers rows rho = 4i + (lane>>3); the row id comes from lane (rho & 31), register rho >> 5.
   const int sub = lane & 7, rsel = lane >> 3;
   const int lane_dst = (rsel >> 1) * kPairFloats + (sub < 4 ? (rsel & 1) * 16 + 4 * sub : 32 + (rsel & 1) * 4);
-  auto issue = [&](int64_t it, int stage) {
+  const unsigned long long src_lane = reinterpret_cast<unsigned long long>(a.packed + 4 * sub);
+  auto issue = [&](int it, int stage) {
     const int64_t b0 = (blockIdx.x + it * (int64_t)gridDim.x) * kTile;
     const bool tile_ok = it < my_tiles;
-    const unsigned char* slot = idx_ring + (size_t)(it % kIdxSlots) * tile_idx_bytes;
+    const unsigned char* slot = idx_ring + (it % kIdxSlots) * tile_idx_bytes;
     int rid[kResolve];
 #pragma unroll
     for (int k = 0; k < kResolve; ++k) {
@@ -232,13 +240,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
         }
       }
     }
-    const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(my_v + (size_t)stage * FPW * kFieldFloats + lane_dst));
-    const float* src0 = a.packed + 4 * sub;
+    const uint32_t base = my_v_s + (stage * FPW * kFieldFloats + lane_dst) * 4;
 #pragma unroll
     for (int i = 0; i < FPW * 4; ++i) {
       const int r = __shfl_sync(0xffffffffu, rid[i >> 3], 4 * (i & 7) + rsel);
       const int dst_f = (i >> 2) * kFieldFloats + 2 * (i & 3) * kPairFloats;   // + lane_dst (folded into base)
-      if (sub < 5) cp_async16(base + dst_f * 4, src0 + (r >= 0 ? (int64_t)r * kRowFloats : 0), r >= 0 ? 16 : 0);
+      // address = lane base + max(r, 0) * 128 in ONE mad.wide.u32; an invalid row (r < 0) copies nothing, zero-fills
+      unsigned long long src;
+      asm("mad.wide.u32 %0, %1, 128, %2;" : "=l"(src) : "r"(static_cast<unsigned>(max(r, 0))), "l"(src_lane));
+      if (sub < 5) cp_async16(base + dst_f * 4, reinterpret_cast<const void*>(src), r >= 0 ? 16 : 0);
     }
   };
 
@@ -254,10 +264,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
   // finisher role of this lane: sample 2*warp + (lane>>4) of every tile, output / FM component (lane & 15)
   const int fs = 2 * warp + (lane >> 4), fo = lane & 15;
 
-  for (int64_t it = 0; it < my_tiles; ++it) {
-    const int stage = static_cast<int>(it % kStages);
+  int stage = 0, fill_stage = kStages - 1;
+  for (int it = 0; it < my_tiles; ++it) {
     // rows of tile it + kStages - 1 (its index tile landed >= 1 barrier ago; zeros past the end) + a new index tile
-    issue(it + kStages - 1, static_cast<int>((it + kStages - 1) % kStages));
+    issue(it + kStages - 1, fill_stage);
     issue_idx(it + kIdxAhead);
     cp_async_commit();
     cp_async_wait<kStages - 1>();   // this lane's copies of tile `it` have landed ...
@@ -334,9 +344,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
     const int src_base = lane & 16;
     for (int layer = 0; layer < a.hidden_layers; ++layer) {
       float o = bias_s[(1 + layer) * 16 + fo];
-      const float* wr = hid_s + (layer * 16 + fo) * kHidPitch;
+      const float4* wr = reinterpret_cast<const float4*>(hid_s + (layer * 16 + fo) * kHidPitch);
 #pragma unroll
-      for (int k = 0; k < 16; ++k) o = fmaf(wr[k], __shfl_sync(0xffffffffu, h, src_base + k), o);
+      for (int k = 0; k < 4; ++k) {
+        const float4 w4 = wr[k];
+        o = fmaf(w4.x, __shfl_sync(0xffffffffu, h, src_base + 4 * k), o);
+        o = fmaf(w4.y, __shfl_sync(0xffffffffu, h, src_base + 4 * k + 1), o);
+        o = fmaf(w4.z, __shfl_sync(0xffffffffu, h, src_base + 4 * k + 2), o);
+        o = fmaf(w4.w, __shfl_sync(0xffffffffu, h, src_base + 4 * k + 3), o);
+      }
       h = fmaxf(o, 0.f);
     }
     float side = fmaf(0.5f * sx, sx, c);
@@ -349,6 +365,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
       const int64_t b = (blockIdx.x + it * (int64_t)gridDim.x) * kTile + fs;
       if (b < a.batch) a.logits[b] = side + bias_s[(1 + kMaxHidden) * 16 + 16];
     }
+    stage = stage + 1 == kStages ? 0 : stage + 1;
+    fill_stage = fill_stage + 1 == kStages ? 0 : fill_stage + 1;
   }
   cp_async_wait<0>();
 }

@@ -10,15 +10,152 @@
 //   trs_session_wait      block until that batch's logits are in the caller's host buffer
 //   trs_session_deepfm_forward_host[_packed] = submit + wait (the synchronous call)
 // Pinned user buffers are copied from/to directly; pageable ones are staged through the slot's pinned buffers.
+#include <sched.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
 namespace {
 
 constexpr int kSlots = 3;
+
+// ---- host-side index narrowing ------------------------------------------------------------------------------------
+// The link is the bound of this path and int64 indices are half zeros: a small pool of host threads converts the
+// caller's int64 (B, N) block into int32 in the slot's pinned staging buffer, slice by slice, while the copy engine
+// is busy with the previous slices/batches; the kernels then run their int32 instantiation.  A value that does not
+// fit int32 becomes INT32_MIN, which stays out of range after the (non-negative, < 2^31) field offset is added, so
+// the lookup is reported exactly as in the int64 path (rows < 2^31 is a precondition of int32 indices anyway).
+struct NarrowBlock {
+  int64_t begin, end;   // element range
+  int chunk;
+};
+
+#define TRS_NARROW_BODY                                                                     \
+  for (int64_t i = 0; i < n; ++i) {                                                         \
+    const int64_t v = s[i];                                                                 \
+    d[i] = static_cast<int64_t>(static_cast<int32_t>(v)) == v ? static_cast<int32_t>(v) : INT32_MIN; \
+  }
+__attribute__((target("avx2"))) void narrow_avx2(const int64_t* __restrict__ s, int32_t* __restrict__ d, int64_t n) {
+  TRS_NARROW_BODY
+}
+void narrow_generic(const int64_t* __restrict__ s, int32_t* __restrict__ d, int64_t n) { TRS_NARROW_BODY }
+#undef TRS_NARROW_BODY
+typedef void (*narrow_fn)(const int64_t*, int32_t*, int64_t);
+narrow_fn pick_narrow() {
+  __builtin_cpu_init();
+  return __builtin_cpu_supports("avx2") ? narrow_avx2 : narrow_generic;
+}
+
+class NarrowPool {
+ public:
+  explicit NarrowPool(int threads) {
+    for (int i = 0; i < threads; ++i) workers_.emplace_back([this] { worker(); });
+  }
+  ~NarrowPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_.store(true, std::memory_order_release);
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  int threads() const { return static_cast<int>(workers_.size()); }
+
+  // starts narrowing src[0, n) -> dst; blocks never straddle a chunk boundary (chunk c = elements [c*per, (c+1)*per))
+  void start(const int64_t* src, int32_t* dst, int64_t n, int64_t per, int chunks) {
+    constexpr int64_t kBlock = 16384;   // 128 KB in, 64 KB out per block
+    blocks_.clear();
+    chunk_blocks_.assign(chunks, 0);
+    for (int c = 0; c < chunks; ++c) {
+      const int64_t lo = c * per, hi = (c + 1) * per < n ? (c + 1) * per : n;
+      for (int64_t b = lo; b < hi; b += kBlock) {
+        blocks_.push_back({b, b + kBlock < hi ? b + kBlock : hi, c});
+        ++chunk_blocks_[c];
+      }
+    }
+    for (int c = 0; c < chunks; ++c) chunk_done_[c].store(0, std::memory_order_relaxed);
+    src_ = src;
+    dst_ = dst;
+    next_.store(0, std::memory_order_relaxed);
+    active_.store(threads(), std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      seq_.fetch_add(1, std::memory_order_release);
+    }
+    cv_.notify_all();
+  }
+  // the calling thread helps until chunk c is complete
+  void finish_chunk(int c) {
+    while (chunk_done_[c].load(std::memory_order_acquire) < chunk_blocks_[c])
+      if (!run_one()) __builtin_ia32_pause();
+  }
+  // all workers have left the job (its block list may be rebuilt)
+  void quiesce() {
+    while (active_.load(std::memory_order_acquire) != 0) __builtin_ia32_pause();
+  }
+  static constexpr int kMaxChunks = 64;
+
+ private:
+  bool run_one() {
+    const int64_t b = next_.fetch_add(1, std::memory_order_relaxed);
+    if (b >= static_cast<int64_t>(blocks_.size())) return false;
+    const NarrowBlock& blk = blocks_[b];
+    fn_(src_ + blk.begin, dst_ + blk.begin, blk.end - blk.begin);
+    chunk_done_[blk.chunk].fetch_add(1, std::memory_order_release);
+    return true;
+  }
+  void worker() {
+    uint64_t seen = 0;
+    for (;;) {
+      int spins = 0;
+      while (seq_.load(std::memory_order_acquire) == seen && !stop_.load(std::memory_order_acquire)) {
+        if (++spins < 20000) {
+          __builtin_ia32_pause();
+        } else {   // idle for ~1 ms: sleep until the next job
+          std::unique_lock<std::mutex> lk(mu_);
+          cv_.wait(lk, [&] { return seq_.load(std::memory_order_acquire) != seen || stop_.load(); });
+        }
+      }
+      if (stop_.load(std::memory_order_acquire)) return;
+      seen = seq_.load(std::memory_order_acquire);
+      while (run_one()) {
+      }
+      active_.fetch_sub(1, std::memory_order_release);
+    }
+  }
+
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::atomic<uint64_t> seq_{0};
+  std::atomic<bool> stop_{false};
+  std::atomic<int> active_{0};
+  std::atomic<int64_t> next_{0};
+  std::atomic<int> chunk_done_[kMaxChunks];
+  std::vector<int> chunk_blocks_;
+  std::vector<NarrowBlock> blocks_;
+  const int64_t* src_ = nullptr;
+  int32_t* dst_ = nullptr;
+  narrow_fn fn_ = pick_narrow();
+};
+
+int usable_cpus() {
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+    const int n = CPU_COUNT(&set);
+    if (n > 0) return n;
+  }
+  const unsigned hc = std::thread::hardware_concurrency();
+  return hc > 0 ? static_cast<int>(hc) : 1;
+}
 
 struct Slot {
   void* idx_pinned;
@@ -43,6 +180,7 @@ struct trs_session {
   int fields;
   int chunks;
   int64_t next_ticket;
+  NarrowPool* narrow;   // null: int64 indices cross the link as they are
   Slot slots[kSlots];
 };
 
@@ -93,6 +231,7 @@ extern "C" int trs_session_create(int64_t max_batch, int fields, int chunks, trs
 
 extern "C" int trs_session_destroy(trs_session* s) {
   if (!s) return TRS_OK;
+  delete s->narrow;
   for (int k = 0; k < kSlots; ++k) {
     Slot& sl = s->slots[k];
     for (int i = 0; i < 2; ++i)
@@ -115,6 +254,25 @@ extern "C" int trs_session_destroy(trs_session* s) {
 }
 
 extern "C" int trs_session_depth(void) { return kSlots; }
+
+extern "C" int trs_session_set_index_narrowing(trs_session* s, int threads) {
+  TRS_REQUIRE(s, "trs_session_set_index_narrowing: null session");
+  TRS_REQUIRE(threads >= -1 && threads <= 256, "trs_session_set_index_narrowing: threads must be in [-1, 256]");
+  for (int k = 0; k < kSlots; ++k)
+    TRS_REQUIRE(!s->slots[k].busy, "trs_session_set_index_narrowing: batches are in flight");
+  if (threads < 0) {   // auto: half of the CPUs this process may run on, at most 8 helpers
+    const int cpus = usable_cpus();
+    threads = cpus / 2 < 8 ? cpus / 2 : 8;
+  }
+  const int helpers = threads > 0 ? threads - 1 : 0;   // the submitting thread is one of the `threads`
+  delete s->narrow;
+  s->narrow = nullptr;
+  if (threads > 0) {
+    s->narrow = new (std::nothrow) NarrowPool(helpers);
+    TRS_REQUIRE(s->narrow, "trs_session_set_index_narrowing: out of host memory");
+  }
+  return threads;
+}
 
 // Enqueues one batch on a free slot.  On any failure after the first enqueue the slot's streams are drained so that
 // the slot is reusable.
@@ -141,8 +299,12 @@ static int session_submit(trs_session* s, const void* idx_host, int idx_bits, co
     TRS_CUDA(cudaEventRecord(sl.done, sl.streams[0]));
     return TRS_OK;
   }
+  // int64 indices of a non-trivial batch are narrowed on the host when the session has a narrowing pool
+  const bool narrow = idx_bits == 64 && s->narrow != nullptr && s->chunks <= NarrowPool::kMaxChunks &&
+                      rows < (int64_t(1) << 31) && batch * fields >= 4096;
+  if (narrow) idx_bits = 32;
   const size_t isz = idx_bits / 8;
-  const bool src_pinned = is_pinned(idx_host);
+  const bool src_pinned = !narrow && is_pinned(idx_host);
   const bool dst_pinned = is_pinned(logits_host);
   if (!dst_pinned) sl.user_logits = logits_host;
   int rc = TRS_OK;
@@ -151,6 +313,9 @@ static int session_submit(trs_session* s, const void* idx_host, int idx_bits, co
   if (e == cudaSuccess) e = cudaStreamWaitEvent(sl.streams[1], sl.forked, 0);
   const int chunks = (int)(batch < s->chunks ? batch : s->chunks);
   const int64_t per = (((batch + chunks - 1) / chunks + 15) / 16) * 16;  // slices start on 16-byte aligned indices
+  if (narrow)
+    s->narrow->start(static_cast<const int64_t*>(idx_host), static_cast<int32_t*>(sl.idx_pinned), batch * fields,
+                     per * fields, chunks);
   for (int c = 0; c < chunks && rc == TRS_OK && e == cudaSuccess; ++c) {
     const int64_t b0 = c * per;
     const int64_t nb = batch - b0 < per ? batch - b0 : per;
@@ -158,7 +323,10 @@ static int session_submit(trs_session* s, const void* idx_host, int idx_bits, co
     cudaStream_t st = sl.streams[c & 1];
     const size_t off = (size_t)b0 * fields * isz, bytes = (size_t)nb * fields * isz;
     const char* src = static_cast<const char*>(idx_host) + off;
-    if (!src_pinned) {
+    if (narrow) {
+      s->narrow->finish_chunk(c);
+      src = static_cast<const char*>(sl.idx_pinned) + off;
+    } else if (!src_pinned) {
       memcpy(static_cast<char*>(sl.idx_pinned) + off, src, bytes);
       src = static_cast<const char*>(sl.idx_pinned) + off;
     }
@@ -176,6 +344,7 @@ static int session_submit(trs_session* s, const void* idx_host, int idx_bits, co
     float* dst = dst_pinned ? logits_host + b0 : sl.logits_pinned + b0;
     e = cudaMemcpyAsync(dst, sl.logits_dev + b0, (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, st);
   }
+  if (narrow) s->narrow->quiesce();
   // join stream 1 into stream 0, read the status words back, mark completion
   if (rc == TRS_OK && e == cudaSuccess) e = cudaEventRecord(sl.joined, sl.streams[1]);
   if (rc == TRS_OK && e == cudaSuccess) e = cudaStreamWaitEvent(sl.streams[0], sl.joined, 0);

@@ -29,6 +29,14 @@ class DeepFMSession:
         self.depth = int(self._lib.trs_session_depth())
         self._keep = {}   # ticket -> tensors that must outlive the asynchronous copies
 
+    def set_index_narrowing(self, threads: int = -1) -> int:
+        """int64 host indices are narrowed to int32 by `threads` host threads before the H2D copy (0 = off,
+        -1 = min(8, usable CPUs / 2)).  Returns the thread count in use."""
+        n = self._lib.trs_session_set_index_narrowing(self._h, threads)
+        if n < 0:
+            check(n, 'trs_session_set_index_narrowing')
+        return n
+
     @staticmethod
     def _check_host(idx_host, logits_host, name):
         if idx_host.is_cuda or logits_host.is_cuda:
