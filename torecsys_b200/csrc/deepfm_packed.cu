@@ -98,6 +98,32 @@ __device__ __forceinline__ void cp_async_wait() {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// mbarriers (arrival count = one elected lane per warp) that order the partial-exchange buffers between warps
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TRS_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TRS_MBAR_DONE;\n"
+      "bra TRS_MBAR_WAIT;\n"
+      "TRS_MBAR_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+
 struct PackedArgs {
   const void* idx;
   const int64_t* offsets;
@@ -120,11 +146,13 @@ struct Smem {
   static constexpr size_t p_bytes = (size_t)2 * kWarps * kPartialFloats * sizeof(float);
   static constexpr size_t h_bytes = (size_t)kMaxHidden * 16 * kHidPitch * sizeof(float);
   static constexpr size_t b_bytes = ((1 + kMaxHidden) * 16 + 16 + 4) * sizeof(float);
-  static constexpr size_t fixed = v_bytes + p_bytes + h_bytes + b_bytes;
-  // + field offsets (int64 per field, padded to 16 B) + index ring (kIdxSlots x 16 samples x fields x idx bytes)
+  static constexpr size_t m_bytes = 4 * sizeof(unsigned long long);   // full[2], empty[2] mbarriers
+  static constexpr size_t fixed = v_bytes + p_bytes + h_bytes + b_bytes + m_bytes;
+  // + field offsets (int64 per field, padded to 16 B)
+  // + per-warp index rings (kWarps x kIdxSlots x [16 samples][FPW fields] indices)
   __host__ __device__ static size_t off_bytes(int fields) { return (((size_t)fields * 8 + 15) / 16) * 16; }
   static size_t total(int fields, int idx_bits) {
-    return fixed + off_bytes(fields) + (size_t)kIdxSlots * kTile * fields * (idx_bits / 8);
+    return fixed + off_bytes(fields) + (size_t)kWarps * kIdxSlots * kTile * FPW * (idx_bits / 8);
   }
 };
 
@@ -138,8 +166,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
   float* pbuf = reinterpret_cast<float*>(smem_raw + S::v_bytes);
   float* hid_s = reinterpret_cast<float*>(smem_raw + S::v_bytes + S::p_bytes);   // [layer][16][17]
   float* bias_s = reinterpret_cast<float*>(smem_raw + S::v_bytes + S::p_bytes + S::h_bytes);
+  const uint32_t mbar_s =
+      static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw + S::v_bytes + S::p_bytes + S::h_bytes + S::b_bytes));
   long long* off_s = reinterpret_cast<long long*>(smem_raw + S::fixed);
-  unsigned char* idx_ring = smem_raw + S::fixed + S::off_bytes(a.fields);   // [kIdxSlots][16 * fields] indices
+  unsigned char* idx_rings = smem_raw + S::fixed + S::off_bytes(a.fields);   // [warp][kIdxSlots][16][FPW] indices
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,31 +181,37 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
   const int64_t tiles = (a.batch + kTile - 1) / kTile;
   const int my_tiles = blockIdx.x < tiles ? static_cast<int>((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
-  // Index tiles: the (16 x fields) indices of a tile are contiguous in global memory; the CTA copies them with
-  // cp.async into slot (it % kIdxSlots) kIdxAhead tiles before the row copies read them.
+  // Index slices: every warp keeps its OWN ring of the (16 samples x FPW fields) indices it resolves, copied with
+  // 8-/4-byte cp.async kIdxAhead tiles before the row copies read them -- no other warp is involved, so the ring
+  // needs no CTA-wide barrier (lane e copies element (s, f) = (e / FPW, e % FPW): a sample's fields are contiguous).
   constexpr int kIdxBytes = IdxBits / 8;
-  const int tile_idx_bytes = kTile * n_fields * kIdxBytes;   // multiple of 16
-  const int64_t total_idx_bytes = a.batch * n_fields * kIdxBytes;
-  const uint32_t idx_ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(idx_ring));
+  constexpr int kSliceBytes = kTile * FPW * kIdxBytes;
+  unsigned char* my_idx = idx_rings + (size_t)warp * kIdxSlots * kSliceBytes;
+  const uint32_t my_idx_s = static_cast<uint32_t>(__cvta_generic_to_shared(my_idx));
   auto issue_idx = [&](int it) {
-    if (it >= my_tiles) return;
-    const int64_t g0 = (blockIdx.x + it * (int64_t)gridDim.x) * tile_idx_bytes;
-    const unsigned char* src = static_cast<const unsigned char*>(a.idx) + g0;
-    const uint32_t dst = idx_ring_s + (it % kIdxSlots) * tile_idx_bytes;
-    if (g0 + tile_idx_bytes <= total_idx_bytes) {   // a whole tile (all but the last one of the batch)
-      for (int c = threadIdx.x * 16; c < tile_idx_bytes; c += kWarps * 32 * 16) cp_async16(dst + c, src + c, 16);
-    } else {
-      for (int c = threadIdx.x * 16; c < tile_idx_bytes; c += kWarps * 32 * 16) {
-        const int64_t remain = total_idx_bytes - (g0 + c);
-        const int sz = remain >= 16 ? 16 : (remain > 0 ? static_cast<int>(remain) : 0);   // zero-fill past the batch
-        cp_async16(dst + c, sz > 0 ? src + c : static_cast<const unsigned char*>(a.idx), sz);
+    const int64_t b0 = (blockIdx.x + it * (int64_t)gridDim.x) * kTile;
+    const uint32_t dst = my_idx_s + (it % kIdxSlots) * kSliceBytes;
+#pragma unroll
+    for (int k = 0; k < kResolve; ++k) {
+      const int e = lane + 32 * k;
+      if (e < kRowsPerWarp) {
+        const int s_ = e / FPW, f = e - s_ * FPW;
+        const bool live = it < my_tiles && f0 + f < n_fields && b0 + s_ < a.batch;
+        const unsigned char* src = static_cast<const unsigned char*>(a.idx) +
+                                   (live ? ((b0 + s_) * n_fields + f0 + f) * kIdxBytes : 0);
+        if (IdxBits == 64) cp_async8(dst + e * 8, src, live ? 8 : 0);
+        else cp_async4(dst + e * 4, src, live ? 4 : 0);
       }
     }
   };
 
-  // the first index tiles are requested before anything else so that they fly during the weight set-up below
+  // the first index slices are requested before anything else so that they fly during the weight set-up below
   for (int s = 0; s < kIdxAhead; ++s) issue_idx(s);
   cp_async_commit();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(mbar_s + 8 * i, kWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
   // ---- one-time: this warp's W1 B-fragments into registers (hi/lo); hidden layers, biases, offsets to smem ----------
   float4 w1h[FPW][2], w1l[FPW][2];
@@ -220,7 +256,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
   auto issue = [&](int it, int stage) {
     const int64_t b0 = (blockIdx.x + it * (int64_t)gridDim.x) * kTile;
     const bool tile_ok = it < my_tiles;
-    const unsigned char* slot = idx_ring + (it % kIdxSlots) * tile_idx_bytes;
+    const unsigned char* slot = my_idx + (it % kIdxSlots) * kSliceBytes;
     int rid[kResolve];
 #pragma unroll
     for (int k = 0; k < kResolve; ++k) {
@@ -230,8 +266,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
       rid[k] = -1;
       if (live) {
         int64_t ix;
-        if (IdxBits == 64) ix = reinterpret_cast<const long long*>(slot)[s * n_fields + f0 + f];
-        else ix = reinterpret_cast<const int*>(slot)[s * n_fields + f0 + f];
+        if (IdxBits == 64) ix = reinterpret_cast<const long long*>(slot)[s * FPW + f];
+        else ix = reinterpret_cast<const int*>(slot)[s * FPW + f];
         const int64_t r = ix + off_s[f0 + f];
         if (r >= 0 && r < a.rows) rid[k] = static_cast<int>(r);
         else {
@@ -264,9 +300,58 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
   // finisher role of this lane: sample 2*warp + (lane>>4) of every tile, output / FM component (lane & 15)
   const int fs = 2 * warp + (lane >> 4), fo = lane & 15;
 
+  // Finisher: lane = (sample fs, output / component fo) reduces the 8 warps' partials of tile `jt`, runs the 16x16
+  // hidden layers, the output layer and FM, and stores two logits per warp.
+  auto finish = [&](int jt) {
+    const int p = jt & 1;
+    mbar_wait(mbar_s + 8 * p, (jt >> 1) & 1);          // every warp has published its partials of tile jt
+    const float* pr = pbuf + (size_t)p * kWarps * kPartialFloats;
+    float h = bias_s[fo], sx = 0.f, c = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      h += pr[w * kPartialFloats + fs * kHPitch + fo];
+      sx += pr[w * kPartialFloats + 16 * kHPitch + fs * 16 + fo];
+    }
+    // the 32 C partials of the sample (8 warps x 4 t), two per lane
+    c = pr[(fo >> 1) * kPartialFloats + 16 * kHPitch + 256 + fs * 4 + 2 * (fo & 1)] +
+        pr[(fo >> 1) * kPartialFloats + 16 * kHPitch + 256 + fs * 4 + 2 * (fo & 1) + 1];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(mbar_s + 16 + 8 * p);    // this warp no longer reads buffer p
+    h = fmaxf(h, 0.f);
+    const int src_base = lane & 16;
+    for (int layer = 0; layer < a.hidden_layers; ++layer) {
+      float o = bias_s[(1 + layer) * 16 + fo];
+      const float4* wr = reinterpret_cast<const float4*>(hid_s + (layer * 16 + fo) * kHidPitch);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 w4 = wr[k];
+        o = fmaf(w4.x, __shfl_sync(0xffffffffu, h, src_base + 4 * k), o);
+        o = fmaf(w4.y, __shfl_sync(0xffffffffu, h, src_base + 4 * k + 1), o);
+        o = fmaf(w4.z, __shfl_sync(0xffffffffu, h, src_base + 4 * k + 2), o);
+        o = fmaf(w4.w, __shfl_sync(0xffffffffu, h, src_base + 4 * k + 3), o);
+      }
+      h = fmaxf(o, 0.f);
+    }
+    float side = fmaf(0.5f * sx, sx, c);
+    side = fmaf(h, bias_s[(1 + kMaxHidden) * 16 + fo], side);
+    side += __shfl_xor_sync(0xffffffffu, side, 8);
+    side += __shfl_xor_sync(0xffffffffu, side, 4);
+    side += __shfl_xor_sync(0xffffffffu, side, 2);
+    side += __shfl_xor_sync(0xffffffffu, side, 1);
+    if (fo == 0) {
+      if (jt == 0) pdl_wait();   // first global write: the overlapped previous grid must be complete
+      const int64_t b = (blockIdx.x + jt * (int64_t)gridDim.x) * kTile + fs;
+      if (b < a.batch) a.logits[b] = side + bias_s[(1 + kMaxHidden) * 16 + 16];
+    }
+  };
+
+  // Main loop.  The warps are NOT barrier-synchronised per tile: warp w publishes its partials of tile `it` into
+  // buffer it & 1, arrives on full[it & 1] and goes on; it finishes tile it - 1 (whose partials the other warps
+  // published about one tile ago) afterwards, so a warp only ever waits for a warp that is a whole tile behind.
+  // empty[p] keeps a fast warp from overwriting buffer p before every warp has read tile it - 2 out of it.
   int stage = 0, fill_stage = kStages - 1;
   for (int it = 0; it < my_tiles; ++it) {
-    // rows of tile it + kStages - 1 (its index tile landed >= 1 barrier ago; zeros past the end) + a new index tile
+    // rows of tile it + kStages - 1 (its index slice landed two iterations ago; zeros past the end) + a new index slice
     issue(it + kStages - 1, fill_stage);
     issue_idx(it + kIdxAhead);
     cp_async_commit();
@@ -316,7 +401,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
       }
     }
     // ---- publish partials: acc[j] = {(g, 8j+2t), (g, 8j+2t+1), (g+8, 8j+2t), (g+8, 8j+2t+1)} ---------------------------
-    float* pw = pbuf + ((size_t)(it & 1) * kWarps + warp) * kPartialFloats;
+    const int p = it & 1;
+    if (it >= 2) mbar_wait(mbar_s + 16 + 8 * p, ((it >> 1) - 1) & 1);   // tile it - 2 has been read out of buffer p
+    float* pw = pbuf + ((size_t)p * kWarps + warp) * kPartialFloats;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       *reinterpret_cast<float2*>(pw + g * kHPitch + 8 * j + 2 * t) = make_float2(acc[j][0], acc[j][1]);
@@ -326,48 +413,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) deepfm_packed_kernel(PackedArg
     *reinterpret_cast<float4*>(pw + 16 * kHPitch + (g + 8) * 16 + 4 * t) = sb;
     pw[16 * kHPitch + 256 + g * 4 + t] = ca;
     pw[16 * kHPitch + 256 + (g + 8) * 4 + t] = cb;
-    if (it == 0) pdl_wait();   // first global write (logits) below: the overlapped previous grid must be complete
-    __syncthreads();
-
-    // ---- finish two samples per warp: lane = (sample fs, output / component fo) -------------------------------------
-    const float* pr = pbuf + (size_t)(it & 1) * kWarps * kPartialFloats;
-    float h = bias_s[fo], sx = 0.f, c = 0.f;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      h += pr[w * kPartialFloats + fs * kHPitch + fo];
-      sx += pr[w * kPartialFloats + 16 * kHPitch + fs * 16 + fo];
-    }
-    // the 32 C partials of the sample (8 warps x 4 t), two per lane
-    c = pr[(fo >> 1) * kPartialFloats + 16 * kHPitch + 256 + fs * 4 + 2 * (fo & 1)] +
-        pr[(fo >> 1) * kPartialFloats + 16 * kHPitch + 256 + fs * 4 + 2 * (fo & 1) + 1];
-    h = fmaxf(h, 0.f);
-    const int src_base = lane & 16;
-    for (int layer = 0; layer < a.hidden_layers; ++layer) {
-      float o = bias_s[(1 + layer) * 16 + fo];
-      const float4* wr = reinterpret_cast<const float4*>(hid_s + (layer * 16 + fo) * kHidPitch);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 w4 = wr[k];
-        o = fmaf(w4.x, __shfl_sync(0xffffffffu, h, src_base + 4 * k), o);
-        o = fmaf(w4.y, __shfl_sync(0xffffffffu, h, src_base + 4 * k + 1), o);
-        o = fmaf(w4.z, __shfl_sync(0xffffffffu, h, src_base + 4 * k + 2), o);
-        o = fmaf(w4.w, __shfl_sync(0xffffffffu, h, src_base + 4 * k + 3), o);
-      }
-      h = fmaxf(o, 0.f);
-    }
-    float side = fmaf(0.5f * sx, sx, c);
-    side = fmaf(h, bias_s[(1 + kMaxHidden) * 16 + fo], side);
-    side += __shfl_xor_sync(0xffffffffu, side, 8);
-    side += __shfl_xor_sync(0xffffffffu, side, 4);
-    side += __shfl_xor_sync(0xffffffffu, side, 2);
-    side += __shfl_xor_sync(0xffffffffu, side, 1);
-    if (fo == 0) {
-      const int64_t b = (blockIdx.x + it * (int64_t)gridDim.x) * kTile + fs;
-      if (b < a.batch) a.logits[b] = side + bias_s[(1 + kMaxHidden) * 16 + 16];
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(mbar_s + 8 * p);
+    if (it > 0) finish(it - 1);
     stage = stage + 1 == kStages ? 0 : stage + 1;
     fill_stage = fill_stage + 1 == kStages ? 0 : fill_stage + 1;
   }
+  if (my_tiles > 0) finish(my_tiles - 1);
   cp_async_wait<0>();
 }
 
