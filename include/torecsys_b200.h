@@ -101,6 +101,31 @@ int trs_bilinear_forward(const float* x, const float* weight, const float* bias,
 int trs_afm_forward(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                     int64_t batch, int fields, int embed, int attn, float* out, float* scores, void* stream);
 
+/* ---- 8f-3: outer product network (PNN) ------------------------------------------------------------------------------
+ * Replaces OuterProductNetworkLayer.forward (torecsys/layers/ctr/outer_product_network.py:80-131), pairs p = (i<j)
+ * in lexicographic order:
+ *     TRS_OPN_MAT  kernel (E, P, E):  out[b,p] = sum_h x[b,j,h] * ( sum_e kernel[h,p,e] * x[b,i,e] )
+ *     TRS_OPN_VEC  kernel (1, P, E):  out[b,p] = sum_e x[b,i,e] * x[b,j,e] * kernel[p,e]
+ *     TRS_OPN_NUM  kernel (1, P, 1):  out[b,p] = sum_e x[b,i,e] * x[b,j,e] * kernel[p]
+ * x (batch, fields, embed) -> out (batch, P). */
+#define TRS_OPN_MAT 0
+#define TRS_OPN_VEC 1
+#define TRS_OPN_NUM 2
+int trs_opn_forward(const float* x, const float* kernel, int kernel_type, int64_t batch, int fields, int embed,
+                    float* out, void* stream);
+
+/* ---- 8f-3: squeeze-and-excitation / compose-excitation network (FiBiNET, FAT-DeepFFM) -----------------------------------
+ * Replaces ComposeExcitationNetworkLayer.forward (torecsys/layers/ctr/compose_excitation_network.py:72-109):
+ *     pooled[b,m] = mean_e x[b,m,e]                                   (nn.AdaptiveAvgPool1d(1))
+ *     a[b,:]      = act( w2 . act( w1 . pooled[b,:] + b1 ) + b2 )     ReductionLinear w1 (R, M), AdditionLinear w2 (M, R)
+ *     out[b,m,:]  = x[b,m,:] * a[b,m]
+ * x (batch, rows_per_sample = M, embed): M = num_fields, or num_fields^2 when the layer is `squared`.
+ * workspace: device scratch of at least trs_senet_workspace_bytes(batch, M) bytes. */
+int64_t trs_senet_workspace_bytes(int64_t batch, int rows_per_sample);
+int trs_senet_forward(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                      int activation, int64_t batch, int rows_per_sample, int embed, int reduced,
+                      float* out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- a7: cross network -------------------------------------------------------------------------------------------
  * Replaces CrossNetworkLayer.forward (torecsys/layers/ctr/cross_network.py:52-87):
  *     h_0 = x ; h_{l+1} = x * (h_l @ W_l^T + b_l) + x    per (b, n) row, W_l (E, E), b_l (E)

@@ -172,21 +172,124 @@ def run_model(trs, kind, b, n, e, dtype):
     return {'out': out.rename(None).numpy()}
 
 
+def _load_senet(layer, params, dtype, prefix='senet'):
+    w1, b1, w2, b2 = cases.senet_list(params, prefix)
+    _set(layer.fc.ReductionLinear.weight, w1, dtype)
+    _set(layer.fc.ReductionLinear.bias, b1, dtype)
+    _set(layer.fc.AdditionLinear.weight, w2, dtype)
+    _set(layer.fc.AdditionLinear.bias, b2, dtype)
+
+
+def run_layer_2(trs, kind, b, n, e, dtype):
+    """SURVEY.md 8f-3 layers: OuterProductNetworkLayer (three kernel types), ComposeExcitationNetworkLayer."""
+    L = trs.layers
+    c = cases.layer_case(kind, b, n, e)
+    x = T(c['inputs']['x']).to(dtype)
+    p = c['params']
+    if kind.startswith('opn_'):
+        m = L.OuterProductNetworkLayer(e, n, kernel_type=kind[4:]).to(dtype)
+        _set(m.kernel, p['kernel'], dtype)
+    elif kind == 'senet':
+        m = L.SENETLayer(n, cases.SENET_REDUCTION, squared=False).to(dtype)
+        _load_senet(m, p, dtype)
+    elif kind == 'senet_sq':
+        m = L.CENLayer(n, cases.CEN_REDUCTION).to(dtype)
+        _load_senet(m, p, dtype)
+    else:
+        raise KeyError(kind)
+    m.eval()
+    with torch.no_grad():
+        out = m(x)
+    return {'out': out.rename(None).numpy()}
+
+
+def run_model_2(trs, kind, b, n, e, dtype):
+    """SURVEY.md 8f-3 models through the reference's own Sequential(Inputs, model)."""
+    I, M = trs.inputs, trs.models
+    c = cases.model_case(kind, b, n, e)
+    fs, p = c['field_sizes'], c['params']
+    schema = {}
+    if 'w_feat' in p:
+        feat = I.base.MultiIndicesEmbedding(1, fs)
+        feat.set_schema(['idx'])
+        _set(feat.embedding.weight, p['w_feat'], torch.float32)
+        schema['feat_inputs'] = feat
+    if kind in ('deep_ffm_model', 'fat_deep_ffm_model'):
+        emb = I.base.MultiIndicesFieldAwareEmbedding(e, fs)
+        for t in range(n):
+            _set(emb.embeddings[t].weight, p[f'w_emb{t}'], torch.float32)
+        emb.set_schema(['idx'])
+        schema['field_emb_inputs'] = emb
+    else:
+        emb = I.base.MultiIndicesEmbedding(e, fs)
+        _set(emb.embedding.weight, p['w_emb'], torch.float32)
+        emb.set_schema(['idx'])
+        schema['emb_inputs'] = emb
+    inputs = I.Inputs(schema)
+    f32 = torch.float32
+    sizes = list(cases.MLP_SIZES)
+    if kind in ('pnn_inner_model', 'pnn_outer_model'):
+        model = M.ProductNeuralNetworkModel(e, n, sizes, prod_method=kind.split('_')[1], kernel_type='mat')
+        _load_mlp(model.deep, p, f32)
+        _set(model.bias, p['bias'], f32)
+        if kind == 'pnn_outer_model':
+            _set(model.pnn.kernel, p['kernel'], f32)
+    elif kind == 'fibinet_model':
+        model = M.FeatureImportanceAndBilinearFeatureInteractionNetwork(e, n, cases.SENET_REDUCTION, 1, sizes)
+        _load_senet(model.senet, p, f32)
+        _set(model.emb_bilinear.bilinear.weight, p['bil_emb_w'], f32)
+        _set(model.emb_bilinear.bilinear.bias, p['bil_emb_b'], f32)
+        _set(model.senet_bilinear.bilinear.weight, p['bil_senet_w'], f32)
+        _set(model.senet_bilinear.bilinear.bias, p['bil_senet_b'], f32)
+        _load_mlp(model.deep, p, f32)
+    elif kind == 'afm_model':
+        model = M.AttentionalFactorizationMachineModel(e, n, cases.AFM_ATTN, dropout_p=0.5)
+        _set(model.afm.attention.Linear.weight, p['w1'], f32)
+        _set(model.afm.attention.Linear.bias, p['b1'], f32)
+        _set(model.afm.attention.OutProj.weight, p['w2'], f32)
+        _set(model.afm.attention.OutProj.bias, p['b2'], f32)
+        _set(model.bias, p['bias'], f32)
+    elif kind == 'nfm_model':
+        model = M.NeuralFactorizationMachineModel(e, sizes, fm_dropout_p=0.5)
+        _load_mlp(model.sequential.Deep, p, f32)
+        _set(model.bias, p['bias'], f32)
+    elif kind == 'fnn_model':
+        model = M.FactorizationMachineSupportedNeuralNetworkModel(e, n, 1, sizes, fm_dropout_p=0.5)
+        _load_mlp(model.deep, p, f32)
+    elif kind == 'deep_ffm_model':
+        model = M.DeepFieldAwareFactorizationMachineModel(e, n, cases.DEEP_FFM_OUT, sizes, ffm_dropout_p=0.5)
+        _load_mlp(model.deep, p, f32)
+    elif kind == 'fat_deep_ffm_model':
+        model = M.FieldAttentiveDeepFieldAwareFactorizationMachineModel(e, n, 1, sizes, cases.CEN_REDUCTION,
+                                                                        ffm_dropout_p=0.5)
+        _load_senet(model.cen, p, f32, 'cen')
+        _load_mlp(model.deep, p, f32)
+    else:
+        raise KeyError(kind)
+    seq = trs.Sequential(inputs, model).to(dtype).eval()
+    with torch.no_grad():
+        out = seq({'idx': T(c['inputs']['idx'])})
+    return {'out': out.rename(None).numpy()}
+
+
 def main():
     trs = load_reference()
     torch.set_num_threads(1)  # fixed reduction order for the stored fp32 outputs
     out_dir = os.path.join(ROOT, 'tests', 'golden')
     os.makedirs(out_dir, exist_ok=True)
-    for fname, kinds, fn in (('layers.npz', cases.LAYER_KINDS, run_layer),
-                             ('embeddings.npz', cases.EMB_KINDS, run_emb),
-                             ('models.npz', cases.MODEL_KINDS, run_model)):
+    only_new = '--new' in sys.argv   # leave the committed round-1 fixtures untouched
+    jobs = [] if only_new else [('layers.npz', cases.LAYER_KINDS, run_layer),
+                                ('embeddings.npz', cases.EMB_KINDS, run_emb),
+                                ('models.npz', cases.MODEL_KINDS, run_model)]
+    jobs += [('layers2.npz', cases.LAYER_KINDS_2, run_layer_2), ('models2.npz', cases.MODEL_KINDS_2, run_model_2)]
+    for fname, kinds, fn in jobs:
         store = {}
         for kind in kinds:
             for (b, n, e) in cases.GRID:
                 cid = cases.case_id(kind, b, n, e)
                 for k, v in fn(trs, kind, b, n, e, torch.float32).items():
                     store[f'{cid}/{k}'] = v
-                if fn is run_model or (fn is run_layer and kind in F64_LAYER_KINDS):
+                if fn in (run_model, run_model_2, run_layer_2) or (fn is run_layer and kind in F64_LAYER_KINDS):
                     for k, v in fn(trs, kind, b, n, e, torch.float64).items():
                         store[f'{cid}/{k}/f64'] = v
         np.savez_compressed(os.path.join(out_dir, fname), **store)

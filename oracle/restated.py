@@ -193,6 +193,32 @@ def mlp_layer(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence
     return F.linear(h, weights[-1], biases[-1])
 
 
+def opn_layer(x: torch.Tensor, kernel: torch.Tensor, kernel_type: str = 'mat') -> torch.Tensor:
+    """torecsys/layers/ctr/outer_product_network.py:80-131.  p = x[:, i_p], q = x[:, j_p] for pairs i<j;
+    'mat' (kernel (E,P,E)): kp[b,h,p] = sum_e p[b,p,e] * kernel[h,p,e] (:105-110), out[b,p] = sum_h kp[b,h,p] * q[b,p,h]
+    (:116); 'vec' (1,P,E) / 'num' (1,P,1): out[b,p] = sum_e p * q * kernel (:124)."""
+    i, j = pair_indices(x.shape[1])
+    p, q = x[:, i], x[:, j]
+    if kernel_type == 'mat':
+        kp = (p.unsqueeze(1) * kernel).sum(dim=-1)          # (B, E=h, P)
+        return (kp.permute(0, 2, 1) * q).sum(dim=-1)
+    if kernel_type in ('vec', 'num'):
+        return (p * q * kernel).sum(dim=-1)
+    raise ValueError('kernel_type only allows: ["mat", "num", "vec"].')
+
+
+def senet_layer(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+                activation: Optional[str] = 'relu') -> torch.Tensor:
+    """torecsys/layers/ctr/compose_excitation_network.py:72-109: AdaptiveAvgPool1d(1) over the embedding (:82),
+    fc = ReductionLinear -> act -> AdditionLinear -> act (:66-70, the SAME activation instance twice),
+    out[b,m,:] = x[b,m,:] * a[b,m] (the einsum 'ijk,ijh->ijk' with h of size 1, :104).  x is (B, M, E) with
+    M = num_fields or num_fields^2 (`squared`)."""
+    act = _activation(activation)
+    pooled = F.adaptive_avg_pool1d(x, 1).squeeze(-1)
+    a = act(F.linear(act(F.linear(pooled, w1, b1)), w2, b2))
+    return x * a.unsqueeze(-1)
+
+
 # ----------------------------------------------------------------------------- model glue (a12)
 def fm_model(feat: torch.Tensor, emb: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
     """torecsys/models/ctr/factorization_machine.py:55-71: sum_n feat + sum_e FM(emb) (+ bias) -> (B,1)."""
@@ -228,6 +254,59 @@ def ffm_model(feat: torch.Tensor, field_emb: torch.Tensor, num_fields: int, bias
     """torecsys/models/ctr/field_aware_factorization_machine.py:55-81: sum_{p,e} FFM + sum_n feat + bias."""
     second = ffm_layer(field_emb, num_fields).sum(dim=(1, 2)).unsqueeze(1)
     return second + feat.sum(dim=1) + bias.reshape(1, 1)
+
+
+# ----------------------------------------------------------------------------- model glue (8f-3: the other consumers)
+def pnn_model(feat, emb, second: torch.Tensor, mlp_w, mlp_b, bias: Optional[torch.Tensor], activation='relu'):
+    """torecsys/models/ctr/product_neural_network.py:81-115: MLP(cat[pnn(emb) (B,P), feat (B,N), bias (B,1)]);
+    `second` = the inner/outer product layer's output."""
+    b = emb.shape[0]
+    parts = [second, feat.reshape(b, -1)]
+    if bias is not None:
+        parts.append(bias.reshape(1, 1).repeat(b, 1))
+    return mlp_layer(torch.cat(parts, dim=1), mlp_w, mlp_b, activation)
+
+
+def fibinet_model(emb, senet_args, bil_emb, bil_senet, bilinear_type, mlp_w, mlp_b, activation='relu'):
+    """torecsys/models/ctr/feature_importance_and_bilinear_feature_interaction_network.py:74-109:
+    MLP(flatten(cat[Bilinear_a(emb), Bilinear_b(SENET(emb))], dim=N))."""
+    b = emb.shape[0]
+    inter = bilinear_layer(emb, bil_emb[0], bil_emb[1], bilinear_type)
+    s_inter = bilinear_layer(senet_layer(emb, *senet_args), bil_senet[0], bil_senet[1], bilinear_type)
+    return mlp_layer(torch.cat([inter, s_inter], dim=1).reshape(b, -1), mlp_w, mlp_b, activation)
+
+
+def afm_model(feat, emb, afm_args, bias: Optional[torch.Tensor]):
+    """torecsys/models/ctr/attentional_factorization_machine.py:53-84: sum_e AFM(emb) + sum_n feat (+ bias)."""
+    out = afm_layer(emb, *afm_args)[0].sum(dim=1, keepdim=True) + feat.sum(dim=1)
+    return out if bias is None else out + bias.reshape(1, 1)
+
+
+def nfm_model(feat, emb, mlp_w, mlp_b, bias: Optional[torch.Tensor], activation='relu'):
+    """torecsys/models/ctr/neural_factorization_machine.py:66-96: MLP(FM(emb)) + sum_n feat (+ bias)."""
+    out = mlp_layer(fm_layer(emb), mlp_w, mlp_b, activation) + feat.sum(dim=1)
+    return out if bias is None else out + bias.reshape(1, 1)
+
+
+def fnn_model(feat, emb, mlp_w, mlp_b, activation='relu'):
+    """torecsys/models/ctr/factorization_machine_supported_neural_network.py:61-101: MLP(cat[feat (B,N), FM(emb)])."""
+    b = emb.shape[0]
+    return mlp_layer(torch.cat([feat.reshape(b, -1), fm_layer(emb)], dim=1), mlp_w, mlp_b, activation)
+
+
+def deep_ffm_model(field_emb, num_fields, mlp_w, mlp_b, activation='relu'):
+    """torecsys/models/ctr/deep_ffm.py:63-104: sum_O MLP(flatten FFM(v)) + sum_{n,e} v."""
+    b = field_emb.shape[0]
+    second = mlp_layer(ffm_layer(field_emb, num_fields).reshape(b, -1), mlp_w, mlp_b, activation)
+    return second.sum(dim=1, keepdim=True) + field_emb.sum(dim=(1, 2)).unsqueeze(1)
+
+
+def fat_deep_ffm_model(field_emb, num_fields, cen_args, mlp_w, mlp_b, activation='relu'):
+    """torecsys/models/ctr/fat_deep_ffm.py:69-112: aem = CEN(v); sum_{n,e} aem + MLP(flatten FFM(aem))."""
+    b = field_emb.shape[0]
+    aem = senet_layer(field_emb, *cen_args)
+    return aem.sum(dim=(1, 2)).unsqueeze(1) + mlp_layer(ffm_layer(aem, num_fields).reshape(b, -1), mlp_w, mlp_b,
+                                                        activation)
 
 
 # ----------------------------------------------------------------------------- end-to-end (indices -> logits)

@@ -17,6 +17,14 @@ LAYER_KINDS = ['fm', 'ffm', 'cross', 'cin', 'cin_direct', 'ipn', 'bilinear_all',
 EMB_KINDS = ['emb_single', 'emb_multi', 'emb_multi_flat', 'emb_field_aware']
 MODEL_KINDS = ['fm_model', 'deepfm_model', 'dcn_model', 'xdeepfm_model', 'ffm_model']
 
+# the layers and models next to the hot path (goldens in layers2.npz / models2.npz)
+LAYER_KINDS_2 = ['opn_mat', 'opn_vec', 'opn_num', 'senet', 'senet_sq']
+MODEL_KINDS_2 = ['pnn_inner_model', 'pnn_outer_model', 'fibinet_model', 'afm_model', 'nfm_model', 'fnn_model',
+                 'deep_ffm_model', 'fat_deep_ffm_model']
+SENET_REDUCTION = 2
+CEN_REDUCTION = 3
+DEEP_FFM_OUT = 4
+
 CROSS_LAYERS = 3
 CIN_SIZES = [8, 6]
 AFM_ATTN = 8
@@ -71,10 +79,33 @@ def _cin_params(cid, n, e, sizes, direct, out_f=1):
     return p
 
 
+def _senet_params(cid, m, reduction, prefix='senet'):
+    r = m // reduction
+    return {f'{prefix}_w1': _u((r, m), f'{cid}/{prefix}_w1', 1.0 / np.sqrt(m)),
+            f'{prefix}_b1': _u((r,), f'{cid}/{prefix}_b1', 0.5),
+            f'{prefix}_w2': _u((m, r), f'{cid}/{prefix}_w2', 1.0 / np.sqrt(r)),
+            f'{prefix}_b2': _u((m,), f'{cid}/{prefix}_b2', 0.5)}
+
+
+def _opn_kernel(cid, n, e, kernel_type):
+    shape = {'mat': (e, _pairs(n), e), 'vec': (1, _pairs(n), e), 'num': (1, _pairs(n), 1)}[kernel_type]
+    return _u(shape, f'{cid}/opn_kernel', 1.0 / np.sqrt(e))
+
+
+def senet_list(params, prefix='senet'):
+    return [params[f'{prefix}_{k}'] for k in ('w1', 'b1', 'w2', 'b2')]
+
+
 def layer_case(kind, b, n, e):
     """Returns dict(inputs={...}, params={...}) of float32 numpy arrays for one layer case."""
     cid = case_id(kind, b, n, e)
     inputs, params = {}, {}
+    if kind.startswith('opn_'):
+        return dict(inputs={'x': _u((b, n, e), f'{cid}/x')}, params={'kernel': _opn_kernel(cid, n, e, kind[4:])})
+    if kind == 'senet':
+        return dict(inputs={'x': _u((b, n, e), f'{cid}/x')}, params=_senet_params(cid, n, SENET_REDUCTION))
+    if kind == 'senet_sq':
+        return dict(inputs={'x': _u((b, n * n, e), f'{cid}/x')}, params=_senet_params(cid, n * n, CEN_REDUCTION))
     if kind == 'ffm':
         inputs['x'] = _u((b, n * n, e), f'{cid}/x')
     else:
@@ -119,7 +150,55 @@ def emb_case(kind, b, n, e):
     return dict(field_sizes=fs, inputs={'idx': idx}, params=params)
 
 
+def model_case_2(kind, b, n, e):
+    """The 8f-3 models: PNN (inner / outer), FiBiNET, AFM, NFM, FNN, DeepFFM, FAT-DeepFFM."""
+    cid = case_id(kind, b, n, e)
+    fs = field_sizes_for(n)
+    r = sum(fs)
+    idx = synth.integers((b, n), f'{cid}/idx', np.asarray(fs)[None, :])
+    params = {}
+    if kind in ('deep_ffm_model', 'fat_deep_ffm_model'):
+        for t in range(n):
+            params[f'w_emb{t}'] = _u((r, e), f'{cid}/w_emb{t}', 0.5)
+    else:
+        params['w_emb'] = _u((r, e), f'{cid}/w_emb')
+        if kind != 'fibinet_model':
+            params['w_feat'] = _u((r, 1), f'{cid}/w_feat')
+    if kind in ('pnn_inner_model', 'pnn_outer_model'):
+        params['bias'] = _u((1,), f'{cid}/bias')
+        params.update(_mlp_params(cid, _pairs(n) + n + 1, MLP_SIZES, 1))
+        if kind == 'pnn_outer_model':
+            params['kernel'] = _opn_kernel(cid, n, e, 'mat')
+    elif kind == 'fibinet_model':
+        params.update(_senet_params(cid, n, SENET_REDUCTION))
+        for tag in ('bil_emb', 'bil_senet'):
+            params[f'{tag}_w'] = _u((e, e), f'{cid}/{tag}_w', 1.0 / np.sqrt(e))
+            params[f'{tag}_b'] = _u((e,), f'{cid}/{tag}_b', 0.5)
+        params.update(_mlp_params(cid, 2 * _pairs(n) * e, MLP_SIZES, 1))
+    elif kind == 'afm_model':
+        params['bias'] = _u((1,), f'{cid}/bias')
+        params['w1'] = _u((AFM_ATTN, e), f'{cid}/w1', 1.0 / np.sqrt(e))
+        params['b1'] = _u((AFM_ATTN,), f'{cid}/b1', 0.5)
+        params['w2'] = _u((1, AFM_ATTN), f'{cid}/w2', 1.0)
+        params['b2'] = _u((1,), f'{cid}/b2', 0.5)
+    elif kind == 'nfm_model':
+        params['bias'] = _u((1,), f'{cid}/bias')
+        params.update(_mlp_params(cid, e, MLP_SIZES, 1))
+    elif kind == 'fnn_model':
+        params.update(_mlp_params(cid, n + e, MLP_SIZES, 1))
+    elif kind == 'deep_ffm_model':
+        params.update(_mlp_params(cid, _pairs(n) * e, MLP_SIZES, DEEP_FFM_OUT))
+    elif kind == 'fat_deep_ffm_model':
+        params.update(_senet_params(cid, n * n, CEN_REDUCTION, prefix='cen'))
+        params.update(_mlp_params(cid, _pairs(n) * e, MLP_SIZES, 1))
+    else:
+        raise KeyError(kind)
+    return dict(field_sizes=fs, inputs={'idx': idx}, params=params)
+
+
 def model_case(kind, b, n, e):
+    if kind in MODEL_KINDS_2:
+        return model_case_2(kind, b, n, e)
     cid = case_id(kind, b, n, e)
     fs = field_sizes_for(n)
     r = sum(fs)

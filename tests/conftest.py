@@ -17,7 +17,7 @@ def pytest_configure(config):
 def golden():
     import numpy as np
     out = {}
-    for name in ('layers', 'embeddings', 'models'):
+    for name in ('layers', 'embeddings', 'models', 'layers2', 'models2'):
         with np.load(os.path.join(ROOT, 'tests', 'golden', f'{name}.npz')) as z:
             out.update({k: z[k] for k in z.files})
     return out

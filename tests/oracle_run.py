@@ -41,6 +41,10 @@ def oracle_layer(kind, b, n, e, dtype=torch.float32):
     if kind == 'mlp':
         ws, bs = cases.mlp_lists(p)
         return {'out': R.mlp_layer(x, _t(ws, dtype), _t(bs, dtype))}
+    if kind.startswith('opn_'):
+        return {'out': R.opn_layer(x, _t(p['kernel'], dtype), kind[4:])}
+    if kind in ('senet', 'senet_sq'):
+        return {'out': R.senet_layer(x, *_t(cases.senet_list(p), dtype))}
     raise KeyError(kind)
 
 
@@ -85,6 +89,38 @@ def oracle_model(kind, b, n, e, dtype=torch.float32):
                                               _t(ws, dtype), _t(bs, dtype), g('bias'))}
     if kind == 'ffm_model':
         return {'out': R.ffm_from_indices(idx, off, g('w_feat'), [g(f'w_emb{t}') for t in range(n)], g('bias'))}
+    if kind in cases.MODEL_KINDS_2:
+        return {'out': oracle_model_2(kind, n, p, idx, off, dtype)}
+    raise KeyError(kind)
+
+
+def oracle_model_2(kind, n, p, idx, off, dtype):
+    """The 8f-3 models: lookups by the oracle's embedding functions, then oracle/restated.py's model glue."""
+    g = lambda k: _t(p[k], dtype)
+    if kind in ('deep_ffm_model', 'fat_deep_ffm_model'):
+        v = R.multi_indices_field_aware_embedding([g(f'w_emb{t}') for t in range(n)], idx, off)
+        ws, bs = cases.mlp_lists(p)
+        if kind == 'deep_ffm_model':
+            return R.deep_ffm_model(v, n, _t(ws, dtype), _t(bs, dtype))
+        return R.fat_deep_ffm_model(v, n, _t(cases.senet_list(p, 'cen'), dtype), _t(ws, dtype), _t(bs, dtype))
+    emb = R.multi_indices_embedding(g('w_emb'), idx, off)
+    feat = R.multi_indices_embedding(g('w_feat'), idx, off) if 'w_feat' in p else None
+    if kind in ('pnn_inner_model', 'pnn_outer_model'):
+        ws, bs = cases.mlp_lists(p)
+        second = R.ipn_layer(emb) if kind == 'pnn_inner_model' else R.opn_layer(emb, g('kernel'), 'mat')
+        return R.pnn_model(feat, emb, second, _t(ws, dtype), _t(bs, dtype), g('bias'))
+    if kind == 'fibinet_model':
+        ws, bs = cases.mlp_lists(p)
+        return R.fibinet_model(emb, _t(cases.senet_list(p), dtype), (g('bil_emb_w'), g('bil_emb_b')),
+                               (g('bil_senet_w'), g('bil_senet_b')), 'all', _t(ws, dtype), _t(bs, dtype))
+    if kind == 'afm_model':
+        return R.afm_model(feat, emb, [g(k) for k in ('w1', 'b1', 'w2', 'b2')], g('bias'))
+    if kind == 'nfm_model':
+        ws, bs = cases.mlp_lists(p)
+        return R.nfm_model(feat, emb, _t(ws, dtype), _t(bs, dtype), g('bias'))
+    if kind == 'fnn_model':
+        ws, bs = cases.mlp_lists(p)
+        return R.fnn_model(feat, emb, _t(ws, dtype), _t(bs, dtype))
     raise KeyError(kind)
 
 

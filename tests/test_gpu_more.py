@@ -1,0 +1,232 @@
+"""GPU parity of the SURVEY.md 8f-3 rows: OuterProductNetworkLayer (mat / vec / num), ComposeExcitationNetworkLayer
+(SENET, CEN on squared inputs) and the seven models built on them (PNN inner/outer, FiBiNET, AFM, NFM, FNN, DeepFFM,
+FAT-DeepFFM) -- C-ABI ops and drop-in modules against the oracle AND the reference's own golden outputs
+(tests/golden/layers2.npz, models2.npz, produced by oracle/make_golden.py from the real reference)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import cases
+from tests.oracle_run import normwise_err, oracle_layer, oracle_model
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+GRID = cases.GRID
+
+
+@pytest.fixture(scope='module')
+def trs():
+    import torecsys_b200 as t
+    t.set_index_check('sync')
+    return t
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _set(p, v):
+    with torch.no_grad():
+        p.copy_(torch.from_numpy(np.ascontiguousarray(v)).reshape(p.shape))
+
+
+def _load_mlp(dnn, params, prefix='mlp'):
+    ws, bs = cases.mlp_lists(params, prefix)
+    for lin, w, b in zip(dnn.linears(), ws, bs):
+        _set(lin.weight, w)
+        _set(lin.bias, b)
+
+
+def _load_senet(layer, params, prefix='senet'):
+    w1, b1, w2, b2 = cases.senet_list(params, prefix)
+    _set(layer.fc.ReductionLinear.weight, w1)
+    _set(layer.fc.ReductionLinear.bias, b1)
+    _set(layer.fc.AdditionLinear.weight, w2)
+    _set(layer.fc.AdditionLinear.bias, b2)
+
+
+# ------------------------------------------------------------------------------------------------ ops (C ABI)
+@pytest.mark.parametrize('kind', cases.LAYER_KINDS_2)
+@pytest.mark.parametrize('b,n,e', GRID)
+def test_op_parity(trs, golden, kind, b, n, e):
+    cid = cases.case_id(kind, b, n, e)
+    c = cases.layer_case(kind, b, n, e)
+    x = _dev(c['inputs']['x'])
+    p = {k: _dev(v) for k, v in c['params'].items()}
+    if kind.startswith('opn_'):
+        got = trs.ops.opn(x, p['kernel'], kind[4:])
+    else:
+        got = trs.ops.senet(x, *cases.senet_list(p), trs.ops.activation_id('relu'))
+    want = oracle_layer(kind, b, n, e, torch.float32)['out'].numpy()
+    g = got.cpu().numpy()
+    assert g.shape == want.shape
+    assert normwise_err(g, want) <= TOL, (cid, 'vs oracle')
+    assert normwise_err(g, golden[f'{cid}/out']) <= TOL, (cid, 'vs reference golden')
+    f64 = golden[f'{cid}/out/f64']
+    assert normwise_err(g, f64) <= max(4 * normwise_err(golden[f'{cid}/out'], f64), 2e-6), cid
+
+
+@pytest.mark.parametrize('kernel_type', ['mat', 'vec', 'num'])
+@pytest.mark.parametrize('n,e,batch', [(39, 16, 1000), (26, 32, 257), (7, 8, 256), (5, 12, 33), (3, 4, 1), (9, 20, 513)])
+def test_opn_shapes_and_ragged_batches(trs, kernel_type, n, e, batch):
+    """register kernels for E in {4, 8, 16, 32}, the shared-memory kernel for any other E, ragged tiles of 256."""
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    pairs = n * (n - 1) // 2
+    x = torch.from_numpy(synth.uniform((batch, n, e), f'opn/{kernel_type}/{n}/{e}/x'))
+    shape = {'mat': (e, pairs, e), 'vec': (1, pairs, e), 'num': (1, pairs, 1)}[kernel_type]
+    k = torch.from_numpy(synth.uniform(shape, f'opn/{kernel_type}/{n}/{e}/k', -0.5, 0.5))
+    got = trs.ops.opn(x.cuda(), k.cuda(), kernel_type).cpu().numpy()
+    want = R.opn_layer(x, k, kernel_type).numpy()
+    want64 = R.opn_layer(x.double(), k.double(), kernel_type).numpy()
+    assert normwise_err(got, want) <= TOL
+    assert normwise_err(got, want64) <= max(4 * normwise_err(want, want64), 2e-6)
+    assert trs.ops.opn(x[:0].cuda(), k.cuda(), kernel_type).shape == (0, pairs)
+
+
+@pytest.mark.parametrize('m,e,r,act', [(39, 16, 13, 'relu'), (1521, 16, 507, 'relu'), (10, 7, 3, 'sigmoid'),
+                                       (64, 4, 64, 'tanh'), (5, 130, 1, None)])
+def test_senet_shapes_and_activations(trs, m, e, r, act):
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    batch = 300
+    x = torch.from_numpy(synth.uniform((batch, m, e), f'senet/{m}/{e}/x'))
+    w1 = torch.from_numpy(synth.uniform((r, m), f'senet/{m}/{e}/w1', -m ** -0.5, m ** -0.5))
+    b1 = torch.from_numpy(synth.uniform((r,), f'senet/{m}/{e}/b1', -0.5, 0.5))
+    w2 = torch.from_numpy(synth.uniform((m, r), f'senet/{m}/{e}/w2', -r ** -0.5, r ** -0.5))
+    b2 = torch.from_numpy(synth.uniform((m,), f'senet/{m}/{e}/b2', -0.5, 0.5))
+    got = trs.ops.senet(x.cuda(), w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), trs.ops.activation_id(act))
+    want = R.senet_layer(x, w1, b1, w2, b2, act).numpy()
+    assert normwise_err(got.cpu().numpy(), want) <= TOL
+    with pytest.raises(RuntimeError):   # no CPU path
+        trs.ops.senet(x, w1, b1, w2, b2, 1)
+
+
+# ------------------------------------------------------------------------------------------------ layer modules
+@pytest.mark.parametrize('kind', cases.LAYER_KINDS_2)
+@pytest.mark.parametrize('b,n,e', GRID)
+def test_layer_module_matches_reference_values_and_names(trs, golden, kind, b, n, e):
+    cid = cases.case_id(kind, b, n, e)
+    c = cases.layer_case(kind, b, n, e)
+    p = c['params']
+    if kind.startswith('opn_'):
+        m = trs.OuterProductNetworkLayer(e, n, kernel_type=kind[4:])
+        assert tuple(m.kernel.shape) == p['kernel'].shape
+        _set(m.kernel, p['kernel'])
+        names = ('B', 'O')
+    elif kind == 'senet':
+        m = trs.SENETLayer(n, cases.SENET_REDUCTION, squared=False)
+        _load_senet(m, p)
+        names = ('B', 'N', 'E')
+    else:
+        m = trs.CENLayer(n, cases.CEN_REDUCTION)
+        _load_senet(m, p)
+        names = ('B', 'N', 'E')
+    m = m.cuda().eval()
+    x = _dev(c['inputs']['x'])
+    with torch.no_grad():
+        out = m(x)
+    assert out.names == names
+    assert normwise_err(out.rename(None).cpu().numpy(), golden[f'{cid}/out']) <= TOL, cid
+
+
+def test_opn_rejects_unknown_kernel_type(trs):
+    with pytest.raises(ValueError):
+        trs.OuterProductNetworkLayer(8, 4, kernel_type='tensor')
+
+
+# ------------------------------------------------------------------------------------------------ models
+def build_sequential(trs, kind, b, n, e):
+    from torecsys_b200 import models_more as M
+    c = cases.model_case(kind, b, n, e)
+    fs, p = c['field_sizes'], c['params']
+    schema = {}
+    if 'w_feat' in p:
+        feat = trs.MultiIndicesEmbedding(1, fs)
+        feat.set_schema(['idx'])
+        _set(feat.embedding.weight, p['w_feat'])
+        schema['feat_inputs'] = feat
+    if kind in ('deep_ffm_model', 'fat_deep_ffm_model'):
+        emb = trs.MultiIndicesFieldAwareEmbedding(e, fs)
+        for t in range(n):
+            _set(emb.embeddings[t].weight, p[f'w_emb{t}'])
+        emb.set_schema(['idx'])
+        schema['field_emb_inputs'] = emb
+    else:
+        emb = trs.MultiIndicesEmbedding(e, fs)
+        _set(emb.embedding.weight, p['w_emb'])
+        emb.set_schema(['idx'])
+        schema['emb_inputs'] = emb
+    sizes = list(cases.MLP_SIZES)
+    if kind in ('pnn_inner_model', 'pnn_outer_model'):
+        model = M.ProductNeuralNetworkModel(e, n, sizes, prod_method=kind.split('_')[1], kernel_type='mat')
+        _load_mlp(model.deep, p)
+        _set(model.bias, p['bias'])
+        if kind == 'pnn_outer_model':
+            _set(model.pnn.kernel, p['kernel'])
+    elif kind == 'fibinet_model':
+        model = M.FeatureImportanceAndBilinearFeatureInteractionNetwork(e, n, cases.SENET_REDUCTION, 1, sizes)
+        _load_senet(model.senet, p)
+        _set(model.emb_bilinear.bilinear.weight, p['bil_emb_w'])
+        _set(model.emb_bilinear.bilinear.bias, p['bil_emb_b'])
+        _set(model.senet_bilinear.bilinear.weight, p['bil_senet_w'])
+        _set(model.senet_bilinear.bilinear.bias, p['bil_senet_b'])
+        _load_mlp(model.deep, p)
+    elif kind == 'afm_model':
+        model = M.AttentionalFactorizationMachineModel(e, n, cases.AFM_ATTN, dropout_p=0.5)
+        _set(model.afm.attention.Linear.weight, p['w1'])
+        _set(model.afm.attention.Linear.bias, p['b1'])
+        _set(model.afm.attention.OutProj.weight, p['w2'])
+        _set(model.afm.attention.OutProj.bias, p['b2'])
+        _set(model.bias, p['bias'])
+    elif kind == 'nfm_model':
+        model = M.NeuralFactorizationMachineModel(e, sizes, fm_dropout_p=0.5)
+        _load_mlp(model.sequential.Deep, p)
+        _set(model.bias, p['bias'])
+    elif kind == 'fnn_model':
+        model = M.FactorizationMachineSupportedNeuralNetworkModel(e, n, 1, sizes, fm_dropout_p=0.5)
+        _load_mlp(model.deep, p)
+    elif kind == 'deep_ffm_model':
+        model = M.DeepFieldAwareFactorizationMachineModel(e, n, cases.DEEP_FFM_OUT, sizes, ffm_dropout_p=0.5)
+        _load_mlp(model.deep, p)
+    elif kind == 'fat_deep_ffm_model':
+        model = M.FieldAttentiveDeepFieldAwareFactorizationMachineModel(e, n, 1, sizes, cases.CEN_REDUCTION,
+                                                                        ffm_dropout_p=0.5)
+        _load_senet(model.cen, p, 'cen')
+        _load_mlp(model.deep, p)
+    else:
+        raise KeyError(kind)
+    return trs.Sequential(trs.Inputs(schema), model).cuda().eval(), c
+
+
+@pytest.mark.parametrize('kind', cases.MODEL_KINDS_2)
+@pytest.mark.parametrize('b,n,e', GRID)
+def test_model_matches_reference(trs, golden, kind, b, n, e):
+    cid = cases.case_id(kind, b, n, e)
+    seq, c = build_sequential(trs, kind, b, n, e)
+    with torch.no_grad():
+        out = seq({'idx': _dev(c['inputs']['idx'])})
+    assert out.names == (None, None) and out.shape == (b, 1)
+    got = out.cpu().numpy()
+    want = oracle_model(kind, b, n, e, torch.float32)['out'].numpy()
+    assert normwise_err(got, want) <= TOL, (cid, 'vs oracle')
+    assert normwise_err(got, golden[f'{cid}/out']) <= TOL, (cid, 'vs reference golden')
+    f64 = golden[f'{cid}/out/f64']
+    assert normwise_err(got, f64) <= max(4 * normwise_err(golden[f'{cid}/out'], f64), 5e-6), cid
+
+
+@pytest.mark.parametrize('kind', ['pnn_outer_model', 'fibinet_model', 'fat_deep_ffm_model'])
+def test_models_train_through_the_drop_ins(trs, kind):
+    """Backward through the recompute autograd of the new layers: every parameter receives a finite gradient."""
+    b, n, e = 16, 6, 8
+    seq, c = build_sequential(trs, kind, b, n, e)
+    seq.train()
+    for m in seq.modules():   # dropout off: the kernels' training path is exercised, not torch's RNG
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    out = seq({'idx': _dev(c['inputs']['idx'])})
+    loss = (out.rename(None) ** 2).mean()
+    loss.backward()
+    for name, p in seq.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad.rename(None)).all(), name
+        assert p.grad.rename(None).abs().sum() > 0, name

@@ -15,7 +15,7 @@ from tests.oracle_run import normwise_err, oracle_emb, oracle_layer, oracle_mode
 GRID = cases.GRID
 
 
-@pytest.mark.parametrize('kind', cases.LAYER_KINDS)
+@pytest.mark.parametrize('kind', cases.LAYER_KINDS + cases.LAYER_KINDS_2)
 @pytest.mark.parametrize('b,n,e', GRID)
 def test_layer_oracle_matches_reference(golden, kind, b, n, e):
     cid = cases.case_id(kind, b, n, e)
@@ -40,7 +40,7 @@ def test_embedding_oracle_bit_exact(golden, kind, b, n, e):
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
 
 
-@pytest.mark.parametrize('kind', cases.MODEL_KINDS)
+@pytest.mark.parametrize('kind', cases.MODEL_KINDS + cases.MODEL_KINDS_2)
 @pytest.mark.parametrize('b,n,e', GRID)
 def test_model_oracle_matches_reference(golden, kind, b, n, e):
     cid = cases.case_id(kind, b, n, e)

@@ -8,15 +8,21 @@ feature-interaction layers) as hand-written sm_100a CUDA behind the reference's 
 
 CUDA only: there is no CPU or PyTorch fallback; CPU tensors and a missing library raise.
 """
-from . import inputs, layers, models, ops  # noqa: F401
+from . import inputs, layers, models, models_more, ops  # noqa: F401
 from .inputs import Inputs, MultiIndicesEmbedding, MultiIndicesFieldAwareEmbedding, SingleIndexEmbedding  # noqa: F401
-from .layers import (AFMLayer, AttentionalFactorizationMachineLayer, BilinearInteractionLayer, CINLayer,  # noqa: F401
-                     CompressInteractionNetworkLayer, CrossNetworkLayer, DNNLayer,
-                     FactorizationMachineLayer, FFMLayer, FieldAwareFactorizationMachineLayer, FMLayer,
-                     InnerProductNetworkLayer, MultilayerPerceptionLayer)
+from .layers import (AFMLayer, AttentionalFactorizationMachineLayer, BilinearInteractionLayer, CENLayer,  # noqa: F401
+                     CINLayer, ComposeExcitationNetworkLayer, CompressInteractionNetworkLayer, CrossNetworkLayer,
+                     DNNLayer, FactorizationMachineLayer, FFMLayer, FieldAwareFactorizationMachineLayer, FMLayer,
+                     InnerProductNetworkLayer, MultilayerPerceptionLayer, OuterProductNetworkLayer, SENETLayer)
 from .models import (DeepAndCrossNetworkModel, DeepFactorizationMachineModel,  # noqa: F401
                      FactorizationMachineModel, FieldAwareFactorizationMachineModel, Sequential,
                      XDeepFactorizationMachineModel)
+from .models_more import (AttentionalFactorizationMachineModel,  # noqa: F401
+                          DeepFieldAwareFactorizationMachineModel,
+                          FactorizationMachineSupportedNeuralNetworkModel,
+                          FeatureImportanceAndBilinearFeatureInteractionNetwork,
+                          FieldAttentiveDeepFieldAwareFactorizationMachineModel, NeuralFactorizationMachineModel,
+                          ProductNeuralNetworkModel)
 from .ops import check_index_errors, set_index_check  # noqa: F401
 from .patch import convert, patch_torecsys, unpatch_torecsys  # noqa: F401
 

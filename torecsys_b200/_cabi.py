@@ -19,6 +19,7 @@ TRS_STATUS_WORDS = 2
 TRS_LAUNCH_OVERLAP_PREVIOUS = 1
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
+OPN_MAT, OPN_VEC, OPN_NUM = 0, 1, 2
 
 _P = c_void_p            # device / host data pointer
 _PP = POINTER(c_void_p)  # host array of device pointers
@@ -36,6 +37,9 @@ PROTOTYPES = {
     'trs_ipn_forward': (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     'trs_bilinear_forward': (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int, _P, _P]),
     'trs_afm_forward': (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
+    'trs_opn_forward': (c_int, [_P, _P, c_int, c_int64, c_int, c_int, _P, _P]),
+    'trs_senet_workspace_bytes': (c_int64, [c_int64, c_int]),
+    'trs_senet_forward': (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_int, _P, _P, c_int64, _P]),
     'trs_cross_forward': (c_int, [_P, _P, _P, c_int, c_int64, c_int, _P, _P]),
     'trs_cin_workspace_bytes': (c_int64, [c_int64, c_int, c_int, _IP, c_int, c_int]),
     'trs_cin_forward': (c_int, [_P, _PP, _PP, _PP, _IP, c_int, c_int, c_int, _P, _P, c_int, c_int64, c_int, c_int,

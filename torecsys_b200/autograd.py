@@ -106,6 +106,19 @@ def _afm(x, w1, b1, w2, b2):
     return (prod * s).sum(1), s
 
 
+def _opn(x, kernel, kernel_type):
+    i, j = _pairs(x.shape[1], x.device)
+    p, q = x[:, i], x[:, j]
+    if kernel_type == 'mat':
+        return ((p.unsqueeze(1) * kernel).sum(-1).permute(0, 2, 1) * q).sum(-1)
+    return (p * q * kernel).sum(-1)
+
+
+def _senet(x, w1, b1, w2, b2, act):
+    a = act(F.linear(act(F.linear(x.mean(-1), w1, b1)), w2, b2))
+    return x * a.unsqueeze(-1)
+
+
 def _cross(x, ws, bs):
     # upstream: outputs = emb_inputs.detach().requires_grad_() (cross_network.py:65) -- h_0 carries no gradient to x
     h = x.detach()
@@ -173,6 +186,31 @@ class AfmFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad, grad_scores):
         return _grad_of(_afm, list(ctx.saved_tensors), (grad, grad_scores))
+
+
+class OpnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel, kernel_type):
+        ctx.save_for_backward(x, kernel)
+        ctx.kernel_type = kernel_type
+        return ops.opn(x, kernel, kernel_type)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return _grad_of(lambda a, k: _opn(a, k, ctx.kernel_type), list(ctx.saved_tensors), grad) + (None,)
+
+
+class SenetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, activation):
+        ctx.save_for_backward(x, w1, b1, w2, b2)
+        ctx.activation = activation
+        return ops.senet(x, w1, b1, w2, b2, ops.activation_id(activation))
+
+    @staticmethod
+    def backward(ctx, grad):
+        act = ctx.activation if ctx.activation is not None else (lambda t: t)
+        return _grad_of(lambda *a: _senet(*a, act), list(ctx.saved_tensors), grad) + (None,)
 
 
 class CrossFn(torch.autograd.Function):

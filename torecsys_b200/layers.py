@@ -14,7 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .autograd import AfmFn, BilinearFn, CinFn, CrossFn, FfmFn, FmFn, IpnFn, MlpFn
+from .autograd import AfmFn, BilinearFn, CinFn, CrossFn, FfmFn, FmFn, IpnFn, MlpFn, OpnFn, SenetFn
 
 
 class BaseLayer(nn.Module):
@@ -374,6 +374,85 @@ class AttentionalFactorizationMachineLayer(BaseLayer):
         return outputs, attn_scores
 
 
+# ------------------------------------------------------------------------------------------------ OPN (8f-3)
+class OuterProductNetworkLayer(BaseLayer):
+    """outer_product_network.py:9-131: (B,N,E) -> (B,NC2) names ('B','O'); kernel (E,NC2,E) | (1,NC2,E) | (1,NC2,1),
+    xavier-normal (:69-70)."""
+
+    @property
+    def inputs_size(self):
+        return {'inputs': ('B', 'N', 'E',)}
+
+    @property
+    def outputs_size(self):
+        return {'inputs': ('B', 'NC2',)}
+
+    def __init__(self, embed_size: int, num_fields: int, kernel_type: Optional[str] = 'mat'):
+        super().__init__()
+        rows, cols = [], []
+        for i in range(num_fields - 1):
+            for j in range(i + 1, num_fields):
+                rows.append(i)
+                cols.append(j)
+        self.row_idx = torch.LongTensor(rows)   # kept for API compatibility; the kernel derives pairs itself
+        self.col_idx = torch.LongTensor(cols)
+        pairs = num_fields * (num_fields - 1) // 2
+        if kernel_type == 'mat':
+            kernel_size = (embed_size, pairs, embed_size)
+        elif kernel_type == 'vec':
+            kernel_size = (1, pairs, embed_size)
+        elif kernel_type == 'num':
+            kernel_size = (1, pairs, 1)
+        else:
+            raise ValueError('kernel_type only allows: ["mat", "num", "vec"].')
+        self.kernel_type = kernel_type
+        self.kernel = nn.Parameter(torch.zeros(kernel_size))
+        nn.init.xavier_normal_(self.kernel.data)
+
+    def extra_repr(self) -> str:
+        return f'kernel_type={self.kernel_type}'
+
+    def forward(self, emb_inputs: torch.Tensor) -> torch.Tensor:
+        outputs = OpnFn.apply(emb_inputs.rename(None), self.kernel, self.kernel_type)
+        outputs.names = ('B', 'O')
+        return outputs
+
+
+# ------------------------------------------------------------------------------------------------ SENET / CEN (8f-3)
+class ComposeExcitationNetworkLayer(BaseLayer):
+    """compose_excitation_network.py:9-109: (B, N or N^2, E) -> same shape, names ('B','N','E').  The ONE activation
+    instance is registered under two names (:67-70), like upstream."""
+
+    @property
+    def inputs_size(self):
+        return {'inputs': ('B', 'N^2', 'E',)}
+
+    @property
+    def outputs_size(self):
+        return {'outputs': ('B', 'N^2', 'E',)}
+
+    def __init__(self, num_fields: int, reduction: int, squared: Optional[bool] = True,
+                 activation: Optional[nn.Module] = nn.ReLU()):
+        super().__init__()
+        inputs_num_fields = num_fields ** 2 if squared else num_fields
+        reduced_num_fields = inputs_num_fields // reduction
+        self.pooling = nn.AdaptiveAvgPool1d(1)
+        self.fc = nn.Sequential()
+        self.fc.add_module('ReductionLinear', nn.Linear(inputs_num_fields, reduced_num_fields))
+        self.fc.add_module('ReductionActivation', activation)
+        self.fc.add_module('AdditionLinear', nn.Linear(reduced_num_fields, inputs_num_fields))
+        self.fc.add_module('AdditionActivation', activation)
+        ops.activation_id(activation)   # unsupported activations fail at construction, not in the middle of a forward
+        self._activation = activation
+
+    def forward(self, emb_inputs: torch.Tensor) -> torch.Tensor:
+        fc = self.fc
+        outputs = SenetFn.apply(emb_inputs.rename(None), fc.ReductionLinear.weight, fc.ReductionLinear.bias,
+                                fc.AdditionLinear.weight, fc.AdditionLinear.bias, self._activation)
+        outputs.names = ('B', 'N', 'E',)
+        return outputs
+
+
 # ------------------------------------------------------------------------------------------------ MLP (adjacent)
 class MultilayerPerceptionLayer(BaseLayer):
     """multilayer_perceptron.py:9-84.  One shared activation instance is registered under several names exactly like
@@ -440,6 +519,9 @@ class MultilayerPerceptionLayer(BaseLayer):
 
 # aliases, torecsys/layers/ctr/__init__.py:23-35
 AFMLayer = AttentionalFactorizationMachineLayer
+CENLayer = ComposeExcitationNetworkLayer
+SqueezeAndExcitationNetworkLayer = ComposeExcitationNetworkLayer
+SENETLayer = SqueezeAndExcitationNetworkLayer
 CINLayer = CompressInteractionNetworkLayer
 DNNLayer = MultilayerPerceptionLayer
 FFMLayer = FieldAwareFactorizationMachineLayer

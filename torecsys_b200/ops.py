@@ -207,6 +207,44 @@ def ipn(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+_OPN_TYPES = {'mat': _cabi.OPN_MAT, 'vec': _cabi.OPN_VEC, 'num': _cabi.OPN_NUM}
+
+
+def opn(x: torch.Tensor, kernel: torch.Tensor, kernel_type: str) -> torch.Tensor:
+    """OuterProductNetworkLayer.forward: x (B,N,E), kernel (E,P,E) | (1,P,E) | (1,P,1) -> (B,P)."""
+    x, b, n, e = _bne('opn', x)
+    _need_cuda('opn', kernel)
+    if kernel_type not in _OPN_TYPES:
+        raise ValueError('kernel_type only allows: ["mat", "num", "vec"].')
+    k = _f32('opn', kernel)
+    pairs = n * (n - 1) // 2
+    want = {'mat': (e, pairs, e), 'vec': (1, pairs, e), 'num': (1, pairs, 1)}[kernel_type]
+    if tuple(k.shape) != want:
+        raise ValueError(f'opn: kernel shape {tuple(k.shape)} != {want}')
+    out = torch.empty((b, pairs), dtype=torch.float32, device=x.device)
+    check(_cabi.load().trs_opn_forward(_ptr(x), _ptr(k), _OPN_TYPES[kernel_type], b, n, e, _ptr(out), _stream()),
+          'trs_opn_forward')
+    return out
+
+
+def senet(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+          act: int) -> torch.Tensor:
+    """ComposeExcitationNetworkLayer.forward: x (B,M,E); w1 (R,M), b1 (R), w2 (M,R), b2 (M) -> (B,M,E)."""
+    x, b, m, e = _bne('senet', x)
+    _need_cuda('senet', w1, b1, w2, b2)
+    w1, b1, w2, b2 = (_f32('senet', t) for t in (w1, b1, w2, b2))
+    r = w1.shape[0]
+    if tuple(w1.shape) != (r, m) or tuple(w2.shape) != (m, r) or b1.numel() != r or b2.numel() != m:
+        raise ValueError(f'senet: parameter shapes do not match x {tuple(x.shape)}')
+    lib = _cabi.load()
+    out = torch.empty_like(x)
+    need = lib.trs_senet_workspace_bytes(b, m)
+    ws = torch.empty(max(need, 4) // 4, dtype=torch.float32, device=x.device)
+    check(lib.trs_senet_forward(_ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), act, b, m, e, r, _ptr(out), _ptr(ws),
+                                need, _stream()), 'trs_senet_forward')
+    return out
+
+
 def bilinear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], each_type: bool) -> torch.Tensor:
     x, b, n, e = _bne('bilinear', x)
     _need_cuda('bilinear', weight, bias)

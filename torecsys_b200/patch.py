@@ -18,6 +18,7 @@ import torch.nn as nn
 from . import inputs as _inputs
 from . import layers as _layers
 from . import models as _models
+from . import models_more as _more
 
 # reference class name -> drop-in class
 LAYER_CLASSES = {
@@ -29,11 +30,15 @@ LAYER_CLASSES = {
     'BilinearInteractionLayer': _layers.BilinearInteractionLayer,
     'AttentionalFactorizationMachineLayer': _layers.AttentionalFactorizationMachineLayer,
     'MultilayerPerceptionLayer': _layers.MultilayerPerceptionLayer,
+    'OuterProductNetworkLayer': _layers.OuterProductNetworkLayer,
+    'ComposeExcitationNetworkLayer': _layers.ComposeExcitationNetworkLayer,
 }
 LAYER_ALIASES = {
     'FMLayer': 'FactorizationMachineLayer', 'FFMLayer': 'FieldAwareFactorizationMachineLayer',
     'CINLayer': 'CompressInteractionNetworkLayer', 'AFMLayer': 'AttentionalFactorizationMachineLayer',
     'DNNLayer': 'MultilayerPerceptionLayer',
+    'CENLayer': 'ComposeExcitationNetworkLayer', 'SqueezeAndExcitationNetworkLayer': 'ComposeExcitationNetworkLayer',
+    'SENETLayer': 'ComposeExcitationNetworkLayer',
 }
 INPUT_CLASSES = {
     'SingleIndexEmbedding': _inputs.SingleIndexEmbedding,
@@ -48,6 +53,15 @@ MODEL_CLASSES = {
     'XDeepFactorizationMachineModel': _models.XDeepFactorizationMachineModel,
     'FieldAwareFactorizationMachineModel': _models.FieldAwareFactorizationMachineModel,
     'Sequential': _models.Sequential,
+    'ProductNeuralNetworkModel': _more.ProductNeuralNetworkModel,
+    'FeatureImportanceAndBilinearFeatureInteractionNetwork':
+        _more.FeatureImportanceAndBilinearFeatureInteractionNetwork,
+    'AttentionalFactorizationMachineModel': _more.AttentionalFactorizationMachineModel,
+    'NeuralFactorizationMachineModel': _more.NeuralFactorizationMachineModel,
+    'FactorizationMachineSupportedNeuralNetworkModel': _more.FactorizationMachineSupportedNeuralNetworkModel,
+    'DeepFieldAwareFactorizationMachineModel': _more.DeepFieldAwareFactorizationMachineModel,
+    'FieldAttentiveDeepFieldAwareFactorizationMachineModel':
+        _more.FieldAttentiveDeepFieldAwareFactorizationMachineModel,
 }
 
 _saved: Dict[tuple, object] = {}
@@ -134,6 +148,13 @@ def _rebuild(m: nn.Module) -> nn.Module:
             m.embed_size, m.layer_sizes[0], m.fc.out_features, list(m.layer_sizes[1:]), is_direct=m.is_direct,
             use_bias=first.Conv1d.bias is not None, use_batchnorm='Batchnorm' in first._modules,
             activation=first._modules.get('Activation'))
+    elif name == 'OuterProductNetworkLayer':
+        n = int((1 + (1 + 8 * len(m.row_idx)) ** 0.5) / 2)
+        new = L.OuterProductNetworkLayer(m.kernel.shape[2], n, m.kernel_type)   # the kernel itself is adopted below
+    elif name == 'ComposeExcitationNetworkLayer':
+        red = m.fc.ReductionLinear
+        new = L.ComposeExcitationNetworkLayer(red.in_features, max(1, red.in_features // max(1, red.out_features)),
+                                              squared=False, activation=m.fc._modules.get('ReductionActivation'))
     elif name == 'MultilayerPerceptionLayer':
         linears = [x for x in m.model._modules.values() if isinstance(x, nn.Linear)]
         drops = [x.p for x in m.model._modules.values() if isinstance(x, nn.Dropout)]
