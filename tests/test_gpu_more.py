@@ -230,3 +230,23 @@ def test_models_train_through_the_drop_ins(trs, kind):
     for name, p in seq.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad.rename(None)).all(), name
         assert p.grad.rename(None).abs().sum() > 0, name
+
+
+@pytest.mark.parametrize('k,sizes,out_f,rows', [(4104, [16, 16], 1, 2048), (23712, [16, 16, 16], 1, 1500),
+                                                (1024, [24, 8], 3, 4099), (11856, [16], 4, 1024)])
+def test_mlp_with_a_tall_first_layer(trs, k, sizes, out_f, rows):
+    """The first Linear of FiBiNET / DeepFFM / FAT-DeepFFM sees K = pairs x embed inputs and 16 outputs: that layer
+    runs on the tcgen05 dense kernel (3xTF32), the narrow rest one warp per row.  fp32-accurate against the oracle."""
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    dims = [k] + sizes + [out_f]
+    x = torch.from_numpy(synth.uniform((rows, k), f'tall/{k}/x'))
+    ws = [torch.from_numpy(synth.uniform((dims[i + 1], dims[i]), f'tall/{k}/w{i}', -dims[i] ** -0.5, dims[i] ** -0.5))
+          for i in range(len(dims) - 1)]
+    bs = [torch.from_numpy(synth.uniform((dims[i + 1],), f'tall/{k}/b{i}', -0.5, 0.5)) for i in range(len(dims) - 1)]
+    pack = trs.ops.MlpPack([w.cuda() for w in ws], [b.cuda() for b in bs], trs.ops.activation_id('relu'))
+    got = trs.ops.mlp(x.cuda(), pack).cpu().numpy()
+    want = R.mlp_layer(x, ws, bs).numpy()
+    want64 = R.mlp_layer(x.double(), [w.double() for w in ws], [b.double() for b in bs]).numpy()
+    assert normwise_err(got, want) <= TOL
+    assert normwise_err(got, want64) <= max(4 * normwise_err(want, want64), 5e-6)

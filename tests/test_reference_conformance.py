@@ -41,6 +41,11 @@ CASES = [
     ('BilinearInteractionLayer', (8, 5), {'bilinear_type': 'each'}),
     ('AFMLayer', (8, 5, 4), {'dropout_p': 0.3}),
     ('DNNLayer', (12, 2, [16, 8]), {'dropout_p': [0.1, 0.2]}),
+    ('OuterProductNetworkLayer', (8, 5), {'kernel_type': 'mat'}),
+    ('OuterProductNetworkLayer', (8, 5), {'kernel_type': 'vec'}),
+    ('OuterProductNetworkLayer', (8, 5), {'kernel_type': 'num'}),
+    ('SENETLayer', (6, 2), {'squared': False}),
+    ('CENLayer', (4, 3), {}),
 ]
 
 
@@ -77,6 +82,14 @@ MODELS = [
     ('DeepAndCrossNetworkModel', (8, 6, 4, [32, 16, 8], 3), {}),
     ('XDeepFactorizationMachineModel', (8, 6, [8, 4], [16, 16]), {}),
     ('FieldAwareFactorizationMachineModel', (6,), {'dropout_p': 0.1}),
+    ('ProductNeuralNetworkModel', (8, 6, [16, 16]), {'prod_method': 'inner'}),
+    ('ProductNeuralNetworkModel', (8, 6, [16, 16]), {'prod_method': 'outer', 'kernel_type': 'vec'}),
+    ('FeatureImportanceAndBilinearFeatureInteractionNetwork', (8, 6, 2, 1, [16, 16]), {'bilinear_type': 'each'}),
+    ('AttentionalFactorizationMachineModel', (8, 6, 4), {'dropout_p': 0.1}),
+    ('NeuralFactorizationMachineModel', (8, [16, 16]), {'fm_dropout_p': 0.1}),
+    ('FactorizationMachineSupportedNeuralNetworkModel', (8, 6, 1, [16, 16]), {}),
+    ('DeepFieldAwareFactorizationMachineModel', (8, 6, 2, [16, 16]), {'ffm_dropout_p': 0.1}),
+    ('FieldAttentiveDeepFieldAwareFactorizationMachineModel', (8, 4, 1, [16, 16], 3), {}),
 ]
 
 

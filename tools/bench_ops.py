@@ -79,7 +79,7 @@ def main():
     B = 65536
     if any(want(x) for x in ('gather16', 'gather1', 'fm_layer', 'deepfm_packed', 'deepfm_split', 'fm_model',
                              'deepfm_generic_mlp400', 'ipn', 'bilinear_all', 'bilinear_each', 'afm', 'xdeepfm',
-                             'cin_layer')):
+                             'cin_layer', 'opn', 'senet', 'models_more')):
         w16 = torch.randn(rows, 16, device=dev)
         w1 = torch.randn(rows, 1, device=dev)
         ring = idx_ring(B)
@@ -140,6 +140,50 @@ def main():
             xb = x[:16384].contiguous()
             t = timeit(lambda i: ops.afm(xb, w1a, b1a, w2a, b2a), reps=5)
             report('afm (a11, attn 16)', 16384, t, N * 64 + 64 + PAIRS * 4, 2 * PAIRS * (16 * 16 + 16 + 16 + 16))
+        if want('opn'):
+            xb = x[:16384].contiguous()
+            for kt, shape, fl in (('mat', (16, PAIRS, 16), 2 * PAIRS * (256 + 16)), ('vec', (1, PAIRS, 16), 3 * PAIRS * 16),
+                                  ('num', (1, PAIRS, 1), 3 * PAIRS * 16)):
+                k = torch.randn(shape, device=dev) * 0.25
+                t = timeit(lambda i: ops.opn(xb, k, kt), reps=5)
+                report(f'opn {kt} (8f-3, OuterProductNetworkLayer)', 16384, t, N * 64 + PAIRS * 4, fl)
+        if want('senet'):
+            relu = ops.activation_id('relu')
+            w1s, b1s = lin(13, N, dev)
+            w2s, b2s = lin(N, 13, dev)
+            t = timeit(lambda i: ops.senet(x, w1s, b1s, w2s, b2s, relu))
+            report('senet (8f-3, FiBiNET: M=39, reduction 3)', B, t, 2 * N * 64, 2 * 2 * N * 13 + 2 * N * 16)
+        if want('models_more'):
+            # the 8f-3 models through Sequential (L1 route: lookup kernels + layer kernels + the reference's glue)
+            import torecsys_b200 as trs
+            from torecsys_b200 import models_more as M
+            fs = [rpf] * N
+            feat, emb = trs.MultiIndicesEmbedding(1, [16] * N), trs.MultiIndicesEmbedding(16, [16] * N)
+            for m_, w_ in ((feat, w1), (emb, w16)):     # adopt the big benchmark tables instead of allocating new ones
+                m_.embedding.weight = torch.nn.Parameter(w_, requires_grad=False)
+                m_.embedding.num_embeddings = rows
+                m_.offsets = torch.from_numpy(__import__('numpy').arange(N) * rpf).reshape(1, N)
+                m_.offsets.names = ('B', 'N')
+                m_.set_schema(['idx'])
+            Bm = 16384
+            rb = [r[:Bm].contiguous() for r in ring]
+            zoo = {
+                'pnn inner': (M.ProductNeuralNetworkModel(16, N, [16, 16, 16], prod_method='inner'), True),
+                'pnn outer (mat)': (M.ProductNeuralNetworkModel(16, N, [16, 16, 16], prod_method='outer'), True),
+                'fibinet (bilinear all)': (M.FeatureImportanceAndBilinearFeatureInteractionNetwork(
+                    16, N, 3, 1, [16, 16, 16]), False),
+                'afm model (attn 16)': (M.AttentionalFactorizationMachineModel(16, N, 16, dropout_p=0.0), True),
+                'nfm': (M.NeuralFactorizationMachineModel(16, [16, 16, 16], fm_dropout_p=0.0), True),
+                'fnn': (M.FactorizationMachineSupportedNeuralNetworkModel(16, N, 1, [16, 16, 16]), True),
+            }
+            for name, (model, with_feat) in zoo.items():
+                schema = {'emb_inputs': emb}
+                if with_feat:
+                    schema['feat_inputs'] = feat
+                seq = trs.Sequential(trs.Inputs(schema), model).to(dev).eval()
+                with torch.no_grad():
+                    t = timeit(lambda i: seq({'idx': rb[i % 4]}), reps=5, warmup=2)
+                report(f'{name} (8f-3 model, Sequential L1 route)', Bm, t, 2968 if with_feat else 2812)
         if want('cin_layer') or want('xdeepfm'):
             sizes = [128, 128]
             conv_w, scale, shift = [], [], []

@@ -49,6 +49,99 @@ __global__ void __launch_bounds__(256) narrow_dense_kernel(const float* __restri
   }
 }
 
+// Tall layers (K in the thousands, few outputs): out[r, o] = act(b[o] + <x[r, :], w[o, :]>) in plain FP32 FFMA with a
+// K-chunked shared-memory tile: 64 rows x (16 CO) outputs per CTA, a thread owns 4 rows x CO outputs.  The first Linear
+// of FiBiNET / DeepFFM / PNN-style MLPs (K = pairs x embed).  Why not the tensor pipe: tcgen05 accumulates K in the
+// thousands inside the tensor core's own fp32 accumulator and drifts past the 1e-5 bar (2e-5 at K = 4 104, 1.5e-4 at
+// K = 11 856, tests/test_gpu_more.py); FFMA keeps the parity and the layer is HBM-bound on x either way.
+constexpr int kTallRows = 64, kTallKC = 64, kTallPitch = kTallKC + 4;
+template <int CO>
+__global__ void __launch_bounds__(256) tall_dense_kernel(const float* __restrict__ x, int64_t rows, int k,
+                                                         const float* __restrict__ w, const float* __restrict__ b,
+                                                         int c0, int c, int c_total, int act, float* __restrict__ out) {
+  __shared__ __align__(16) float xs[kTallRows * kTallPitch];
+  __shared__ __align__(16) float ws[16 * CO * kTallPitch];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const bool vec = (k & 3) == 0 && aligned16(x) && aligned16(w);
+  for (int64_t r0 = (int64_t)blockIdx.x * kTallRows; r0 < rows; r0 += (int64_t)gridDim.x * kTallRows) {
+    float acc[4][CO];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < CO; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < k; k0 += kTallKC) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (kTallRows + 16 * CO) * (kTallKC / 4); t += blockDim.x) {
+        const int row = t / (kTallKC / 4), kk = 4 * (t - row * (kTallKC / 4));
+        const bool is_x = row < kTallRows;
+        const int wr = row - kTallRows;                      // weight row within this block (when !is_x)
+        const bool live = is_x ? (r0 + row < rows) : (wr < c);
+        const float* src = is_x ? x + (r0 + row) * k : w + (int64_t)(c0 + wr) * k;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+          if (vec && k0 + kk + 3 < k) {
+            v = is_x ? ldg_stream_f4(reinterpret_cast<const float4*>(src + k0 + kk))
+                     : __ldg(reinterpret_cast<const float4*>(src + k0 + kk));
+          } else {
+            if (k0 + kk < k) v.x = __ldg(src + k0 + kk);
+            if (k0 + kk + 1 < k) v.y = __ldg(src + k0 + kk + 1);
+            if (k0 + kk + 2 < k) v.z = __ldg(src + k0 + kk + 2);
+            if (k0 + kk + 3 < k) v.w = __ldg(src + k0 + kk + 3);
+          }
+        }
+        float* dst = is_x ? xs + row * kTallPitch + kk : ws + wr * kTallPitch + kk;
+        *reinterpret_cast<float4*>(dst) = v;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int kk = 0; kk < kTallKC; kk += 4) {
+        float4 xv[4], wv[CO];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xs + (4 * ty + i) * kTallPitch + kk);
+#pragma unroll
+        for (int j = 0; j < CO; ++j) wv[j] = *reinterpret_cast<const float4*>(ws + (tx + 16 * j) * kTallPitch + kk);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < CO; ++j) {
+            acc[i][j] = fmaf(xv[i].x, wv[j].x, acc[i][j]);
+            acc[i][j] = fmaf(xv[i].y, wv[j].y, acc[i][j]);
+            acc[i][j] = fmaf(xv[i].z, wv[j].z, acc[i][j]);
+            acc[i][j] = fmaf(xv[i].w, wv[j].w, acc[i][j]);
+          }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t r = r0 + 4 * ty + i;
+      if (r >= rows) continue;
+#pragma unroll
+      for (int j = 0; j < CO; ++j) {
+        const int o = tx + 16 * j;
+        if (o < c) out[r * c_total + c0 + o] = apply_act(acc[i][j] + (b ? __ldg(b + c0 + o) : 0.f), act);
+      }
+    }
+  }
+}
+
+int tall_dense_run(const float* x, int64_t rows, int k, const float* w, const float* b, int c, int act, float* out,
+                   cudaStream_t s) {
+  const int64_t tiles = (rows + kTallRows - 1) / kTallRows;
+  const int grid = static_cast<int>(tiles < kNumSMs * 4 ? tiles : kNumSMs * 4);
+  for (int c0 = 0; c0 < c; c0 += 64) {   // blocks of at most 64 outputs (x is re-read per block; C <= 64 is the case)
+    const int cc = c - c0 < 64 ? c - c0 : 64;
+    switch ((cc + 15) / 16) {
+      case 1: tall_dense_kernel<1><<<grid, 256, 0, s>>>(x, rows, k, w, b, c0, cc, c, act, out); break;
+      case 2: tall_dense_kernel<2><<<grid, 256, 0, s>>>(x, rows, k, w, b, c0, cc, c, act, out); break;
+      case 3: tall_dense_kernel<3><<<grid, 256, 0, s>>>(x, rows, k, w, b, c0, cc, c, act, out); break;
+      default: tall_dense_kernel<4><<<grid, 256, 0, s>>>(x, rows, k, w, b, c0, cc, c, act, out); break;
+    }
+    const int rc = check_launch("tall_dense_kernel");
+    if (rc != TRS_OK) return rc;
+  }
+  return TRS_OK;
+}
+
 __global__ void __launch_bounds__(256) mlp_kernel(const float* __restrict__ x, int64_t rows, MlpParams mp, int ts,
                                                   int in_pitch, int hpitch, float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
@@ -115,13 +208,25 @@ __global__ void __launch_bounds__(256) cross_kernel(const float* __restrict__ x,
 // fp32-accurate), narrower ones (the logit layer) one warp per row; activations ping-pong through stream-ordered
 // scratch.  Taken when some layer is at least 64 x 64 -- below that the one-kernel shared-memory tile MLP wins.
 // `accumulate` adds the last layer's output onto `out` (the deep branch of DeepFM / xDeepFM joining the other terms).
+// A layer of the chain runs on tcgen05 when it has >= 32 outputs; a TALL layer with few outputs (the first layer of
+// FiBiNET / DeepFFM / PNN-style MLPs: K = pairs x embed in the thousands, 16 outputs) runs tall_dense_kernel -- the
+// one-kernel shared-memory tile MLP would hold only a couple of such rows per CTA and re-read the whole weight matrix
+// for each of them.
+constexpr int kTallK = 1024;
+static bool chain_layer_tall(int k_dim, int c_dim) { return k_dim >= kTallK && c_dim <= 64; }
+static bool chain_layer_on_tc(int k_dim, int c_dim) { return !chain_layer_tall(k_dim, c_dim) && c_dim >= 32; }
+
 int mlp_chain_supported(const int* dims, int layers, int64_t rows, const void* x, const void* out, int accumulate) {
   static const bool disabled = getenv("TRS_DISABLE_TC") != nullptr;
   if (disabled || rows < 1024 || !aligned16(x) || !aligned16(out)) return 0;
   if (accumulate && dims[layers] >= 32) return 0;
   bool wide = false;
   for (int l = 0; l < layers; ++l) {
-    if (dims[l + 1] < 32) continue;
+    if (chain_layer_tall(dims[l], dims[l + 1])) {
+      wide = true;
+      continue;
+    }
+    if (!chain_layer_on_tc(dims[l], dims[l + 1])) continue;
     if (!dense_tc_supported(dims[l], dims[l + 1], x, out)) return 0;
     if (dims[l] >= 64 && dims[l + 1] >= 64) wide = true;
   }
@@ -140,7 +245,9 @@ int mlp_chain_run(const float* x, int64_t rows, const MlpParams& mp, float* out,
     const bool last = l == mp.layers - 1;
     float* dst = last ? out : buf + (l & 1) * half;
     const int act = last ? TRS_ACT_NONE : mp.act;
-    if (mp.dims[l + 1] >= 32) {
+    if (chain_layer_tall(mp.dims[l], mp.dims[l + 1]) && !(last && accumulate)) {
+      rc = tall_dense_run(cur, rows, mp.dims[l], mp.w[l], mp.b[l], mp.dims[l + 1], act, dst, s);
+    } else if (chain_layer_on_tc(mp.dims[l], mp.dims[l + 1])) {
       rc = dense_tc_run(cur, rows, mp.dims[l], mp.w[l], mp.b[l], mp.dims[l + 1], act, dst, s);
     } else {
       narrow_dense_kernel<<<grid_for(rows * 32, 256, 8), 256, 0, s>>>(cur, rows, mp.dims[l], mp.w[l], mp.b[l],
