@@ -133,6 +133,13 @@ int trs_senet_forward(const float* x, const float* w1, const float* b1, const fl
 int trs_cross_forward(const float* x, const float* weights, const float* biases, int layers,
                       int64_t rows, int embed, float* out, void* stream);
 
+/* Experimental: the same cross network with the whole layer chain in TENSOR MEMORY (tcgen05.mma, A operand in TMEM,
+ * 3xTF32).  Same results; measured slower than trs_cross_forward's mma.sync chain at embed = 32 (the per-instruction
+ * cost of a narrow tcgen05.mma), so it is not on the default path.  embed 16 or 32, rows >= 640
+ * (TRS_ERR_UNSUPPORTED otherwise). */
+int trs_cross_forward_tc5(const float* x, const float* weights, const float* biases, int layers,
+                          int64_t rows, int embed, float* out, void* stream);
+
 /* ---- a8: compress interaction network ------------------------------------------------------------------------------
  * Replaces CompressInteractionNetworkLayer.forward (torecsys/layers/ctr/compress_interaction_network.py:85-184), eval:
  *     per layer l:  z[b, xf*H + y, e] = x[b,xf,e] * h[b,y,e]

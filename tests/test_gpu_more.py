@@ -250,3 +250,25 @@ def test_mlp_with_a_tall_first_layer(trs, k, sizes, out_f, rows):
     want64 = R.mlp_layer(x.double(), [w.double() for w in ws], [b.double() for b in bs]).numpy()
     assert normwise_err(got, want) <= TOL
     assert normwise_err(got, want64) <= max(4 * normwise_err(want, want64), 5e-6)
+
+
+@pytest.mark.parametrize('e', [16, 32])
+@pytest.mark.parametrize('layers,rows', [(1, 640), (6, 39 * 300), (3, 128 * 4 * 148 + 77), (9, 5000)])
+def test_cross_layer_on_tcgen05(trs, e, layers, rows):
+    """cross_tc5.cu (experimental entry point trs_cross_forward_tc5): the L-layer chain of a 128-row tile lives in
+    tensor memory (tcgen05.mma with the A operand in TMEM, 3xTF32).  FP32-accurate against the oracle, identical to
+    the default mma.sync path within rounding, ragged last tiles, more tiles than slots x SMs."""
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    x = torch.from_numpy(synth.uniform((rows // 13 + 1, 13, e), f'tc5/{e}/{layers}/{rows}/x'))[:rows // 13 + 1]
+    x = x.reshape(-1, e)[:rows].reshape(1, rows, e).contiguous()
+    ws = [torch.from_numpy(synth.uniform((e, e), f'tc5/{e}/{layers}/w{l}', -e ** -0.5, e ** -0.5)) for l in range(layers)]
+    bs = [torch.from_numpy(synth.uniform((e,), f'tc5/{e}/{layers}/b{l}', -0.5, 0.5)) for l in range(layers)]
+    got = trs.ops.cross(x.cuda(), torch.stack(ws).cuda(), torch.stack(bs).cuda(), tc5=True).cpu().numpy()
+    default = trs.ops.cross(x.cuda(), torch.stack(ws).cuda(), torch.stack(bs).cuda()).cpu().numpy()
+    assert normwise_err(got, default) <= TOL
+    want = R.cross_layer(x, ws, bs).numpy()
+    want64 = R.cross_layer(x.double(), [w.double() for w in ws], [b.double() for b in bs]).numpy()
+    assert got.shape == want.shape
+    assert normwise_err(got, want) <= TOL
+    assert normwise_err(got, want64) <= max(4 * normwise_err(want, want64), 2e-6)

@@ -41,6 +41,7 @@ PROTOTYPES = {
     'trs_senet_workspace_bytes': (c_int64, [c_int64, c_int]),
     'trs_senet_forward': (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_int, _P, _P, c_int64, _P]),
     'trs_cross_forward': (c_int, [_P, _P, _P, c_int, c_int64, c_int, _P, _P]),
+    'trs_cross_forward_tc5': (c_int, [_P, _P, _P, c_int, c_int64, c_int, _P, _P]),
     'trs_cin_workspace_bytes': (c_int64, [c_int64, c_int, c_int, _IP, c_int, c_int]),
     'trs_cin_forward': (c_int, [_P, _PP, _PP, _PP, _IP, c_int, c_int, c_int, _P, _P, c_int, c_int64, c_int, c_int,
                                 _P, _P, c_int64, _P]),

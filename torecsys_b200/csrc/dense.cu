@@ -297,7 +297,8 @@ extern "C" int trs_cross_forward(const float* x, const float* weights, const flo
   TRS_REQUIRE(x && out && (layers == 0 || (weights && biases)), "trs_cross_forward: null pointer");
   TRS_REQUIRE(rows >= 0 && embed > 0 && layers >= 0, "trs_cross_forward: bad sizes");
   if (rows == 0) return TRS_OK;
-  // E in {8,16,32,64}: register-resident 3xTF32 mma.sync chain (dcn_tc.cu); FP32 FFMA tiles otherwise
+  // E in {8,16,32,64}: register-resident 3xTF32 mma.sync chain (dcn_tc.cu); FP32 FFMA tiles otherwise.  (A tcgen05
+  // version with the chain in tensor memory exists -- cross_tc5.cu, trs_cross_forward_tc5 -- and measured slower.)
   {
     const int rc = cross_tc_launch(x, weights, biases, layers, rows, embed, out, static_cast<cudaStream_t>(stream));
     if (rc != TRS_ERR_UNSUPPORTED) return rc;

@@ -276,8 +276,9 @@ def afm(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b
     return out, scores
 
 
-def cross(x: torch.Tensor, weights: torch.Tensor, biases: torch.Tensor) -> torch.Tensor:
-    """x (..., E); weights (L, E, E); biases (L, E)."""
+def cross(x: torch.Tensor, weights: torch.Tensor, biases: torch.Tensor, tc5: bool = False) -> torch.Tensor:
+    """x (..., E); weights (L, E, E); biases (L, E).  tc5=True runs the experimental tcgen05 / tensor-memory chain
+    (trs_cross_forward_tc5; same results, measured slower -- see csrc/cross_tc5.cu)."""
     _need_cuda('cross', x, weights, biases)
     x = _f32('cross', x)
     w, bs = _f32('cross', weights), _f32('cross', biases)
@@ -287,8 +288,9 @@ def cross(x: torch.Tensor, weights: torch.Tensor, biases: torch.Tensor) -> torch
         raise ValueError('cross: weights must be (L, E, E) and biases (L, E)')
     rows = x.numel() // e
     out = torch.empty_like(x)
-    check(_cabi.load().trs_cross_forward(_ptr(x), _ptr(w), _ptr(bs), layers, rows, e, _ptr(out), _stream()),
-          'trs_cross_forward')
+    fn = _cabi.load().trs_cross_forward_tc5 if tc5 else _cabi.load().trs_cross_forward
+    check(fn(_ptr(x), _ptr(w), _ptr(bs), layers, rows, e, _ptr(out), _stream()),
+          'trs_cross_forward_tc5' if tc5 else 'trs_cross_forward')
     return out
 
 
