@@ -71,6 +71,19 @@ int trs_embedding_gather_field_aware(const float* const* tables, int64_t rows, i
  *     out[b, e] = 0.5 * ((sum_n x[b,n,e])^2 - sum_n x[b,n,e]^2)      x (batch, fields, embed) -> out (batch, embed) */
 int trs_fm_forward(const float* x, int64_t batch, int fields, int embed, float* out, void* stream);
 
+/* ---- 8f-2: backward kernels of the two ops every training step goes through ----------------------------------------
+ * trs_embedding_grad: the dense weight gradient of nn.Embedding behind MultiIndicesEmbedding / SingleIndexEmbedding
+ * (multi_indices_emb.py:48, single_index_emb.py:41; sparse=False):
+ *     grad_weight[idx[b,n] + offsets[n], :] += grad_out[b, n, :]       (grad_weight is NOT zeroed here)
+ * padding_row (-1 = none) is skipped like nn.Embedding's padding_idx; out-of-range lookups are skipped (the forward
+ * reported them).  Vector reductions (red.global.add.v4.f32): colliding rows add in an unspecified order.
+ * trs_fm_backward: grad_x[b,n,e] = grad_out[b,e] * (sum_m x[b,m,e] - x[b,n,e])  (factorization_machine.py:46-81). */
+int trs_embedding_grad(const float* grad_out, const void* idx, int idx_bits, const int64_t* offsets,
+                       int64_t batch, int fields, int64_t rows, int embed, int64_t padding_row,
+                       float* grad_weight, void* stream);
+int trs_fm_backward(const float* x, const float* grad_out, int64_t batch, int fields, int embed,
+                    float* grad_x, void* stream);
+
 /* ---- a6: field-aware FM ------------------------------------------------------------------------------------------
  * Replaces FieldAwareFactorizationMachineLayer.forward
  * (torecsys/layers/ctr/field_aware_factorization_machine.py:50-94), eval mode:

@@ -179,3 +179,44 @@ def test_models_train_one_step_like_the_reference_formula(trs, kind):
     torch.nn.functional.mse_loss(out, target.cpu()).backward()
     for ours, theirs in pairs:
         assert normwise_err(ours.grad.cpu().numpy().reshape(-1), theirs.grad.numpy().reshape(-1)) <= GTOL, kind
+
+
+# ---------------------------------------------------------------------------------------------- backward kernels (8f-2)
+@pytest.mark.parametrize('e', [1, 7, 16, 32])
+@pytest.mark.parametrize('idx_dtype', [torch.int64, torch.int32])
+def test_embedding_grad_kernel(e, idx_dtype):
+    """trs_embedding_grad = nn.Embedding's dense weight gradient: scatter-add with heavy collisions, field offsets,
+    padding row, both index widths; compared with torch's index_add_ in float64."""
+    from torecsys_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    fs = [16, 48, 32, 16]
+    rows, b, n = sum(fs), 3000, len(fs)
+    off = torch.tensor([0, 16, 64, 96])
+    idx = torch.stack([torch.randint(0, f, (b,), generator=gen) for f in fs], 1)
+    g = torch.randn(b, n, e, generator=gen)
+    flat = (idx + off).reshape(-1)
+    want = torch.zeros(rows, e, dtype=torch.float64).index_add_(0, flat, g.reshape(-1, e).double())
+    got = ops.embedding_grad(g.cuda(), idx.to(idx_dtype).cuda(), off.cuda(), rows).cpu().double()
+    assert (got - want).abs().max() <= 1e-4 * want.abs().max()
+    pad = 17
+    keep = (flat != pad).unsqueeze(1)
+    want_p = torch.zeros(rows, e, dtype=torch.float64).index_add_(0, flat, (g.reshape(-1, e) * keep).double())
+    got_p = ops.embedding_grad(g.cuda(), idx.to(idx_dtype).cuda(), off.cuda(), rows, padding_idx=pad).cpu().double()
+    assert (got_p - want_p).abs().max() <= 1e-4 * want.abs().max()
+    assert not got_p[pad].any()
+    # no offsets (SingleIndexEmbedding), empty batch
+    got1 = ops.embedding_grad(g[:, :1].contiguous().cuda(), idx[:, :1].contiguous().to(idx_dtype).cuda(), None, rows)
+    want1 = torch.zeros(rows, e, dtype=torch.float64).index_add_(0, idx[:, 0], g[:, 0].double())
+    assert (got1.cpu().double() - want1).abs().max() <= 1e-4 * want1.abs().max()
+    assert not ops.embedding_grad(g[:0].cuda(), idx[:0].to(idx_dtype).cuda(), off.cuda(), rows).any()
+
+
+@pytest.mark.parametrize('b,n,e', [(1, 39, 16), (777, 5, 40), (64, 12, 8), (300, 4, 128)])
+def test_fm_backward_kernel(b, n, e):
+    from torecsys_b200 import ops
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(b, n, e, generator=gen, dtype=torch.float64, requires_grad=True)
+    g = torch.randn(b, e, generator=gen, dtype=torch.float64)
+    (0.5 * (x.sum(1) ** 2 - (x ** 2).sum(1)) * g).sum().backward()
+    got = ops.fm_backward(x.detach().float().cuda(), g.float().cuda()).cpu().double()
+    assert (got - x.grad).abs().max() <= 1e-5 * x.grad.abs().max()

@@ -208,6 +208,36 @@ def main():
         del w16, w1, x, ring
         torch.cuda.empty_cache()
 
+    # ---------------------------------------------------------------- cfg 2, layout C: Criteo-shaped fields, Zipf
+    if want('deepfm_layout_c'):
+        import numpy as np
+        kaggle = [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 8351593, 3194, 27, 14992,
+                  5461306, 10, 5652, 2173, 4, 7046547, 18, 15, 286181, 105, 142572]   # Criteo-Kaggle C1..C26
+        total = 200_000_000 - 13 * 112
+        scale = total / sum(kaggle)
+        fs = [112] * 13 + [max(16, int(round(c * scale / 16)) * 16) for c in kaggle]
+        rows_c = sum(fs)
+        off_c = torch.from_numpy(np.concatenate([[0], np.cumsum(fs)[:-1]]).astype(np.float32).astype(np.int64)).to(dev)
+        w16 = torch.randn(rows_c, 16, device=dev)
+        w1 = torch.randn(rows_c, 1, device=dev)
+        packed = ops.fm_pack_table(w16, w1)
+        pack = mlp_pack([N * 16, 16, 16, 16, 1], dev)
+        gen = np.random.default_rng(1234)
+        ring_c = []
+        for _ in range(8):
+            cols = []
+            for f in fs:   # Zipf(1.05) within the field, folded into [0, f)
+                cols.append((gen.zipf(1.05, B) - 1) % f)
+            ring_c.append(torch.from_numpy(np.stack(cols, 1).astype(np.int64)).to(dev))
+        t = timeit(lambda i: ops.deepfm_packed(ring_c[i % 8], off_c, packed, pack, overlap_previous=True), reps=100)
+        report('deepfm fused, packed table, layout C (Criteo-shaped field sizes, Zipf(1.05) indices)', B, t, 2968,
+               note=f'{rows_c} rows; hot rows stay in L2, so this exceeds the uniform-index number')
+        ring_u = [torch.stack([torch.randint(0, f, (B,), device=dev) for f in fs], 1) for _ in range(8)]
+        t = timeit(lambda i: ops.deepfm_packed(ring_u[i % 8], off_c, packed, pack, overlap_previous=True), reps=100)
+        report('deepfm fused, packed table, layout C field sizes, uniform indices', B, t, 2968)
+        del w16, w1, packed, ring_c, ring_u
+        torch.cuda.empty_cache()
+
     # ---------------------------------------------------------------- E = 32 (cfg 3: DCN)
     if any(want(x) for x in ('dcn', 'cross_layer')):
         B3 = 131072

@@ -46,12 +46,9 @@ class GatherFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         idx, offsets = ctx.saved_tensors
-        rows = idx.long() + (offsets.view(1, -1) if offsets.numel() else 0)
-        flat = rows.reshape(-1)
-        g = grad.reshape(flat.numel(), -1)
-        if ctx.padding_idx is not None:
-            g = g * (flat != ctx.padding_idx).unsqueeze(1)
-        dw = torch.zeros((ctx.rows, g.shape[1]), dtype=g.dtype, device=g.device).index_add_(0, flat, g)
+        # dense nn.Embedding gradient by the scatter-add kernel (trs_embedding_grad, csrc/backward.cu)
+        dw = ops.embedding_grad(grad.contiguous(), idx, offsets if offsets.numel() else None, ctx.rows,
+                                ctx.padding_idx)
         return dw, None, None, None
 
 
@@ -68,10 +65,7 @@ class GatherFieldAwareFn(torch.autograd.Function):
         b, n = idx.shape
         flat = (idx.long() + offsets.view(1, -1)).reshape(-1)
         g = grad.reshape(b, n, n, -1)                      # (B, table t, field f, E)
-        grads = []
-        for t in range(n):
-            gt = g[:, t].reshape(b * n, -1)
-            grads.append(torch.zeros((ctx.rows, gt.shape[1]), dtype=gt.dtype, device=gt.device).index_add_(0, flat, gt))
+        grads = [ops.embedding_grad(g[:, t].contiguous(), idx, offsets, ctx.rows) for t in range(n)]
         return (None, None, None) + tuple(grads)
 
 
@@ -136,7 +130,7 @@ class FmFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         (x,) = ctx.saved_tensors
-        return grad.unsqueeze(1) * (x.sum(1, keepdim=True) - x)     # closed form of d/dx 0.5((sum x)^2 - sum x^2)
+        return ops.fm_backward(x, grad.contiguous())   # grad * (sum_n x - x): closed form of d/dx 0.5((sum x)^2 - sum x^2)
 
 
 class FfmFn(torch.autograd.Function):

@@ -190,6 +190,36 @@ def fm(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def embedding_grad(grad_out: torch.Tensor, idx: torch.Tensor, offsets: Optional[torch.Tensor], rows: int,
+                   padding_idx: Optional[int] = None) -> torch.Tensor:
+    """Dense weight gradient of the embedding lookup: zeros(rows, E) with grad_out (B, N, E) scatter-added at
+    idx + offsets (trs_embedding_grad)."""
+    _need_cuda('embedding_grad', grad_out, idx, offsets)
+    g = _f32('embedding_grad', grad_out)
+    ix = idx if idx.is_contiguous() else idx.contiguous()
+    if ix.dtype not in (torch.int64, torch.int32):
+        ix = ix.long()
+    if ix.dim() == 1:
+        ix = ix.unsqueeze(-1)
+    b, n = ix.shape
+    e = g.numel() // max(b * n, 1) if b * n else (g.shape[-1] if g.dim() else 1)
+    dw = torch.zeros((rows, e), dtype=torch.float32, device=g.device)
+    off = offsets.reshape(-1).contiguous() if offsets is not None and offsets.numel() else None
+    check(_cabi.load().trs_embedding_grad(_ptr(g), _ptr(ix), 64 if ix.dtype == torch.int64 else 32,
+                                          _ptr(off) if off is not None else None, b, n, rows, e,
+                                          -1 if padding_idx is None else int(padding_idx), _ptr(dw), _stream()),
+          'trs_embedding_grad')
+    return dw
+
+
+def fm_backward(x: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    x, b, n, e = _bne('fm_backward', x)
+    g = _f32('fm_backward', grad_out)
+    out = torch.empty_like(x)
+    check(_cabi.load().trs_fm_backward(_ptr(x), _ptr(g), b, n, e, _ptr(out), _stream()), 'trs_fm_backward')
+    return out
+
+
 def ffm(v: torch.Tensor, num_fields: int) -> torch.Tensor:
     v, b, nn_, e = _bne('ffm', v)
     if nn_ != num_fields * num_fields:
