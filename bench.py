@@ -234,6 +234,27 @@ def run_ours(args):
     ms_per_step = ms_total / args.steps
     value = world * batch * args.steps / (ms_total * 1e-3)
 
+    # ---- the same K steps replayed from ONE CUDA graph (launch overhead off the critical path) --------
+    graph_ms = None
+    if packed is not None and world == 1:
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for i in range(RING):
+                    step(i)
+            g.replay()
+            torch.cuda.synchronize()
+            reps = max(1, args.steps // RING)
+            ev0.record()
+            for _ in range(reps):
+                g.replay()
+            ev1.record()
+            torch.cuda.synchronize()
+            graph_ms = ev0.elapsed_time(ev1) / (reps * RING)
+            ops.check_index_errors()
+        except RuntimeError as e:   # reported, never fatal for the bench line
+            graph_ms = f'capture failed: {e}'
+
     # ---- e2e: host buffers through the C-ABI session entry points --------------------------------------------------
     # Every step: pinned host int64 indices -> H2D -> kernel -> D2H logits -> one logit read on the host.  The
     # pipelined number keeps `depth` batches in flight (trs_session_submit_* / trs_session_wait), the way a serving
@@ -336,6 +357,9 @@ def run_ours(args):
                                   '(TRS_LAUNCH_OVERLAP_PREVIOUS)') if (packed is not None and args.overlap)
                                  else 'back-to-back fully ordered launches'},
             'roofline': roof, 'cpu_baseline': cpu,
+            'graph_replay': ({'ms_per_step': graph_ms, 'value': batch / (graph_ms * 1e-3),
+                              'note': f'{RING} launches captured in one CUDA graph and replayed'}
+                             if isinstance(graph_ms, float) else graph_ms),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': batch * NUM_FIELDS * 8,
                     'd2h_bytes_per_step': batch * 4, 'steps': e2e_steps, 'chunks': 1, 'sync_call_chunks': args.e2e_chunks,
                     'mode': f'pipelined, {depth} batches in flight (trs_session_submit_deepfm_packed / '

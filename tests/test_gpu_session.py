@@ -177,3 +177,41 @@ def test_session_host_narrowing_is_transparent(setup, threads):
         assert torch.equal(out, s['ops'].deepfm_packed(base.cuda(), s['off_d'], s['packed'], s['pack']).cpu())
     finally:
         sess.close()
+
+
+def test_fused_forward_is_cuda_graph_capturable(setup):
+    """The C-ABI entry points never synchronise or allocate on the fast path: the fused DeepFM forward (ordered and
+    with TRS_LAUNCH_OVERLAP_PREVIOUS), the gather and the FM layer are captured into ONE CUDA graph and replayed on
+    new index contents."""
+    s = setup
+    ops = s['ops']
+    batch = 5000
+    idx_a = _idx(s, batch, 'graph_a').cuda()
+    idx_b = _idx(s, batch, 'graph_b').cuda()
+    static_idx = idx_a.clone()
+    out1 = torch.empty(batch, 1, device='cuda')
+    out2 = torch.empty(batch, 1, device='cuda')
+    ops.set_index_check('deferred')
+    try:
+        # warm-up outside the capture (first-call attribute opt-ins)
+        ops.deepfm_packed(static_idx, s['off_d'], s['packed'], s['pack'], out=out1)
+        ops.deepfm_packed(static_idx, s['off_d'], s['packed'], s['pack'], out=out2, overlap_previous=True)
+        x_w = ops.embedding_gather(s['w_emb_d'], static_idx, s['off_d'])
+        fm_w = ops.fm(x_w)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ops.deepfm_packed(static_idx, s['off_d'], s['packed'], s['pack'], out=out1)
+            ops.deepfm_packed(static_idx, s['off_d'], s['packed'], s['pack'], out=out2, overlap_previous=True)
+            x_g = ops.embedding_gather(s['w_emb_d'], static_idx, s['off_d'])
+            fm_g = ops.fm(x_g)
+        for src in (idx_b, idx_a, idx_b):
+            static_idx.copy_(src)
+            graph.replay()
+            torch.cuda.synchronize()
+            want = ops.deepfm_packed(src, s['off_d'], s['packed'], s['pack'])
+            assert torch.equal(out1, want) and torch.equal(out2, want)
+            assert torch.equal(fm_g, ops.fm(ops.embedding_gather(s['w_emb_d'], src, s['off_d'])))
+        ops.check_index_errors()
+    finally:
+        ops.set_index_check('sync')
