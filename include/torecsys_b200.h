@@ -266,6 +266,29 @@ int trs_ffm_model_forward(const void* idx, int idx_bits, const int64_t* offsets,
                           const float* w_feat, const float* const* tables, int64_t rows, int embed,
                           const float* bias, float* logits, int32_t* status, void* stream);
 
+/* ---- 8f-3: fused indices -> logits forwards of three more models (Sequential.forward = Inputs.forward + model) --------
+ * Arguments as in trs_deepfm_forward; the MLP (HOST arrays of DEVICE pointers) must end in ONE output.
+ *   trs_nfm_forward        NeuralFactorizationMachineModel.forward (neural_factorization_machine.py:66-96):
+ *                          logit = MLP(FM(emb)) + sum_n w_feat[r_n] (+ bias[0]);              MLP in = embed
+ *   trs_fnn_forward        FactorizationMachineSupportedNeuralNetworkModel.forward
+ *                          (factorization_machine_supported_neural_network.py:61-101):
+ *                          logit = MLP(cat[w_feat[r_0..r_{N-1}], FM(emb)]);   `bias` ignored;   MLP in = fields + embed
+ *   trs_pnn_inner_forward  ProductNeuralNetworkModel.forward with prod_method='inner' (product_neural_network.py:81-115):
+ *                          logit = MLP(cat[IPN(emb), w_feat[r_0..r_{N-1}], bias[0]]);         MLP in = NC2 + fields + 1
+ *                          (bias == NULL feeds 0 in that slot) */
+int trs_nfm_forward(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                    const float* w_feat, const float* w_emb, int64_t rows, int embed,
+                    const int* mlp_dims, int mlp_layers, const float* const* mlp_w, const float* const* mlp_b,
+                    int activation, const float* bias, float* logits, int32_t* status, void* stream);
+int trs_fnn_forward(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                    const float* w_feat, const float* w_emb, int64_t rows, int embed,
+                    const int* mlp_dims, int mlp_layers, const float* const* mlp_w, const float* const* mlp_b,
+                    int activation, const float* bias, float* logits, int32_t* status, void* stream);
+int trs_pnn_inner_forward(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                          const float* w_feat, const float* w_emb, int64_t rows, int embed,
+                          const int* mlp_dims, int mlp_layers, const float* const* mlp_w, const float* const* mlp_b,
+                          int activation, const float* bias, float* logits, int32_t* status, void* stream);
+
 /* ---- host-buffer entry points (the e2e path: pageable/pinned host indices in, host logits out) ----------------------
  * This is the step BEFORE the hot path in the reference: the DataLoader's collate function hands Sequential.forward a
  * host (B, N) int64 tensor (torecsys/data/dataloader/collate_fn.py:82, torecsys/models/sequential.py:31-44) and the

@@ -272,3 +272,30 @@ def test_cross_layer_on_tcgen05(trs, e, layers, rows):
     assert got.shape == want.shape
     assert normwise_err(got, want) <= TOL
     assert normwise_err(got, want64) <= max(4 * normwise_err(want, want64), 2e-6)
+
+
+@pytest.mark.parametrize('kind', ['nfm_model', 'fnn_model', 'pnn_inner_model'])
+@pytest.mark.parametrize('b,n,e', GRID + [(777, 39, 16), (130, 7, 12)])
+@pytest.mark.parametrize('idx_dtype', [torch.int64, torch.int32])
+def test_fused_feature_models(trs, kind, b, n, e, idx_dtype):
+    """csrc/fused_more.cu: NFM / FNN / inner-product PNN as ONE kernel indices -> logits, against the oracle, and
+    Sequential picks it (eval, no grad) and agrees with its own per-layer route."""
+    from oracle.restated import field_offsets
+    seq, c = build_sequential(trs, kind, b, n, e)
+    assert seq.uses_fused_kernel() is False      # grad mode: per-layer route
+    idx = _dev(c['inputs']['idx']).to(idx_dtype)
+    with torch.no_grad():
+        assert seq.uses_fused_kernel() is True
+        fused = seq({'idx': idx}).cpu().numpy()
+        embedded = seq._inputs({'idx': idx})
+        layered = seq._model(**embedded).cpu().numpy()
+    want = oracle_model(kind, b, n, e, torch.float32)['out'].numpy()
+    want64 = oracle_model(kind, b, n, e, torch.float64)['out'].numpy()
+    assert fused.shape == (b, 1)
+    assert normwise_err(fused, want) <= TOL
+    assert normwise_err(fused, layered) <= TOL
+    assert normwise_err(fused, want64) <= max(4 * normwise_err(want, want64), 5e-6)
+    bad = idx.clone()
+    bad[b - 1, n - 1] = 10 ** 6
+    with torch.no_grad(), pytest.raises(IndexError):
+        seq({'idx': bad})

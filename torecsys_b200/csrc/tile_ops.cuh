@@ -98,6 +98,35 @@ __device__ __forceinline__ void dense_layer_tile(const float* in, int in_pitch, 
   const int groups = (o_dim + 3) >> 2;
   const int items = ts * groups;
   const bool vec = ((k_dim & 3) == 0) && ((reinterpret_cast<uintptr_t>(w) & 15u) == 0);
+  if (items * 2 <= static_cast<int>(blockDim.x) && k_dim >= 64) {
+    // few rows x few outputs but a long K (e.g. 16 samples x 16 outputs x K = 781 of the fused PNN): with 4 outputs
+    // per thread most of the CTA would idle, so every (row, output) pair gets its own thread
+    const int singles = ts * o_dim;
+    for (int item = threadIdx.x; item < singles; item += blockDim.x) {
+      const int o = item / ts;
+      const int s = item - o * ts;
+      const float* xr = in + s * in_pitch;
+      const float* wr = w + (int64_t)o * k_dim;
+      float acc0 = 0.f, acc1 = 0.f;
+      if (vec) {
+        for (int k = 0; k < k_dim; k += 4) {
+          const float4 xv = *reinterpret_cast<const float4*>(xr + k);
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + k));
+          acc0 = fmaf(xv.x, wv.x, acc0); acc1 = fmaf(xv.y, wv.y, acc1);
+          acc0 = fmaf(xv.z, wv.z, acc0); acc1 = fmaf(xv.w, wv.w, acc1);
+        }
+      } else {
+        int k = 0;
+        for (; k + 1 < k_dim; k += 2) {
+          acc0 = fmaf(xr[k], __ldg(wr + k), acc0);
+          acc1 = fmaf(xr[k + 1], __ldg(wr + k + 1), acc1);
+        }
+        if (k < k_dim) acc0 = fmaf(xr[k], __ldg(wr + k), acc0);
+      }
+      epi(s, o, acc0 + acc1 + (bias ? __ldg(bias + o) : 0.f));
+    }
+    return;
+  }
   for (int item = threadIdx.x; item < items; item += blockDim.x) {
     const int og = item / ts;
     const int s = item - og * ts;

@@ -6,17 +6,34 @@ Reference: torecsys/models/ctr/{product_neural_network, feature_importance_and_b
 attentional_factorization_machine, neural_factorization_machine, factorization_machine_supported_neural_network,
 deep_ffm, fat_deep_ffm}.py.  Every interaction layer and every MLP runs one of the sm_100a kernels (layers.py); what
 stays in torch is the reference's own named-tensor glue on the small per-sample vectors (cat / sum / add), exactly
-as in the L1 path of models.py.  These models take the L1 route inside Sequential (no fused indices -> logits kernel
-yet): lookup kernels, then the layer kernels.
+as in the L1 path of models.py.  NFM, FNN and inner-product PNN also have a fused indices -> logits kernel
+(csrc/fused_more.cu) that Sequential picks for the canonical Inputs schema in eval / no-grad mode; the others take
+the L1 route: lookup kernels, then the layer kernels.
 """
 from typing import List, Optional
 
 import torch
 import torch.nn as nn
 
+from . import ops
+from .inputs import MultiIndicesEmbedding
 from .layers import (AFMLayer, BilinearInteractionLayer, CENLayer, DNNLayer, FFMLayer, FMLayer,
                      InnerProductNetworkLayer, OuterProductNetworkLayer, SENETLayer, _combination)
-from .models import CtrBaseModel
+from .models import CtrBaseModel, _canonical, _index_batch, _same_lookup
+
+
+def _feat_emb_pair(inputs_module) -> bool:
+    """The canonical schema {feat_inputs: MultiIndicesEmbedding(1, fs), emb_inputs: MultiIndicesEmbedding(E, fs)} on the
+    same batch columns -- what the fused indices -> logits kernels read."""
+    return (_canonical(inputs_module, ['feat_inputs', 'emb_inputs'], [MultiIndicesEmbedding] * 2)
+            and inputs_module.schema['feat_inputs'].embed_size == 1
+            and _same_lookup(inputs_module, 'feat_inputs', 'emb_inputs'))
+
+
+def _fused_args(inputs_module, batch):
+    feat, emb = inputs_module.schema['feat_inputs'], inputs_module.schema['emb_inputs']
+    w = emb.embedding.weight
+    return _index_batch(inputs_module, 'emb_inputs', batch), emb._offsets_on(w.device), feat.embedding.weight, w
 
 
 class ProductNeuralNetworkModel(CtrBaseModel):
@@ -57,6 +74,20 @@ class ProductNeuralNetworkModel(CtrBaseModel):
         outputs = torch.cat(pnn_outputs, dim='O')
         outputs = self.deep(outputs)
         return outputs.rename(None)
+
+    def can_fuse(self, inputs_module) -> bool:
+        """One kernel indices -> logits (trs_pnn_inner_forward) for the inner-product variant with one output."""
+        lin = self.deep.linears()
+        return (isinstance(self.pnn, InnerProductNetworkLayer) and lin[-1].out_features == 1
+                and _feat_emb_pair(inputs_module)
+                and not (self.training and any(isinstance(m, nn.Dropout) and m.p > 0 for m in self.deep.model)))
+
+    def fused_forward(self, inputs_module, batch) -> torch.Tensor:
+        idx, off, w_feat, w_emb = _fused_args(inputs_module, batch)
+        bias = self.bias.rename(None) if self.use_bias else None
+        if not self.use_bias:
+            raise NotImplementedError('fused PNN needs use_bias=True (the MLP input has the bias column)')
+        return ops.pnn_inner(idx, off, w_feat, w_emb, self.deep.mlp_pack(), bias)
 
 
 class FeatureImportanceAndBilinearFeatureInteractionNetwork(CtrBaseModel):
@@ -136,6 +167,17 @@ class NeuralFactorizationMachineModel(CtrBaseModel):
             outputs += self.bias
         return outputs.rename(None)
 
+    def can_fuse(self, inputs_module) -> bool:
+        """One kernel indices -> logits (trs_nfm_forward)."""
+        fm, deep = self.sequential.B_interaction, self.sequential.Deep
+        return (_feat_emb_pair(inputs_module) and not (self.training and (fm.dropout.p > 0 or any(
+            isinstance(m, nn.Dropout) and m.p > 0 for m in deep.model))))
+
+    def fused_forward(self, inputs_module, batch) -> torch.Tensor:
+        idx, off, w_feat, w_emb = _fused_args(inputs_module, batch)
+        bias = self.bias.rename(None) if self.use_bias else None
+        return ops.nfm(idx, off, w_feat, w_emb, self.sequential.Deep.mlp_pack(), bias)
+
 
 class FactorizationMachineSupportedNeuralNetworkModel(CtrBaseModel):
     """factorization_machine_supported_neural_network.py:10-101: MLP(cat[feat (B,N), FM(emb) (B,E)])."""
@@ -161,6 +203,16 @@ class FactorizationMachineSupportedNeuralNetworkModel(CtrBaseModel):
         fm_out = torch.cat([fm_first, fm_second], dim='O')
         outputs = self.deep(fm_out)
         return outputs.rename(None)
+
+    def can_fuse(self, inputs_module) -> bool:
+        """One kernel indices -> logits (trs_fnn_forward) when the MLP has one output."""
+        return (self.deep.linears()[-1].out_features == 1 and _feat_emb_pair(inputs_module)
+                and not (self.training and (self.fm.dropout.p > 0 or any(
+                    isinstance(m, nn.Dropout) and m.p > 0 for m in self.deep.model))))
+
+    def fused_forward(self, inputs_module, batch) -> torch.Tensor:
+        idx, off, w_feat, w_emb = _fused_args(inputs_module, batch)
+        return ops.fnn(idx, off, w_feat, w_emb, self.deep.mlp_pack())
 
 
 class DeepFieldAwareFactorizationMachineModel(CtrBaseModel):

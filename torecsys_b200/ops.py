@@ -419,6 +419,36 @@ def deepfm(idx, offsets, w_feat, w_emb, pack: MlpPack, out: Optional[torch.Tenso
     return out
 
 
+def _feature_model(name, idx, offsets, w_feat, w_emb, pack: MlpPack, bias, out):
+    ix, bits, off = _fused_common(name, idx, offsets, w_feat, w_emb, bias)
+    wf, we = _f32(name, w_feat), _f32(name, w_emb)
+    bs = _f32(name, bias).reshape(-1) if bias is not None else None
+    b, n = ix.shape
+    out = out if out is not None else torch.empty((b, 1), dtype=torch.float32, device=we.device)
+    st = _status_tensor(we.device)
+    fn = getattr(_cabi.load(), f'trs_{name}_forward')
+    check(fn(_ptr(ix), bits, _ptr(off), b, n, _ptr(wf), _ptr(we), we.shape[0], we.shape[1], pack.dims, pack.layers,
+             pack.w, pack.b, pack.act, _ptr(bs) if bs is not None else None, _ptr(out), _ptr(st), _stream()),
+          f'trs_{name}_forward')
+    _after_lookup(we.device)
+    return out
+
+
+def nfm(idx, offsets, w_feat, w_emb, pack: MlpPack, bias=None, out: Optional[torch.Tensor] = None):
+    """Fused NFM forward: logit = MLP(FM(emb)) + sum_n feat (+ bias)."""
+    return _feature_model('nfm', idx, offsets, w_feat, w_emb, pack, bias, out)
+
+
+def fnn(idx, offsets, w_feat, w_emb, pack: MlpPack, out: Optional[torch.Tensor] = None):
+    """Fused FNN forward: logit = MLP(cat[feat, FM(emb)])."""
+    return _feature_model('fnn', idx, offsets, w_feat, w_emb, pack, None, out)
+
+
+def pnn_inner(idx, offsets, w_feat, w_emb, pack: MlpPack, bias=None, out: Optional[torch.Tensor] = None):
+    """Fused PNN (inner product) forward: logit = MLP(cat[IPN(emb), feat, bias])."""
+    return _feature_model('pnn_inner', idx, offsets, w_feat, w_emb, pack, bias, out)
+
+
 def fm_pack_table(w_emb: torch.Tensor, w_feat: torch.Tensor) -> torch.Tensor:
     """Builds the 128-byte-row shadow table [v(16) | w | pad] (trs_fm_pack_table); (R, 32) fp32."""
     _need_cuda('fm_pack_table', w_emb, w_feat)
