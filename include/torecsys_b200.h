@@ -58,6 +58,14 @@ int trs_embedding_gather(const float* weight, int64_t rows, int embed,
                          const void* idx, int idx_bits, const int64_t* offsets,
                          int64_t batch, int fields, float* out, int32_t* status, void* stream);
 
+/* ---- a4: index-column concatenation --------------------------------------------------------------------------------
+ * Replaces the `torch.cat(inputs, dim=1)` of Inputs.forward (torecsys/inputs/inputs.py:76-81): the batch dict holds one
+ * (batch,) or (batch, w) index tensor per feature; the embedding's (batch, N) index matrix is their concatenation.
+ *     out[b, off_c + j] = columns[c][b * widths[c] + j]            off_c = widths[0] + ... + widths[c-1]
+ * columns / widths: HOST arrays of length ncols (DEVICE pointers / elements per row); all columns int64 or all int32. */
+int trs_index_concat(const void* const* columns, const int* widths, int ncols, int idx_bits, int64_t batch,
+                     void* out, void* stream);
+
 /* ---- a3: field-aware gather -----------------------------------------------------------------------------------
  * Replaces MultiIndicesFieldAwareEmbedding.forward (torecsys/inputs/base/multi_indices_field_aware_emb.py:90-111):
  *     out[b, t*N + f, :] = tables[t][idx[b, f] + offsets[f], :]   for t, f in [0, N)

@@ -215,3 +215,43 @@ def test_fused_forward_is_cuda_graph_capturable(setup):
         ops.check_index_errors()
     finally:
         ops.set_index_check('sync')
+
+
+@pytest.mark.parametrize('idx_dtype', [torch.int64, torch.int32])
+def test_index_column_concatenation_kernel(setup, idx_dtype):
+    """trs_index_concat = the torch.cat(columns, dim=1) of Inputs.forward (inputs/inputs.py:76-81): bit-exact, ragged
+    batches, mixed column widths; and the 39-columns-per-feature batch dict gives the same logits as one (B, 39)
+    tensor through Inputs / Sequential."""
+    import torecsys_b200 as trs
+    s = setup
+    ops = s['ops']
+    gen = torch.Generator().manual_seed(3)
+    for batch in (1, 63, 64, 65, 5000):
+        widths = [1, 3, 1, 1, 7, 2, 1, 40, 1]
+        cols = [torch.randint(0, 1000, (batch, w) if k % 2 else ((batch,) if w == 1 else (batch, w)), generator=gen)
+                .to(idx_dtype).cuda() for k, w in enumerate(widths)]
+        want = torch.cat([c.unsqueeze(-1) if c.dim() == 1 else c for c in cols], dim=1)
+        assert torch.equal(ops.index_concat(cols), want)
+    with pytest.raises(ValueError):
+        ops.index_concat([cols[0], cols[1].to(torch.int32 if idx_dtype == torch.int64 else torch.int64)])
+    # the per-feature batch dict of a DataLoader through the drop-in modules
+    n, fs = s['n'], s['fs']
+    feat, emb = trs.MultiIndicesEmbedding(1, fs), trs.MultiIndicesEmbedding(16, fs)
+    names = [f'C{k}' for k in range(n)]
+    feat.set_schema(names)
+    emb.set_schema(names)
+    model = trs.DeepFactorizationMachineModel(16, n, [16, 16, 16], fm_dropout_p=0.0)
+    seq = trs.Sequential(trs.Inputs({'feat_inputs': feat, 'emb_inputs': emb}), model).cuda().eval()
+    idx = _idx(s, 3000, 'cols').to(idx_dtype).cuda()
+    batch_dict = {name: idx[:, k].contiguous() for k, name in enumerate(names)}
+    feat1, emb1 = trs.MultiIndicesEmbedding(1, fs), trs.MultiIndicesEmbedding(16, fs)
+    feat1.set_schema(['idx'])
+    emb1.set_schema(['idx'])
+    feat1.load_state_dict(feat.state_dict())
+    emb1.load_state_dict(emb.state_dict())
+    seq1 = trs.Sequential(trs.Inputs({'feat_inputs': feat1, 'emb_inputs': emb1}), model).cuda().eval()
+    with torch.no_grad():
+        assert seq.uses_fused_kernel() and seq1.uses_fused_kernel()
+        assert torch.equal(seq(batch_dict), seq1({'idx': idx}))
+        embedded = seq._inputs(batch_dict)
+        assert torch.equal(embedded['emb_inputs'].rename(None), seq1._inputs({'idx': idx})['emb_inputs'].rename(None))

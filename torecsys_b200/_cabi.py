@@ -32,6 +32,7 @@ PROTOTYPES = {
     'trs_device_arch': (c_int, []),
     'trs_embedding_gather': (c_int, [_P, c_int64, c_int, _P, c_int, _P, c_int64, c_int, _P, _P, _P]),
     'trs_embedding_gather_field_aware': (c_int, [_P, c_int64, c_int, _P, c_int, _P, c_int64, c_int, _P, _P, _P]),
+    'trs_index_concat': (c_int, [_PP, _IP, c_int, c_int, c_int64, _P, _P]),
     'trs_fm_forward': (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     'trs_embedding_grad': (c_int, [_P, _P, c_int, _P, c_int64, c_int, c_int64, c_int, c_int64, _P, _P]),
     'trs_fm_backward': (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P]),

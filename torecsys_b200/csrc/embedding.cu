@@ -225,3 +225,77 @@ extern "C" int trs_embedding_gather_field_aware(const float* const* tables, int6
   }
   return TRS_OK;
 }
+
+// ---- a4: the column concatenation of Inputs.forward (torecsys/inputs/inputs.py:76-81) -----------------------------------
+// The DataLoader hands the model one (B,) or (B, w) index tensor per feature field; Inputs.forward concatenates the
+// columns an embedding asked for into its (B, N) index matrix (39 tensors for the Criteo shape).  One kernel: a CTA
+// transposes a tile of rows through shared memory, so every column is read and the matrix is written with full
+// coalesced requests.
+namespace trs {
+namespace {
+
+constexpr int kMaxConcatCols = 128;
+
+struct ConcatArgs {
+  const void* col[kMaxConcatCols];
+  int width[kMaxConcatCols];
+  int off[kMaxConcatCols];
+  int ncols, total, tile_rows;
+  int64_t batch;
+  void* out;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) index_concat_kernel(ConcatArgs a) {
+  extern __shared__ __align__(16) unsigned char concat_smem[];
+  T* tile = reinterpret_cast<T*>(concat_smem);
+  T* out = static_cast<T*>(a.out);
+  for (int64_t b0 = (int64_t)blockIdx.x * a.tile_rows; b0 < a.batch; b0 += (int64_t)gridDim.x * a.tile_rows) {
+    const int nb = static_cast<int>(a.batch - b0 < a.tile_rows ? a.batch - b0 : a.tile_rows);
+    for (int c = 0; c < a.ncols; ++c) {
+      const int w = a.width[c];
+      const T* src = static_cast<const T*>(a.col[c]) + b0 * w;
+      for (int t = threadIdx.x; t < nb * w; t += blockDim.x) {
+        const int r = t / w, j = t - r * w;
+        tile[r * a.total + a.off[c] + j] = src[t];
+      }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nb * a.total; t += blockDim.x) out[b0 * a.total + t] = tile[t];
+    __syncthreads();
+  }
+}
+
+}  // namespace
+}  // namespace trs
+
+extern "C" int trs_index_concat(const void* const* columns, const int* widths, int ncols, int idx_bits, int64_t batch,
+                                void* out, void* stream) {
+  TRS_REQUIRE(columns && widths && out, "trs_index_concat: null pointer");
+  TRS_REQUIRE(idx_bits == 32 || idx_bits == 64, "trs_index_concat: idx_bits must be 32 or 64");
+  TRS_REQUIRE(batch >= 0 && ncols > 0, "trs_index_concat: bad sizes");
+  TRS_UNSUPPORTED(ncols > kMaxConcatCols, "trs_index_concat: at most %d columns per call", kMaxConcatCols);
+  ConcatArgs a{};
+  int total = 0;
+  for (int c = 0; c < ncols; ++c) {
+    TRS_REQUIRE(columns[c] && widths[c] > 0, "trs_index_concat: bad column %d", c);
+    a.col[c] = columns[c];
+    a.width[c] = widths[c];
+    a.off[c] = total;
+    total += widths[c];
+  }
+  if (batch == 0) return TRS_OK;
+  const int esz = idx_bits / 8;
+  int tile_rows = 64;
+  while (tile_rows > 1 && (size_t)tile_rows * total * esz > 48 * 1024) tile_rows >>= 1;
+  TRS_UNSUPPORTED((size_t)tile_rows * total * esz > 48 * 1024, "trs_index_concat: %d index columns per row is too wide",
+                  total);
+  a.ncols = ncols; a.total = total; a.tile_rows = tile_rows; a.batch = batch; a.out = out;
+  const int64_t tiles = (batch + tile_rows - 1) / tile_rows;
+  const int grid = static_cast<int>(tiles < kNumSMs * 8 ? tiles : kNumSMs * 8);
+  const size_t smem = (size_t)tile_rows * total * esz;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (idx_bits == 64) index_concat_kernel<long long><<<grid, 256, smem, s>>>(a);
+  else index_concat_kernel<int><<<grid, 256, smem, s>>>(a);
+  return check_launch("index_concat_kernel");
+}

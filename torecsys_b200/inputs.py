@@ -169,6 +169,21 @@ def _as_column(v: torch.Tensor) -> torch.Tensor:
     return v.unsqueeze(-1) if v.dim() == 1 else v
 
 
+def concat_columns(columns) -> torch.Tensor:
+    """torch.cat(columns, dim=1) of inputs/inputs.py:81.  Index columns on the GPU (the hot path: one tensor per feature
+    field from the DataLoader) go through the concatenation kernel; anything else (float features of non-embedding
+    inputs, CPU tensors that the embedding will reject anyway) keeps the reference's own call."""
+    if len(columns) == 1:
+        return columns[0]
+    first = columns[0]
+    if (first.is_cuda and first.dtype in (torch.int64, torch.int32) and len(columns) <= 128
+            and all(c.is_cuda and c.dtype == first.dtype and c.device == first.device and c.dim() == 2
+                    and c.shape[0] == first.shape[0] and not c.requires_grad for c in columns)
+            and all(n is None for c in columns for n in c.names)):
+        return ops.index_concat(columns)
+    return torch.cat(columns, dim=1)
+
+
 class Inputs(BaseInput):
     """Dict-of-modules router of torecsys/inputs/inputs.py:9-132: for every schema entry, collect the batch columns the
     entry's module asked for (`module.schema.inputs`), concatenate them on dim 1 and call the module; returns a dict
@@ -188,7 +203,7 @@ class Inputs(BaseInput):
         if kind in _DICT_FED:
             return [{name: batch[name] for name in wanted}]
         columns = [_as_column(batch[name]) for name in wanted]
-        args = [columns[0] if len(columns) == 1 else torch.cat(columns, dim=1)]
+        args = [concat_columns(columns)]
         if kind in _LENGTH_FED:
             args.append(batch[module.schema.lengths])
         return args

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .inputs import Inputs, MultiIndicesEmbedding, MultiIndicesFieldAwareEmbedding
+from .inputs import Inputs, MultiIndicesEmbedding, MultiIndicesFieldAwareEmbedding, concat_columns
 from .layers import CINLayer, CrossNetworkLayer, DNNLayer, FFMLayer, FMLayer
 
 
@@ -39,7 +39,7 @@ def _index_batch(inputs_module: Inputs, key: str, batch: Dict[str, torch.Tensor]
     for name in emb.schema.inputs:
         v = batch[name]
         cols.append(v.unsqueeze(-1) if v.dim() == 1 else v)
-    return cols[0] if len(cols) == 1 else torch.cat(cols, dim=1)
+    return concat_columns(cols)
 
 
 def _same_lookup(inputs_module: Inputs, key_a: str, key_b: str) -> bool:

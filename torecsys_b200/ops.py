@@ -135,6 +135,24 @@ def embedding_gather(weight: torch.Tensor, idx: torch.Tensor, offsets: Optional[
     return out
 
 
+def index_concat(columns: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Inputs.forward's column concatenation (inputs/inputs.py:76-81): (B,) / (B, w) index tensors -> (B, sum w), by
+    trs_index_concat.  All columns on the same CUDA device with the same integer dtype (int64 or int32)."""
+    cols = [c.unsqueeze(-1) if c.dim() == 1 else c for c in columns]
+    _need_cuda('index_concat', *cols)
+    dt = cols[0].dtype
+    if dt not in (torch.int64, torch.int32) or any(c.dtype != dt or c.dim() != 2 or c.shape[0] != cols[0].shape[0]
+                                                     for c in cols):
+        raise ValueError('index_concat: columns must be (B,) or (B, w) tensors of one integer dtype (int64 / int32)')
+    cols = [c if c.is_contiguous() else c.contiguous() for c in cols]
+    b = cols[0].shape[0]
+    out = torch.empty((b, sum(c.shape[1] for c in cols)), dtype=dt, device=cols[0].device)
+    check(_cabi.load().trs_index_concat(_cabi.ptr_array([_ptr(c) for c in cols]),
+                                        _cabi.int_array([c.shape[1] for c in cols]), len(cols),
+                                        64 if dt == torch.int64 else 32, b, _ptr(out), _stream()), 'trs_index_concat')
+    return out
+
+
 class TablePointers:
     """Device array of table base pointers for the field-aware entry points (rebuilt when a table moves)."""
 
