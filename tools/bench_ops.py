@@ -281,6 +281,25 @@ def main():
             v = ops.embedding_gather_field_aware(tables, small, fs_off, tp)
             t = timeit(lambda i: ops.ffm(v, N), reps=5)
             report('ffm layer (a6)', 4096, t, 2 * PAIRS * 64 + PAIRS * 64)
+        del tables, wf, ring
+        torch.cuda.empty_cache()
+
+    # ---------------------------------------------------------------- cfg 5 at FULL table size on one GPU (64 GB resident)
+    if want('ffm_model_full'):
+        rpf5 = 657_472                 # 39 tables x (39 x 657 472) rows = 1.000 B rows of 64 B
+        rfa = N * rpf5
+        fs_off = (torch.arange(N, dtype=torch.int64) * rpf5).to(dev)
+        tables = [torch.empty(rfa, 16, device=dev).uniform_(-0.1, 0.1) for _ in range(N)]
+        wf = torch.randn(rfa, 1, device=dev)
+        bias = torch.rand(1, device=dev)
+        B5 = 32768
+        ring = [torch.randint(0, rpf5, (B5, N), device=dev) for _ in range(4)]
+        tp = ops.TablePointers()
+        t = timeit(lambda i: ops.ffm_model(ring[i % 4], fs_off, wf, tables, bias, tp), reps=10)
+        report('ffm model fused (a12, cfg5: all 39 tables = 1.0 B rows = 64 GB on ONE GPU, per-GPU batch 32 768)', B5, t,
+               95320, 2 * PAIRS * 16)
+        del tables, wf, ring
+        torch.cuda.empty_cache()
     ops.check_index_errors()
     if args.json:
         with open(args.json, 'w') as f:
