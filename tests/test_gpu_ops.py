@@ -207,7 +207,8 @@ def test_deepfm_packed_table_path(ops, n):
             assert normwise_err(got, want64) <= max(4 * normwise_err(want, want64), 2e-6), (n, batch)
 
 
-def test_deepfm_packed_overlapped_launches(ops):
+@pytest.mark.parametrize('batch', [1, 17, 16 * 148 * 3 + 5])
+def test_deepfm_packed_overlapped_launches(ops, batch):
     """TRS_LAUNCH_OVERLAP_PREVIOUS (programmatic dependent launch): a train of back-to-back launches, each reading
     its own index batch, must give the same logits as ordered launches -- both into separate outputs and into ONE
     reused output buffer (the last launch must win: writes stay ordered behind the previous grid)."""
@@ -225,7 +226,7 @@ def test_deepfm_packed_overlapped_launches(ops):
     bs = [torch.from_numpy(synth.uniform((dims[i + 1],), f'pdl/b{i}', -0.5, 0.5)) for i in range(4)]
     pack = ops.MlpPack([w.cuda() for w in ws], [b.cuda() for b in bs], ops.activation_id('relu'))
     packed = ops.fm_pack_table(w_emb.cuda(), w_feat.cuda())
-    batch, trains = 16 * 148 * 3 + 5, 12
+    trains = 12
     idx = [torch.from_numpy(synth.integers((batch, n), f'pdl/idx{k}', np.asarray(fs)[None, :])).cuda()
            for k in range(trains)]
     ordered = [ops.deepfm_packed(ix, off.cuda(), packed, pack) for ix in idx]
@@ -251,7 +252,7 @@ def test_deepfm_packed_overlapped_launches(ops):
         ops.set_index_check('sync')
     # out-of-range lookups are still reported from an overlapped launch
     bad = idx[0].clone()
-    bad[7, 3] = 10 ** 9
+    bad[min(7, batch - 1), 3] = 10 ** 9
     with pytest.raises(IndexError):
         ops.deepfm_packed(bad, off.cuda(), packed, pack, overlap_previous=True)
 

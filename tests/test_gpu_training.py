@@ -220,3 +220,76 @@ def test_fm_backward_kernel(b, n, e):
     (0.5 * (x.sum(1) ** 2 - (x ** 2).sum(1)) * g).sum().backward()
     got = ops.fm_backward(x.detach().float().cuda(), g.float().cuda()).cpu().double()
     assert (got - x.grad).abs().max() <= 1e-5 * x.grad.abs().max()
+
+
+def test_cin_train_mode_batchnorm_matches_torch_modules():
+    """Training with BatchNorm in CIN (batch statistics over (B, E), running-stat update) runs the registered torch
+    modules on the device: forward, gradients and the updated running statistics match the same modules on the CPU;
+    .eval() afterwards takes the kernel again and agrees with the eval-mode formula of those modules."""
+    import copy
+    import torecsys_b200 as trs
+    torch.manual_seed(21)
+    b, n, e = 64, 6, 8
+    layer = trs.CINLayer(e, n, 3, [8, 6])
+    ref = copy.deepcopy(layer)          # CPU copy of the very same nn.Conv1d / nn.BatchNorm1d / nn.Linear modules
+    layer = layer.cuda().train()
+    ref.train()
+    x = torch.randn(b, n, e)
+    xg = x.cuda().requires_grad_()
+    out = layer(xg)
+    assert out.names == ('B', 'O') and out.shape == (b, 3)
+    out.rename(None).square().sum().backward()
+
+    def cpu_forward(mod, xx):           # upstream's op sequence on the CPU copy
+        h, directs = xx, []
+        for block in mod.model:
+            z = (xx.unsqueeze(2) * h.unsqueeze(1)).reshape(xx.shape[0], -1, xx.shape[2])
+            o = block(z)
+            d, h = torch.chunk(o, 2, dim=1)
+            directs.append(d)
+        return mod.fc(torch.cat(directs, 1).sum(-1))
+
+    xc = x.clone().requires_grad_()
+    want = cpu_forward(ref, xc)
+    want.square().sum().backward()
+    assert torch.allclose(out.rename(None).cpu(), want, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(xg.grad.cpu(), xc.grad, rtol=1e-3, atol=1e-5)
+    for (k, p), (_, q) in zip(layer.named_parameters(), ref.named_parameters()):
+        # (a Conv1d bias in front of a BatchNorm has a mathematically zero gradient: only rounding noise on both sides)
+        assert torch.allclose(p.grad.cpu(), q.grad, rtol=1e-3, atol=1e-4), k
+    for (k, u), (_, v) in zip(layer.named_buffers(), ref.named_buffers()):
+        assert torch.allclose(u.cpu().float(), v.float(), rtol=1e-4, atol=1e-6), k     # running stats were updated
+    layer.eval()
+    ref.eval()
+    with torch.no_grad():
+        got_eval = layer(x.cuda()).rename(None).cpu()
+        want_eval = cpu_forward(ref, x)
+    assert ((got_eval - want_eval).abs() / (want_eval.abs() + want_eval.abs().mean())).max() <= 1e-5
+
+
+def test_afm_train_mode_attention_dropout_runs():
+    """Dropout on the attention scores exists only in training: that path runs the registered torch modules; with
+    p = 0 it must equal the kernel, with p > 0 it must zero some scores and still back-propagate."""
+    import torecsys_b200 as trs
+    torch.manual_seed(22)
+    b, n, e = 32, 7, 8
+    layer = trs.AFMLayer(e, n, 4, dropout_p=0.5).cuda()
+    x = torch.randn(b, n, e, device='cuda')
+    layer.eval()
+    with torch.no_grad():
+        want, want_s = layer(x.clone())
+    layer.train()
+    layer.attention.Dropout.p = 0.0
+    layer.dropout.p = 0.0
+    # p = 0 in train mode: the kernel path again (nothing to drop)
+    out, s = layer(x.clone())
+    assert torch.allclose(out.rename(None), want.rename(None), rtol=1e-5, atol=1e-6)
+    layer.attention.Dropout.p = 0.5
+    xg = x.clone().requires_grad_()
+    out, s = layer(xg)
+    assert out.names == ('B', 'E') and s.shape == (b, n * (n - 1) // 2, 1)
+    assert (s == 0).any() and (s != 0).any()
+    out.rename(None).sum().backward()
+    assert torch.isfinite(xg.grad).all() and xg.grad.abs().sum() > 0
+    for k, p in layer.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k

@@ -200,11 +200,36 @@ class CompressInteractionNetworkLayer(BaseLayer):
             self._pack_key = key
         return self._pack
 
+    def _train_forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError('CompressInteractionNetworkLayer: CUDA tensors only (no CPU fallback)')
+        b, _, e = x.shape
+        h, directs = x, []
+        for block in self.model:
+            z = (x.unsqueeze(2) * h.unsqueeze(1)).reshape(b, -1, e)      # channel index x-major: xf * H + y
+            # Conv1d(kernel_size=1) as the FP32 matmul it is (cuDNN would pick TF32 for the convolution and its backward)
+            o = torch.einsum('oc,bce->boe', block.Conv1d.weight.squeeze(-1), z)
+            if block.Conv1d.bias is not None:
+                o = o + block.Conv1d.bias.view(1, -1, 1)
+            for name, module in block._modules.items():                  # BatchNorm1d (batch statistics), activation
+                if name != 'Conv1d':
+                    o = module(o)
+            if self.is_direct:
+                d = h = o
+            else:
+                d, h = torch.chunk(o, 2, dim=1)                          # EVERY layer splits (upstream quirk, 8a)
+            directs.append(d)
+        return self.fc(torch.cat(directs, dim=1).sum(dim=-1))
+
     def forward(self, emb_inputs: torch.Tensor) -> torch.Tensor:
         emb_inputs.names = ('B', 'N', 'E',)
         if self.training and any('Batchnorm' in b._modules for b in self.model):
-            raise NotImplementedError('CompressInteractionNetworkLayer: train-mode BatchNorm (batch statistics) has '
-                                      'no kernel; the forward hot path is eval mode (call .eval())')
+            # train-mode BatchNorm needs batch statistics over (B, E) and updates running_mean / running_var: this one
+            # training-only case runs the registered torch modules on the device (cuDNN / native autograd), exactly
+            # upstream's op sequence (:102-184).  Eval -- the measured path -- always takes the kernel.
+            outputs = self._train_forward(emb_inputs.rename(None))
+            outputs.names = ('B', 'O',)
+            return outputs
         outputs = CinFn.apply(emb_inputs.rename(None), self, self.fc.out_features,
                               *[p for _, p in self.named_parameters()])
         outputs.names = ('B', 'O',)
@@ -363,10 +388,18 @@ class AttentionalFactorizationMachineLayer(BaseLayer):
         self.dropout = nn.Dropout(dropout_p)
 
     def forward(self, emb_inputs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        if self.training and self.attention.Dropout.p > 0:
-            raise NotImplementedError('AttentionalFactorizationMachineLayer: train-mode attention dropout has no '
-                                      'kernel; the forward hot path is eval mode (call .eval())')
         att = self.attention
+        if self.training and att.Dropout.p > 0:
+            # dropout INSIDE the attention (on the softmax scores) only exists in training: that case runs the
+            # registered torch modules on the device (upstream's op sequence, :98-118); eval takes the kernel
+            x = emb_inputs.rename(None)
+            if not x.is_cuda:
+                raise RuntimeError('AttentionalFactorizationMachineLayer: CUDA tensors only (no CPU fallback)')
+            prod = x[:, self.row_idx.to(x.device)] * x[:, self.col_idx.to(x.device)]
+            attn_scores = att(prod)
+            outputs = self.dropout((prod * attn_scores).sum(dim=1))
+            outputs.names = ('B', 'E',)
+            return outputs, attn_scores
         outputs, attn_scores = AfmFn.apply(emb_inputs.rename(None), att.Linear.weight, att.Linear.bias,
                                            att.OutProj.weight, att.OutProj.bias)
         outputs = _train_dropout(outputs, self.dropout)
