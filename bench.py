@@ -337,6 +337,10 @@ def run_ours(args):
         roof = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': traffic, 'traffic_source': 'profiles/r01c_traffic.json (ncu --set full, dram__bytes_read.sum '
                                                       '+ dram__bytes_write.sum of one launch)' if traffic else None,
+                'traffic_frac': (traffic / (ms_per_step * 1e-3) / 1e9 / peak) if traffic else None,
+                'note': ('achieved/frac count the ALGORITHMIC bytes (2 968 B/sample: 64-byte rows); DRAM moves a whole '
+                         '128-byte line per random row, so traffic_frac = measured DRAM bytes / time / peak is the '
+                         'physical utilisation of the same launch'),
                 'peak_source': peak_src, 'kernel': kernel,
                 'algorithmic_bytes_per_launch': ALGO_BYTES_PER_SAMPLE * batch}
         cpu = None
