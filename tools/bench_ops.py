@@ -208,6 +208,8 @@ def main():
                 rb = [r[:8192].contiguous() for r in ring]
                 t = timeit(lambda i: ops.xdeepfm(rb[i % 4], off, w1, w16, cpack, pack, bias), reps=3, warmup=1)
                 report('xdeepfm fused (a12, cfg4 at B=8192)', 8192, t, 2968, flops + 2 * (624 * 16 + 512 + 16))
+                t = timeit(lambda i: ops.xdeepfm(ring[i % 4], off, w1, w16, cpack, pack, bias), reps=3, warmup=1)
+                report('xdeepfm fused (a12, cfg4 at the full batch 65 536)', B, t, 2968, flops + 2 * (624 * 16 + 512 + 16))
         del w16, w1, x, ring
         torch.cuda.empty_cache()
 
