@@ -77,7 +77,7 @@ def main():
 
     # ---------------------------------------------------------------- E = 16 tables (cfg 2)
     B = 65536
-    if any(want(x) for x in ('gather16', 'gather1', 'fm_layer', 'deepfm_packed', 'deepfm_split', 'fm_model',
+    if any(want(x) for x in ('gather16', 'gather1', 'fm_layer', 'deepfm_packed', 'deepfm_split', 'fm_model', 'latency',
                              'deepfm_generic_mlp400', 'ipn', 'bilinear_all', 'bilinear_each', 'afm', 'xdeepfm',
                              'cin_layer', 'opn', 'senet', 'models_more')):
         w16 = torch.randn(rows, 16, device=dev)
@@ -100,6 +100,26 @@ def main():
             packed = ops.fm_pack_table(w16, w1)
             t = timeit(lambda i: ops.deepfm_packed(ring[i % 4], off, packed, pack), reps=50)
             report('deepfm fused, packed table (a12, cfg2)', B, t, 2968)
+            del packed
+        if want('latency'):
+            # serving latency of ONE fused DeepFM call (host launch + kernel + sync), small batches, packed table
+            import time as _time
+            packed = ops.fm_pack_table(w16, w1)
+            for bs_ in (1, 64, 1024, 16384):
+                ib = ring[0][:bs_].contiguous()
+                ob = torch.empty(bs_, 1, device=dev)
+                for _ in range(20):
+                    ops.deepfm_packed(ib, off, packed, pack, out=ob)
+                torch.cuda.synchronize()
+                lat = []
+                for _ in range(200):
+                    t0 = _time.perf_counter()
+                    ops.deepfm_packed(ib, off, packed, pack, out=ob)
+                    torch.cuda.synchronize()
+                    lat.append(_time.perf_counter() - t0)
+                lat.sort()
+                report(f'deepfm fused latency, batch {bs_} (launch + kernel + sync, p50)', bs_, lat[len(lat) // 2],
+                       note=f'p99 {lat[int(len(lat) * 0.99)] * 1e6:.1f} us')
             del packed
         if want('deepfm_split'):
             t = timeit(lambda i: ops.deepfm(ring[i % 4], off, w1, w16, pack), reps=50)
