@@ -274,6 +274,16 @@ int trs_ffm_model_forward(const void* idx, int idx_bits, const int64_t* offsets,
                           const float* w_feat, const float* const* tables, int64_t rows, int embed,
                           const float* bias, float* logits, int32_t* status, void* stream);
 
+/* The same forward restricted to a LIST of pairs -- one rank's share when the tables are sharded over GPUs
+ * (SURVEY.md 8e, configs[4]).  pair_list: DEVICE array of n_pairs entries (i << 16) | j, i < j (NULL = every pair);
+ * the first-order term and the bias are added only for samples b in [first_begin, first_end), so that summing the
+ * outputs of all ranks (reduce-scatter) counts them once.  `tables` may hold peer-mapped addresses of other GPUs. */
+int trs_ffm_model_forward_pairs(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                                const float* w_feat, const float* const* tables, int64_t rows, int embed,
+                                const float* bias, const int* pair_list, int n_pairs,
+                                int64_t first_begin, int64_t first_end,
+                                float* logits, int32_t* status, void* stream);
+
 /* ---- 8f-3: fused indices -> logits forwards of three more models (Sequential.forward = Inputs.forward + model) --------
  * Arguments as in trs_deepfm_forward; the MLP (HOST arrays of DEVICE pointers) must end in ONE output.
  *   trs_nfm_forward        NeuralFactorizationMachineModel.forward (neural_factorization_machine.py:66-96):

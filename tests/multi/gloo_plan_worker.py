@@ -33,6 +33,21 @@ def main():
     assert len(set(ptrs)) == 39
     for t in range(39):
         assert ptrs[t] == base[t % world] + (t // world) * table_bytes
+    # owner-side pair assignment: every pair computed exactly once, by an owner of one of its tables, evenly spread
+    pairs = [None] * world
+    dist.all_gather_object(pairs, plan.pairs_of(rank))
+    flat_pairs = sorted(c for part in pairs for c in part)
+    assert flat_pairs == [(i << 16) | j for i in range(38) for j in range(i + 1, 39)]
+    for r, part in enumerate(pairs):
+        assert all(r in (plan.owner(c >> 16), plan.owner(c & 0xffff)) for c in part)
+    sizes = [len(part) for part in pairs]
+    assert max(sizes) <= 1.15 * min(sizes), sizes
+    full_plan = TableShardPlan(39, 8)
+    sizes8 = [len(full_plan.pairs_of(r)) for r in range(8)]
+    assert sum(sizes8) == 741 and max(sizes8) <= 1.25 * min(sizes8), sizes8
+    # NVLink rows per sample: at most one per pair (the sample-side scheme reads 2 * 741 * 7/8 = 1 297 at world 8)
+    assert all(full_plan.remote_rows_per_sample(r) <= len(full_plan.pairs_of(r)) for r in range(8))
+    assert sum(full_plan.remote_rows_per_sample(r) for r in range(8)) <= 741
     # batch sharding: slices tile the batch exactly
     for batch in (0, 1, 7, 262144, 262145):
         sl = [None] * world

@@ -36,6 +36,25 @@ def main():
     want = R.ffm_from_indices(idx[lo:hi], R.field_offsets(fs), w_feat, [torch.from_numpy(t) for t in full],
                               bias).numpy()
     err = normwise_err(got, want)
+    # owner-side scheme: all-gather(idx) -> pairs of this rank over all samples -> reduce-scatter(partial logits)
+    per = batch // world                      # equal slices for the collectives
+    sl = slice(rank * per, (rank + 1) * per)
+    got2 = model.forward_owner_side(idx[sl].to(dev)).cpu().numpy()
+    want2 = R.ffm_from_indices(idx[sl], R.field_offsets(fs), w_feat, [torch.from_numpy(t) for t in full],
+                               bias).numpy()
+    err = max(err, normwise_err(got2, want2))
+    bad = idx[sl].clone()
+    if rank == 0:
+        bad[3, 2] = 10 ** 7                   # ONE rank's sample is out of range: every rank must raise together
+    try:
+        model.forward_owner_side(bad.to(dev))
+        raised = False
+    except IndexError:
+        raised = True
+    flag = torch.tensor([1 if raised else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    assert int(flag.item()) == 1, 'out-of-range lookup was not reported on every rank'
+    ops.check_index_errors()
     remote = sum(1 for t in range(n) if tables.plan.owner(t) != rank)
     ok = torch.tensor([1 if err <= 1e-5 else 0], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)

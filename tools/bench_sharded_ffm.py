@@ -30,6 +30,9 @@ def main():
     ap.add_argument('--batch', type=int, default=262_144, help='global batch')
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--scheme', default='both', choices=['sample', 'owner', 'both'],
+                    help='sample: pairs computed at the rank of the sample (peer loads only); owner: pairs reduced at a '
+                         'table owner (all-gather of indices + reduce-scatter of logits, half the NVLink volume)')
     args = ap.parse_args()
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
@@ -46,32 +49,43 @@ def main():
     per = args.batch // world
     igen = torch.Generator(device=dev).manual_seed(1234 + rank)
     ring = [torch.randint(0, args.rows_per_field, (per, N), device=dev, generator=igen) for _ in range(4)]
-    for i in range(args.warmup):
-        model(ring[i % 4])
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        model(ring[i % 4])
-    e1.record()
-    dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ops.check_index_errors()
-    ms = float(t.item()) / args.steps
-    if rank == 0:
-        remote = tables.plan.remote_fraction()
-        nv_bytes = per * N * (N - 1) * 64 * remote
-        print(json.dumps({
-            'metric': 'ctr_forward_samples_per_sec', 'value': per * world / (ms * 1e-3), 'unit': 'samples/s',
-            'n_gpus': world, 'ms_per_step': ms, 'scaling': 'weak' if False else 'strong(global batch fixed)',
-            'config': {'workload': f'configs[4]: FFM {N} fields, {N} tables x {rows} rows x {E} (={N * rows * E * 4 / 1e9:.1f} GB), '
-                                   f'global batch {per * world}, tables sharded table-wise over {world} GPUs'},
-            'nvlink_bytes_in_per_gpu_per_step': nv_bytes,
-            'nvlink_GBps_per_gpu': nv_bytes / (ms * 1e-3) / 1e9,
-            'hbm_algorithmic_GBps_per_gpu': per * 95320 / (ms * 1e-3) / 1e9}))
+    def measure(fn):
+        for i in range(args.warmup):
+            fn(ring[i % 4])
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            fn(ring[i % 4])
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ops.check_index_errors()
+        return float(t.item()) / args.steps
+
+    schemes = ['sample', 'owner'] if args.scheme == 'both' else [args.scheme]
+    for scheme in schemes:
+        ms = measure(model.forward if scheme == 'sample' else model.forward_owner_side)
+        if rank == 0:
+            if scheme == 'sample':
+                nv_rows = per * N * (N - 1) * tables.plan.remote_fraction()
+            else:
+                nv_rows = per * world * max(tables.plan.remote_rows_per_sample(r) for r in range(world))
+            nv_bytes = nv_rows * 64
+            print(json.dumps({
+                'metric': 'ctr_forward_samples_per_sec', 'value': per * world / (ms * 1e-3), 'unit': 'samples/s',
+                'n_gpus': world, 'ms_per_step': ms, 'scaling': 'strong (global batch fixed)', 'scheme': scheme,
+                'config': {'workload': f'configs[4]: FFM {N} fields, {N} tables x {rows} rows x {E} '
+                                       f'(={N * rows * E * 4 / 1e9:.1f} GB), global batch {per * world}, tables sharded '
+                                       f'table-wise over {world} GPUs',
+                           'collectives': 'none (in-kernel peer loads)' if scheme == 'sample' else
+                                          'NCCL all-gather of indices + reduce-scatter of partial logits, in-kernel peer loads'},
+                'nvlink_bytes_in_per_gpu_per_step': nv_bytes,
+                'nvlink_GBps_per_gpu': nv_bytes / (ms * 1e-3) / 1e9,
+                'hbm_algorithmic_GBps_per_gpu': per * 95320 / (ms * 1e-3) / 1e9}), flush=True)
     dist.destroy_process_group()
 
 

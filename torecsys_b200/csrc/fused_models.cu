@@ -193,18 +193,28 @@ __global__ void __launch_bounds__(256) ffm_model_kernel(const void* __restrict__
                                                         int fields, const float* __restrict__ w_feat,
                                                         const float* const* __restrict__ tables, int64_t rows,
                                                         int embed, const float* __restrict__ bias,
-                                                        float* __restrict__ logits, int32_t* status) {
+                                                        float* __restrict__ logits, int32_t* status,
+                                                        const int* __restrict__ pair_list, int n_pairs,
+                                                        int64_t first_begin, int64_t first_end) {
+  // pair_list == null: all N(N-1)/2 pairs.  Otherwise only the listed pairs ((i << 16) | j) are summed -- the share of
+  // one rank in the owner-side sharded scheme -- and the first-order term + bias are added only for the samples in
+  // [first_begin, first_end) (each sample's first-order term must enter the cross-rank sum exactly once).
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pairs = fields * (fields - 1) / 2;
-  int* ptab = reinterpret_cast<int*>(smem_raw);                                   // [pairs]
-  const float** tabs = reinterpret_cast<const float**>(ptab + ((pairs + 1) & ~1));  // [fields]
+  const int all_pairs = fields * (fields - 1) / 2;
+  const int pairs = pair_list ? n_pairs : all_pairs;
+  int* ptab = reinterpret_cast<int*>(smem_raw);                                   // [all_pairs]
+  const float** tabs = reinterpret_cast<const float**>(ptab + ((all_pairs + 1) & ~1));  // [fields]
   int64_t* rid = reinterpret_cast<int64_t*>(tabs + fields) + (size_t)warp * fields;  // [warps][fields]
   for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
-    int i, j;
-    pair_from_index(p, fields, i, j);
-    ptab[p] = (i << 16) | j;
+    if (pair_list) {
+      ptab[p] = __ldg(pair_list + p);
+    } else {
+      int i, j;
+      pair_from_index(p, fields, i, j);
+      ptab[p] = (i << 16) | j;
+    }
   }
   for (int t = threadIdx.x; t < fields; t += blockDim.x) tabs[t] = tables[t];
   __syncthreads();
@@ -213,13 +223,14 @@ __global__ void __launch_bounds__(256) ffm_model_kernel(const void* __restrict__
   const int items = pairs * chunks;
   for (int64_t b = (int64_t)blockIdx.x * warps + warp; b < batch; b += (int64_t)gridDim.x * warps) {
     float first = 0.f;
+    const bool with_first = b >= first_begin && b < first_end;
     for (int n = lane; n < fields; n += 32) {
       const int64_t pos = b * fields + n;
       int64_t r = load_index<IdxBits>(idx, pos) + __ldg(offsets + n);
       if (r < 0 || r >= rows) {
-        report_oob(status, pos);
+        if (with_first) report_oob(status, pos);   // reported once, by the rank that owns the sample
         r = -1;
-      } else if (w_feat != nullptr) {
+      } else if (w_feat != nullptr && with_first) {
         first += ldg_stream_f1(w_feat + r);
       }
       rid[n] = r;
@@ -271,7 +282,7 @@ __global__ void __launch_bounds__(256) ffm_model_kernel(const void* __restrict__
       }
     }
     const float tot = warp_sum(acc + first);
-    if (lane == 0) logits[b] = tot + (bias ? __ldg(bias) : 0.f);
+    if (lane == 0) logits[b] = tot + ((bias && with_first) ? __ldg(bias) : 0.f);
     __syncwarp();
   }
 }
@@ -456,7 +467,18 @@ extern "C" int trs_xdeepfm_forward(const void* idx, int idx_bits, const int64_t*
 extern "C" int trs_ffm_model_forward(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch,
                                      int fields, const float* w_feat, const float* const* tables, int64_t rows,
                                      int embed, const float* bias, float* logits, int32_t* status, void* stream) {
+  return trs_ffm_model_forward_pairs(idx, idx_bits, offsets, batch, fields, w_feat, tables, rows, embed, bias, nullptr,
+                                     0, 0, batch, logits, status, stream);
+}
+
+extern "C" int trs_ffm_model_forward_pairs(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch,
+                                           int fields, const float* w_feat, const float* const* tables, int64_t rows,
+                                           int embed, const float* bias, const int* pair_list, int n_pairs,
+                                           int64_t first_begin, int64_t first_end, float* logits, int32_t* status,
+                                           void* stream) {
   TRS_REQUIRE(idx && offsets && tables && logits, "trs_ffm_model_forward: null pointer");
+  TRS_REQUIRE(pair_list == nullptr || (n_pairs >= 0 && n_pairs <= fields * (fields - 1) / 2),
+              "trs_ffm_model_forward_pairs: bad pair list length %d", n_pairs);
   TRS_REQUIRE(idx_bits == 32 || idx_bits == 64, "trs_ffm_model_forward: idx_bits must be 32 or 64");
   TRS_REQUIRE(batch >= 0 && fields > 1 && embed > 0 && rows > 0, "trs_ffm_model_forward: bad sizes");
   TRS_REQUIRE(fields <= 4096, "trs_ffm_model_forward: too many fields");
@@ -473,7 +495,8 @@ extern "C" int trs_ffm_model_forward(const void* idx, int idx_bits, const int64_
   do {                                                                                                           \
     TRS_SMEM_OPT_IN((ffm_model_kernel<BITS, VEC>));                                                              \
     ffm_model_kernel<BITS, VEC><<<grid, warps * 32, smem, s>>>(idx, offsets, batch, fields, w_feat, tables, rows, \
-                                                               embed, bias, logits, status);                     \
+                                                               embed, bias, logits, status, pair_list, n_pairs,  \
+                                                               first_begin, first_end);                          \
   } while (0)
   if (idx_bits == 64) {
     if (vec) LAUNCH(64, true); else LAUNCH(64, false);

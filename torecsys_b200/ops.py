@@ -578,6 +578,40 @@ def ffm_model_from_pointers(idx, offsets, w_feat, table_ptrs: torch.Tensor, rows
     return out
 
 
+def index_check_mode() -> str:
+    return _index_check
+
+
+def status_tensor(device: torch.device) -> torch.Tensor:
+    """The device status words (out-of-range count, one offender) the lookups of this process update."""
+    return _status_tensor(device)
+
+
+def ffm_model_pairs(idx, offsets, w_feat, table_ptrs: torch.Tensor, rows: int, embed: int, bias,
+                    pair_list: torch.Tensor, first_range, out: Optional[torch.Tensor] = None,
+                    check_now: bool = True):
+    """trs_ffm_model_forward_pairs: the FFM forward restricted to `pair_list` (int32 device tensor of (i << 16) | j);
+    first-order term and bias only for samples in first_range = (begin, end).  One rank's share of the owner-side
+    sharded scheme (torecsys_b200.sharded)."""
+    ix, bits, off = _fused_common('ffm_model', idx, offsets, w_feat, bias, table_ptrs, pair_list)
+    wf = _f32('ffm_model', w_feat)
+    bs = _f32('ffm_model', bias).reshape(-1) if bias is not None else None
+    b, n = ix.shape
+    if table_ptrs.dtype != torch.int64 or table_ptrs.numel() != n:
+        raise ValueError(f'ffm_model_pairs: need int64[{n}] table addresses')
+    if pair_list.dtype != torch.int32 or not pair_list.is_contiguous():
+        raise ValueError('ffm_model_pairs: pair_list must be a contiguous int32 tensor')
+    out = out if out is not None else torch.empty((b, 1), dtype=torch.float32, device=ix.device)
+    st = _status_tensor(ix.device)
+    check(_cabi.load().trs_ffm_model_forward_pairs(_ptr(ix), bits, _ptr(off), b, n, _ptr(wf), _ptr(table_ptrs), rows,
+                                                   embed, _ptr(bs), _ptr(pair_list), pair_list.numel(),
+                                                   int(first_range[0]), int(first_range[1]), _ptr(out), _ptr(st),
+                                                   _stream()), 'trs_ffm_model_forward_pairs')
+    if check_now:
+        _after_lookup(ix.device)
+    return out
+
+
 def ffm_model(idx, offsets, w_feat, tables: Sequence[torch.Tensor], bias, table_ptrs: Optional[TablePointers] = None,
               out: Optional[torch.Tensor] = None):
     ix, bits, off = _fused_common('ffm_model', idx, offsets, w_feat, bias, *tables)

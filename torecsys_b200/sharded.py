@@ -9,6 +9,10 @@ cuMem fabric handles).  The exchange of looked-up vectors therefore happens INSI
 row by row, overlapped with the dot products -- there is no separate all-to-all, no staging buffer and no second
 kernel.  Volume: (world-1)/world of the 1 482 rows x 64 B per sample cross NVLink (83 KB/sample at world 8).
 
+`ShardedFFM.forward_owner_side` halves that volume: the pair (i, j) is reduced on the rank that owns one of its two
+tables, for ALL samples (indices all-gathered over NCCL, 312 B per sample), so at most one of the two rows of a pair
+crosses NVLink; the (B,) partial logits are then summed and distributed with one NCCL reduce-scatter.
+
 Host logic (`TableShardPlan`) is pure Python and is what the CPU/gloo tests cover; `ShardedFieldAwareTables` needs
 CUDA + NCCL.
 """
@@ -45,6 +49,25 @@ class TableShardPlan:
         if len(base_ptrs) != self.world_size:
             raise ValueError('one base pointer per rank expected')
         return [base_ptrs[self.owner(t)] + self.slot(t) * table_bytes for t in range(self.num_tables)]
+
+    def pair_rank(self, i: int, j: int) -> int:
+        """Rank that computes the pair (i < j) in the owner-side scheme: the owner of ONE of its two tables, alternating
+        with the parity of i + j so that the 741 pairs spread evenly.  That rank reads one row of the pair from its own
+        HBM and at most one over NVLink -- half the exchange volume of computing at the sample's rank."""
+        return self.owner(i) if (i + j) % 2 == 0 else self.owner(j)
+
+    def pairs_of(self, rank: int) -> List[int]:
+        """(i << 16) | j of the pairs `rank` computes, in lexicographic order."""
+        n = self.num_tables
+        return [(i << 16) | j for i in range(n - 1) for j in range(i + 1, n) if self.pair_rank(i, j) == rank]
+
+    def remote_rows_per_sample(self, rank: int) -> int:
+        """Rows per sample that `rank` reads over NVLink in the owner-side scheme."""
+        total = 0
+        for code in self.pairs_of(rank):
+            i, j = code >> 16, code & 0xffff
+            total += (self.owner(i) != rank) + (self.owner(j) != rank)
+        return total
 
     def remote_fraction(self) -> float:
         """Fraction of the row reads of a rank that cross NVLink (uniform over tables)."""
@@ -105,10 +128,42 @@ class ShardedFFM:
         self.tables = tables
         self.w_feat = w_feat      # (rows, 1), replicated: 4 B per row
         self.bias = bias
+        self._pairs = None        # device list of the pairs this rank computes in the owner-side scheme
 
     def forward(self, idx_local: torch.Tensor) -> torch.Tensor:
+        """Sample-side scheme: this rank computes every pair of ITS samples, reading remote tables row by row."""
         t = self.tables
         return ops.ffm_model_from_pointers(idx_local, t.offsets, self.w_feat, t.table_ptrs, t.rows, t.embed_size,
                                            self.bias)
+
+    def forward_owner_side(self, idx_local: torch.Tensor) -> torch.Tensor:
+        """Owner-side scheme (SURVEY.md 8e "volume-halving"): the looked-up vectors are reduced where one of them lives.
+          1. all-gather of the (B/W, N) index slices (NCCL; 312 B per sample);
+          2. every rank runs the FFM kernel over ALL samples for the pairs assigned to it (TableShardPlan.pair_rank):
+             per pair one row from its own HBM and at most one peer load -- half the NVLink volume of `forward`;
+             the first-order term and the bias are added by the rank that owns the sample;
+          3. reduce-scatter (sum) of the (B,) partial logits (NCCL): each rank receives the logits of its samples.
+        All ranks must pass slices of the same length."""
+        t = self.tables
+        world, rank = t.world, t.rank
+        b_local, n = idx_local.shape
+        if self._pairs is None:
+            self._pairs = torch.tensor(t.plan.pairs_of(rank), dtype=torch.int32, device=t.device)
+        idx_all = torch.empty((world * b_local, n), dtype=idx_local.dtype, device=t.device)
+        dist.all_gather_into_tensor(idx_all, idx_local.contiguous(), group=t.group)
+        partial = ops.ffm_model_pairs(idx_all, t.offsets, self.w_feat, t.table_ptrs, t.rows, t.embed_size, self.bias,
+                                      self._pairs, (rank * b_local, (rank + 1) * b_local), check_now=False)
+        out = torch.empty((b_local, 1), dtype=torch.float32, device=t.device)
+        dist.reduce_scatter_tensor(out, partial, op=dist.ReduceOp.SUM, group=t.group)
+        if ops.index_check_mode() == 'sync':
+            # an out-of-range lookup is counted by the rank that owns the sample; every rank must raise together
+            # (a rank that raised alone would leave the others inside the next collective)
+            st = ops.status_tensor(t.device)
+            seen = st[:1].clone()
+            dist.all_reduce(seen, op=dist.ReduceOp.SUM, group=t.group)
+            if int(seen.item()) != 0:
+                st.zero_()
+                raise IndexError(f'index out of range in self ({int(seen.item())} lookups across the ranks)')
+        return out
 
     __call__ = forward
