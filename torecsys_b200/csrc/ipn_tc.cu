@@ -3,7 +3,9 @@
 // out[b, p(i,j)] = <x_i, x_j>, i < j.  One warp per sample: X (N, E) is staged in shared memory already split into TF32
 // hi / lo planes; for every 16 x 8 output tile that touches the strict upper triangle (9 of 15 at N = 39) the warp
 // issues E/8 k-steps of 3 mma.sync.m16n8k8 (3xTF32, fp32-accurate) with A and B fragments both read from those planes,
-// then scatters the accumulator elements with i < j < N to their pair slots (row base table in shared memory).
+// then scatters the accumulator elements with i < j < N to their pair slots (row base table in shared memory) of a
+// per-warp staging row in shared memory, which leaves for HBM as fully coalesced 128-byte stores (the accumulator
+// layout would otherwise turn the (B, P) output into scattered 4-byte writes).
 // The generic kernel in pairwise.cu does 2 LDS per FMA; this one is bound by the (B, P) output write.
 #include <stdlib.h>
 
@@ -35,6 +37,8 @@ __global__ void __launch_bounds__(kWarps * 32) ipn_tc_kernel(const float* __rest
   uint32_t* xh = planes;                                                 // [rows_pad][kPitch] TF32 hi
   uint32_t* xl = planes + rows_pad * kPitch;                             // lo
   const int pairs = fields * (fields - 1) / 2;
+  float* obuf = reinterpret_cast<float*>(reinterpret_cast<uint32_t*>(rowbase + rows_pad) +
+                                         (size_t)kWarps * 2 * rows_pad * kPitch) + (size_t)warp * pairs;   // [pairs]
   for (int i = threadIdx.x; i < rows_pad; i += blockDim.x) rowbase[i] = i * (2 * fields - i - 1) / 2 - i - 1;
   // zero the padding rows once (they are never rewritten)
   for (int i = lane + fields * kPitch; i < rows_pad * kPitch; i += 32) {
@@ -44,14 +48,45 @@ __global__ void __launch_bounds__(kWarps * 32) ipn_tc_kernel(const float* __rest
   __syncthreads();
   const int mt_count = rows_pad / 16, nt_count = (fields + 7) / 8;
 
-  for (int64_t b = (int64_t)blockIdx.x * kWarps + warp; b < batch; b += (int64_t)gridDim.x * kWarps) {
-    const float* src = x + b * fields * E;
-    for (int i = lane; i < fields * E; i += 32) {
-      const int n = i / E, e = i - n * E;
-      const float v = ldg_stream_f1(src + i);
-      const uint32_t hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
-      xh[n * kPitch + e] = hi;
-      xl[n * kPitch + e] = (__float_as_uint(v - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
+  // The next sample's tile is prefetched into registers (up to kPre values per lane) while the current one is in its
+  // MMA phase, so the global-load latency is off the warp's critical path; larger tiles load in place.
+  constexpr int kPre = 24;
+  const int tile = fields * E;
+  const bool prefetch = tile <= 32 * kPre;
+  const int64_t stride = (int64_t)gridDim.x * kWarps;
+  float nxt[kPre];
+  auto load_tile = [&](int64_t bb) {
+    const float* src = x + bb * tile;
+#pragma unroll
+    for (int k = 0; k < kPre; ++k) {
+      const int i = lane + 32 * k;
+      nxt[k] = (bb < batch && i < tile) ? ldg_stream_f1(src + i) : 0.f;
+    }
+  };
+  if (prefetch) load_tile((int64_t)blockIdx.x * kWarps + warp);
+  for (int64_t b = (int64_t)blockIdx.x * kWarps + warp; b < batch; b += stride) {
+    if (prefetch) {
+#pragma unroll
+      for (int k = 0; k < kPre; ++k) {
+        const int i = lane + 32 * k;
+        if (i < tile) {
+          const int n = i / E, e = i - n * E;
+          const float v = nxt[k];
+          const uint32_t hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+          xh[n * kPitch + e] = hi;
+          xl[n * kPitch + e] = (__float_as_uint(v - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
+        }
+      }
+      load_tile(b + stride);
+    } else {
+      const float* src = x + b * tile;
+      for (int i = lane; i < tile; i += 32) {
+        const int n = i / E, e = i - n * E;
+        const float v = ldg_stream_f1(src + i);
+        const uint32_t hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+        xh[n * kPitch + e] = hi;
+        xl[n * kPitch + e] = (__float_as_uint(v - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
+      }
     }
     __syncwarp();
     float* dst = out + b * pairs;
@@ -77,12 +112,14 @@ __global__ void __launch_bounds__(kWarps * 32) ipn_tc_kernel(const float* __rest
           mma_tf32(acc, ah[ks], bh0, bh1);
         }
         const int i0 = 16 * mt + g, i1 = i0 + 8, j0 = 8 * nt + 2 * t, j1 = j0 + 1;
-        if (i0 < j0 && j0 < fields) dst[rowbase[i0] + j0] = acc[0];
-        if (i0 < j1 && j1 < fields) dst[rowbase[i0] + j1] = acc[1];
-        if (i1 < j0 && j0 < fields) dst[rowbase[i1] + j0] = acc[2];
-        if (i1 < j1 && j1 < fields) dst[rowbase[i1] + j1] = acc[3];
+        if (i0 < j0 && j0 < fields) obuf[rowbase[i0] + j0] = acc[0];
+        if (i0 < j1 && j1 < fields) obuf[rowbase[i0] + j1] = acc[1];
+        if (i1 < j0 && j0 < fields) obuf[rowbase[i1] + j0] = acc[2];
+        if (i1 < j1 && j1 < fields) obuf[rowbase[i1] + j1] = acc[3];
       }
     }
+    __syncwarp();
+    for (int p = lane; p < pairs; p += 32) dst[p] = obuf[p];   // coalesced: 128 contiguous bytes per instruction
     __syncwarp();
   }
 }
@@ -91,7 +128,8 @@ template <int KS>
 int ipn_tc_dispatch(const float* x, int64_t batch, int fields, float* out, cudaStream_t s) {
   constexpr int E = 8 * KS;
   const int rows_pad = (fields + 15) & ~15;
-  const size_t smem = (size_t)rows_pad * sizeof(int) + (size_t)kWarps * 2 * rows_pad * (E + 4) * sizeof(uint32_t);
+  const size_t smem = (size_t)rows_pad * sizeof(int) + (size_t)kWarps * 2 * rows_pad * (E + 4) * sizeof(uint32_t) +
+                      (size_t)kWarps * (fields * (fields - 1) / 2) * sizeof(float);
   if (smem > (size_t)kMaxDynSmem) return TRS_ERR_UNSUPPORTED;
   static size_t configured = 0;
   if (smem > configured) {
