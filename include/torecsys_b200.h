@@ -79,7 +79,7 @@ int trs_embedding_gather_field_aware(const float* const* tables, int64_t rows, i
  *     out[b, e] = 0.5 * ((sum_n x[b,n,e])^2 - sum_n x[b,n,e]^2)      x (batch, fields, embed) -> out (batch, embed) */
 int trs_fm_forward(const float* x, int64_t batch, int fields, int embed, float* out, void* stream);
 
-/* ---- 8f-2: backward kernels of the two ops every training step goes through ----------------------------------------
+/* ---- 8f-2: backward kernels of the ops the a12 models' training steps go through ----------------------------------------
  * trs_embedding_grad: the dense weight gradient of nn.Embedding behind MultiIndicesEmbedding / SingleIndexEmbedding
  * (multi_indices_emb.py:48, single_index_emb.py:41; sparse=False):
  *     grad_weight[idx[b,n] + offsets[n], :] += grad_out[b, n, :]       (grad_weight is NOT zeroed here)
@@ -91,6 +91,22 @@ int trs_embedding_grad(const float* grad_out, const void* idx, int idx_bits, con
                        float* grad_weight, void* stream);
 int trs_fm_backward(const float* x, const float* grad_out, int64_t batch, int fields, int embed,
                     float* grad_x, void* stream);
+
+/* trs_ffm_backward: gradient of FieldAwareFactorizationMachineLayer.forward (field_aware_factorization_machine.py:50-94)
+ *     grad_v[b, a*N + c, :] = grad_out[b, p(min(a,c), max(a,c)), :] * v[b, c*N + a, :]   (a != c), 0 on the diagonal
+ * trs_ipn_backward: gradient of InnerProductNetworkLayer.forward (inner_product_network.py:54-79)
+ *     grad_x[b, i, :] = sum_{j != i} grad_out[b, p(i,j)] * x[b, j, :]
+ * trs_cross_backward: gradients of CrossNetworkLayer.forward (cross_network.py:52-87) for x, every W_l and b_l.  The
+ * chain starts from h_0 = x.detach() as upstream does (:65): x receives gradient through the `x * (...) + x` terms
+ * only.  grad_weights (layers, E, E) and grad_biases (layers, E) are OVERWRITTEN (zeroed on the stream, then
+ * accumulated with float atomics, one add per CTA).  embed 8, 16, 32 or 64 (TRS_ERR_UNSUPPORTED otherwise). */
+int trs_ffm_backward(const float* v, const float* grad_out, int64_t batch, int fields, int embed,
+                     float* grad_v, void* stream);
+int trs_ipn_backward(const float* x, const float* grad_out, int64_t batch, int fields, int embed,
+                     float* grad_x, void* stream);
+int trs_cross_backward(const float* x, const float* weights, const float* biases, const float* grad_out,
+                       int layers, int64_t rows, int embed, float* grad_x, float* grad_weights,
+                       float* grad_biases, void* stream);
 
 /* ---- a6: field-aware FM ------------------------------------------------------------------------------------------
  * Replaces FieldAwareFactorizationMachineLayer.forward

@@ -222,6 +222,76 @@ def test_fm_backward_kernel(b, n, e):
     assert (got - x.grad).abs().max() <= 1e-5 * x.grad.abs().max()
 
 
+@pytest.mark.parametrize('b,n,e', [(3, 39, 16), (65, 5, 7), (1, 2, 4), (40, 12, 32)])
+def test_ffm_backward_kernel(b, n, e):
+    from torecsys_b200 import ops
+    gen = torch.Generator().manual_seed(10)
+    v = torch.randn(b, n * n, e, generator=gen, dtype=torch.float64, requires_grad=True)
+    i, j = torch.triu_indices(n, n, offset=1)
+    g = torch.randn(b, i.numel(), e, generator=gen, dtype=torch.float64)
+    v4 = v.reshape(b, n, n, e)
+    ((v4[:, i, j] * v4[:, j, i]) * g).sum().backward()
+    got = ops.ffm_backward(v.detach().float().cuda(), g.float().cuda(), n).cpu().double()
+    assert (got - v.grad).abs().max() <= 1e-6 * v.grad.abs().max()
+    assert not got.reshape(b, n, n, e)[:, torch.arange(n), torch.arange(n)].any()   # dead diagonal rows: exactly zero
+    with pytest.raises(ValueError):
+        ops.ffm_backward(v.detach().float().cuda(), g.float().cuda()[:, :-1], n)
+    assert ops.ffm_backward(v.detach().float().cuda()[:0], g.float().cuda()[:0], n).shape == (0, n * n, e)
+
+
+@pytest.mark.parametrize('b,n,e', [(1, 39, 16), (500, 39, 16), (33, 5, 40), (64, 2, 8), (7, 100, 128)])
+def test_ipn_backward_kernel(b, n, e):
+    from torecsys_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(b, n, e, generator=gen, dtype=torch.float64, requires_grad=True)
+    i, j = torch.triu_indices(n, n, offset=1)
+    g = torch.randn(b, i.numel(), generator=gen, dtype=torch.float64)
+    ((x[:, i] * x[:, j]).sum(-1) * g).sum().backward()
+    got = ops.ipn_backward(x.detach().float().cuda(), g.float().cuda()).cpu().double()
+    assert (got - x.grad).abs().max() <= 1e-5 * x.grad.abs().max()
+
+
+@pytest.mark.parametrize('rows,e,layers', [(1, 32, 6), (64 * 300 + 17, 32, 6), (5000, 16, 3), (999, 8, 2),
+                                           (777, 64, 4), (130, 32, 1)])
+def test_cross_backward_kernel(rows, e, layers):
+    """x, W_l and b_l gradients of the cross network against float64 autograd on the upstream formula (h_0 detached,
+    cross_network.py:65); several tiles per CTA, a ragged last tile, every supported width."""
+    from torecsys_b200 import ops
+    gen = torch.Generator().manual_seed(12)
+    x = (0.5 * torch.randn(rows, e, generator=gen, dtype=torch.float64)).requires_grad_()
+    w = (torch.randn(layers, e, e, generator=gen, dtype=torch.float64) / e ** 0.5).requires_grad_()
+    bb = (0.1 * torch.randn(layers, e, generator=gen, dtype=torch.float64)).requires_grad_()
+    g = torch.randn(rows, e, generator=gen, dtype=torch.float64)
+    h = x.detach()
+    for l in range(layers):
+        h = x * torch.nn.functional.linear(h, w[l], bb[l]) + x
+    (h * g).sum().backward()
+    gx, gw, gb = ops.cross_backward(x.detach().float().cuda(), w.detach().float().cuda(), bb.detach().float().cuda(),
+                                    g.float().cuda())
+    for got, want, what in ((gx, x.grad, 'dx'), (gw, w.grad, 'dW'), (gb, bb.grad, 'db')):
+        err = (got.cpu().double() - want).abs().max() / want.abs().max()
+        assert err <= 2e-5, (what, float(err))
+
+
+def test_cross_function_backward_routes():
+    """CrossFn uses the kernel for the widths it supports and the torch recompute for the others; both honour
+    needs_input_grad (a frozen weight gets no gradient)."""
+    from torecsys_b200.autograd import CrossFn
+    for e in (32, 40):
+        gen = torch.Generator().manual_seed(13)
+        x = torch.randn(50, 3, e, generator=gen).cuda().requires_grad_()
+        w = (torch.randn(2, e, e, generator=gen) / e ** 0.5).cuda()
+        bb = torch.zeros(2, e).cuda().requires_grad_()
+        CrossFn.apply(x, w, bb).sum().backward()
+        assert x.grad is not None and bb.grad is not None and w.grad is None
+        xd = x.detach().double().cpu().requires_grad_()
+        h = xd.detach()
+        for l in range(2):
+            h = xd * torch.nn.functional.linear(h, w[l].double().cpu(), bb[l].detach().double().cpu()) + xd
+        h.sum().backward()
+        assert (x.grad.cpu().double() - xd.grad).abs().max() <= 2e-5 * xd.grad.abs().max()
+
+
 def test_cin_train_mode_batchnorm_matches_torch_modules():
     """Training with BatchNorm in CIN (batch statistics over (B, E), running-stat update) runs the registered torch
     modules on the device: forward, gradients and the updated running statistics match the same modules on the CPU;

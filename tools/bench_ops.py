@@ -322,6 +322,33 @@ def main():
                95320, 2 * PAIRS * 16)
         del tables, wf, ring
         torch.cuda.empty_cache()
+    # ---------------------------------------------------------------- 8f-2: backward kernels next to the torch recompute
+    if want('backward'):
+        from torecsys_b200 import autograd as ag
+        Bb = 16384
+        # cross network, cfg3 shape: rows = Bb x 39, E = 32, 6 layers
+        xc = torch.randn(Bb, N, 32, device=dev) * 0.5
+        wc = torch.randn(6, 32, 32, device=dev) / 32 ** 0.5
+        bc = torch.randn(6, 32, device=dev) * 0.1
+        gc = torch.randn(Bb, N, 32, device=dev)
+        t = timeit(lambda i: ops.cross_backward(xc, wc, bc, gc), reps=10)
+        report('cross backward kernel (dx, dW, db; cfg3 shape)', Bb, t, N * 32 * 4 * 3, N * 6 * 6 * 32 * 32)
+        xr, wr, br = xc.clone().requires_grad_(), wc.clone().requires_grad_(), bc.clone().requires_grad_()
+        t = timeit(lambda i: ag._grad_of(ag._cross, [xr, wr, br], gc), reps=10)
+        report('cross backward, torch recompute (same shape)', Bb, t, N * 32 * 4 * 3, N * 6 * 6 * 32 * 32)
+        del xc, gc, xr
+        # IPN and FFM, cfg2 / cfg5 shapes
+        xi = torch.randn(Bb, N, 16, device=dev)
+        gi = torch.randn(Bb, PAIRS, device=dev)
+        t = timeit(lambda i: ops.ipn_backward(xi, gi), reps=10)
+        report('ipn backward kernel', Bb, t, N * 64 * 2 + PAIRS * 4, 2 * 2 * PAIRS * 16)
+        Bf = 4096
+        vf = torch.randn(Bf, N * N, 16, device=dev)
+        gf = torch.randn(Bf, PAIRS, 16, device=dev)
+        t = timeit(lambda i: ops.ffm_backward(vf, gf, N), reps=10)
+        report('ffm backward kernel', Bf, t, 2 * PAIRS * 64 * 2 + N * N * 64)
+        del xi, gi, vf, gf
+        torch.cuda.empty_cache()
     ops.check_index_errors()
     if args.json:
         with open(args.json, 'w') as f:

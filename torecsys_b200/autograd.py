@@ -1,10 +1,12 @@
-"""autograd.Function wrappers: forward = the hand-written sm_100a kernels, backward = recompute through torch CUDA ops.
+"""autograd.Function wrappers: forward = the hand-written sm_100a kernels; backward = dedicated kernels where they
+exist, else a recompute through torch CUDA ops.
 
 Scope: this repository's product is the FORWARD hot path.  So that the drop-ins
-still "construct and train unchanged" on a GPU, every Function saves its inputs and, in `backward`, re-evaluates the
-layer's formula with differentiable torch ops ON THE SAME CUDA DEVICE and lets torch differentiate it (a composite
-recompute backward).  Nothing here runs on the CPU and nothing is imported from `oracle/`; dedicated backward kernels
-(embedding gradient as a sorted segmented scatter-add, etc.) are the next step.  Gradient parity with the reference
+still "construct and train unchanged" on a GPU, every Function saves its inputs.  The embedding lookups, FM, FFM, IPN
+and the cross network back-propagate through their own kernels (csrc/backward.cu: trs_embedding_grad,
+trs_fm_backward, trs_ffm_backward, trs_ipn_backward, trs_cross_backward); the other layers re-evaluate their formula
+with differentiable torch ops ON THE SAME CUDA DEVICE and let torch differentiate it (a composite recompute
+backward).  Nothing here runs on the CPU and nothing is imported from `oracle/`.  Gradient parity with the reference
 is covered by tests/test_gpu_training.py, including the upstream quirk that CrossNetworkLayer cuts the gradient path
 through h_0 (cross_network.py:65).
 """
@@ -74,18 +76,6 @@ def _fm(x):
     return 0.5 * (x.sum(1) ** 2 - (x ** 2).sum(1))
 
 
-def _ffm(v, n):
-    b, _, e = v.shape
-    v4 = v.reshape(b, n, n, e)
-    i, j = _pairs(n, v.device)
-    return v4[:, i, j] * v4[:, j, i]
-
-
-def _ipn(x):
-    i, j = _pairs(x.shape[1], x.device)
-    return (x[:, i] * x[:, j]).sum(-1)
-
-
 def _bilinear(x, w, bias, each):
     i, j = _pairs(x.shape[1], x.device)
     p, q = x[:, i], x[:, j]
@@ -143,7 +133,7 @@ class FfmFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         (v,) = ctx.saved_tensors
-        return _grad_of(lambda t: _ffm(t, ctx.n), [v], grad) + (None,)
+        return ops.ffm_backward(v, grad.contiguous(), ctx.n), None   # trs_ffm_backward (csrc/backward.cu)
 
 
 class IpnFn(torch.autograd.Function):
@@ -155,7 +145,7 @@ class IpnFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         (x,) = ctx.saved_tensors
-        return _grad_of(_ipn, [x], grad)
+        return ops.ipn_backward(x, grad.contiguous())   # trs_ipn_backward (csrc/backward.cu)
 
 
 class BilinearFn(torch.autograd.Function):
@@ -215,7 +205,12 @@ class CrossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad):
-        return _grad_of(_cross, list(ctx.saved_tensors), grad)
+        x, w, b = ctx.saved_tensors
+        if ops.cross_backward_supported(x.shape[-1]):
+            gx, gw, gb = ops.cross_backward(x, w, b, grad.contiguous())   # trs_cross_backward (csrc/backward.cu)
+            need = ctx.needs_input_grad
+            return (gx if need[0] else None, gw if need[1] else None, gb if need[2] else None)
+        return _grad_of(_cross, [x, w, b], grad)   # other widths: recompute through torch CUDA ops
 
 
 class CinFn(torch.autograd.Function):

@@ -238,6 +238,47 @@ def fm_backward(x: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def ffm_backward(v: torch.Tensor, grad_out: torch.Tensor, num_fields: int) -> torch.Tensor:
+    """d v of ffm(): grad_v[b, a*N+c] = grad_out[b, pair(a,c)] * v[b, c*N+a], zero on the diagonal rows."""
+    v, b, nn_, e = _bne('ffm_backward', v)
+    g = _f32('ffm_backward', grad_out)
+    if nn_ != num_fields * num_fields or tuple(g.shape) != (b, num_fields * (num_fields - 1) // 2, e):
+        raise ValueError(f'ffm_backward: v {tuple(v.shape)} / grad_out {tuple(g.shape)} do not match {num_fields} fields')
+    out = torch.empty_like(v)
+    check(_cabi.load().trs_ffm_backward(_ptr(v), _ptr(g), b, num_fields, e, _ptr(out), _stream()), 'trs_ffm_backward')
+    return out
+
+
+def ipn_backward(x: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    """d x of ipn(): grad_x[b,i] = sum_{j != i} grad_out[b, pair(i,j)] * x[b,j]."""
+    x, b, n, e = _bne('ipn_backward', x)
+    g = _f32('ipn_backward', grad_out)
+    if tuple(g.shape) != (b, n * (n - 1) // 2):
+        raise ValueError(f'ipn_backward: grad_out {tuple(g.shape)} does not match x {tuple(x.shape)}')
+    out = torch.empty_like(x)
+    check(_cabi.load().trs_ipn_backward(_ptr(x), _ptr(g), b, n, e, _ptr(out), _stream()), 'trs_ipn_backward')
+    return out
+
+
+def cross_backward_supported(embed: int) -> bool:
+    return embed in (8, 16, 32, 64)
+
+
+def cross_backward(x: torch.Tensor, weights: torch.Tensor, biases: torch.Tensor, grad_out: torch.Tensor):
+    """Gradients of cross() for (x, weights, biases); h_0 is detached as upstream (cross_network.py:65)."""
+    _need_cuda('cross_backward', x, weights, biases, grad_out)
+    x, g = _f32('cross_backward', x), _f32('cross_backward', grad_out)
+    w, bs = _f32('cross_backward', weights), _f32('cross_backward', biases)
+    e = x.shape[-1]
+    layers = w.shape[0]
+    if tuple(w.shape) != (layers, e, e) or tuple(bs.shape) != (layers, e) or g.shape != x.shape:
+        raise ValueError('cross_backward: weights (L, E, E), biases (L, E), grad_out like x')
+    gx, gw, gb = torch.empty_like(x), torch.empty_like(w), torch.empty_like(bs)
+    check(_cabi.load().trs_cross_backward(_ptr(x), _ptr(w), _ptr(bs), _ptr(g), layers, x.numel() // e, e,
+                                          _ptr(gx), _ptr(gw), _ptr(gb), _stream()), 'trs_cross_backward')
+    return gx, gw, gb
+
+
 def ffm(v: torch.Tensor, num_fields: int) -> torch.Tensor:
     v, b, nn_, e = _bne('ffm', v)
     if nn_ != num_fields * num_fields:
