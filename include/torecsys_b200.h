@@ -290,6 +290,23 @@ int trs_ffm_model_forward(const void* idx, int idx_bits, const int64_t* offsets,
                           const float* w_feat, const float* const* tables, int64_t rows, int embed,
                           const float* bias, float* logits, int32_t* status, void* stream);
 
+/* Interleaved-table variant of the FFM model forward: the B200-first memory layout of configs[4].  The N rows
+ * T_0[r] .. T_{N-1}[r] of one row id are always read together (field_emb[b, t*N+f] = T_t[r_f] for every t,
+ * multi_indices_field_aware_emb.py:100-105), so the shadow stores them contiguously, with the first-order weight:
+ *     packed[r] = [ T_0[r] | T_1[r] | ... | T_{N-1}[r] | w_feat[r] | 0.. ]   pitch = trs_ffm_interleaved_pitch() floats
+ * (a multiple of 32 floats = 128 bytes).  A sample then reads N contiguous chunks (one TMA bulk copy each) instead
+ * of N(N-1) scattered 64-byte rows.  trs_ffm_pack_tables builds the shadow from the registered tables (w_feat may be
+ * NULL: zeros; run again whenever they change; costs rows x pitch x 4 bytes);
+ * trs_ffm_model_forward_interleaved computes exactly what trs_ffm_model_forward computes.
+ * Restrictions: embed a power of two in [4, 128], fields <= 64, two samples' chunks within 227 KB of shared memory
+ * (TRS_ERR_UNSUPPORTED otherwise). */
+int64_t trs_ffm_interleaved_pitch(int fields, int embed);
+int trs_ffm_pack_tables(const float* const* tables, const float* w_feat, int64_t rows, int fields, int embed,
+                        float* packed, void* stream);
+int trs_ffm_model_forward_interleaved(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                                      const float* packed, int64_t rows, int embed,
+                                      const float* bias, float* logits, int32_t* status, void* stream);
+
 /* The same forward restricted to a LIST of pairs -- one rank's share when the tables are sharded over GPUs
  * (SURVEY.md 8e, configs[4]).  pair_list: DEVICE array of n_pairs entries (i << 16) | j, i < j (NULL = every pair);
  * the first-order term and the bias are added only for samples b in [first_begin, first_end), so that summing the

@@ -260,3 +260,27 @@ def test_state_dict_round_trip_between_instances(trs):
         ya = a(feat.clone(), x.clone())
         yb = b(feat.clone(), x.clone())
     assert torch.equal(ya, yb)
+
+
+def test_ffm_model_keeps_an_interleaved_shadow(trs):
+    """The FFM model under Sequential builds the interleaved shadow once (eval, no grad), rebuilds it after an in-place
+    update of a table, drops it when switched off, and all routes agree."""
+    seq, idx = build_sequential(trs, 'ffm_model', 64, 6, 16)
+    model = seq._model
+    with torch.no_grad():
+        a = seq({'idx': idx})
+        shadow = model._shadow
+        assert shadow is not None and shadow.shape[1] == 128
+        assert seq({'idx': idx}) is not None and model._shadow is shadow          # cached
+        model.interleaved_tables = False
+        b = seq({'idx': idx})
+        model.interleaved_tables = 'auto'
+        assert normwise_err(a.cpu().numpy(), b.cpu().numpy()) <= TOL
+        emb = seq._inputs.schema['field_emb_inputs']
+        emb.embeddings[2].weight.mul_(0.5)
+        c = seq({'idx': idx})
+        assert model._shadow is not shadow
+        model.interleaved_tables = False
+        d = seq({'idx': idx})
+        assert normwise_err(c.cpu().numpy(), d.cpu().numpy()) <= TOL
+        assert normwise_err(c.cpu().numpy(), a.cpu().numpy()) > 1e-3               # the update is visible

@@ -455,3 +455,60 @@ def test_empty_batch(ops):
     assert ops.ipn(x).shape == (0, 10)
     w = torch.randn(7, 8, device='cuda')
     assert ops.embedding_gather(w, torch.empty(0, 3, dtype=torch.long, device='cuda'), None).shape == (0, 3, 8)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# interleaved field-aware tables (csrc/ffm_interleaved.cu): the packed layout and the forward on it
+@pytest.mark.parametrize('n,e,rpf', [(39, 16, 48), (5, 8, 32), (2, 4, 16), (12, 32, 16), (7, 128, 16), (64, 4, 16)])
+def test_ffm_interleaved_tables_and_forward(ops, n, e, rpf):
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    fs = [rpf + 16 * (i % 3) for i in range(n)]
+    rows = sum(fs)
+    off = R.field_offsets(fs)
+    tables = [torch.from_numpy(synth.uniform((rows, e), f'il/t{t}/{n}/{e}', -0.5, 0.5)) for t in range(n)]
+    w_feat = torch.from_numpy(synth.uniform((rows, 1), f'il/wf/{n}/{e}'))
+    bias = torch.tensor([[0.25]])
+    assert ops.ffm_interleaved_supported(n, e)
+    dt = [t.cuda() for t in tables]
+    packed = ops.ffm_pack_tables(dt, w_feat.cuda())
+    pitch = packed.shape[1]
+    assert pitch % 32 == 0 and n * e + 1 <= pitch < n * e + 1 + 32
+    pk = packed.cpu()
+    for t in range(n):
+        assert torch.equal(pk[:, t * e:(t + 1) * e], tables[t])          # bit-exact copies of the table rows
+    assert torch.equal(pk[:, n * e], w_feat[:, 0]) and not pk[:, n * e + 1:].any()
+    no_first = ops.ffm_pack_tables(dt, None).cpu()
+    assert not no_first[:, n * e:].any() and torch.equal(no_first[:, :n * e], pk[:, :n * e])
+    for batch in (1, 2, 147, 149, 700):
+        idx = torch.from_numpy(synth.integers((batch, n), f'il/idx{batch}/{n}', np.asarray(fs)[None, :]))
+        want = R.ffm_from_indices(idx, off, w_feat, tables, bias).numpy()
+        want64 = R.ffm_from_indices(idx, off, w_feat.double(), [t.double() for t in tables], bias.double()).numpy()
+        for idt in (torch.int64, torch.int32):
+            got = ops.ffm_model_interleaved(idx.cuda().to(idt), off.cuda(), packed, n, e, bias.cuda()).cpu().numpy()
+            assert got.shape == (batch, 1)
+            assert normwise_err(got, want) <= TOL, (batch, idt)
+            assert normwise_err(got, want64) <= max(4 * normwise_err(want, want64), 2e-6), (batch, idt)
+        ptr = ops.ffm_model(idx.cuda(), off.cuda(), w_feat.cuda(), dt, bias.cuda()).cpu().numpy()
+        assert normwise_err(got, ptr) <= TOL
+    # no bias, empty batch, out-of-range lookups, wrong shadow shape
+    idx = torch.from_numpy(synth.integers((33, n), f'il/idxnb/{n}', np.asarray(fs)[None, :]))
+    got = ops.ffm_model_interleaved(idx.cuda(), off.cuda(), packed, n, e, None).cpu().numpy()
+    assert normwise_err(got, R.ffm_from_indices(idx, off, w_feat, tables, torch.zeros(1, 1)).numpy()) <= TOL
+    assert ops.ffm_model_interleaved(idx[:0].cuda(), off.cuda(), packed, n, e, bias.cuda()).shape == (0, 1)
+    bad = idx.clone()
+    bad[5, n - 1] = fs[-1] + 3
+    with pytest.raises(IndexError):
+        ops.ffm_model_interleaved(bad.cuda(), off.cuda(), packed, n, e, bias.cuda())
+    with pytest.raises(ValueError):
+        ops.ffm_model_interleaved(idx.cuda(), off.cuda(), packed[:, :-1].contiguous(), n, e, bias.cuda())
+
+
+def test_ffm_interleaved_unsupported_shapes(ops):
+    assert not ops.ffm_interleaved_supported(39, 12) and not ops.ffm_interleaved_supported(65, 16)
+    assert not ops.ffm_interleaved_supported(60, 64)      # two samples' chunks exceed shared memory
+    lib_pitch = 60 * 64 + 32
+    packed = torch.zeros(16, lib_pitch, device='cuda')
+    with pytest.raises(NotImplementedError):
+        ops.ffm_model_interleaved(torch.zeros(4, 60, dtype=torch.int64, device='cuda'),
+                                  torch.zeros(60, dtype=torch.int64, device='cuda'), packed, 60, 64, None)

@@ -296,6 +296,14 @@ def main():
         if want('ffm_model'):
             t = timeit(lambda i: ops.ffm_model(ring[i % 4], fs_off, wf, tables, bias, tp), reps=10)
             report('ffm model fused (a12, cfg5 per-GPU batch, tables at 1/10 scale)', B5, t, 95320, 2 * PAIRS * 16)
+            packed = ops.ffm_pack_tables(tables, wf, tp)
+            got = ops.ffm_model_interleaved(ring[0], fs_off, packed, N, 16, bias)
+            ref = ops.ffm_model(ring[0], fs_off, wf, tables, bias, tp)
+            note = f'max |diff| vs pointer kernel {float((got - ref).abs().max()):.2e} (|logit| max {float(ref.abs().max()):.2f})'
+            t = timeit(lambda i: ops.ffm_model_interleaved(ring[i % 4], fs_off, packed, N, 16, bias), reps=10)
+            report('ffm model fused, INTERLEAVED tables (a12, cfg5 per-GPU batch, tables at 1/10 scale)', B5, t, 95320,
+                   2 * PAIRS * 16, note=note)
+            del packed
         if want('gather_fa') or want('ffm_layer'):
             small = ring[0][:4096].contiguous()
             t = timeit(lambda i: ops.embedding_gather_field_aware(tables, small, fs_off, tp), reps=5)
@@ -320,7 +328,17 @@ def main():
         t = timeit(lambda i: ops.ffm_model(ring[i % 4], fs_off, wf, tables, bias, tp), reps=10)
         report('ffm model fused (a12, cfg5: all 39 tables = 1.0 B rows = 64 GB on ONE GPU, per-GPU batch 32 768)', B5, t,
                95320, 2 * PAIRS * 16)
-        del tables, wf, ring
+        del tables, wf
+        torch.cuda.empty_cache()
+        # the same 1.0 B rows as the interleaved shadow (25.6 M row ids x 2 560 B = 65.6 GB), filled directly
+        pitch = 640
+        packed = torch.empty(rfa, pitch, device=dev)
+        for lo in range(0, rfa, 1 << 21):
+            packed[lo:lo + (1 << 21)].uniform_(-0.1, 0.1)
+        t = timeit(lambda i: ops.ffm_model_interleaved(ring[i % 4], fs_off, packed, N, 16, bias), reps=10)
+        report('ffm model fused, INTERLEAVED tables (a12, cfg5: 1.0 B rows = 65.6 GB shadow on ONE GPU, per-GPU batch '
+               '32 768)', B5, t, 95320, 2 * PAIRS * 16)
+        del packed, ring
         torch.cuda.empty_cache()
     # ---------------------------------------------------------------- 8f-2: backward kernels next to the torch recompute
     if want('backward'):

@@ -67,6 +67,9 @@ PROTOTYPES = {
     'trs_xdeepfm_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _PP, _PP, _PP, _IP, c_int,
                                     c_int, c_int, _P, _P, _IP, c_int, _PP, _PP, c_int, _P, _P, _P, c_int64, _P, _P]),
     'trs_ffm_model_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _P, _P, _P, _P]),
+    'trs_ffm_interleaved_pitch': (c_int64, [c_int, c_int]),
+    'trs_ffm_pack_tables': (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P]),
+    'trs_ffm_model_forward_interleaved': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, c_int, _P, _P, _P, _P]),
     'trs_ffm_model_forward_pairs': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _P, _P, c_int,
                                             c_int64, c_int64, _P, _P, _P]),
     'trs_nfm_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _IP, c_int, _PP, _PP, c_int, _P,

@@ -265,8 +265,35 @@ class FieldAwareFactorizationMachineModel(CtrBaseModel):
         feat, femb = inputs_module.schema['feat_inputs'], inputs_module.schema['field_emb_inputs']
         idx = _index_batch(inputs_module, 'field_emb_inputs', batch)
         tables = [e.weight for e in femb.embeddings]
+        packed = self._interleaved_shadow(feat.embedding.weight, tables, femb._table_ptrs)
+        if packed is not None:
+            return ops.ffm_model_interleaved(idx, femb._offsets_on(tables[0].device), packed, len(tables),
+                                             tables[0].shape[1], self.bias.rename(None))
         return ops.ffm_model(idx, femb._offsets_on(tables[0].device), feat.embedding.weight, tables,
                              self.bias.rename(None), femb._table_ptrs)
+
+    # 'auto': build the interleaved shadow of the field-aware tables (ops.ffm_pack_tables: rows x pitch x 4 bytes, about
+    # the size of the tables themselves) when the shape is supported and it fits comfortably in free HBM; True / False
+    # force it on / off.  The shadow is rebuilt when a table or the first-order table was modified in place or moved.
+    interleaved_tables = 'auto'
+
+    def _interleaved_shadow(self, w_feat, tables, table_ptrs):
+        mode = self.interleaved_tables
+        rows, embed = tables[0].shape
+        if mode is False or torch.is_grad_enabled() or not ops.ffm_interleaved_supported(len(tables), embed):
+            return None
+        key = (w_feat.data_ptr(), w_feat._version) + tuple(x for t in tables for x in (t.data_ptr(), t._version))
+        if getattr(self, '_shadow_key', None) == key:
+            return self._shadow
+        self._shadow, self._shadow_key = None, None
+        if mode == 'auto':
+            need = rows * ((len(tables) * embed + 1 + 31) // 32 * 32) * 4
+            free, _ = torch.cuda.mem_get_info(tables[0].device)
+            if need > 0.45 * free:
+                return None
+        self._shadow = ops.ffm_pack_tables([t.detach() for t in tables], w_feat.detach(), table_ptrs)
+        self._shadow_key = key
+        return self._shadow
 
 
 class Sequential(nn.Module):

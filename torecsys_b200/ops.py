@@ -653,6 +653,59 @@ def ffm_model_pairs(idx, offsets, w_feat, table_ptrs: torch.Tensor, rows: int, e
     return out
 
 
+def ffm_interleaved_supported(fields: int, embed: int) -> bool:
+    """Shapes trs_ffm_model_forward_interleaved takes (power-of-two embed, two samples' chunks in shared memory)."""
+    if fields < 2 or fields > 64 or embed < 4 or embed > 128 or embed & (embed - 1):
+        return False
+    copy = (4 * (fields * embed + 1) + 15) // 16 * 16
+    return 2 * fields * ((copy + 127) // 128 * 128 + 64) + 4 * fields * fields + 256 <= 227 * 1024
+
+
+def ffm_pack_tables(tables: Sequence[torch.Tensor], w_feat: Optional[torch.Tensor],
+                    table_ptrs: Optional[TablePointers] = None) -> torch.Tensor:
+    """Builds the interleaved shadow [T_0[r] | ... | T_{N-1}[r] | w_feat[r] | 0..] of the field-aware tables
+    (trs_ffm_pack_tables); (rows, pitch) fp32 with pitch a multiple of 32 floats."""
+    _need_cuda('ffm_pack_tables', *tables)
+    ws = [_f32('ffm_pack_tables', t) for t in tables]
+    rows, e = ws[0].shape
+    if any(tuple(t.shape) != (rows, e) for t in ws):
+        raise ValueError('ffm_pack_tables: all tables must have the same (rows, embed) shape')
+    wf = None
+    if w_feat is not None:
+        _need_cuda('ffm_pack_tables', w_feat)
+        wf = _f32('ffm_pack_tables', w_feat)
+        if wf.numel() != rows:
+            raise ValueError('ffm_pack_tables: w_feat must have one value per table row')
+    lib = _cabi.load()
+    pitch = int(lib.trs_ffm_interleaved_pitch(len(ws), e))
+    packed = torch.empty((rows, pitch), dtype=torch.float32, device=ws[0].device)
+    tp = (table_ptrs or TablePointers()).get(ws)
+    check(lib.trs_ffm_pack_tables(_ptr(tp), _ptr(wf), rows, len(ws), e, _ptr(packed), _stream()), 'trs_ffm_pack_tables')
+    return packed
+
+
+def ffm_model_interleaved(idx, offsets, packed: torch.Tensor, fields: int, embed: int, bias,
+                          out: Optional[torch.Tensor] = None):
+    """FieldAwareFactorizationMachineModel forward on the interleaved shadow (trs_ffm_model_forward_interleaved)."""
+    ix, bits, off = _fused_common('ffm_model_interleaved', idx, offsets, packed, bias)
+    lib = _cabi.load()
+    if (packed.dtype != torch.float32 or packed.dim() != 2 or not packed.is_contiguous()
+            or packed.shape[1] != int(lib.trs_ffm_interleaved_pitch(fields, embed))):
+        raise ValueError('ffm_model_interleaved: packed must be the contiguous float32 tensor ffm_pack_tables built '
+                         f'for {fields} fields x {embed}')
+    b, n = ix.shape
+    if n != fields:
+        raise ValueError(f'ffm_model_interleaved: {n} index columns but {fields} fields')
+    bs = _f32('ffm_model_interleaved', bias).reshape(-1) if bias is not None else None
+    out = out if out is not None else torch.empty((b, 1), dtype=torch.float32, device=packed.device)
+    st = _status_tensor(packed.device)
+    check(lib.trs_ffm_model_forward_interleaved(_ptr(ix), bits, _ptr(off), b, n, _ptr(packed), packed.shape[0], embed,
+                                                _ptr(bs), _ptr(out), _ptr(st), _stream()),
+          'trs_ffm_model_forward_interleaved')
+    _after_lookup(packed.device)
+    return out
+
+
 def ffm_model(idx, offsets, w_feat, tables: Sequence[torch.Tensor], bias, table_ptrs: Optional[TablePointers] = None,
               out: Optional[torch.Tensor] = None):
     ix, bits, off = _fused_common('ffm_model', idx, offsets, w_feat, bias, *tables)
