@@ -1,5 +1,6 @@
 // Library-level entry points: version, error string, device probe.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -11,6 +12,34 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
+}
+
+// Stream-ordered scratch (activation ping-pong buffers of the MLP chain, pre-split tensor-core weights, xDeepFM's
+// embedding tile).  The device's default memory pool releases everything it holds at every synchronisation point unless
+// told otherwise, which turns the allocation in each call into a fresh physical mapping (milliseconds) whenever the
+// caller synchronises between calls -- e.g. the 'sync' index-check mode of the Python modules.  Keep up to 4 GB cached.
+cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t s) {
+  static thread_local int prepared_device = -1;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  static const bool leave_pool_alone = getenv("TRS_POOL_RELEASE_DEFAULT") != nullptr;   // for A/B measurements
+  if (dev != prepared_device && !leave_pool_alone) {
+    cudaMemPool_t pool;
+    e = cudaDeviceGetDefaultMemPool(&pool, dev);
+    if (e != cudaSuccess) return e;
+    uint64_t keep = 0;
+    e = cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (e != cudaSuccess) return e;
+    const uint64_t want = 4ull << 30;
+    if (keep < want) {
+      keep = want;
+      e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      if (e != cudaSuccess) return e;
+    }
+    prepared_device = dev;
+  }
+  return cudaMallocAsync(ptr, bytes, s);
 }
 }  // namespace trs
 

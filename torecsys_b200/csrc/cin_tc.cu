@@ -501,7 +501,7 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
   const bool a_tmem = block <= 128;
   const size_t w_floats = (size_t)(kp / 16) * 2 * 4 * block * 4;   // upper bound per channel block
   float* wp = nullptr;
-  TRS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&wp), w_floats * sizeof(float) * passes, s));
+  TRS_CUDA(scratch_alloc(reinterpret_cast<void**>(&wp), w_floats * sizeof(float) * passes, s));
   int rc = TRS_OK;
   for (int pass = 0; pass < passes && rc == TRS_OK; ++pass) {
     const int c0 = pass * block;

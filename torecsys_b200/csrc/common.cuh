@@ -20,6 +20,8 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multi
 
 // ---- host-side error plumbing -----------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
+// cudaMallocAsync from the device's default pool, with the pool told to keep its memory across synchronisation points
+cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t s);
 
 #define TRS_REQUIRE(cond, ...)                 \
   do {                                         \

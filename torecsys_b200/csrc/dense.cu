@@ -238,7 +238,7 @@ int mlp_chain_run(const float* x, int64_t rows, const MlpParams& mp, float* out,
   for (int l = 1; l < mp.layers; ++l) hmax = mp.dims[l] > hmax ? mp.dims[l] : hmax;
   const size_t half = ((size_t)rows * hmax + 63) / 64 * 64;
   float* buf = nullptr;
-  if (mp.layers > 1) TRS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&buf), 2 * half * sizeof(float), s));
+  if (mp.layers > 1) TRS_CUDA(scratch_alloc(reinterpret_cast<void**>(&buf), 2 * half * sizeof(float), s));
   const float* cur = x;
   int rc = TRS_OK;
   for (int l = 0; l < mp.layers && rc == TRS_OK; ++l) {

@@ -320,7 +320,7 @@ int launch_fm_family(const void* idx, int idx_bits, const int64_t* offsets, int6
     a.mp.layers = 0;
     mlp_layers = 0;
     if (a.x_out == nullptr) {
-      TRS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&x_scratch), (size_t)batch * fields * embed * sizeof(float), s));
+      TRS_CUDA(scratch_alloc(reinterpret_cast<void**>(&x_scratch), (size_t)batch * fields * embed * sizeof(float), s));
       a.x_out = x_scratch;
     }
   }
