@@ -156,47 +156,85 @@ __global__ void __launch_bounds__(kWarps * 32, E <= 32 ? 2 : 1) dcn_tc_kernel(Dc
   const int64_t groups = (a.batch + kSamples - 1) / kSamples;
   const float fc_bias = __ldg(a.fc_b);
 
-  // copies of one 16-row tile (rows row0 .. row0+15 of the flattened (b, n) index space) into staging buffer `buf`
-  auto issue_tile = [&](int64_t row0, int64_t row_end, int buf) {
-    const uint32_t dst0 = static_cast<uint32_t>(__cvta_generic_to_shared(stage + buf * 16 * kPitch));
+  // Every warp walks its own sequence of 16-row tiles: tile w, w+8, ... of group blockIdx.x, then of the next group
+  // of this CTA, and so on.  The raw indices of tile q+2 and the rows of tile q+1 are in flight (cp.async) while tile q
+  // is computed, ACROSS group boundaries -- a warp never waits for an index load it has just issued.
+  // The raw index of row r of tile q waits in the 32 unused bytes behind row r of staging buffer q & 1 (the row pitch
+  // is E + 8 floats for conflict-free fragment loads): two tiles of indices are alive at a time, no extra shared memory.
+  constexpr int kIdxBytes = IdxBits / 8;
+  auto idx_slot = [&](int64_t q, int r) -> unsigned char* {
+    return reinterpret_cast<unsigned char*>(stage + ((q & 1) * 16 + r) * kPitch + E);
+  };
+  const int64_t all_rows = a.batch * n_fields;
+  const int cnt_w = warp < n_fields ? (n_fields - warp + kWarps - 1) / kWarps : 0;   // tiles of this warp per group
+  const int64_t my_groups = blockIdx.x < groups ? (groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t my_tiles = my_groups * cnt_w;
+  auto tile_row0 = [&](int64_t q) -> int64_t {
+    const int64_t ord = q / cnt_w;
+    const int j = static_cast<int>(q - ord * cnt_w);
+    return ((int64_t)blockIdx.x + ord * gridDim.x) * kSamples * n_fields + (int64_t)(warp + kWarps * j) * 16;
+  };
+  // raw indices of tile q (lanes 0-15, one index each); always commits a group
+  auto issue_idx = [&](int64_t q) {
+    if (q < my_tiles && lane < 16) {
+      const int64_t row = tile_row0(q) + lane;
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(idx_slot(q, lane)));
+      const unsigned char* src = static_cast<const unsigned char*>(a.idx) + (row < all_rows ? row : 0) * kIdxBytes;
+      const int bytes = row < all_rows ? kIdxBytes : 0;
+      if (IdxBits == 64)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+      else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // rows of tile q (its indices have landed) -> staging buffer q & 1; always commits a group
+  auto issue_rows = [&](int64_t q) {
+    if (q < my_tiles) {
+      const int64_t row0 = tile_row0(q);
+      const uint32_t dst0 = static_cast<uint32_t>(__cvta_generic_to_shared(stage + (q & 1) * 16 * kPitch));
 #pragma unroll
-    for (int k = 0; k < kCopies; ++k) {
-      const int c = lane + 32 * k;
-      const int r = c / kChunks, ch = c - r * kChunks;
-      const int64_t row = row0 + r;
-      int src_bytes = 0;
-      const float* src = a.w_emb;
-      if (row < row_end) {
-        const int n = static_cast<int>(row % n_fields);
-        const int64_t ix = load_index<IdxBits>(a.idx, row) + __ldg(a.offsets + n);
-        if (ix >= 0 && ix < a.rows) {
-          src = a.w_emb + ix * E + 4 * ch;
-          src_bytes = 16;
-        } else if (ch == 0) {
-          report_oob(a.status, row);
+      for (int k = 0; k < kCopies; ++k) {
+        const int c = lane + 32 * k;
+        const int r = c / kChunks, ch = c - r * kChunks;
+        const int64_t row = row0 + r;
+        int src_bytes = 0;
+        const float* src = a.w_emb;
+        if (row < all_rows) {
+          const int n = static_cast<int>(row % n_fields);
+          const unsigned char* slot = idx_slot(q, r);
+          const int64_t raw = IdxBits == 64 ? *reinterpret_cast<const long long*>(slot)
+                                            : static_cast<int64_t>(*reinterpret_cast<const int*>(slot));
+          const int64_t ix = raw + __ldg(a.offsets + n);
+          if (ix >= 0 && ix < a.rows) {
+            src = a.w_emb + ix * E + 4 * ch;
+            src_bytes = 16;
+          } else if (ch == 0) {
+            report_oob(a.status, row);
+          }
         }
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (r * kPitch + 4 * ch) * 4), "l"(src),
+                     "r"(src_bytes) : "memory");
       }
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (r * kPitch + 4 * ch) * 4), "l"(src),
-                   "r"(src_bytes) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
+  issue_idx(0);
+  issue_idx(1);
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
+  __syncwarp();
+  issue_rows(0);
+  int64_t seq = 0;
   for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x) {
     const int64_t b0 = grp * kSamples;
     const int nsamp = static_cast<int>(a.batch - b0 < kSamples ? a.batch - b0 : kSamples);
-    const int64_t row_base = b0 * n_fields, row_end = row_base + (int64_t)nsamp * n_fields;
-    // tiles of this group: 0 .. n_fields-1 (16 samples x N rows = N tiles of 16 rows); warp w takes w, w+8, ...
-    int buf = 0;
-    if (warp < n_fields) issue_tile(row_base + (int64_t)warp * 16, row_end, 0);
-    for (int tile = warp; tile < n_fields; tile += kWarps) {
-      if (tile + kWarps < n_fields) {
-        issue_tile(row_base + (int64_t)(tile + kWarps) * 16, row_end, buf ^ 1);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-      } else {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      }
+    for (int tile = warp; tile < n_fields; tile += kWarps, ++seq) {
+      const int buf = static_cast<int>(seq & 1);
+      issue_idx(seq + 2);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");   // indices of tile seq+1 and rows of tile seq have landed
       __syncwarp();
+      issue_rows(seq + 1);
       // ---- x in accumulator layout ---------------------------------------------------------------------------------
       const float* sx = stage + buf * 16 * kPitch;
       float x[T][4], h[T][4], acc[T][4];
@@ -283,7 +321,6 @@ __global__ void __launch_bounds__(kWarps * 32, E <= 32 ? 2 : 1) dcn_tc_kernel(Dc
         part[ra] = dot_a;
         part[rb] = dot_b;
       }
-      buf ^= 1;
     }
     __syncthreads();
     if (threadIdx.x < nsamp) {
