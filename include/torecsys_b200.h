@@ -129,6 +129,17 @@ int trs_ipn_forward(const float* x, int64_t batch, int fields, int embed, float*
 int trs_bilinear_forward(const float* x, const float* weight, const float* bias, int each_type,
                          int64_t batch, int fields, int embed, float* out, void* stream);
 
+/* trs_bilinear_backward: gradients of BilinearInteractionLayer.forward (bilinear_interaction.py:230-255) for x, the
+ * weight and the bias, given grad_out (batch, P, embed).  With t[b,p,:] = grad_out[b,p,:] * x[b,j,:]:
+ *     grad_x[b,i,:] += W_(p) t[b,p,:]        grad_x[b,j,:] += grad_out[b,p,:] * (x[b,i,:] @ W_(p))
+ *     grad_weight_(p) += sum_b x[b,i,:]^T t[b,p,:]        grad_bias_(p) += sum_b grad_out[b,p,:]
+ * grad_x (batch, fields, embed), grad_weight ((P,)E,E) and grad_bias ((P,)E; may be NULL) are OVERWRITTEN (the
+ * parameter gradients are zeroed on the stream, then accumulated with float atomics, one add per CTA).
+ * embed 8, 16 or 32 and 2*16*fields*embed*4 bytes of shared memory (TRS_ERR_UNSUPPORTED otherwise). */
+int trs_bilinear_backward(const float* x, const float* weight, const float* grad_out, int each_type,
+                          int64_t batch, int fields, int embed, float* grad_x, float* grad_weight,
+                          float* grad_bias, void* stream);
+
 /* ---- a11: attentional FM -----------------------------------------------------------------------------------------
  * Replaces AttentionalFactorizationMachineLayer.forward
  * (torecsys/layers/ctr/attentional_factorization_machine.py:86-120), eval mode (dropouts are identity):

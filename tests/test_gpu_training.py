@@ -273,6 +273,62 @@ def test_cross_backward_kernel(rows, e, layers):
         assert err <= 2e-5, (what, float(err))
 
 
+@pytest.mark.parametrize('each', [False, True])
+@pytest.mark.parametrize('b,n,e', [(1, 2, 8), (37, 39, 16), (200, 12, 32), (65, 5, 8), (16 * 148 * 2 + 5, 4, 16),
+                                   (64 * 7 + 1, 3, 32)])
+def test_bilinear_backward_kernel(b, n, e, each):
+    """x, weight and bias gradients of the bilinear interaction (csrc/bilinear_bwd.cu) against float64 autograd on the
+    upstream formula (bilinear_interaction.py:72-76 / :144-149): both weight types, every supported width, ragged last
+    tiles of the sample-major kernel (16 samples) and of the pair-major kernel (64-sample chunks, several slices)."""
+    from torecsys_b200 import ops
+    gen = torch.Generator().manual_seed(14)
+    x = torch.randn(b, n, e, generator=gen, dtype=torch.float64, requires_grad=True)
+    i, j = torch.triu_indices(n, n, offset=1)
+    pairs = i.numel()
+    w = (torch.randn(*((pairs, e, e) if each else (e, e)), generator=gen, dtype=torch.float64) / e ** 0.5).requires_grad_()
+    bb = (0.1 * torch.randn(*((pairs, e) if each else (e,)), generator=gen, dtype=torch.float64)).requires_grad_()
+    g = torch.randn(b, pairs, e, generator=gen, dtype=torch.float64)
+    y = torch.matmul(x[:, i].unsqueeze(-2), w).squeeze(-2) if each else torch.matmul(x[:, i], w)
+    ((y * x[:, j] + bb) * g).sum().backward()
+    gx, gw, gb = ops.bilinear_backward(x.detach().float().cuda(), w.detach().float().cuda(), g.float().cuda(), each)
+    for got, want, what in ((gx, x.grad, 'dx'), (gw, w.grad, 'dW'), (gb, bb.grad, 'db')):
+        assert got.shape == want.shape, what
+        err = (got.cpu().double() - want).abs().max() / want.abs().max()
+        assert err <= 2e-5, (what, float(err))
+    gx2, gw2, gb2 = ops.bilinear_backward(x.detach().float().cuda(), w.detach().float().cuda(), g.float().cuda(), each,
+                                          with_bias=False)
+    assert gb2 is None and torch.equal(gx2, gx)   # grad_x has one owner thread per element: deterministic
+    assert (gw2 - gw).abs().max() <= 1e-5 * gw.abs().max()
+
+
+def test_bilinear_backward_edges_and_routes():
+    """Empty batch -> zero parameter gradients; mismatched shapes -> ValueError; unsupported widths -> the C ABI says
+    so (NotImplementedError) and BilinearFn takes the torch recompute instead; a frozen weight gets no gradient."""
+    from torecsys_b200 import ops
+    from torecsys_b200.autograd import BilinearFn
+    x = torch.randn(0, 5, 16).cuda()
+    w = torch.randn(16, 16).cuda()
+    gx, gw, gb = ops.bilinear_backward(x, w, torch.zeros(0, 10, 16).cuda(), False)
+    assert gx.shape == (0, 5, 16) and not gw.any() and not gb.any()
+    with pytest.raises(ValueError):
+        ops.bilinear_backward(torch.randn(4, 5, 16).cuda(), w, torch.zeros(4, 9, 16).cuda(), False)
+    with pytest.raises(NotImplementedError):
+        ops.bilinear_backward(torch.randn(4, 5, 12).cuda(), torch.randn(12, 12).cuda(), torch.zeros(4, 10, 12).cuda(), False)
+    assert not ops.bilinear_backward_supported(5, 12) and ops.bilinear_backward_supported(39, 16)
+    for e in (16, 12):
+        gen = torch.Generator().manual_seed(15)
+        xg = torch.randn(20, 6, e, generator=gen).cuda().requires_grad_()
+        wg = (torch.randn(15, e, e, generator=gen) / e ** 0.5).cuda()
+        bg = torch.zeros(15, e).cuda().requires_grad_()
+        BilinearFn.apply(xg, wg, bg, True).sum().backward()
+        assert xg.grad is not None and bg.grad is not None and wg.grad is None
+        xd = xg.detach().double().cpu().requires_grad_()
+        i, j = torch.triu_indices(6, 6, offset=1)
+        (torch.matmul(xd[:, i].unsqueeze(-2), wg.double().cpu()).squeeze(-2) * xd[:, j]).sum().backward()
+        assert (xg.grad.cpu().double() - xd.grad).abs().max() <= 2e-5 * xd.grad.abs().max()
+        assert (bg.grad.cpu() - 20.0).abs().max() <= 1e-4
+
+
 def test_cross_function_backward_routes():
     """CrossFn uses the kernel for the widths it supports and the torch recompute for the others; both honour
     needs_input_grad (a frozen weight gets no gradient)."""

@@ -367,6 +367,27 @@ def main():
         report('ffm backward kernel', Bf, t, 2 * PAIRS * 64 * 2 + N * N * 64)
         del xi, gi, vf, gf
         torch.cuda.empty_cache()
+    # bilinear interaction backward (FiBiNET shape: 39 fields, E = 16): own flag, it is not part of `backward`'s history
+    if want('bilinear_backward'):
+        from torecsys_b200 import autograd as ag
+        Bb = 16384
+        xb = torch.randn(Bb, N, 16, device=dev)
+        gb_ = torch.randn(Bb, PAIRS, 16, device=dev)
+        for each in (False, True):
+            wb = torch.randn(*((PAIRS, 16, 16) if each else (16, 16)), device=dev) / 4
+            bb = torch.zeros(*((PAIRS, 16) if each else (16,)), device=dev)
+            kind = 'each' if each else 'all'
+            # algorithmic bytes: grad_out read twice (once per kernel), x read and grad_x written once
+            t = timeit(lambda i: ops.bilinear_backward(xb, wb, gb_, each), reps=10)
+            report(f'bilinear-{kind} backward kernels (dx, dW, db)', Bb, t, 2 * PAIRS * 64 + 2 * N * 64,
+                   3 * 2 * PAIRS * 16 * 16)
+            xr, wr, br = xb.clone().requires_grad_(), wb.clone().requires_grad_(), bb.clone().requires_grad_()
+            t = timeit(lambda i: ag._grad_of(lambda a, c, d: ag._bilinear(a, c, d, each), [xr, wr, br], gb_), reps=5)
+            report(f'bilinear-{kind} backward, torch recompute (same shape)', Bb, t, 2 * PAIRS * 64 + 2 * N * 64,
+                   3 * 2 * PAIRS * 16 * 16)
+            del xr, wr, br
+        del xb, gb_
+        torch.cuda.empty_cache()
     ops.check_index_errors()
     if args.json:
         with open(args.json, 'w') as f:

@@ -42,6 +42,7 @@ PROTOTYPES = {
     'trs_ffm_forward': (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     'trs_ipn_forward': (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     'trs_bilinear_forward': (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int, _P, _P]),
+    'trs_bilinear_backward': (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int, _P, _P, _P, _P]),
     'trs_afm_forward': (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
     'trs_opn_forward': (c_int, [_P, _P, c_int, c_int64, c_int, c_int, _P, _P]),
     'trs_senet_workspace_bytes': (c_int64, [c_int64, c_int]),

@@ -2,9 +2,10 @@
 exist, else a recompute through torch CUDA ops.
 
 Scope: this repository's product is the FORWARD hot path.  So that the drop-ins
-still "construct and train unchanged" on a GPU, every Function saves its inputs.  The embedding lookups, FM, FFM, IPN
-and the cross network back-propagate through their own kernels (csrc/backward.cu: trs_embedding_grad,
-trs_fm_backward, trs_ffm_backward, trs_ipn_backward, trs_cross_backward); the other layers re-evaluate their formula
+still "construct and train unchanged" on a GPU, every Function saves its inputs.  The embedding lookups, FM, FFM, IPN,
+the bilinear interaction and the cross network back-propagate through their own kernels (csrc/backward.cu:
+trs_embedding_grad, trs_fm_backward, trs_ffm_backward, trs_ipn_backward, trs_cross_backward; csrc/bilinear_bwd.cu:
+trs_bilinear_backward for embed 8 / 16 / 32); the other layers re-evaluate their formula
 with differentiable torch ops ON THE SAME CUDA DEVICE and let torch differentiate it (a composite recompute
 backward).  Nothing here runs on the CPU and nothing is imported from `oracle/`.  Gradient parity with the reference
 is covered by tests/test_gpu_training.py, including the upstream quirk that CrossNetworkLayer cuts the gradient path
@@ -158,6 +159,9 @@ class BilinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         x, w, b = ctx.saved_tensors
+        if ops.bilinear_backward_supported(x.shape[-2], x.shape[-1]):   # trs_bilinear_backward (csrc/bilinear_bwd.cu)
+            gx, gw, gb = ops.bilinear_backward(x, w, grad.contiguous(), ctx.each, with_bias=b is not None)
+            return gx, gw, gb, None
         return _grad_of(lambda a, c, d: _bilinear(a, c, d, ctx.each), [x, w, b], grad) + (None,)
 
 

@@ -349,6 +349,31 @@ def bilinear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]
     return out
 
 
+def bilinear_backward_supported(num_fields: int, embed: int) -> bool:
+    """Shapes trs_bilinear_backward takes: embed 8 / 16 / 32 and 16 samples of x and grad_x in shared memory."""
+    return embed in (8, 16, 32) and 2 * 16 * num_fields * embed * 4 <= 227 * 1024
+
+
+def bilinear_backward(x: torch.Tensor, weight: torch.Tensor, grad_out: torch.Tensor, each_type: bool,
+                      with_bias: bool = True) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """(d x, d weight, d bias) of bilinear(): csrc/bilinear_bwd.cu (bilinear_interaction.py:230-255 differentiated)."""
+    x, b, n, e = _bne('bilinear_backward', x)
+    _need_cuda('bilinear_backward', weight, grad_out)
+    w = _f32('bilinear_backward', weight)
+    g = _f32('bilinear_backward', grad_out)
+    pairs = n * (n - 1) // 2
+    want = (pairs, e, e) if each_type else (e, e)
+    if tuple(w.shape) != want or tuple(g.shape) != (b, pairs, e):
+        raise ValueError(f'bilinear_backward: weight {tuple(w.shape)} / grad_out {tuple(g.shape)} do not match '
+                         f'x {tuple(x.shape)}')
+    gx = torch.empty_like(x)
+    gw = torch.empty_like(w)
+    gb = torch.empty(want[:-1], dtype=torch.float32, device=x.device) if with_bias else None
+    check(_cabi.load().trs_bilinear_backward(_ptr(x), _ptr(w), _ptr(g), int(each_type), b, n, e, _ptr(gx), _ptr(gw),
+                                             _ptr(gb), _stream()), 'trs_bilinear_backward')
+    return gx, gw, gb
+
+
 def afm(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor
         ) -> Tuple[torch.Tensor, torch.Tensor]:
     x, b, n, e = _bne('afm', x)
