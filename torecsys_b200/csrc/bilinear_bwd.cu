@@ -40,7 +40,8 @@ struct VecLoad<2> {
     v[0] = r.x, v[1] = r.y;
   }
   static __device__ __forceinline__ void ld_stream(const float* p, float* v) {
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "l"(p));
+    const float2 r = ldg_stream_f2(reinterpret_cast<const float2*>(p));
+    v[0] = r.x, v[1] = r.y;
   }
 };
 template <>
