@@ -76,6 +76,7 @@ namespace trs {
 static inline float4 ldg_stream_f4(const float4* p) { return *p; }
 static inline float2 ldg_stream_f2(const float2* p) { return *p; }
 static inline float ldg_stream_f1(const float* p) { return *p; }
+static inline int opaque_zero() { return 0; }
 static inline void stg_stream_f4(float4* p, const float4& v) { *p = v; }
 // lexicographic pair index -> (i, j): the plain definition (csrc/common.cuh has the closed form)
 static inline void pair_from_index(int p, int n, int& i, int& j) {

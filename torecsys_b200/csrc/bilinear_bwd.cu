@@ -10,7 +10,7 @@
 //   bilinear_backward_x_kernel  sample-major.  CTA = 16 samples x 8 lanes; the lane group of a sample keeps the
 //       sample's fields and its grad_x accumulators in shared memory, lane `og` owns the output columns
 //       [og*E/8, (og+1)*E/8) of every pair.  The pair loop is flat (p = 0..P-1) with a 4-deep register ring of
-//       grad_out prefetches; x_i and the partial grad_x[i] stay in registers for the whole run of pairs (i, *), and are
+//       grad_out prefetches; the partial grad_x[i] stays in registers for the whole run of pairs (i, *) and is
 //       reduced over the 8 lanes once per field.  No CTA barrier and no atomics inside the loop: every shared-memory
 //       accumulator has exactly one owner thread.  W_(p) is read through L1 (1 KB per pair at E = 16, shared by the CTA).
 //   bilinear_backward_w_kernel  pair-major.  CTA = one pair (x one slice of the batch); chunks of 64 samples of x_i,
@@ -91,16 +91,23 @@ __global__ void __launch_bounds__(kBxSamples * 8) bilinear_backward_x_kernel(
       for (int c = 0; c < V; ++c) gq[d][c] = 0.f;
       if (valid && d < pairs) VecLoad<V>::ld_stream(grow + (int64_t)d * E, gq[d]);
     }
-    float xi[E], acc[E];
+    float acc[E];
 #pragma unroll
-    for (int k = 0; k < E; ++k) xi[k] = xrow[k], acc[k] = 0.f;
-    int i = 0, j = 1;
+    for (int k = 0; k < E; ++k) acc[k] = 0.f;
+    // (i, j) live in per-thread registers: with CTA-uniform counters ptxas 12.9 kept them in uniform registers and
+    // re-read x_i from field i + 2 after the first run of pairs (seen in the SASS and in the results)
+    int i = opaque_zero(), j = i + 1;
     for (int p0 = 0; p0 < pairs; p0 += kBxDepth) {
 #pragma unroll
       for (int d = 0; d < kBxDepth; ++d) {
         const int p = p0 + d;
         if (p < pairs) {   // uniform over the CTA
-          float g[V], xj[V], tt[V], y[V];
+          float g[V], xj[V], tt[V], y[V], xi[E];
+#pragma unroll
+          for (int k = 0; k < E; k += 4) {   // x_i: a 16-byte broadcast per four components
+            const float4 v = *reinterpret_cast<const float4*>(xrow + i * E + k);
+            xi[k] = v.x, xi[k + 1] = v.y, xi[k + 2] = v.z, xi[k + 3] = v.w;
+          }
 #pragma unroll
           for (int c = 0; c < V; ++c) {
             g[c] = gq[d][c];
@@ -138,10 +145,6 @@ __global__ void __launch_bounds__(kBxSamples * 8) bilinear_backward_x_kernel(
             }
             ++i;
             j = i + 1;
-            if (i < fields - 1) {
-#pragma unroll
-              for (int k = 0; k < E; ++k) xi[k] = xrow[i * E + k];
-            }
           }
         }
       }

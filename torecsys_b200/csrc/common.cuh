@@ -124,6 +124,13 @@ __device__ __forceinline__ void report_oob(int32_t* status, int64_t flat_pos) {
   }
 }
 
+// a zero the compiler cannot see through: keeps loop counters derived from it out of the uniform datapath
+__device__ __forceinline__ int opaque_zero() {
+  int z;
+  asm volatile("mov.u32 %0, 0;" : "=r"(z));
+  return z;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
