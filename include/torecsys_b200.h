@@ -149,6 +149,21 @@ int trs_bilinear_backward(const float* x, const float* weight, const float* grad
 int trs_afm_forward(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                     int64_t batch, int fields, int embed, int attn, float* out, float* scores, void* stream);
 
+/* trs_afm_backward: gradients of AttentionalFactorizationMachineLayer.forward (:86-120, eval mode) for x, W1, b1, w2
+ * and b2, given the attention `scores` (batch, P) the forward returned, grad_out (batch, embed) and, optionally,
+ * grad_scores (batch, P; NULL = zero).  With da_p = <grad_out, prod_p> + grad_scores_p, c = sum_q s_q da_q,
+ * ds_p = s_p (da_p - c), dh_p = w2 * ds_p * [W1 prod_p + b1 > 0], dprod_p = s_p grad_out + W1^T dh_p:
+ *     grad_x[b,i,:] += dprod_p * x[b,j,:]   grad_x[b,j,:] += dprod_p * x[b,i,:]
+ *     grad_w1 += dh_p (x) prod_p   grad_b1 += dh_p   grad_w2 += ds_p relu(W1 prod_p + b1)   grad_b2 += ds_p
+ * Every output is OVERWRITTEN (parameter gradients zeroed on the stream, then one float atomic per word and CTA).
+ * (embed, attn) in {(8, 8|16|32), (16, 8|16), (32, 8)} -- trs_afm_backward_supported() -- and
+ * 2*16*fields*embed*4 bytes of shared memory; TRS_ERR_UNSUPPORTED otherwise. */
+int trs_afm_backward_supported(int embed, int attn);
+int trs_afm_backward(const float* x, const float* w1, const float* b1, const float* w2, const float* scores,
+                     const float* grad_out, const float* grad_scores, int64_t batch, int fields, int embed,
+                     int attn, float* grad_x, float* grad_w1, float* grad_b1, float* grad_w2, float* grad_b2,
+                     void* stream);
+
 /* ---- 8f-3: outer product network (PNN) ------------------------------------------------------------------------------
  * Replaces OuterProductNetworkLayer.forward (torecsys/layers/ctr/outer_product_network.py:80-131), pairs p = (i<j)
  * in lexicographic order:

@@ -329,6 +329,71 @@ def test_bilinear_backward_edges_and_routes():
         assert (bg.grad.cpu() - 20.0).abs().max() <= 1e-4
 
 
+@pytest.mark.parametrize('with_gs', [False, True])
+@pytest.mark.parametrize('b,n,e,a', [(1, 2, 8, 8), (37, 39, 16, 16), (130, 6, 8, 32), (40, 5, 32, 8), (16 * 148 * 2 + 3, 3, 16, 8),
+                                     (50, 12, 8, 16)])
+def test_afm_backward_kernel(b, n, e, a, with_gs):
+    """x, W1, b1, w2, b2 gradients of the attentional FM layer (csrc/afm_bwd.cu) against float64 autograd on the upstream
+    formula (attentional_factorization_machine.py:86-120, eval mode), with and without a gradient arriving through
+    the returned attention scores; every supported (embed, attn), ragged last tiles, several tiles per CTA."""
+    from torecsys_b200 import ops
+    gen = torch.Generator().manual_seed(16)
+    x = torch.randn(b, n, e, generator=gen, dtype=torch.float64, requires_grad=True)
+    w1 = (torch.randn(a, e, generator=gen, dtype=torch.float64) / e ** 0.5).requires_grad_()
+    b1 = (0.2 * torch.randn(a, generator=gen, dtype=torch.float64)).requires_grad_()
+    w2 = (torch.randn(1, a, generator=gen, dtype=torch.float64) / a ** 0.5).requires_grad_()
+    b2 = torch.zeros(1, dtype=torch.float64, requires_grad=True)
+    i, j = torch.triu_indices(n, n, offset=1)
+    go = torch.randn(b, e, generator=gen, dtype=torch.float64)
+    gs = torch.randn(b, i.numel(), 1, generator=gen, dtype=torch.float64)
+    prod = x[:, i] * x[:, j]
+    sc = torch.softmax(torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(prod, w1, b1)), w2, b2), dim=1)
+    loss = ((prod * sc).sum(1) * go).sum()
+    if with_gs:
+        loss = loss + (sc * gs).sum()
+    loss.backward()
+    f = lambda t: t.detach().float().cuda()
+    _, scores = ops.afm(f(x), f(w1), f(b1), f(w2), f(b2))
+    assert (scores.cpu().double() - sc.detach()).abs().max() <= 1e-5 * sc.detach().abs().max()
+    got = ops.afm_backward(f(x), f(w1), f(b1), f(w2), scores, go.float().cuda(), gs.float().cuda() if with_gs else None)
+    for g, want, what in zip(got[:4], (x.grad, w1.grad, b1.grad, w2.grad), ('dx', 'dW1', 'db1', 'dw2')):
+        assert g.shape == want.shape, what
+        err = (g.cpu().double() - want).abs().max() / max(want.abs().max().item(), 1e-6)   # n = 2: one pair, zero grads
+        assert err <= 5e-5, (what, float(err))
+    assert got[4].abs().item() <= 1e-4 * max(1.0, w2.grad.abs().max().item())   # d b2 is mathematically zero (softmax shift)
+
+
+def test_afm_function_backward_routes():
+    """AfmFn: kernel for the supported attention sizes, torch recompute otherwise; a loss that only uses the returned
+    attention scores (no gradient through the pooled output) and a frozen W1."""
+    from torecsys_b200 import ops
+    from torecsys_b200.autograd import AfmFn
+    assert ops.afm_backward_supported(39, 16, 16) and not ops.afm_backward_supported(39, 16, 12)
+    with pytest.raises(NotImplementedError):
+        ops.afm_backward(torch.randn(4, 3, 16).cuda(), torch.randn(12, 16).cuda(), torch.randn(12).cuda(),
+                         torch.randn(1, 12).cuda(), torch.rand(4, 3, 1).cuda(), torch.randn(4, 16).cuda())
+    for a in (16, 12):
+        gen = torch.Generator().manual_seed(17)
+        x = torch.randn(30, 5, 16, generator=gen)
+        w1 = torch.randn(a, 16, generator=gen) / 4
+        b1 = 0.1 * torch.randn(a, generator=gen)
+        w2 = torch.randn(1, a, generator=gen) / a ** 0.5
+        b2 = torch.zeros(1)
+        i, j = torch.triu_indices(5, 5, offset=1)
+        wsc = torch.randn(30, 10, 1, generator=gen)
+        for use_out in (True, False):
+            xg, b1g, w2g = x.cuda().requires_grad_(), b1.cuda().requires_grad_(), w2.cuda().requires_grad_()
+            out, sc = AfmFn.apply(xg, w1.cuda(), b1g, w2g, b2.cuda())
+            ((out.sum() if use_out else 0) + (sc * wsc.cuda()).sum()).backward()
+            xd, b1d, w2d = (t.double().requires_grad_() for t in (x, b1, w2))
+            prod = xd[:, i] * xd[:, j]
+            s = torch.softmax(torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(prod, w1.double(), b1d)),
+                                                         w2d, b2.double()), dim=1)
+            (((prod * s).sum(1).sum() if use_out else 0) + (s * wsc.double()).sum()).backward()
+            for g, want in ((xg.grad, xd.grad), (b1g.grad, b1d.grad), (w2g.grad, w2d.grad)):
+                assert (g.cpu().double() - want).abs().max() <= 5e-5 * want.abs().max(), (a, use_out)
+
+
 def test_cross_function_backward_routes():
     """CrossFn uses the kernel for the widths it supports and the torch recompute for the others; both honour
     needs_input_grad (a frozen weight gets no gradient)."""

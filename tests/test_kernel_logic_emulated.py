@@ -1,4 +1,4 @@
-"""Kernel LOGIC checks without a GPU: the device code of csrc/bilinear_bwd.cu is compiled as plain C++ against
+"""Kernel LOGIC checks without a GPU: the device code of csrc/bilinear_bwd.cu and csrc/afm_bwd.cu is compiled as plain C++ against
 tests/emu/cuda_emu.h (one OS thread per CUDA thread, std::barrier for __syncthreads, CTA-uniform shuffles) and compared
 with a float64 restatement of the layer's gradient formulas (bilinear_interaction.py:72-76 / :144-149 differentiated).
 This is test infrastructure: it proves index arithmetic, accumulator ownership, the prefetch ring and the reductions,
@@ -13,24 +13,34 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, 'tests', 'emu')
 
 
-@pytest.fixture(scope='module')
-def emulated_binary(tmp_path_factory):
+def _emulated(tmp_path_factory, source, end_marker, smem_decl, smem_name, driver):
     if shutil.which('g++') is None:
         pytest.skip('g++ not available')
-    src = open(os.path.join(ROOT, 'torecsys_b200', 'csrc', 'bilinear_bwd.cu')).read()
-    body = src.split('#include "common.cuh"', 1)[1].split('template <int E>\nint bilinear_backward_run', 1)[0]
-    marker = 'extern __shared__ __align__(16) float bx_smem[];'
-    assert marker in body
-    body = body.replace(marker, 'float* bx_smem = emu::dyn_smem;')
+    src = open(os.path.join(ROOT, 'torecsys_b200', 'csrc', source)).read()
+    body = src.split('#include "common.cuh"', 1)[1].split(end_marker, 1)[0]
+    assert smem_decl in body
+    body = body.replace(smem_decl, f'float* {smem_name} = emu::dyn_smem;')
     out = tmp_path_factory.mktemp('emu')
-    cpp = out / 'bilinear_bwd_emu.cpp'
+    cpp = out / (source.replace('.cu', '_emu.cpp'))
     cpp.write_text('#include "cuda_emu.h"\n' + body + '}  // namespace\n}  // namespace trs\nusing namespace trs;\n'
-                   + open(os.path.join(EMU, 'bilinear_bwd_main.inc')).read())
-    exe = out / 'bilinear_bwd_emu'
+                   + open(os.path.join(EMU, driver)).read())
+    exe = out / source.replace('.cu', '_emu')
     res = subprocess.run(['g++', '-std=c++20', '-O1', '-pthread', '-I', EMU, '-Wno-unknown-pragmas', str(cpp), '-o',
                           str(exe)], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     return str(exe)
+
+
+@pytest.fixture(scope='module')
+def emulated_binary(tmp_path_factory):
+    return _emulated(tmp_path_factory, 'bilinear_bwd.cu', 'template <int E>\nint bilinear_backward_run',
+                     'extern __shared__ __align__(16) float bx_smem[];', 'bx_smem', 'bilinear_bwd_main.inc')
+
+
+@pytest.fixture(scope='module')
+def emulated_afm(tmp_path_factory):
+    return _emulated(tmp_path_factory, 'afm_bwd.cu', 'template <int E, int A>\nint afm_backward_run',
+                     'extern __shared__ __align__(16) float ab_smem[];', 'ab_smem', 'afm_bwd_main.inc')
 
 
 # embed, batch, fields, each_type, CTAs of the sample-major kernel, samples per slice of the pair-major kernel
@@ -38,4 +48,11 @@ def emulated_binary(tmp_path_factory):
                                   (16, 2, 39, 1, 1, 64), (8, 1, 2, 0, 1, 64)])
 def test_bilinear_backward_kernel_logic(emulated_binary, args):
     res = subprocess.run([emulated_binary] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+
+
+# embed, attn, batch, fields, with grad_scores, CTAs
+@pytest.mark.parametrize('args', [(16, 16, 19, 4, 1, 2), (8, 32, 5, 4, 1, 1), (32, 8, 3, 3, 0, 1)])
+def test_afm_backward_kernel_logic(emulated_afm, args):
+    res = subprocess.run([emulated_afm] + [str(a) for a in args], capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout + res.stderr

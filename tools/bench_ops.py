@@ -388,6 +388,24 @@ def main():
             del xr, wr, br
         del xb, gb_
         torch.cuda.empty_cache()
+    # attentional FM backward (AFM model shape: 39 fields, E = 16, attention size 16)
+    if want('afm_backward'):
+        from torecsys_b200 import autograd as ag
+        Bb = 16384
+        xa = torch.randn(Bb, N, 16, device=dev)
+        w1, b1 = lin(16, 16, dev)
+        w2, b2 = lin(1, 16, dev)
+        goa = torch.randn(Bb, 16, device=dev)
+        _, sca = ops.afm(xa, w1, b1, w2, b2)
+        # algorithmic bytes: x read, grad_x written, scores read twice; flops: recompute h, W1^T dh, dW1 (2AE each) + prod/dots
+        t = timeit(lambda i: ops.afm_backward(xa, w1, b1, w2, sca, goa), reps=10)
+        report('afm backward kernel (dx, dW1, db1, dw2, db2)', Bb, t, 2 * N * 64 + 2 * PAIRS * 4, PAIRS * (6 * 16 * 16 + 6 * 16))
+        xr = xa.clone().requires_grad_()
+        ps = [p.clone().requires_grad_() for p in (w1, b1, w2, b2)]
+        t = timeit(lambda i: ag._grad_of(ag._afm, [xr] + ps, (goa, torch.zeros_like(sca))), reps=5)
+        report('afm backward, torch recompute (same shape)', Bb, t, 2 * N * 64 + 2 * PAIRS * 4, PAIRS * (6 * 16 * 16 + 6 * 16))
+        del xa, xr, sca
+        torch.cuda.empty_cache()
     ops.check_index_errors()
     if args.json:
         with open(args.json, 'w') as f:

@@ -44,6 +44,8 @@ PROTOTYPES = {
     'trs_bilinear_forward': (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int, _P, _P]),
     'trs_bilinear_backward': (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int, _P, _P, _P, _P]),
     'trs_afm_forward': (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
+    'trs_afm_backward_supported': (c_int, [c_int, c_int]),
+    'trs_afm_backward': (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     'trs_opn_forward': (c_int, [_P, _P, c_int, c_int64, c_int, c_int, _P, _P]),
     'trs_senet_workspace_bytes': (c_int64, [c_int64, c_int]),
     'trs_senet_forward': (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_int, _P, _P, c_int64, _P]),

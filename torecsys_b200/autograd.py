@@ -3,9 +3,10 @@ exist, else a recompute through torch CUDA ops.
 
 Scope: this repository's product is the FORWARD hot path.  So that the drop-ins
 still "construct and train unchanged" on a GPU, every Function saves its inputs.  The embedding lookups, FM, FFM, IPN,
-the bilinear interaction and the cross network back-propagate through their own kernels (csrc/backward.cu:
+the bilinear interaction, the attentional FM and the cross network back-propagate through their own kernels (csrc/backward.cu:
 trs_embedding_grad, trs_fm_backward, trs_ffm_backward, trs_ipn_backward, trs_cross_backward; csrc/bilinear_bwd.cu:
-trs_bilinear_backward for embed 8 / 16 / 32); the other layers re-evaluate their formula
+trs_bilinear_backward for embed 8 / 16 / 32; csrc/afm_bwd.cu: trs_afm_backward for the attention sizes listed in the
+header); the other layers re-evaluate their formula
 with differentiable torch ops ON THE SAME CUDA DEVICE and let torch differentiate it (a composite recompute
 backward).  Nothing here runs on the CPU and nothing is imported from `oracle/`.  Gradient parity with the reference
 is covered by tests/test_gpu_training.py, including the upstream quirk that CrossNetworkLayer cuts the gradient path
@@ -168,12 +169,26 @@ class BilinearFn(torch.autograd.Function):
 class AfmFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2):
-        ctx.save_for_backward(x, w1, b1, w2, b2)
-        return ops.afm(x, w1, b1, w2, b2)
+        out, scores = ops.afm(x, w1, b1, w2, b2)
+        ctx.save_for_backward(x, w1, b1, w2, b2, scores)
+        ctx.set_materialize_grads(False)
+        return out, scores
 
     @staticmethod
     def backward(ctx, grad, grad_scores):
-        return _grad_of(_afm, list(ctx.saved_tensors), (grad, grad_scores))
+        x, w1, b1, w2, b2, scores = ctx.saved_tensors
+        if grad is None and grad_scores is None:
+            return None, None, None, None, None
+        if ops.afm_backward_supported(x.shape[-2], x.shape[-1], w1.shape[0]):   # trs_afm_backward (csrc/afm_bwd.cu)
+            go = grad.contiguous() if grad is not None else torch.zeros(x.shape[0], x.shape[-1], device=x.device)
+            gs = grad_scores.contiguous() if grad_scores is not None else None
+            gx, gw1, gb1, gw2, gb2 = ops.afm_backward(x, w1, b1, w2, scores, go, gs)
+            return gx, gw1, gb1, gw2.view_as(w2), gb2.view_as(b2)
+        if grad is None:
+            grad = torch.zeros(x.shape[0], x.shape[-1], device=x.device)
+        if grad_scores is None:
+            grad_scores = torch.zeros_like(scores)
+        return _grad_of(_afm, [x, w1, b1, w2, b2], (grad, grad_scores))
 
 
 class OpnFn(torch.autograd.Function):

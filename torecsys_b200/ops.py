@@ -390,6 +390,35 @@ def afm(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b
     return out, scores
 
 
+def afm_backward_supported(num_fields: int, embed: int, attn: int) -> bool:
+    """Shapes trs_afm_backward takes (the (embed, attn) list of the header, 16 samples of x and grad_x in smem)."""
+    return bool(_cabi.load().trs_afm_backward_supported(embed, attn)) and 2 * 16 * num_fields * embed * 4 <= 227 * 1024
+
+
+def afm_backward(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, scores: torch.Tensor,
+                 grad_out: torch.Tensor, grad_scores: Optional[torch.Tensor] = None):
+    """(d x, d W1, d b1, d w2, d b2) of afm(), from the attention scores the forward returned: csrc/afm_bwd.cu
+    (attentional_factorization_machine.py:86-120 differentiated, eval mode)."""
+    x, b, n, e = _bne('afm_backward', x)
+    _need_cuda('afm_backward', w1, b1, w2, scores, grad_out, grad_scores)
+    w1, b1, w2, sc, go = (_f32('afm_backward', t) for t in (w1, b1, w2, scores, grad_out))
+    gs = _f32('afm_backward', grad_scores) if grad_scores is not None else None
+    attn = w1.shape[0]
+    pairs = n * (n - 1) // 2
+    if tuple(w1.shape) != (attn, e) or w2.numel() != attn or b1.numel() != attn:
+        raise ValueError('afm_backward: attention weights do not match (attn, embed)')
+    if sc.numel() != b * pairs or tuple(go.shape) != (b, e) or (gs is not None and gs.numel() != b * pairs):
+        raise ValueError(f'afm_backward: scores {tuple(sc.shape)} / grad_out {tuple(go.shape)} do not match '
+                         f'x {tuple(x.shape)}')
+    gx = torch.empty_like(x)
+    gw1, gb1, gw2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2)
+    gb2 = torch.empty(1, dtype=torch.float32, device=x.device)
+    check(_cabi.load().trs_afm_backward(_ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(sc), _ptr(go), _ptr(gs), b, n, e,
+                                        attn, _ptr(gx), _ptr(gw1), _ptr(gb1), _ptr(gw2), _ptr(gb2), _stream()),
+          'trs_afm_backward')
+    return gx, gw1, gb1, gw2, gb2
+
+
 def cross(x: torch.Tensor, weights: torch.Tensor, biases: torch.Tensor, tc5: bool = False) -> torch.Tensor:
     """x (..., E); weights (L, E, E); biases (L, E).  tc5=True runs the experimental tcgen05 / tensor-memory chain
     (trs_cross_forward_tc5; same results, measured slower -- see csrc/cross_tc5.cu)."""
