@@ -92,6 +92,18 @@ int trs_embedding_grad(const float* grad_out, const void* idx, int idx_bits, con
 int trs_fm_backward(const float* x, const float* grad_out, int64_t batch, int fields, int embed,
                     float* grad_x, void* stream);
 
+/* Sparse form of the embedding gradient: what nn.Embedding(sparse=True) hands autograd (multi_indices_emb.py:48 forwards
+ * **kwargs to nn.Embedding, so MultiIndicesEmbedding(..., sparse=True) is part of the reference's interface).
+ * trs_embedding_rows: out_rows[b*N + n] = idx[b,n] + offsets[n] (int64): the COO indices, in lookup order; the COO values
+ * are grad_out viewed (B*N, E).  trs_embedding_grad_segments coalesces that tensor once its row ids have been sorted:
+ *     out_values[s, :] = sum over m in [starts[s], starts[s+1]) of grad_out[perm[m], :]      (summed in sorted order)
+ * perm (lookups) = permutation of the sort, starts (segments + 1) = first sorted position of each distinct row, closed by
+ * the number of lookups.  Deterministic, unlike trs_embedding_grad's reductions. */
+int trs_embedding_rows(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                       int64_t* out_rows, void* stream);
+int trs_embedding_grad_segments(const float* grad_out, const int64_t* perm, const int64_t* starts, int64_t segments,
+                                int embed, float* out_values, void* stream);
+
 /* trs_ffm_backward: gradient of FieldAwareFactorizationMachineLayer.forward (field_aware_factorization_machine.py:50-94)
  *     grad_v[b, a*N + c, :] = grad_out[b, p(min(a,c), max(a,c)), :] * v[b, c*N + a, :]   (a != c), 0 on the diagonal
  * trs_ipn_backward: gradient of InnerProductNetworkLayer.forward (inner_product_network.py:54-79)

@@ -103,6 +103,67 @@ def test_embedding_gradient_is_a_scatter_add(trs):
         assert gt.sum().item() == pytest.approx(3 * 3 * 4) and gt[rows[0, 0]].sum().item() == pytest.approx(8.0)
 
 
+@pytest.mark.parametrize('idx_dtype', [torch.int64, torch.int32])
+def test_sparse_embedding_gradient_matches_nn_embedding(trs, idx_dtype):
+    """MultiIndicesEmbedding(..., sparse=True) (multi_indices_emb.py:48 forwards the kwarg to nn.Embedding): weight.grad is
+    the same uncoalesced COO tensor torch's own nn.Embedding(sparse=True) produces on the CPU -- same indices in the same
+    order, bit-identical values -- also with a padding_idx, and for SingleIndexEmbedding; SparseAdam steps on it."""
+    fs = [16, 32, 48]
+    gen = torch.Generator().manual_seed(20)
+    idx = torch.stack([torch.randint(0, f, (50,), generator=gen) for f in fs], dim=1)
+    idx[::7, 1] = 5                                       # duplicates
+    wts = torch.randn(50, 3, 8, generator=gen)
+    for pad in (None, 16 + 5):
+        emb = trs.MultiIndicesEmbedding(8, fs, sparse=True, padding_idx=pad).cuda()
+        ref = torch.nn.Embedding(sum(fs), 8, sparse=True, padding_idx=pad)
+        with torch.no_grad():
+            ref.weight.copy_(emb.embedding.weight.cpu())
+        (emb(idx.to(idx_dtype).cuda()).rename(None) * wts.cuda()).sum().backward()
+        (ref(idx + torch.tensor([0, 16, 48])) * wts).sum().backward()
+        g, want = emb.embedding.weight.grad, ref.weight.grad
+        assert g.is_sparse and g.shape == want.shape
+        assert torch.equal(g._indices().cpu(), want._indices()) and torch.equal(g._values().cpu(), want._values())
+        opt = torch.optim.SparseAdam(list(emb.parameters()), lr=0.1)
+        before = emb.embedding.weight.detach().clone()
+        opt.step()
+        touched = torch.zeros(sum(fs), dtype=torch.bool)
+        touched[want._indices()[0]] = True
+        moved = (emb.embedding.weight.detach() != before).any(1).cpu()
+        assert torch.equal(moved, touched)
+    single = trs.SingleIndexEmbedding(4, 10, sparse=True).cuda()
+    single(torch.tensor([[1], [3], [1]], device='cuda')).rename(None).sum().backward()
+    gs = single.embedding.weight.grad
+    assert gs.is_sparse and gs._indices().cpu().tolist() == [[1, 3, 1]]
+    assert torch.equal(gs.to_dense().cpu()[1], torch.full((4,), 2.0))
+
+
+@pytest.mark.parametrize('b,n,e', [(64, 39, 16), (1000, 5, 7), (1, 1, 4), (300, 3, 1)])
+def test_sparse_embedding_gradient_coalesced_by_segments(b, n, e):
+    """ops.embedding_grad_sparse(coalesce=True): sorted row ids + trs_embedding_grad_segments = the coalesced form of the
+    same gradient: equal to the dense scatter-add, indices strictly increasing, and bit-identical from run to run."""
+    from torecsys_b200 import ops
+    gen = torch.Generator().manual_seed(21)
+    fs = [7 + 3 * k for k in range(n)]                     # small fields: many duplicate rows
+    off = torch.tensor([0] + list(np.cumsum(fs)[:-1]), dtype=torch.int64)
+    idx = torch.stack([torch.randint(0, f, (b,), generator=gen) for f in fs], dim=1)
+    g = torch.randn(b, n, e, generator=gen)
+    sp = ops.embedding_grad_sparse(g.cuda(), idx.cuda(), off.cuda(), sum(fs), coalesce=True)
+    assert sp.is_sparse and sp.is_coalesced()
+    rows = sp._indices()[0].cpu()
+    assert (rows[1:] > rows[:-1]).all() and set(rows.tolist()) == set((idx + off).reshape(-1).tolist())
+    want = torch.zeros(sum(fs), e, dtype=torch.float64).index_add_(0, (idx + off).reshape(-1), g.reshape(-1, e).double())
+    assert (sp.to_dense().cpu().double() - want).abs().max() <= 1e-5 * want.abs().max()
+    again = ops.embedding_grad_sparse(g.cuda(), idx.cuda(), off.cuda(), sum(fs), coalesce=True)
+    assert torch.equal(again._values(), sp._values())
+    dense = ops.embedding_grad(g.cuda(), idx.cuda(), off.cuda(), sum(fs))
+    assert (dense.cpu().double() - want).abs().max() <= 1e-5 * want.abs().max()
+    pad = int((idx + off)[0, 0])
+    spp = ops.embedding_grad_sparse(g.cuda(), idx.cuda(), off.cuda(), sum(fs), padding_idx=pad, coalesce=True)
+    assert pad not in spp._indices()[0].cpu().tolist()
+    empty = ops.embedding_grad_sparse(g.cuda()[:0], idx.cuda()[:0], off.cuda(), sum(fs), coalesce=True)
+    assert empty._nnz() == 0
+
+
 @pytest.mark.parametrize('kind', ['deepfm_model', 'xdeepfm_model', 'dcn_model', 'ffm_model', 'fm_model'])
 def test_models_train_one_step_like_the_reference_formula(trs, kind):
     """Full Sequential(Inputs, model) in train mode (dropout 0): loss.backward() populates every parameter gradient and

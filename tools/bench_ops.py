@@ -79,7 +79,7 @@ def main():
     B = 65536
     if any(want(x) for x in ('gather16', 'gather1', 'fm_layer', 'deepfm_packed', 'deepfm_split', 'fm_model', 'latency',
                              'deepfm_generic_mlp400', 'ipn', 'bilinear_all', 'bilinear_each', 'afm', 'xdeepfm',
-                             'cin_layer', 'opn', 'senet', 'models_more')):
+                             'cin_layer', 'opn', 'senet', 'models_more', 'train_step_sparse')):
         w16 = torch.randn(rows, 16, device=dev)
         w1 = torch.randn(rows, 1, device=dev)
         ring = idx_ring(B)
@@ -140,6 +140,22 @@ def main():
             t = timeit(lambda i: ops.mlp(xf, big), reps=5)
             report('mlp [624,400,400,400,1] (DNNLayer, tcgen05 chain)', B, t, 624 * 4 + 4,
                    2 * (624 * 400 + 2 * 400 * 400 + 400))
+        if want('train_step_sparse'):
+            # one SGD step of lookup -> FM layer -> sum at the full cfg-2 table (200 M rows x 16): the embedding gradient as
+            # the sparse COO tensor of nn.Embedding(sparse=True) against the dense (rows, 16) gradient
+            from torecsys_b200.autograd import FmFn, GatherFn
+            wp = torch.nn.Parameter(w16)
+            for sparse in (True, False):
+                def step(i):
+                    out = GatherFn.apply(wp, ring[i % 4], off, None, sparse)
+                    FmFn.apply(out).sum().backward()
+                    with torch.no_grad():
+                        wp.add_(wp.grad, alpha=-0.01)
+                    wp.grad = None
+                t = timeit(step, reps=5, warmup=2)
+                report(f'train step lookup->FM->SGD, {"sparse COO" if sparse else "dense"} embedding gradient ({rows} rows)',
+                       B, t, note=f'gradient tensor {B * N * 16 * 4 / 1e6:.0f} MB' if sparse else f'gradient tensor {rows * 64 / 1e9:.1f} GB')
+            del wp
         if want('ipn'):
             t = timeit(lambda i: ops.ipn(x))
             report('ipn (a9)', B, t, N * 64 + PAIRS * 4, 2 * PAIRS * 16)

@@ -36,6 +36,8 @@ PROTOTYPES = {
     'trs_fm_forward': (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     'trs_embedding_grad': (c_int, [_P, _P, c_int, _P, c_int64, c_int, c_int64, c_int, c_int64, _P, _P]),
     'trs_fm_backward': (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P]),
+    'trs_embedding_rows': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P]),
+    'trs_embedding_grad_segments': (c_int, [_P, _P, _P, c_int64, c_int, _P, _P]),
     'trs_ffm_backward': (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P]),
     'trs_ipn_backward': (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P]),
     'trs_cross_backward': (c_int, [_P, _P, _P, _P, c_int, c_int64, c_int, _P, _P, _P, _P]),

@@ -41,19 +41,24 @@ def _grad_of(fn, inputs, grad_outputs):
 # ------------------------------------------------------------------------------------------------ embeddings
 class GatherFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, weight, idx, offsets, padding_idx):
+    def forward(ctx, weight, idx, offsets, padding_idx, sparse=False):
         ctx.save_for_backward(idx, offsets if offsets is not None else idx.new_zeros(0))
         ctx.rows = weight.shape[0]
         ctx.padding_idx = padding_idx
+        ctx.sparse = bool(sparse)
         return ops.embedding_gather(weight, idx, offsets)
 
     @staticmethod
     def backward(ctx, grad):
         idx, offsets = ctx.saved_tensors
-        # dense nn.Embedding gradient by the scatter-add kernel (trs_embedding_grad, csrc/backward.cu)
-        dw = ops.embedding_grad(grad.contiguous(), idx, offsets if offsets.numel() else None, ctx.rows,
-                                ctx.padding_idx)
-        return dw, None, None, None
+        off = offsets if offsets.numel() else None
+        if ctx.sparse:
+            # nn.Embedding(sparse=True): an uncoalesced COO gradient, indices in lookup order (trs_embedding_rows)
+            dw = ops.embedding_grad_sparse(grad.contiguous(), idx, off, ctx.rows, ctx.padding_idx)
+        else:
+            # dense nn.Embedding gradient by the scatter-add kernel (trs_embedding_grad, csrc/backward.cu)
+            dw = ops.embedding_grad(grad.contiguous(), idx, off, ctx.rows, ctx.padding_idx)
+        return dw, None, None, None, None
 
 
 class GatherFieldAwareFn(torch.autograd.Function):

@@ -4,6 +4,8 @@
 //
 //   trs_embedding_grad   d weight of MultiIndicesEmbedding / SingleIndexEmbedding (nn.Embedding's dense gradient,
 //                        torecsys/inputs/base/multi_indices_emb.py:48, sparse=False): grad_weight[idx + off] += grad_out
+//   trs_embedding_rows / trs_embedding_grad_segments   the same gradient as a sparse COO tensor (nn.Embedding(sparse=True)):
+//                        row ids in lookup order, and the deterministic coalescing of their sorted form
 //   trs_fm_backward      d x of FactorizationMachineLayer (factorization_machine.py:46-81):
 //                        grad_x[b,n,e] = grad_out[b,e] * (sum_m x[b,m,e] - x[b,n,e])
 //   trs_ffm_backward     d v of FieldAwareFactorizationMachineLayer (field_aware_factorization_machine.py:50-94)
@@ -52,6 +54,50 @@ __global__ void __launch_bounds__(256) embedding_grad_scalar_kernel(const float*
     if (offsets != nullptr) r += __ldg(offsets + pos % fields);
     if (r < 0 || r >= rows || r == padding_row) continue;
     atomicAdd(grad_weight + r * embed + e, ldg_stream_f1(grad_out + item));
+  }
+}
+
+// Sparse (COO) form of the same gradient, what nn.Embedding(sparse=True) produces: the row ids idx + offsets of every
+// lookup, in lookup order; the values are grad_out itself, viewed (B*N, E).
+template <int IdxBits>
+__global__ void __launch_bounds__(256) embedding_rows_kernel(const void* __restrict__ idx,
+                                                             const int64_t* __restrict__ offsets, uint32_t fields,
+                                                             int64_t lookups, int64_t* __restrict__ out_rows) {
+  for (int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pos < lookups;
+       pos += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = load_index<IdxBits>(idx, pos);
+    if (offsets != nullptr) r += __ldg(offsets + pos % fields);
+    out_rows[pos] = r;
+  }
+}
+
+// Coalescing of that sparse gradient after its row ids have been sorted (perm = the sort's permutation, starts[s] = first
+// sorted position of the s-th distinct row, starts[segments] = number of lookups).  Work item = (segment, 16-byte chunk):
+// the rows of a segment are added in sorted order, so the sums are deterministic (unlike the red.global.add path).
+template <int VEC>
+__global__ void __launch_bounds__(256) embedding_grad_segments_kernel(const float* __restrict__ grad_out,
+                                                                      const int64_t* __restrict__ perm,
+                                                                      const int64_t* __restrict__ starts,
+                                                                      int64_t segments, uint32_t chunks,
+                                                                      float* __restrict__ out_values) {
+  const int64_t items = segments * chunks;
+  for (int64_t item = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; item < items;
+       item += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t seg = item / chunks;
+    const uint32_t chunk = static_cast<uint32_t>(item - seg * chunks);
+    const int64_t lo = __ldg(starts + seg), hi = __ldg(starts + seg + 1);
+    if (VEC == 4) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t m = lo; m < hi; ++m) {
+        const float4 g = ldg_stream_f4(reinterpret_cast<const float4*>(grad_out) + __ldg(perm + m) * chunks + chunk);
+        acc.x += g.x, acc.y += g.y, acc.z += g.z, acc.w += g.w;
+      }
+      reinterpret_cast<float4*>(out_values)[item] = acc;
+    } else {
+      float acc = 0.f;
+      for (int64_t m = lo; m < hi; ++m) acc += ldg_stream_f1(grad_out + __ldg(perm + m) * chunks + chunk);
+      out_values[item] = acc;
+    }
   }
 }
 
@@ -340,6 +386,39 @@ extern "C" int trs_embedding_grad(const float* grad_out, const void* idx, int id
     embedding_grad_scalar_kernel<32><<<grid, 256, 0, s>>>(grad_out, idx, offsets, rows, embed, fields, items, padding_row,
                                                           grad_weight);
   return check_launch("embedding_grad_scalar_kernel");
+}
+
+extern "C" int trs_embedding_rows(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                                  int64_t* out_rows, void* stream) {
+  TRS_REQUIRE(idx && out_rows, "trs_embedding_rows: null pointer");
+  TRS_REQUIRE(idx_bits == 32 || idx_bits == 64, "trs_embedding_rows: idx_bits must be 32 or 64");
+  TRS_REQUIRE(batch >= 0 && fields > 0, "trs_embedding_rows: bad sizes");
+  if (batch == 0) return TRS_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t lookups = batch * fields;
+  const int grid = grid_for(lookups, 256, 8);
+  if (idx_bits == 64)
+    embedding_rows_kernel<64><<<grid, 256, 0, s>>>(idx, offsets, fields, lookups, out_rows);
+  else
+    embedding_rows_kernel<32><<<grid, 256, 0, s>>>(idx, offsets, fields, lookups, out_rows);
+  return check_launch("embedding_rows_kernel");
+}
+
+extern "C" int trs_embedding_grad_segments(const float* grad_out, const int64_t* perm, const int64_t* starts,
+                                           int64_t segments, int embed, float* out_values, void* stream) {
+  TRS_REQUIRE(grad_out && perm && starts && out_values, "trs_embedding_grad_segments: null pointer");
+  TRS_REQUIRE(segments >= 0 && embed > 0, "trs_embedding_grad_segments: bad sizes");
+  if (segments == 0) return TRS_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if ((embed & 3) == 0 && aligned16(grad_out) && aligned16(out_values)) {
+    const uint32_t chunks = embed / 4;
+    embedding_grad_segments_kernel<4><<<grid_for(segments * chunks, 256, 16), 256, 0, s>>>(grad_out, perm, starts,
+                                                                                            segments, chunks, out_values);
+  } else {
+    embedding_grad_segments_kernel<1><<<grid_for(segments * embed, 256, 16), 256, 0, s>>>(grad_out, perm, starts, segments,
+                                                                                         embed, out_values);
+  }
+  return check_launch("embedding_grad_segments_kernel");
 }
 
 extern "C" int trs_fm_backward(const float* x, const float* grad_out, int64_t batch, int fields, int embed,

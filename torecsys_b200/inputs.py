@@ -43,8 +43,6 @@ def _reference_offsets(field_sizes) -> torch.Tensor:
 def _reject_unsupported_embedding_kwargs(kwargs):
     if kwargs.get('max_norm') is not None:
         raise NotImplementedError('max_norm renormalises the table inside forward; no sm_100a kernel for it')
-    if kwargs.get('sparse'):
-        raise NotImplementedError('sparse gradients are not produced by the CUDA backward')
 
 
 class SingleIndexEmbedding(BaseInput):
@@ -65,7 +63,7 @@ class SingleIndexEmbedding(BaseInput):
         inputs = inputs.rename(None)
         if inputs.dim() == 1:
             inputs = inputs.unsqueeze(-1)
-        out = GatherFn.apply(self.embedding.weight, inputs, None, self.embedding.padding_idx)
+        out = GatherFn.apply(self.embedding.weight, inputs, None, self.embedding.padding_idx, self.embedding.sparse)
         out.names = ('B', 'N', 'E',)
         return out
 
@@ -110,7 +108,8 @@ class MultiIndicesEmbedding(BaseInput):
     def forward(self, inputs: torch.Tensor) -> torch.Tensor:
         w = self.embedding.weight
         off = self._offsets_on(w.device)
-        out = GatherFn.apply(w, inputs.rename(None), off.rename(None).reshape(-1), self.padding_idx)
+        out = GatherFn.apply(w, inputs.rename(None), off.rename(None).reshape(-1), self.padding_idx,
+                             self.embedding.sparse)
         if self.flatten:
             out = out.reshape(out.shape[0], 1, -1)
         out.names = ('B', 'N', 'E',)

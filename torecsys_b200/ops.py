@@ -230,6 +230,53 @@ def embedding_grad(grad_out: torch.Tensor, idx: torch.Tensor, offsets: Optional[
     return dw
 
 
+def _coo(row_ids: torch.Tensor, values: torch.Tensor, size, coalesced: bool) -> torch.Tensor:
+    # the indices come straight from our kernels (in range: the forward checked them); skip torch's invariant pass
+    with torch.sparse.check_sparse_tensor_invariants(False):
+        return torch.sparse_coo_tensor(row_ids.unsqueeze(0), values, size, is_coalesced=coalesced or None)
+
+
+def embedding_grad_sparse(grad_out: torch.Tensor, idx: torch.Tensor, offsets: Optional[torch.Tensor], rows: int,
+                          padding_idx: Optional[int] = None, coalesce: bool = False) -> torch.Tensor:
+    """Sparse COO weight gradient of the embedding lookup, as nn.Embedding(sparse=True) produces it: indices = idx +
+    offsets in lookup order (trs_embedding_rows), values = grad_out viewed (B*N, E), lookups of padding_idx dropped.
+    coalesce=True sorts the row ids (torch.sort: plumbing) and sums duplicates in sorted order with
+    trs_embedding_grad_segments -- a deterministic, coalesced gradient."""
+    _need_cuda('embedding_grad_sparse', grad_out, idx, offsets)
+    g = _f32('embedding_grad_sparse', grad_out)
+    ix = idx if idx.is_contiguous() else idx.contiguous()
+    if ix.dtype not in (torch.int64, torch.int32):
+        ix = ix.long()
+    if ix.dim() == 1:
+        ix = ix.unsqueeze(-1)
+    b, n = ix.shape
+    e = g.numel() // (b * n) if b * n else (g.shape[-1] if g.dim() else 1)
+    off = offsets.reshape(-1).contiguous() if offsets is not None and offsets.numel() else None
+    lib = _cabi.load()
+    flat = torch.empty(b * n, dtype=torch.int64, device=g.device)
+    check(lib.trs_embedding_rows(_ptr(ix), 64 if ix.dtype == torch.int64 else 32,
+                                 _ptr(off) if off is not None else None, b, n, _ptr(flat), _stream()),
+          'trs_embedding_rows')
+    vals = g.reshape(b * n, e)
+    if padding_idx is not None:
+        keep = flat != int(padding_idx)
+        flat, vals = flat[keep], vals[keep].contiguous()
+    if not coalesce:
+        return _coo(flat, vals, (rows, e), False)
+    m = flat.numel()
+    if m == 0:
+        return _coo(flat, vals, (rows, e), True)
+    keys, perm = torch.sort(flat, stable=True)
+    head = torch.ones(m, dtype=torch.bool, device=g.device)
+    head[1:] = keys[1:] != keys[:-1]
+    first = torch.nonzero(head).reshape(-1)
+    starts = torch.cat([first, torch.tensor([m], dtype=torch.int64, device=g.device)])
+    out = torch.empty((first.numel(), e), dtype=torch.float32, device=g.device)
+    check(lib.trs_embedding_grad_segments(_ptr(vals), _ptr(perm), _ptr(starts), first.numel(), e, _ptr(out), _stream()),
+          'trs_embedding_grad_segments')
+    return _coo(keys[first], out, (rows, e), True)
+
+
 def fm_backward(x: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
     x, b, n, e = _bne('fm_backward', x)
     g = _f32('fm_backward', grad_out)
