@@ -216,3 +216,66 @@ def test_ffm_configs4_one_gpu_full_tables(ops):
     ops.check_index_errors()
     del tables, w_feat
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize('each', [False, True])
+def test_bilinear_backward_full_batch_properties(ops, each):
+    """trs_bilinear_backward at the BASELINE batch (65 536 x 39 x 16; grad_out 3.1 GB): grad_x of a batch split at a
+    ragged point is bit-identical to the full run (one owner thread per accumulator, no atomics), the parameter
+    gradients of the two parts add up to the full ones, the op is linear in grad_out, and a random subset of the samples
+    agrees with float64 autograd on the upstream formula (bilinear_interaction.py:72-76 / :144-149)."""
+    b, e = 65536, 16
+    pairs = N * (N - 1) // 2
+    gen = torch.Generator(device='cuda').manual_seed(31)
+    x = torch.randn(b, N, e, device='cuda', generator=gen)
+    w = torch.randn(*((pairs, e, e) if each else (e, e)), device='cuda', generator=gen) / 4
+    g = torch.randn(b, pairs, e, device='cuda', generator=gen)
+    gx, gw, gb = ops.bilinear_backward(x, w, g, each)
+    k = b // 3 + 5
+    ga = ops.bilinear_backward(x[:k].contiguous(), w, g[:k].contiguous(), each)
+    gb_ = ops.bilinear_backward(x[k:].contiguous(), w, g[k:].contiguous(), each)
+    assert torch.equal(torch.cat([ga[0], gb_[0]]), gx)
+    # parameter gradients are fp32 sums over up to 48.6 M terms in two different orders: 1e-4, not the 1e-5 forward bar
+    assert normwise_err((ga[1] + gb_[1]).cpu().numpy(), gw.cpu().numpy()) <= 1e-4
+    assert normwise_err((ga[2] + gb_[2]).cpu().numpy(), gb.cpu().numpy()) <= 1e-4
+    g2x, g2w, _ = ops.bilinear_backward(x, w, 2.0 * g, each)
+    assert torch.equal(g2x, 2.0 * gx) and normwise_err(g2w.cpu().numpy(), (2.0 * gw).cpu().numpy()) <= 1e-4
+    del ga, gb_, g2x, g2w
+    pick = torch.from_numpy(np.random.default_rng(5).choice(b, 48, replace=False)).cuda()
+    xs = x[pick].double().cpu().requires_grad_()
+    i, j = torch.triu_indices(N, N, offset=1)
+    wd = w.double().cpu()
+    y = torch.matmul(xs[:, i].unsqueeze(-2), wd).squeeze(-2) if each else torch.matmul(xs[:, i], wd)
+    ((y * xs[:, j]) * g[pick].double().cpu()).sum().backward()
+    assert normwise_err(gx[pick].cpu().numpy(), xs.grad.float().numpy()) <= TOL
+    assert normwise_err(gb.cpu().numpy(), (g.sum(0) if each else g.sum((0, 1))).cpu().numpy()) <= 1e-4   # long fp32 sums
+
+
+def test_afm_backward_full_batch_properties(ops):
+    """trs_afm_backward at the BASELINE batch (65 536 x 39 x 16, attention size 16): split-invariant grad_x (bit for bit),
+    additive parameter gradients, and a sampled float64 autograd check on the upstream formula
+    (attentional_factorization_machine.py:86-120)."""
+    b, e, a = 65536, 16, 16
+    gen = torch.Generator(device='cuda').manual_seed(32)
+    x = torch.randn(b, N, e, device='cuda', generator=gen) * 0.7
+    w1 = torch.randn(a, e, device='cuda', generator=gen) / 4
+    b1 = torch.randn(a, device='cuda', generator=gen) * 0.2
+    w2 = torch.randn(1, a, device='cuda', generator=gen) / 4
+    b2 = torch.zeros(1, device='cuda')
+    go = torch.randn(b, e, device='cuda', generator=gen)
+    _, sc = ops.afm(x, w1, b1, w2, b2)
+    full = ops.afm_backward(x, w1, b1, w2, sc, go)
+    k = b // 3 + 5
+    pa = ops.afm_backward(x[:k].contiguous(), w1, b1, w2, sc[:k].contiguous(), go[:k].contiguous())
+    pb = ops.afm_backward(x[k:].contiguous(), w1, b1, w2, sc[k:].contiguous(), go[k:].contiguous())
+    assert torch.equal(torch.cat([pa[0], pb[0]]), full[0])
+    for q in (1, 2, 3):
+        assert normwise_err((pa[q] + pb[q]).cpu().numpy(), full[q].cpu().numpy()) <= 1e-4
+    pick = torch.from_numpy(np.random.default_rng(6).choice(b, 48, replace=False)).cuda()
+    xs = x[pick].double().cpu().requires_grad_()
+    i, j = torch.triu_indices(N, N, offset=1)
+    prod = xs[:, i] * xs[:, j]
+    lin = torch.nn.functional.linear
+    s = torch.softmax(lin(torch.relu(lin(prod, w1.double().cpu(), b1.double().cpu())), w2.double().cpu(), b2.double().cpu()), dim=1)
+    ((prod * s).sum(1) * go[pick].double().cpu()).sum().backward()
+    assert normwise_err(full[0][pick].cpu().numpy(), xs.grad.float().numpy()) <= 5e-5
