@@ -404,6 +404,15 @@ def main():
             del xr, wr, br
         del xb, gb_
         torch.cuda.empty_cache()
+    # the tall first Linear of FiBiNET / DeepFFM-style MLPs: K = 2 x 741 x 16 inputs, 16 outputs
+    if want('tall_mlp'):
+        Bt = 16384
+        xt = torch.randn(Bt, 23712, device=dev)
+        tall = mlp_pack([23712, 16, 16, 16, 1], dev)
+        t = timeit(lambda i: ops.mlp(xt, tall), reps=10)
+        report('mlp [23712,16,16,16,1] (tall first layer, mma.sync 3xTF32 stream)', Bt, t, 23712 * 4 + 4, 2 * 23712 * 16)
+        del xt
+        torch.cuda.empty_cache()
     # attentional FM backward (AFM model shape: 39 fields, E = 16, attention size 16)
     if want('afm_backward'):
         from torecsys_b200 import autograd as ag

@@ -124,8 +124,156 @@ __global__ void __launch_bounds__(256) tall_dense_kernel(const float* __restrict
   }
 }
 
+// Tensor-core form of the tall layer (K in the thousands, <= 32 outputs; K a multiple of 4): the layer is a stream of x
+// (8 FLOP per byte at 16 outputs), so the kernel reads x ONCE, straight from global memory into mma.sync fragments -- no
+// shared-memory staging.  The sum over k is order-free, so the k slots of an m16n8k8 fragment are assigned to suit the
+// loads: lane (g, t) reads the 16 bytes x[row g][k0 + 4t .. 4t + 3] (and row g + 8, and the same columns of W rows
+// n = g of every 8-output tile); the first mma of a 16-k step takes components (.x, .y) as fragment columns (t, t + 4),
+// the second (.z, .w).  3xTF32 (hi/lo split of both operands, small terms first) with FP32 accumulators that are
+// flushed into FP32 master sums every 128 k, so the error does not grow with K the way a single long tensor-core
+// accumulation does.  CTA = 4 warps on one 16-row tile, each warp a quarter of the k range; the quarters are added in a
+// fixed order through shared memory (deterministic).
+__device__ __forceinline__ void tall_mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                              uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void tall_split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+  lo = (__float_as_uint(v - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
+}
+
+constexpr int kTallTcWarps = 4, kTallTcFlush = 8;   // flush the mma accumulators every 8 steps of 16 k
+
+template <int NT, int U>
+__global__ void __launch_bounds__(kTallTcWarps * 32, U == 2 ? 4 : 3) tall_dense_tc_kernel(const float* __restrict__ x, int64_t rows, int k,
+                                                                          const float* __restrict__ w,
+                                                                          const float* __restrict__ b, int c, int act,
+                                                                          float* __restrict__ out) {
+  __shared__ float red[kTallTcWarps][16][NT * 8 + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int steps = (k + 15) / 16;
+  const int s_begin = static_cast<int>((int64_t)steps * warp / kTallTcWarps);
+  const int s_end = static_cast<int>((int64_t)steps * (warp + 1) / kTallTcWarps);
+  const int64_t tiles = (rows + 15) / 16;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t r_lo = tile * 16 + g, r_hi = r_lo + 8;
+    const float* x_lo = x + r_lo * k;
+    const float* x_hi = x + r_hi * k;
+    const bool lo_ok = r_lo < rows, hi_ok = r_hi < rows;
+    float master[NT][4], acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) master[nt][q] = acc[nt][q] = 0.f;
+    int since_flush = 0;
+    for (int s = s_begin; s < s_end; s += U) {
+      // U 16-k steps per iteration, all their loads issued before the first mma (U KB of x in flight per warp)
+      float4 xa[U], xb[U], wv[U][NT];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int kk = 16 * (s + u) + 4 * t;
+        const bool in_k = s + u < s_end && kk < k;   // k is a multiple of 4: the 16 bytes are entirely inside or outside
+        xa[u] = xb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in_k && lo_ok) xa[u] = ldg_stream_f4(reinterpret_cast<const float4*>(x_lo + kk));
+        if (in_k && hi_ok) xb[u] = ldg_stream_f4(reinterpret_cast<const float4*>(x_hi + kk));
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int n = nt * 8 + g;
+          wv[u][nt] = (in_k && n < c) ? __ldg(reinterpret_cast<const float4*>(w + (int64_t)n * k + kk))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        uint32_t ah[8], al[8];   // (row g: x y z w, row g+8: x y z w)
+        tall_split_tf32(xa[u].x, ah[0], al[0]);
+        tall_split_tf32(xa[u].y, ah[1], al[1]);
+        tall_split_tf32(xa[u].z, ah[2], al[2]);
+        tall_split_tf32(xa[u].w, ah[3], al[3]);
+        tall_split_tf32(xb[u].x, ah[4], al[4]);
+        tall_split_tf32(xb[u].y, ah[5], al[5]);
+        tall_split_tf32(xb[u].z, ah[6], al[6]);
+        tall_split_tf32(xb[u].w, ah[7], al[7]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          uint32_t bh[4], bl[4];
+          tall_split_tf32(wv[u][nt].x, bh[0], bl[0]);
+          tall_split_tf32(wv[u][nt].y, bh[1], bl[1]);
+          tall_split_tf32(wv[u][nt].z, bh[2], bl[2]);
+          tall_split_tf32(wv[u][nt].w, bh[3], bl[3]);
+          // fragment columns (t, t+4) = components (.x, .y) in the first mma, (.z, .w) in the second
+          tall_mma_tf32(acc[nt], al[0], al[4], al[1], al[5], bh[0], bh[1]);
+          tall_mma_tf32(acc[nt], ah[0], ah[4], ah[1], ah[5], bl[0], bl[1]);
+          tall_mma_tf32(acc[nt], ah[0], ah[4], ah[1], ah[5], bh[0], bh[1]);
+          tall_mma_tf32(acc[nt], al[2], al[6], al[3], al[7], bh[2], bh[3]);
+          tall_mma_tf32(acc[nt], ah[2], ah[6], ah[3], ah[7], bl[2], bl[3]);
+          tall_mma_tf32(acc[nt], ah[2], ah[6], ah[3], ah[7], bh[2], bh[3]);
+        }
+      }
+      since_flush += U;
+      if (since_flush >= kTallTcFlush) {
+        since_flush = 0;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            master[nt][q] += acc[nt][q];
+            acc[nt][q] = 0.f;
+          }
+      }
+    }
+    // accumulator layout: (row g, cols 2t, 2t+1), (row g+8, cols 2t, 2t+1) of every 8-output tile
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      red[warp][g][nt * 8 + 2 * t] = master[nt][0] + acc[nt][0];
+      red[warp][g][nt * 8 + 2 * t + 1] = master[nt][1] + acc[nt][1];
+      red[warp][g + 8][nt * 8 + 2 * t] = master[nt][2] + acc[nt][2];
+      red[warp][g + 8][nt * 8 + 2 * t + 1] = master[nt][3] + acc[nt][3];
+    }
+    __syncthreads();
+    for (int el = threadIdx.x; el < 16 * NT * 8; el += kTallTcWarps * 32) {
+      const int r = el / (NT * 8), o = el - r * (NT * 8);
+      const int64_t row = tile * 16 + r;
+      if (row < rows && o < c) {
+        float v = red[0][r][o];
+#pragma unroll
+        for (int q = 1; q < kTallTcWarps; ++q) v += red[q][r][o];
+        out[row * c + o] = apply_act(v + (b ? __ldg(b + o) : 0.f), act);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static bool tall_dense_tc_ok(const float* x, int k, const float* w, int c) {
+  static const bool disabled = getenv("TRS_DISABLE_TC") != nullptr;
+  return !disabled && (k & 3) == 0 && c <= 32 && aligned16(x) && aligned16(w);
+}
+
 int tall_dense_run(const float* x, int64_t rows, int k, const float* w, const float* b, int c, int act, float* out,
                    cudaStream_t s) {
+  if (tall_dense_tc_ok(x, k, w, c)) {
+    const int64_t tiles16 = (rows + 15) / 16;
+    const int grid16 = static_cast<int>(tiles16 < kNumSMs * 8 ? tiles16 : kNumSMs * 8);
+    static const int unroll = getenv("TRS_TALL_U") ? atoi(getenv("TRS_TALL_U")) : 4;   // measured: 474 us (4) vs 520 us (2)
+#define TRS_TALL_TC(NT_)                                                                                      \
+  if (unroll == 4)                                                                                            \
+    tall_dense_tc_kernel<NT_, 4><<<grid16, kTallTcWarps * 32, 0, s>>>(x, rows, k, w, b, c, act, out);          \
+  else                                                                                                        \
+    tall_dense_tc_kernel<NT_, 2><<<grid16, kTallTcWarps * 32, 0, s>>>(x, rows, k, w, b, c, act, out);
+    switch ((c + 7) / 8) {
+      case 1: TRS_TALL_TC(1) break;
+      case 2: TRS_TALL_TC(2) break;
+      case 3: TRS_TALL_TC(3) break;
+      default: TRS_TALL_TC(4) break;
+    }
+#undef TRS_TALL_TC
+    return check_launch("tall_dense_tc_kernel");
+  }
   const int64_t tiles = (rows + kTallRows - 1) / kTallRows;
   const int grid = static_cast<int>(tiles < kNumSMs * 4 ? tiles : kNumSMs * 4);
   for (int c0 = 0; c0 < c; c0 += 64) {   // blocks of at most 64 outputs (x is re-read per block; C <= 64 is the case)
