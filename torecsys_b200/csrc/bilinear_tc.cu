@@ -36,7 +36,12 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 // smallest pitch >= width + 4 with pitch = 4 (mod 32): the 8 rows x 4 columns of a fragment load hit 32 banks
 __host__ __device__ inline int row_pitch(int width) { return width + 4 + ((32 - width % 32) % 32); }
 
-template <int E>
+// OPN = true: the same tiles compute OuterProductNetworkLayer's 'mat' kernel (outer_product_network.py:80-131),
+//     out[b, p] = sum_h x_j[h] * (sum_e kernel[h, p, e] * x_i[e]),    kernel (E, P, E),
+// i.e. the bilinear form with W_p[k = e][o = h] = kernel[h, p, e] read in place (8 consecutive floats per fragment
+// pair) and the product with x_j summed over o: four lanes add their columns with two shuffles, one 4-byte store per
+// (sample, pair) -- the (B, P) output is 16x smaller than the bilinear layer's, so this form is bound by the tensor pipe.
+template <int E, bool OPN>
 __global__ void __launch_bounds__(kWarps * 32, E <= 16 ? 2 : 1) bilinear_tc_kernel(const float* __restrict__ x,
                                                                      const float* __restrict__ w,
                                                                      const float* __restrict__ bias, int each_type,
@@ -106,8 +111,14 @@ __global__ void __launch_bounds__(kWarps * 32, E <= 16 ? 2 : 1) bilinear_tc_kern
       for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-          split_tf32(__ldg(wp + (8 * ks + t) * E + 8 * nt + g), bh[ks][nt][0], bl[ks][nt][0]);
-          split_tf32(__ldg(wp + (8 * ks + t + 4) * E + 8 * nt + g), bh[ks][nt][1], bl[ks][nt][1]);
+          if constexpr (OPN) {   // B[k = e][n = h] = kernel[h, p, e]
+            const float* kp = w + ((int64_t)(8 * nt + g) * pairs + p) * E + 8 * ks + t;
+            split_tf32(__ldg(kp), bh[ks][nt][0], bl[ks][nt][0]);
+            split_tf32(__ldg(kp + 4), bh[ks][nt][1], bl[ks][nt][1]);
+          } else {
+            split_tf32(__ldg(wp + (8 * ks + t) * E + 8 * nt + g), bh[ks][nt][0], bl[ks][nt][0]);
+            split_tf32(__ldg(wp + (8 * ks + t + 4) * E + 8 * nt + g), bh[ks][nt][1], bl[ks][nt][1]);
+          }
         }
       float2 bv[NT];
 #pragma unroll
@@ -131,6 +142,24 @@ __global__ void __launch_bounds__(kWarps * 32, E <= 16 ? 2 : 1) bilinear_tc_kern
         const int s0 = 16 * mt + g, s1 = s0 + 8;
         const float* xj0 = xs + s0 * xpitch + j * E;
         const float* xj1 = xs + s1 * xpitch + j * E;
+        if constexpr (OPN) {
+          float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const int c = 8 * nt + 2 * t;
+            const float2 a0 = *reinterpret_cast<const float2*>(xj0 + c);
+            const float2 a1 = *reinterpret_cast<const float2*>(xj1 + c);
+            v0 = fmaf(acc[nt][0], a0.x, fmaf(acc[nt][1], a0.y, v0));
+            v1 = fmaf(acc[nt][2], a1.x, fmaf(acc[nt][3], a1.y, v1));
+          }
+          v0 += __shfl_xor_sync(0xffffffffu, v0, 1);
+          v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+          v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
+          v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+          if (t == 0 && s0 < valid) out[(b0 + s0) * pairs + p] = v0;
+          if (t == 0 && s1 < valid) out[(b0 + s1) * pairs + p] = v1;
+          continue;
+        }
         float* o0 = out + ((b0 + s0) * pairs + p) * E;
         float* o1 = out + ((b0 + s1) * pairs + p) * E;
 #pragma unroll
@@ -150,7 +179,7 @@ __global__ void __launch_bounds__(kWarps * 32, E <= 16 ? 2 : 1) bilinear_tc_kern
   }
 }
 
-template <int E>
+template <int E, bool OPN>
 int bilinear_tc_dispatch(const float* x, const float* w, const float* bias, int each_type, int64_t batch, int fields,
                          float* out, cudaStream_t s) {
   const int xpitch = row_pitch(fields * E);
@@ -159,13 +188,13 @@ int bilinear_tc_dispatch(const float* x, const float* w, const float* bias, int 
   if (smem > (size_t)kMaxDynSmem) return TRS_ERR_UNSUPPORTED;
   static size_t configured = 0;
   if (smem > configured) {
-    TRS_CUDA(cudaFuncSetAttribute(bilinear_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TRS_CUDA(cudaFuncSetAttribute(bilinear_tc_kernel<E, OPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const int64_t tiles = (batch + kSamples - 1) / kSamples;
   const int per_sm = smem > 110 * 1024 ? 1 : 2;
   const int grid = static_cast<int>(tiles < (int64_t)kNumSMs * per_sm ? tiles : (int64_t)kNumSMs * per_sm);
-  bilinear_tc_kernel<E><<<grid, kWarps * 32, smem, s>>>(x, w, bias, each_type, batch, fields, out);
+  bilinear_tc_kernel<E, OPN><<<grid, kWarps * 32, smem, s>>>(x, w, bias, each_type, batch, fields, out);
   return check_launch("bilinear_tc_kernel");
 }
 
@@ -179,9 +208,22 @@ int bilinear_tc_launch(const float* x, const float* w, const float* bias, int ea
       (bias && (reinterpret_cast<uintptr_t>(bias) & 7u)))
     return TRS_ERR_UNSUPPORTED;
   switch (embed) {
-    case 8: return bilinear_tc_dispatch<8>(x, w, bias, each_type, batch, fields, out, s);
-    case 16: return bilinear_tc_dispatch<16>(x, w, bias, each_type, batch, fields, out, s);
-    case 32: return bilinear_tc_dispatch<32>(x, w, bias, each_type, batch, fields, out, s);
+    case 8: return bilinear_tc_dispatch<8, false>(x, w, bias, each_type, batch, fields, out, s);
+    case 16: return bilinear_tc_dispatch<16, false>(x, w, bias, each_type, batch, fields, out, s);
+    case 32: return bilinear_tc_dispatch<32, false>(x, w, bias, each_type, batch, fields, out, s);
+  }
+  return TRS_ERR_UNSUPPORTED;
+}
+
+// OuterProductNetworkLayer, kernel_type 'mat', on the same tiles (TRS_ERR_UNSUPPORTED -> the FFMA kernel of pnn_senet.cu)
+int opn_mat_tc_launch(const float* x, const float* kernel, int64_t batch, int fields, int embed, float* out,
+                      cudaStream_t s) {
+  static const bool disabled = getenv("TRS_DISABLE_TC") != nullptr;
+  if (disabled || fields < 2 || fields > 1024 || !aligned16(x)) return TRS_ERR_UNSUPPORTED;
+  switch (embed) {
+    case 8: return bilinear_tc_dispatch<8, true>(x, kernel, nullptr, 1, batch, fields, out, s);
+    case 16: return bilinear_tc_dispatch<16, true>(x, kernel, nullptr, 1, batch, fields, out, s);
+    case 32: return bilinear_tc_dispatch<32, true>(x, kernel, nullptr, 1, batch, fields, out, s);
   }
   return TRS_ERR_UNSUPPORTED;
 }

@@ -6,6 +6,8 @@
 #include "common.cuh"
 
 namespace trs {
+int opn_mat_tc_launch(const float* x, const float* kernel, int64_t batch, int fields, int embed, float* out,
+                      cudaStream_t s);   // bilinear_tc.cu
 namespace {
 
 constexpr int kMatTile = 256;   // samples per CTA of the 'mat' kernel (one thread per sample)
@@ -206,6 +208,10 @@ extern "C" int trs_opn_forward(const float* x, const float* kernel, int kernel_t
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int pairs = fields * (fields - 1) / 2;
   if (kernel_type == TRS_OPN_MAT) {
+    {   // embed 8 / 16 / 32: 3xTF32 mma.sync tiles shared with the bilinear layer (bilinear_tc.cu)
+      const int rc = opn_mat_tc_launch(x, kernel, batch, fields, embed, out, s);
+      if (rc != TRS_ERR_UNSUPPORTED) return rc;
+    }
     if (aligned16(x)) {
       switch (embed) {
         case 4: return launch_opn_mat<4>(x, kernel, batch, fields, out, s);
