@@ -140,6 +140,13 @@ int trs_ipn_forward(const float* x, int64_t batch, int fields, int embed, float*
  * x (batch, fields, embed) -> out (batch, P, embed). */
 int trs_bilinear_forward(const float* x, const float* weight, const float* bias, int each_type,
                          int64_t batch, int fields, int embed, float* out, void* stream);
+/* The same forward writing sample b's (P, embed) block at out + b * out_stride (floats): lets a caller that concatenates
+ * several interaction outputs per sample (FiBiNET: torch.cat([emb_interaction, senet_interaction], dim='N'),
+ * feature_importance_and_bilinear_feature_interaction_network.py forward) have them written in place.  Tensor-core
+ * kernel only: embed 8 / 16 / 32, 16-byte aligned x / out, out_stride a multiple of 4 (TRS_ERR_UNSUPPORTED otherwise). */
+int trs_bilinear_forward_strided(const float* x, const float* weight, const float* bias, int each_type,
+                                 int64_t batch, int fields, int embed, int64_t out_stride, float* out,
+                                 void* stream);
 
 /* trs_bilinear_backward: gradients of BilinearInteractionLayer.forward (bilinear_interaction.py:230-255) for x, the
  * weight and the bias, given grad_out (batch, P, embed).  With t[b,p,:] = grad_out[b,p,:] * x[b,j,:]:

@@ -299,3 +299,29 @@ def test_fused_feature_models(trs, kind, b, n, e, idx_dtype):
     bad[b - 1, n - 1] = 10 ** 6
     with torch.no_grad(), pytest.raises(IndexError):
         seq({'idx': bad})
+
+
+@pytest.mark.parametrize('each', [False, True])
+@pytest.mark.parametrize('b,n,e', [(70, 39, 16), (33, 5, 8), (1, 2, 32)])
+def test_bilinear_written_in_place_into_a_concatenated_buffer(trs, b, n, e, each):
+    """trs_bilinear_forward_strided (FiBiNET's torch.cat([emb_interaction, senet_interaction], dim='N') without the copy):
+    every slot of the (B, S*P, E) buffer holds exactly the bits ops.bilinear returns, the other slots are untouched;
+    shapes outside the tensor-core kernel are refused, not emulated."""
+    from torecsys_b200 import synth
+    pairs = n * (n - 1) // 2
+    xs = [torch.from_numpy(synth.uniform((b, n, e), f'into/{b}{n}{e}/x{k}')).cuda() for k in range(3)]
+    w = torch.from_numpy(synth.uniform((pairs, e, e) if each else (e, e), f'into/{b}{n}{e}/w', -0.3, 0.3)).cuda()
+    bias = torch.from_numpy(synth.uniform((pairs, e) if each else (e,), f'into/{b}{n}{e}/b')).cuda()
+    buf = torch.full((b, 3 * pairs, e), -7.0, device='cuda')
+    for slot in (2, 0):
+        trs.ops.bilinear_into(xs[slot], w, bias, each, buf, slot)
+    assert torch.equal(buf[:, :pairs], trs.ops.bilinear(xs[0], w, bias, each))
+    assert torch.equal(buf[:, 2 * pairs:], trs.ops.bilinear(xs[2], w, bias, each))
+    assert (buf[:, pairs:2 * pairs] == -7.0).all()
+    with pytest.raises(ValueError):
+        trs.ops.bilinear_into(xs[0], w, bias, each, buf, 3)
+    with pytest.raises(ValueError):
+        trs.ops.bilinear_into(xs[0], w, bias, each, torch.zeros(b, 3 * pairs, e + 4, device='cuda'), 0)
+    x12 = torch.zeros(4, 3, 12, device='cuda')
+    with pytest.raises(NotImplementedError):
+        trs.ops.bilinear_into(x12, torch.zeros(12, 12, device='cuda'), None, False, torch.zeros(4, 6, 12, device='cuda'), 0)

@@ -44,6 +44,7 @@ PROTOTYPES = {
     'trs_ffm_forward': (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     'trs_ipn_forward': (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     'trs_bilinear_forward': (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int, _P, _P]),
+    'trs_bilinear_forward_strided': (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int, c_int64, _P, _P]),
     'trs_bilinear_backward': (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int, _P, _P, _P, _P]),
     'trs_afm_forward': (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
     'trs_afm_backward_supported': (c_int, [c_int, c_int]),

@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(kWarps * 32, E <= 16 ? 2 : 1) bilinear_tc_kern
                                                                      const float* __restrict__ w,
                                                                      const float* __restrict__ bias, int each_type,
                                                                      int64_t batch, int fields,
-                                                                     float* __restrict__ out) {
-  constexpr int KS = E / 8, NT = E / 8;
+                                                                     int64_t out_stride, float* __restrict__ out) {
+  constexpr int KS = E / 8, NT = E / 8;   // out_stride: floats between the output rows of consecutive samples
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int width = fields * E;
   const int pairs = fields * (fields - 1) / 2;
@@ -160,8 +160,8 @@ __global__ void __launch_bounds__(kWarps * 32, E <= 16 ? 2 : 1) bilinear_tc_kern
           if (t == 0 && s1 < valid) out[(b0 + s1) * pairs + p] = v1;
           continue;
         }
-        float* o0 = out + ((b0 + s0) * pairs + p) * E;
-        float* o1 = out + ((b0 + s1) * pairs + p) * E;
+        float* o0 = out + (b0 + s0) * out_stride + (int64_t)p * E;
+        float* o1 = out + (b0 + s1) * out_stride + (int64_t)p * E;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
           const int c = 8 * nt + 2 * t;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kWarps * 32, E <= 16 ? 2 : 1) bilinear_tc_kern
 
 template <int E, bool OPN>
 int bilinear_tc_dispatch(const float* x, const float* w, const float* bias, int each_type, int64_t batch, int fields,
-                         float* out, cudaStream_t s) {
+                         int64_t out_stride, float* out, cudaStream_t s) {
   const int xpitch = row_pitch(fields * E);
   const int pairs = fields * (fields - 1) / 2;
   const size_t smem = (size_t)kSamples * xpitch * sizeof(float) + (size_t)pairs * sizeof(int);
@@ -194,7 +194,7 @@ int bilinear_tc_dispatch(const float* x, const float* w, const float* bias, int 
   const int64_t tiles = (batch + kSamples - 1) / kSamples;
   const int per_sm = smem > 110 * 1024 ? 1 : 2;
   const int grid = static_cast<int>(tiles < (int64_t)kNumSMs * per_sm ? tiles : (int64_t)kNumSMs * per_sm);
-  bilinear_tc_kernel<E, OPN><<<grid, kWarps * 32, smem, s>>>(x, w, bias, each_type, batch, fields, out);
+  bilinear_tc_kernel<E, OPN><<<grid, kWarps * 32, smem, s>>>(x, w, bias, each_type, batch, fields, out_stride, out);
   return check_launch("bilinear_tc_kernel");
 }
 
@@ -202,15 +202,15 @@ int bilinear_tc_dispatch(const float* x, const float* w, const float* bias, int 
 
 // returns TRS_ERR_UNSUPPORTED when the shape is not covered (caller falls back to the generic kernels)
 int bilinear_tc_launch(const float* x, const float* w, const float* bias, int each_type, int64_t batch, int fields,
-                       int embed, float* out, cudaStream_t s) {
+                       int embed, int64_t out_stride, float* out, cudaStream_t s) {
   static const bool disabled = getenv("TRS_DISABLE_TC") != nullptr;
-  if (disabled || fields < 2 || fields > 1024 || !aligned16(x) || !aligned16(out) ||
+  if (disabled || fields < 2 || fields > 1024 || !aligned16(x) || !aligned16(out) || (out_stride & 3) ||
       (bias && (reinterpret_cast<uintptr_t>(bias) & 7u)))
     return TRS_ERR_UNSUPPORTED;
   switch (embed) {
-    case 8: return bilinear_tc_dispatch<8, false>(x, w, bias, each_type, batch, fields, out, s);
-    case 16: return bilinear_tc_dispatch<16, false>(x, w, bias, each_type, batch, fields, out, s);
-    case 32: return bilinear_tc_dispatch<32, false>(x, w, bias, each_type, batch, fields, out, s);
+    case 8: return bilinear_tc_dispatch<8, false>(x, w, bias, each_type, batch, fields, out_stride, out, s);
+    case 16: return bilinear_tc_dispatch<16, false>(x, w, bias, each_type, batch, fields, out_stride, out, s);
+    case 32: return bilinear_tc_dispatch<32, false>(x, w, bias, each_type, batch, fields, out_stride, out, s);
   }
   return TRS_ERR_UNSUPPORTED;
 }
@@ -221,9 +221,9 @@ int opn_mat_tc_launch(const float* x, const float* kernel, int64_t batch, int fi
   static const bool disabled = getenv("TRS_DISABLE_TC") != nullptr;
   if (disabled || fields < 2 || fields > 1024 || !aligned16(x)) return TRS_ERR_UNSUPPORTED;
   switch (embed) {
-    case 8: return bilinear_tc_dispatch<8, true>(x, kernel, nullptr, 1, batch, fields, out, s);
-    case 16: return bilinear_tc_dispatch<16, true>(x, kernel, nullptr, 1, batch, fields, out, s);
-    case 32: return bilinear_tc_dispatch<32, true>(x, kernel, nullptr, 1, batch, fields, out, s);
+    case 8: return bilinear_tc_dispatch<8, true>(x, kernel, nullptr, 1, batch, fields, 0, out, s);
+    case 16: return bilinear_tc_dispatch<16, true>(x, kernel, nullptr, 1, batch, fields, 0, out, s);
+    case 32: return bilinear_tc_dispatch<32, true>(x, kernel, nullptr, 1, batch, fields, 0, out, s);
   }
   return TRS_ERR_UNSUPPORTED;
 }

@@ -9,7 +9,7 @@ namespace trs {
 
 int ipn_tc_launch(const float* x, int64_t batch, int fields, int embed, float* out, cudaStream_t s);
 int bilinear_tc_launch(const float* x, const float* w, const float* bias, int each_type, int64_t batch, int fields,
-                       int embed, float* out, cudaStream_t s);
+                       int embed, int64_t out_stride, float* out, cudaStream_t s);
 int afm_tc_launch(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, int64_t batch,
                   int fields, int embed, int attn, float* out, float* scores, cudaStream_t s);
 
@@ -381,6 +381,22 @@ extern "C" int trs_ipn_forward(const float* x, int64_t batch, int fields, int em
   return check_launch("ipn_kernel");
 }
 
+extern "C" int trs_bilinear_forward_strided(const float* x, const float* weight, const float* bias, int each_type,
+                                            int64_t batch, int fields, int embed, int64_t out_stride, float* out,
+                                            void* stream) {
+  TRS_REQUIRE(x && weight && out, "trs_bilinear_forward_strided: null pointer");
+  TRS_REQUIRE(batch >= 0 && fields > 1 && embed > 0, "trs_bilinear_forward_strided: bad sizes");
+  TRS_REQUIRE(out_stride >= (int64_t)fields * (fields - 1) / 2 * embed,
+              "trs_bilinear_forward_strided: out_stride smaller than one sample's output");
+  if (batch == 0) return TRS_OK;
+  const int rc = bilinear_tc_launch(x, weight, bias, each_type, batch, fields, embed, out_stride, out,
+                                    static_cast<cudaStream_t>(stream));
+  if (rc == TRS_ERR_UNSUPPORTED)
+    set_error("trs_bilinear_forward_strided: embed must be 8, 16 or 32, x / out 16-byte aligned, out_stride a multiple "
+              "of 4 (got embed %d)", embed);
+  return rc;
+}
+
 extern "C" int trs_bilinear_forward(const float* x, const float* weight, const float* bias, int each_type,
                                     int64_t batch, int fields, int embed, float* out, void* stream) {
   TRS_REQUIRE(x && weight && out, "trs_bilinear_forward: null pointer");
@@ -389,7 +405,7 @@ extern "C" int trs_bilinear_forward(const float* x, const float* weight, const f
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int pairs = fields * (fields - 1) / 2;
   {   // tensor-pipe kernel (bilinear_tc.cu) for embed 8 / 16 / 32; anything else takes the generic kernels below
-    const int rc = bilinear_tc_launch(x, weight, bias, each_type, batch, fields, embed, out, s);
+    const int rc = bilinear_tc_launch(x, weight, bias, each_type, batch, fields, embed, (int64_t)pairs * embed, out, s);
     if (rc != TRS_ERR_UNSUPPORTED) return rc;
   }
   if (!each_type) {

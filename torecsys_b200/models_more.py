@@ -107,6 +107,17 @@ class FeatureImportanceAndBilinearFeatureInteractionNetwork(CtrBaseModel):
                              dropout_p=deep_dropout_p, activation=deep_activation)
 
     def forward(self, emb_inputs: torch.Tensor) -> torch.Tensor:
+        x = emb_inputs.rename(None)
+        if not torch.is_grad_enabled() and x.is_cuda and x.dim() == 3 and x.shape[-1] in (8, 16, 32):
+            # inference: both bilinear kernels write straight into the halves of the concatenated (B, 2P, E) buffer
+            # (trs_bilinear_forward_strided) -- the reference's torch.cat re-copies 2 x (B, P, E)
+            b, n, e = x.shape
+            buf = torch.empty((b, n * (n - 1), e), dtype=torch.float32, device=x.device)
+            for slot, (layer, src) in enumerate(((self.emb_bilinear, x), (self.senet_bilinear, None))):
+                if src is None:
+                    src = self.senet(x).rename(None)
+                ops.bilinear_into(src, layer.bilinear.weight, layer.bilinear.bias, layer.bilinear_type == 'each', buf, slot)
+            return self.deep(buf.reshape(b, -1)).rename(None)
         emb_interaction = self.emb_bilinear(emb_inputs.rename(None))
         emb_interaction.names = ('B', 'N', 'E',)
         senet_emb = self.senet(emb_inputs.rename(None))

@@ -396,6 +396,29 @@ def bilinear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]
     return out
 
 
+def bilinear_into(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], each_type: bool,
+                  out: torch.Tensor, slot: int) -> None:
+    """bilinear() written in place into out[:, slot*P:(slot+1)*P, :] of a (B, S*P, E) buffer that concatenates several
+    interaction outputs per sample (trs_bilinear_forward_strided; tensor-core shapes only -> NotImplementedError)."""
+    x, b, n, e = _bne('bilinear_into', x)
+    _need_cuda('bilinear_into', weight, bias, out)
+    w = _f32('bilinear_into', weight)
+    bs = _f32('bilinear_into', bias) if bias is not None else None
+    pairs = n * (n - 1) // 2
+    want = (pairs, e, e) if each_type else (e, e)
+    if tuple(w.shape) != want:
+        raise ValueError(f'bilinear_into: weight must be {want}, got {tuple(w.shape)}')
+    if (out.dtype != torch.float32 or not out.is_contiguous() or out.dim() != 3 or out.shape[0] != b or out.shape[2] != e
+            or out.shape[1] % pairs or not 0 <= slot < out.shape[1] // pairs):
+        raise ValueError(f'bilinear_into: out {tuple(out.shape)} is not a contiguous (B, S*{pairs}, {e}) float32 buffer '
+                         f'with a slot {slot}')
+    if b == 0:
+        return
+    check(_cabi.load().trs_bilinear_forward_strided(_ptr(x), _ptr(w), _ptr(bs), int(each_type), b, n, e,
+                                                    out.shape[1] * e, out.data_ptr() + slot * pairs * e * 4, _stream()),
+          'trs_bilinear_forward_strided')
+
+
 def bilinear_backward_supported(num_fields: int, embed: int) -> bool:
     """Shapes trs_bilinear_backward takes: embed 8 / 16 / 32 and 16 samples of x and grad_x in shared memory."""
     return embed in (8, 16, 32) and 2 * 16 * num_fields * embed * 4 <= 227 * 1024
