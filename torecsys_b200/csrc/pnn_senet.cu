@@ -144,6 +144,111 @@ __global__ void __launch_bounds__(256) opn_vec_kernel(const float* __restrict__ 
   }
 }
 
+// Pair-major form for E in {8, 16, 32} and up to 4 pairs per thread: thread <-> pair for the whole kernel, so k[p, :] (or
+// k[p]) and (i, j) stay in registers; a tile of samples is staged row-major with pitch E + 4 (the 8 lanes of a quarter
+// warp read 8 consecutive x_j rows from 8 different bank groups; x_i is a broadcast) and every thread walks the tile's
+// samples: 2 x E/4 LDS.128 per 2E flops instead of three scalar loads per FMA, coalesced 4-byte stores across pairs.
+// Same arithmetic order as opn_vec_kernel: fma(x_i[e] * x_j[e], k, acc) for e = 0 .. E-1.
+constexpr int kVecThreads = 256;
+
+template <int E, int PT, bool kVec>
+__global__ void __launch_bounds__(kVecThreads) opn_vec_pairs_kernel(const float* __restrict__ x,
+                                                                    const float* __restrict__ kernel, int64_t batch,
+                                                                    int fields, int tile_samples,
+                                                                    float* __restrict__ out) {
+  extern __shared__ __align__(16) float vsm[];
+  constexpr int PITCH = E + 4;
+  const int pairs = fields * (fields - 1) / 2;
+  const int row = fields * PITCH;   // floats per staged sample
+  int pi[PT], pj[PT];
+  float kr[PT][kVec ? E : 1];
+#pragma unroll
+  for (int q = 0; q < PT; ++q) {
+    const int p = threadIdx.x + q * kVecThreads;
+    pi[q] = pj[q] = 0;
+#pragma unroll
+    for (int e = 0; e < (kVec ? E : 1); ++e) kr[q][e] = 0.f;
+    if (p < pairs) {
+      pair_from_index(p, fields, pi[q], pj[q]);
+      if (kVec) {
+#pragma unroll
+        for (int e = 0; e < (kVec ? E : 1); ++e) kr[q][e] = __ldg(kernel + (int64_t)p * E + e);
+      } else {
+        kr[q][0] = __ldg(kernel + p);
+      }
+    }
+  }
+  const int64_t tiles = (batch + tile_samples - 1) / tile_samples;
+  constexpr int CH = E / 4;   // 16-byte chunks per field row
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t b0 = tile * tile_samples;
+    const int valid = static_cast<int>(batch - b0 < tile_samples ? batch - b0 : tile_samples);
+    __syncthreads();   // previous tile fully consumed
+    for (int c = threadIdx.x; c < valid * fields * CH; c += kVecThreads) {
+      const int r = c / CH, k = c - r * CH;   // r = sample * fields + field
+      *reinterpret_cast<float4*>(vsm + (size_t)r * PITCH + 4 * k) =
+          ldg_stream_f4(reinterpret_cast<const float4*>(x + b0 * fields * E) + c);
+    }
+    __syncthreads();
+    for (int smp = 0; smp < valid; ++smp) {
+      const float* xs = vsm + (size_t)smp * row;
+#pragma unroll
+      for (int q = 0; q < PT; ++q) {
+        const int p = threadIdx.x + q * kVecThreads;
+        if (p < pairs) {
+          const float* xi = xs + pi[q] * PITCH;
+          const float* xj = xs + pj[q] * PITCH;
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < CH; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(xi + 4 * k);
+            const float4 b = *reinterpret_cast<const float4*>(xj + 4 * k);
+            acc = fmaf(a.x * b.x, kr[q][kVec ? 4 * k : 0], acc);
+            acc = fmaf(a.y * b.y, kr[q][kVec ? 4 * k + 1 : 0], acc);
+            acc = fmaf(a.z * b.z, kr[q][kVec ? 4 * k + 2 : 0], acc);
+            acc = fmaf(a.w * b.w, kr[q][kVec ? 4 * k + 3 : 0], acc);
+          }
+          out[(b0 + smp) * pairs + p] = acc;
+        }
+      }
+    }
+  }
+}
+
+template <int E, int PT, bool kVec>
+int launch_opn_vec_pairs(const float* x, const float* kernel, int64_t batch, int fields, float* out, cudaStream_t s) {
+  const size_t per_sample = (size_t)fields * (E + 4) * sizeof(float);
+  int tile_samples = static_cast<int>((size_t)(100 * 1024) / per_sample);   // two CTAs per SM
+  if (tile_samples > 64) tile_samples = 64;
+  if (tile_samples < 1) return TRS_ERR_UNSUPPORTED;
+  const size_t smem = per_sample * tile_samples;
+  TRS_SMEM_OPT_IN((opn_vec_pairs_kernel<E, PT, kVec>));
+  const int64_t tiles = (batch + tile_samples - 1) / tile_samples;
+  const int64_t cap = (int64_t)kNumSMs * 2;
+  opn_vec_pairs_kernel<E, PT, kVec><<<static_cast<int>(tiles < cap ? tiles : cap), kVecThreads, smem, s>>>(
+      x, kernel, batch, fields, tile_samples, out);
+  return check_launch("opn_vec_pairs_kernel");
+}
+
+template <bool kVec>
+int opn_vec_pairs_dispatch(const float* x, const float* kernel, int64_t batch, int fields, int embed, float* out,
+                           cudaStream_t s) {
+  const int pairs = fields * (fields - 1) / 2;
+  const int pt = (pairs + kVecThreads - 1) / kVecThreads;
+  if (!aligned16(x) || pt > 4 || (kVec && pt * embed > 64)) return TRS_ERR_UNSUPPORTED;
+#define TRS_OPN_VEC_CASE(E_, PT_)                \
+  if (embed == E_ && pt == PT_) return launch_opn_vec_pairs<E_, PT_, kVec>(x, kernel, batch, fields, out, s);
+  TRS_OPN_VEC_CASE(8, 1) TRS_OPN_VEC_CASE(8, 2) TRS_OPN_VEC_CASE(8, 3) TRS_OPN_VEC_CASE(8, 4)
+  TRS_OPN_VEC_CASE(16, 1) TRS_OPN_VEC_CASE(16, 2) TRS_OPN_VEC_CASE(16, 3) TRS_OPN_VEC_CASE(16, 4)
+  TRS_OPN_VEC_CASE(32, 1) TRS_OPN_VEC_CASE(32, 2)
+#undef TRS_OPN_VEC_CASE
+  if (!kVec && embed == 32 && (pt == 3 || pt == 4)) {
+    if (pt == 3) return launch_opn_vec_pairs<32, 3, false>(x, kernel, batch, fields, out, s);
+    return launch_opn_vec_pairs<32, 4, false>(x, kernel, batch, fields, out, s);
+  }
+  return TRS_ERR_UNSUPPORTED;
+}
+
 // ---- SENET -----------------------------------------------------------------------------------------------------------
 // pooled[b,m] = mean_e x[b,m,e]  (nn.AdaptiveAvgPool1d(1)); one thread per (b, m) row, 16-byte loads when E % 4 == 0
 __global__ void __launch_bounds__(256) senet_pool_kernel(const float* __restrict__ x, int64_t rows, int embed, int vec,
@@ -228,6 +333,11 @@ extern "C" int trs_opn_forward(const float* x, const float* kernel, int kernel_t
     TRS_UNSUPPORTED(tiles > 65535, "trs_opn_forward: batch too large for one launch of the 'mat' kernel");
     opn_mat_generic_kernel<<<dim3(pairs, (unsigned)tiles), kMatTile, smem, s>>>(x, kernel, batch, fields, embed, out);
     return check_launch("opn_mat_generic_kernel");
+  }
+  {   // pair-major register kernel for embed 8 / 16 / 32 and up to 1 024 pairs
+    const int rc = kernel_type == TRS_OPN_VEC ? opn_vec_pairs_dispatch<true>(x, kernel, batch, fields, embed, out, s)
+                                              : opn_vec_pairs_dispatch<false>(x, kernel, batch, fields, embed, out, s);
+    if (rc != TRS_ERR_UNSUPPORTED) return rc;
   }
   int warps = 8;
   size_t smem;
