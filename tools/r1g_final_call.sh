@@ -13,3 +13,5 @@ timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 stamp "launch list rc=$?"
 timeout 400 python tools/bench_ops.py --json gpurun_out/r1g_ops_baseline_shapes.json > gpurun_out/r1g_ops.log 2>&1
 stamp "bench_ops rc=$?"
+timeout 100 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_more.py -q -p no:cacheprovider -k "test_opn_shapes_and_ragged_batches and (vec or num) and (39-16 or 7-8 or 26-32)" > gpurun_out/r1g_memcheck_opn_vec.log 2>&1
+stamp "memcheck opn vec/num rc=$? $(grep -E 'ERROR SUMMARY' gpurun_out/r1g_memcheck_opn_vec.log | tail -1) $(grep -E 'passed|failed' gpurun_out/r1g_memcheck_opn_vec.log | tail -1)"
