@@ -62,10 +62,41 @@ def _load_cross(cross, params, dtype):
 
 
 def run_layer(trs, kind, b, n, e, dtype):
-    L = trs.layers
     c = cases.layer_case(kind, b, n, e)
     x = T(c['inputs']['x']).to(dtype)
-    p = c['params']
+    m = _build_layer(trs, kind, n, e, c['params'], dtype)
+    m.eval()
+    with torch.no_grad():
+        out = m(x)
+    if isinstance(out, tuple):
+        return {'out': out[0].rename(None).numpy(), 'scores': out[1].rename(None).numpy()}
+    return {'out': out.rename(None).numpy()}
+
+
+# layers whose backward has its own kernel: the reference's own gradients are frozen too (fp64, eval mode)
+GRAD_LAYER_KINDS = ('fm', 'ffm', 'ipn', 'bilinear_all', 'bilinear_each', 'afm', 'cross')
+
+
+def run_layer_grads(trs, kind, b, n, e, dtype=torch.float64):
+    """d (sum(out * g)) / d x and / d every parameter (named_parameters order) of the REFERENCE layer, autograd on the
+    reference's own forward -- including CrossNetworkLayer's gradient cut through h_0 (cross_network.py:65).  g is the
+    deterministic upstream gradient cases.upstream_grad(cid, shape)."""
+    c = cases.layer_case(kind, b, n, e)
+    x = T(c['inputs']['x']).to(dtype).requires_grad_()
+    m = _build_layer(trs, kind, n, e, c['params'], dtype)
+    m.eval()
+    out = m(x)
+    out = (out[0] if isinstance(out, tuple) else out).rename(None)
+    g = T(cases.upstream_grad(cases.case_id(kind, b, n, e), tuple(out.shape))).to(dtype)
+    (out * g).sum().backward()
+    res = {'dx': x.grad.rename(None).numpy()}
+    for k, (_, prm) in enumerate(m.named_parameters()):
+        res[f'dp{k}'] = prm.grad.rename(None).numpy()
+    return res
+
+
+def _build_layer(trs, kind, n, e, p, dtype):
+    L = trs.layers
     if kind == 'fm':
         m = L.FMLayer(0.5)
     elif kind == 'ffm':
@@ -93,12 +124,7 @@ def run_layer(trs, kind, b, n, e, dtype):
         _load_mlp(m, p, dtype)
     else:
         raise KeyError(kind)
-    m.eval()
-    with torch.no_grad():
-        out = m(x)
-    if isinstance(out, tuple):
-        return {'out': out[0].rename(None).numpy(), 'scores': out[1].rename(None).numpy()}
-    return {'out': out.rename(None).numpy()}
+    return m
 
 
 def run_emb(trs, kind, b, n, e, dtype):
@@ -278,6 +304,16 @@ def main():
     out_dir = os.path.join(ROOT, 'tests', 'golden')
     os.makedirs(out_dir, exist_ok=True)
     only_new = '--new' in sys.argv   # leave the committed round-1 fixtures untouched
+    if '--grads' in sys.argv:        # only the gradient fixture (round 1g)
+        store = {}
+        for kind in GRAD_LAYER_KINDS:
+            for (b, n, e) in cases.GRID:
+                cid = cases.case_id(kind, b, n, e)
+                for k, v in run_layer_grads(trs, kind, b, n, e).items():
+                    store[f'{cid}/{k}'] = v
+        np.savez_compressed(os.path.join(out_dir, 'layer_grads.npz'), **store)
+        print('layer_grads.npz', len(store), 'arrays', os.path.getsize(os.path.join(out_dir, 'layer_grads.npz')) // 1024, 'KiB')
+        return
     jobs = [] if only_new else [('layers.npz', cases.LAYER_KINDS, run_layer),
                                 ('embeddings.npz', cases.EMB_KINDS, run_emb),
                                 ('models.npz', cases.MODEL_KINDS, run_model)]

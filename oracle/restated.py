@@ -89,10 +89,12 @@ def ffm_layer(v: torch.Tensor, num_fields: int) -> torch.Tensor:
     return torch.cat(outs, dim=1)
 
 
-def cross_layer(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]) -> torch.Tensor:
+def cross_layer(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
+                cut_gradient_through_h0: bool = False) -> torch.Tensor:
     """torecsys/layers/ctr/cross_network.py:65-79: h <- x * Linear_l(h) + x (Linear(E,E) on the last dim,
-    residual is x0, not h).  (B,N,E)->(B,N,E)."""
-    h = x
+    residual is x0, not h).  (B,N,E)->(B,N,E).  The reference starts the chain from emb_inputs.detach() (:65): same
+    forward values, but no gradient reaches x through h_0 -- cut_gradient_through_h0 restates that for gradient tests."""
+    h = x.detach() if cut_gradient_through_h0 else x
     for w, b in zip(weights, biases):
         h = F.linear(h, w, b)
         h = x * h

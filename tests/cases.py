@@ -45,6 +45,11 @@ def _u(shape, tag, scale=1.0, dtype=np.float32):
     return synth.uniform(shape, tag, -scale, scale, dtype)
 
 
+def upstream_grad(cid, shape):
+    """Deterministic gradient arriving at a layer's output (gradient fixtures, tests/golden/layer_grads.npz)."""
+    return _u(tuple(shape), f'{cid}/upstream_grad')
+
+
 def _pairs(n):
     return n * (n - 1) // 2
 

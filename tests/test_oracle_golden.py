@@ -61,3 +61,58 @@ def test_offsets_follow_the_float32_rounding_quirk():
     assert off[2] == int(np.float32(110_015_444))
     fs16 = [5_128_192] * 39
     assert field_offsets(fs16).tolist() == [5_128_192 * i for i in range(39)]
+
+
+GRAD_KINDS = ['fm', 'ffm', 'ipn', 'bilinear_all', 'bilinear_each', 'afm', 'cross']
+
+
+@pytest.fixture(scope='module')
+def golden_grads():
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'layer_grads.npz')
+    return np.load(path)
+
+
+@pytest.mark.parametrize('kind', GRAD_KINDS)
+@pytest.mark.parametrize('b,n,e', GRID)
+def test_layer_oracle_gradients_match_reference(golden_grads, kind, b, n, e):
+    """The layers with backward kernels: torch differentiating the ORACLE formula (fp64) reproduces the gradients the
+    reference's own modules produced (oracle/make_golden.py --grads: autograd on the reference forward, eval mode),
+    for x and every parameter -- including CrossNetworkLayer's gradient cut through h_0 (cross_network.py:65).  The
+    GPU kernels are held to autograd on these same oracle formulas (tests/test_gpu_training.py), which closes the
+    chain reference -> oracle -> kernels for the backward path."""
+    from oracle import restated as R
+    c = cases.layer_case(kind, b, n, e)
+    p = c['params']
+    t64 = lambda a: torch.from_numpy(np.ascontiguousarray(a)).double().requires_grad_()
+    x = t64(c['inputs']['x'])
+    if kind == 'fm':
+        params, out = [], R.fm_layer(x)
+    elif kind == 'ffm':
+        params, out = [], R.ffm_layer(x, n)
+    elif kind == 'ipn':
+        params, out = [], R.ipn_layer(x)
+    elif kind in ('bilinear_all', 'bilinear_each'):
+        params = [t64(p['w']), t64(p['b'])]
+        out = R.bilinear_layer(x, params[0], params[1], kind.split('_')[1])
+    elif kind == 'afm':
+        params = [t64(p[k]) for k in ('w1', 'b1', 'w2', 'b2')]
+        out = R.afm_layer(x, *params)[0]
+    else:
+        ws, bs = cases.cross_lists(p)
+        ws, bs = [t64(w) for w in ws], [t64(v) for v in bs]
+        params = [t for pair in zip(ws, bs) for t in pair]          # named_parameters order: model.l.weight, model.l.bias
+        out = R.cross_layer(x, ws, bs, cut_gradient_through_h0=True)
+    cid = cases.case_id(kind, b, n, e)
+    g = torch.from_numpy(cases.upstream_grad(cid, tuple(out.shape))).double()
+    (out * g).sum().backward()
+    want = golden_grads[f'{cid}/dx']
+    assert normwise_err(x.grad.numpy(), want) <= 1e-10, (cid, 'dx')
+    for k, prm in enumerate(params):
+        ref = golden_grads[f'{cid}/dp{k}']
+        assert prm.grad is not None
+        got = prm.grad.reshape(ref.shape).numpy()
+        if max(np.abs(got).max(), np.abs(ref).max()) < 1e-12:
+            continue   # mathematically zero (the bias in front of AFM's softmax): rounding noise on both sides
+        assert normwise_err(got, ref) <= 1e-10, (cid, f'dp{k}')
+    assert f'{cid}/dp{len(params)}' not in golden_grads.files
