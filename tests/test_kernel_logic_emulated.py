@@ -1,4 +1,5 @@
-"""Kernel LOGIC checks without a GPU: the device code of csrc/bilinear_bwd.cu, csrc/afm_bwd.cu and of opn_vec_pairs_kernel (csrc/pnn_senet.cu) is compiled as plain C++ against
+"""Kernel LOGIC checks without a GPU: the device code of csrc/bilinear_bwd.cu, csrc/afm_bwd.cu, of opn_vec_pairs_kernel (csrc/pnn_senet.cu) and of tall_dense_tc_kernel
+(csrc/dense.cu, mma.sync through a fragment-layout emulation) is compiled as plain C++ against
 tests/emu/cuda_emu.h (one OS thread per CUDA thread, std::barrier for __syncthreads, CTA-uniform shuffles) and compared
 with a float64 restatement of the layer's gradient formulas (bilinear_interaction.py:72-76 / :144-149 differentiated).
 This is test infrastructure: it proves index arithmetic, accumulator ownership, the prefetch ring and the reductions,
@@ -74,4 +75,38 @@ def test_opn_vec_pairs_kernel_logic(emulated_opn_vec, args):
     """Bit-identical to the reference's operation order ((x_i * x_j) first, the kernel second, summed over e in order):
     ragged last tiles, two pairs per thread (276 pairs), both kernel types."""
     res = subprocess.run([emulated_opn_vec] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+
+
+@pytest.fixture(scope='module')
+def emulated_tall_dense(tmp_path_factory):
+    """tall_dense_tc_kernel with mma.sync replaced by the fragment-layout emulation of cuda_emu.h; the hi/lo split is the
+    product's own text."""
+    if shutil.which('g++') is None:
+        pytest.skip('g++ not available')
+    src = open(os.path.join(ROOT, 'torecsys_b200', 'csrc', 'dense.cu')).read()
+    split = '__device__ __forceinline__ void tall_split_tf32' + src.split(
+        '__device__ __forceinline__ void tall_split_tf32', 1)[1].split('\n}\n', 1)[0] + '\n}\n'
+    start = 'constexpr int kTallTcWarps = 4, kTallTcFlush = 8;'
+    kernel = start + src.split(start, 1)[1].split('static bool tall_dense_tc_ok', 1)[0]
+    mma = ('static inline void tall_mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, '
+           'uint32_t b0, uint32_t b1) { emu_mma_m16n8k8_tf32(d, a0, a1, a2, a3, b0, b1); }\n')
+    out = tmp_path_factory.mktemp('emu')
+    cpp = out / 'tall_dense_emu.cpp'
+    cpp.write_text('#include "cuda_emu.h"\nnamespace trs {\nnamespace {\n' + mma + split + kernel
+                   + '}  // namespace\n}  // namespace trs\nusing namespace trs;\n'
+                   + open(os.path.join(EMU, 'tall_dense_main.inc')).read())
+    exe = out / 'tall_dense_emu'
+    res = subprocess.run(['g++', '-std=c++20', '-O1', '-pthread', '-I', EMU, '-Wno-unknown-pragmas', str(cpp), '-o',
+                          str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return str(exe)
+
+
+# rows, K, outputs, activation id, CTAs
+@pytest.mark.parametrize('args', [(37, 1000, 16, 1, 2), (16, 268, 5, 0, 1), (20, 2052, 32, 1, 3), (3, 64, 24, 0, 1)])
+def test_tall_dense_tensor_core_kernel_logic(emulated_tall_dense, args):
+    """Fragment mapping of the k-permuted 16-byte loads, the four k-quarters of a CTA, flush into the FP32 master sums,
+    ragged rows / K tails (K a multiple of 4 but not of 16 or 64) / output counts that are not a multiple of 8."""
+    res = subprocess.run([emulated_tall_dense] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
