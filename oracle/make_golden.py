@@ -147,7 +147,7 @@ def run_emb(trs, kind, b, n, e, dtype):
     return {'out': out.rename(None).numpy()}
 
 
-def run_model(trs, kind, b, n, e, dtype):
+def run_model(trs, kind, b, n, e, dtype, grads=False):
     I, M = trs.inputs, trs.models
     c = cases.model_case(kind, b, n, e)
     fs, p = c['field_sizes'], c['params']
@@ -193,6 +193,20 @@ def run_model(trs, kind, b, n, e, dtype):
     else:
         raise KeyError(kind)
     seq = trs.Sequential(inputs, model).to(dtype).eval()
+    if grads:
+        # d (sum(out * g)) / d every parameter of the reference Sequential (embedding tables included), keyed by the
+        # tests/cases.py array the parameter was loaded from (matched by value)
+        out = seq({'idx': T(c['inputs']['idx'])}).rename(None)
+        g = T(cases.upstream_grad(cases.case_id(kind, b, n, e), tuple(out.shape))).to(dtype)
+        (out * g).sum().backward()
+        res = {}
+        for name, prm in seq.named_parameters():
+            flat = prm.detach().rename(None).reshape(-1).numpy()
+            keys = [k for k, v in p.items() if isinstance(v, np.ndarray) and v.size == flat.size and
+                    np.array_equal(v.reshape(-1).astype(flat.dtype), flat)]
+            assert len(keys) == 1, (kind, name, keys)
+            res[f'd/{keys[0]}'] = prm.grad.rename(None).reshape(p[keys[0]].shape).numpy()
+        return res
     with torch.no_grad():
         out = seq({'idx': T(c['inputs']['idx'])})
     return {'out': out.rename(None).numpy()}
@@ -313,6 +327,14 @@ def main():
                     store[f'{cid}/{k}'] = v
         np.savez_compressed(os.path.join(out_dir, 'layer_grads.npz'), **store)
         print('layer_grads.npz', len(store), 'arrays', os.path.getsize(os.path.join(out_dir, 'layer_grads.npz')) // 1024, 'KiB')
+        store = {}
+        for kind in cases.MODEL_KINDS:
+            for (b, n, e) in cases.GRID[2:]:          # the two Criteo-like shapes keep the fixture small
+                cid = cases.case_id(kind, b, n, e)
+                for k, v in run_model(trs, kind, b, n, e, torch.float64, grads=True).items():
+                    store[f'{cid}/{k}'] = v
+        np.savez_compressed(os.path.join(out_dir, 'model_grads.npz'), **store)
+        print('model_grads.npz', len(store), 'arrays', os.path.getsize(os.path.join(out_dir, 'model_grads.npz')) // 1024, 'KiB')
         return
     jobs = [] if only_new else [('layers.npz', cases.LAYER_KINDS, run_layer),
                                 ('embeddings.npz', cases.EMB_KINDS, run_emb),

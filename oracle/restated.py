@@ -239,9 +239,12 @@ def deepfm_model(feat: torch.Tensor, emb: torch.Tensor, mlp_w, mlp_b, activation
 
 
 def dcn_model(emb: torch.Tensor, cross_w, cross_b, mlp_w, mlp_b, fc_w, fc_b, activation='relu') -> torch.Tensor:
-    """torecsys/models/ctr/deep_and_cross_network.py:76-98: fc(flatten(cat[Cross(x), MLP_per_field(x)], -1))."""
+    """torecsys/models/ctr/deep_and_cross_network.py:76-98: fc(flatten(cat[Cross(x), MLP_per_field(x)], -1)).
+    The cross branch starts from emb.detach() as the reference layer does (cross_network.py:65): identical forward
+    values, and differentiating this formula gives the reference's embedding gradient (quirk 3 of SURVEY.md 8a)."""
     b = emb.shape[0]
-    cat = torch.cat([cross_layer(emb, cross_w, cross_b), mlp_layer(emb, mlp_w, mlp_b, activation)], dim=-1)
+    cat = torch.cat([cross_layer(emb, cross_w, cross_b, cut_gradient_through_h0=True),
+                     mlp_layer(emb, mlp_w, mlp_b, activation)], dim=-1)
     return F.linear(cat.reshape(b, -1), fc_w, fc_b)
 
 

@@ -116,3 +116,47 @@ def test_layer_oracle_gradients_match_reference(golden_grads, kind, b, n, e):
             continue   # mathematically zero (the bias in front of AFM's softmax): rounding noise on both sides
         assert normwise_err(got, ref) <= 1e-10, (cid, f'dp{k}')
     assert f'{cid}/dp{len(params)}' not in golden_grads.files
+
+
+@pytest.mark.parametrize('kind', cases.MODEL_KINDS)
+@pytest.mark.parametrize('b,n,e', GRID[2:])
+def test_model_oracle_gradients_match_reference(monkeypatch, kind, b, n, e):
+    """One backward pass of the five a12 models: torch differentiating the oracle's indices -> logits formulas (fp64)
+    gives, for EVERY parameter (embedding tables, MLP, cross, CIN, fc, bias), the gradient autograd produced on the
+    reference's own Sequential(Inputs, model) in eval mode (make_golden.py --grads -> tests/golden/model_grads.npz,
+    keyed by the tests/cases.py array each reference parameter was loaded from)."""
+    import os
+    import tests.oracle_run as orun
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'model_grads.npz'))
+    c = cases.model_case(kind, b, n, e)
+    p = c['params']
+    leaves = {}
+
+    def t_leaf(a, dtype):   # oracle_run._t, with every floating array a leaf that records its gradient
+        if isinstance(a, (list, tuple)):
+            return [t_leaf(v, dtype) for v in a]
+        if a is None or isinstance(a, float):
+            return a
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        if not t.is_floating_point():
+            return t
+        if id(a) not in leaves:
+            leaves[id(a)] = t.to(dtype).requires_grad_()
+        return leaves[id(a)]
+
+    monkeypatch.setattr(orun, '_t', t_leaf)
+    monkeypatch.setattr(cases, 'model_case', lambda *a: c)   # the same array objects the ids were taken from
+    out = orun.oracle_model(kind, b, n, e, torch.float64)['out']
+    cid = cases.case_id(kind, b, n, e)
+    g = torch.from_numpy(cases.upstream_grad(cid, tuple(out.shape))).double()
+    (out * g).sum().backward()
+    keys = [k[len(cid) + 3:] for k in golden.files if k.startswith(cid + '/d/')]
+    assert keys, cid
+    for k in keys:
+        ref = golden[f'{cid}/d/{k}']
+        leaf = leaves.get(id(p[k]))
+        assert leaf is not None and leaf.grad is not None, (cid, k)
+        got = leaf.grad.reshape(ref.shape).numpy()
+        if max(np.abs(got).max(), np.abs(ref).max()) < 1e-12:
+            continue
+        assert normwise_err(got, ref) <= 1e-9, (cid, k)
