@@ -147,6 +147,23 @@ def run_emb(trs, kind, b, n, e, dtype):
     return {'out': out.rename(None).numpy()}
 
 
+def _model_grads(seq, c, kind, b, n, e, dtype):
+    """d (sum(out * g)) / d every parameter of the reference Sequential (embedding tables included), keyed by the
+    tests/cases.py array the parameter was loaded from (matched by value)."""
+    p = c['params']
+    out = seq({'idx': T(c['inputs']['idx'])}).rename(None)
+    g = T(cases.upstream_grad(cases.case_id(kind, b, n, e), tuple(out.shape))).to(dtype)
+    (out * g).sum().backward()
+    res = {}
+    for name, prm in seq.named_parameters():
+        flat = prm.detach().rename(None).reshape(-1).numpy()
+        keys = [k for k, v in p.items() if isinstance(v, np.ndarray) and v.size == flat.size and
+                np.array_equal(v.reshape(-1).astype(flat.dtype), flat)]
+        assert len(keys) == 1, (kind, name, keys)
+        res[f'd/{keys[0]}'] = prm.grad.rename(None).reshape(p[keys[0]].shape).numpy()
+    return res
+
+
 def run_model(trs, kind, b, n, e, dtype, grads=False):
     I, M = trs.inputs, trs.models
     c = cases.model_case(kind, b, n, e)
@@ -194,19 +211,7 @@ def run_model(trs, kind, b, n, e, dtype, grads=False):
         raise KeyError(kind)
     seq = trs.Sequential(inputs, model).to(dtype).eval()
     if grads:
-        # d (sum(out * g)) / d every parameter of the reference Sequential (embedding tables included), keyed by the
-        # tests/cases.py array the parameter was loaded from (matched by value)
-        out = seq({'idx': T(c['inputs']['idx'])}).rename(None)
-        g = T(cases.upstream_grad(cases.case_id(kind, b, n, e), tuple(out.shape))).to(dtype)
-        (out * g).sum().backward()
-        res = {}
-        for name, prm in seq.named_parameters():
-            flat = prm.detach().rename(None).reshape(-1).numpy()
-            keys = [k for k, v in p.items() if isinstance(v, np.ndarray) and v.size == flat.size and
-                    np.array_equal(v.reshape(-1).astype(flat.dtype), flat)]
-            assert len(keys) == 1, (kind, name, keys)
-            res[f'd/{keys[0]}'] = prm.grad.rename(None).reshape(p[keys[0]].shape).numpy()
-        return res
+        return _model_grads(seq, c, kind, b, n, e, dtype)
     with torch.no_grad():
         out = seq({'idx': T(c['inputs']['idx'])})
     return {'out': out.rename(None).numpy()}
@@ -243,7 +248,7 @@ def run_layer_2(trs, kind, b, n, e, dtype):
     return {'out': out.rename(None).numpy()}
 
 
-def run_model_2(trs, kind, b, n, e, dtype):
+def run_model_2(trs, kind, b, n, e, dtype, grads=False):
     """SURVEY.md 8f-3 models through the reference's own Sequential(Inputs, model)."""
     I, M = trs.inputs, trs.models
     c = cases.model_case(kind, b, n, e)
@@ -307,6 +312,8 @@ def run_model_2(trs, kind, b, n, e, dtype):
     else:
         raise KeyError(kind)
     seq = trs.Sequential(inputs, model).to(dtype).eval()
+    if grads:
+        return _model_grads(seq, c, kind, b, n, e, dtype)
     with torch.no_grad():
         out = seq({'idx': T(c['inputs']['idx'])})
     return {'out': out.rename(None).numpy()}
@@ -328,11 +335,13 @@ def main():
         np.savez_compressed(os.path.join(out_dir, 'layer_grads.npz'), **store)
         print('layer_grads.npz', len(store), 'arrays', os.path.getsize(os.path.join(out_dir, 'layer_grads.npz')) // 1024, 'KiB')
         store = {}
-        for kind in cases.MODEL_KINDS:
-            for (b, n, e) in cases.GRID[2:]:          # the two Criteo-like shapes keep the fixture small
-                cid = cases.case_id(kind, b, n, e)
-                for k, v in run_model(trs, kind, b, n, e, torch.float64, grads=True).items():
-                    store[f'{cid}/{k}'] = v
+        for kinds, fn in ((cases.MODEL_KINDS, run_model), (cases.MODEL_KINDS_2, run_model_2)):
+            for kind in kinds:
+                # the Criteo-like shapes; one of them for the 8f-3 models (field-aware tables are large)
+                for (b, n, e) in (cases.GRID[2:] if fn is run_model else cases.GRID[2:3]):
+                    cid = cases.case_id(kind, b, n, e)
+                    for k, v in fn(trs, kind, b, n, e, torch.float64, grads=True).items():
+                        store[f'{cid}/{k}'] = v
         np.savez_compressed(os.path.join(out_dir, 'model_grads.npz'), **store)
         print('model_grads.npz', len(store), 'arrays', os.path.getsize(os.path.join(out_dir, 'model_grads.npz')) // 1024, 'KiB')
         return

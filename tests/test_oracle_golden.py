@@ -118,13 +118,14 @@ def test_layer_oracle_gradients_match_reference(golden_grads, kind, b, n, e):
     assert f'{cid}/dp{len(params)}' not in golden_grads.files
 
 
-@pytest.mark.parametrize('kind', cases.MODEL_KINDS)
-@pytest.mark.parametrize('b,n,e', GRID[2:])
+@pytest.mark.parametrize('kind,b,n,e', [(k,) + g for k in cases.MODEL_KINDS for g in GRID[2:]] +
+                         [(k,) + GRID[2] for k in cases.MODEL_KINDS_2])
 def test_model_oracle_gradients_match_reference(monkeypatch, kind, b, n, e):
-    """One backward pass of the five a12 models: torch differentiating the oracle's indices -> logits formulas (fp64)
-    gives, for EVERY parameter (embedding tables, MLP, cross, CIN, fc, bias), the gradient autograd produced on the
-    reference's own Sequential(Inputs, model) in eval mode (make_golden.py --grads -> tests/golden/model_grads.npz,
-    keyed by the tests/cases.py array each reference parameter was loaded from)."""
+    """One backward pass of the five a12 models and the seven 8f-3 models: torch differentiating the oracle's
+    indices -> logits formulas (fp64) gives, for EVERY parameter (embedding tables, MLP, cross, CIN, bilinear, SENET,
+    attention, outer-product kernel, fc, bias), the gradient autograd produced on the reference's own
+    Sequential(Inputs, model) in eval mode (make_golden.py --grads -> tests/golden/model_grads.npz, keyed by the
+    tests/cases.py array each reference parameter was loaded from)."""
     import os
     import tests.oracle_run as orun
     golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'model_grads.npz'))
