@@ -204,7 +204,8 @@ def run_ours(args):
         if packed is not None:
             # back-to-back batches that are already resident: TRS_LAUNCH_OVERLAP_PREVIOUS lets batch k+1 start on
             # the SMs batch k has left (its inputs are never written by a kernel; its logits stay ordered)
-            ops.deepfm_packed(dev_idx[i % RING], offsets, packed, pack, out=out, overlap_previous=args.overlap)
+            ops.deepfm_packed(dev_idx[i % RING], offsets, packed, pack, out=out, overlap_previous=args.overlap,
+                              kernel=args.kernel, variant=args.variant)
         else:
             ops.deepfm(dev_idx[i % RING], offsets, w_feat, w_emb, pack, out=out)
 
@@ -394,6 +395,10 @@ def main():
                     help='launch the timed kernels fully ordered (no programmatic dependent launch)')
     ap.add_argument('--layout', default='packed', choices=['packed', 'split'],
                     help='packed: one 128-byte shadow row per table row (default); split: the two reference tables')
+    ap.add_argument('--kernel', default='auto', choices=['auto', 'tc5', 'mma'],
+                    help='packed layout: tcgen05 kernel (deepfm_tc5.cu) or the round-1 mma.sync kernel')
+    ap.add_argument('--variant', type=int, default=None, help='pipeline shape of the tcgen05 kernel (0 or 1)')
+    ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer (e2e) measurements')
     ap.add_argument('--traffic', type=float, default=None,
                     help='ncu dram bytes per launch of the dominant kernel (from profiles/), copied into the JSON')
     args = ap.parse_args()

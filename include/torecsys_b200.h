@@ -303,6 +303,27 @@ int trs_deepfm_forward_packed_ex(const void* idx, int idx_bits, const int64_t* o
                                  const float* const* mlp_b, int activation, float* logits, int32_t* status,
                                  unsigned flags, void* stream);
 
+/* DeepFM forward on the packed table with layer 1 on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
+ * accumulators in tensor memory, 3xTF32 = fp32-accurate): the same computation as trs_deepfm_forward_packed
+ * (torecsys/models/ctr/deep_fm.py:55-110 behind torecsys/models/sequential.py:31-44) -- csrc/deepfm_tc5.cu.
+ * W1 = mlp_w[0] is pre-split ONCE per model into the tensor-core operand layout by trs_deepfm_tc_prepare (run it
+ * again whenever W1 changes); `workspace` holds trs_deepfm_tc_workspace_bytes(fields, variant) bytes of device
+ * memory, 16-byte aligned.  variant 0: one CTA of 19 warps per SM (4 stages of 128 samples x 3 fields);
+ * variant 1: two CTAs of 13 warps per SM (2 stages of 128 x 2), so that back-to-back launches with
+ * TRS_LAUNCH_OVERLAP_PREVIOUS overlap on every SM.  Restrictions as for the packed kernel (hidden widths 16, ReLU,
+ * rows < 2^31); trs_deepfm_tc_supported() answers without launching. */
+int64_t trs_deepfm_tc_workspace_bytes(int fields, int variant);
+int trs_deepfm_tc_supported(int fields, int embed, const int* mlp_dims, int mlp_layers, int activation, int64_t rows,
+                            int variant);
+int trs_deepfm_tc_prepare(int fields, const float* w1, int variant, float* workspace, void* stream);
+/* debug: event clocks of CTA 0's warp roles into a device buffer of 7 x 512 x 4 int64 (NULL switches it off) */
+int trs_debug_tc5_trace(long long* device_buf);
+int trs_deepfm_forward_tc(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                          const float* packed, int64_t rows,
+                          const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                          const float* const* mlp_b, int activation, const float* workspace, int variant,
+                          float* logits, int32_t* status, unsigned flags, void* stream);
+
 /* DeepAndCrossNetworkModel.forward (torecsys/models/ctr/deep_and_cross_network.py:58-98):
  *     logit = fc( flatten( cat[ Cross(emb) (B,N,E), MLP_per_field(emb) (B,N,Od) ], dim=-1 ) )
  * cross_w (cross_layers, E, E), cross_b (cross_layers, E); MLP in = embed, out = Od; fc_w (1, N*(E+Od)), fc_b (1). */
@@ -408,6 +429,56 @@ int trs_session_depth(void);
  * reported as out-of-range lookups exactly as in the int64 path.  threads = 0 turns it off, -1 picks
  * min(8, usable CPUs / 2).  Returns the thread count in use (>= 0) or a negative TRS_ERR_* code. */
 int trs_session_set_index_narrowing(trs_session* session, int threads);
+/* Ordering against the caller's own work: the slots run on private streams, so device work the caller enqueued on
+ * `stream` before a submit (packing the shadow table, uploading offsets, an optimizer step, load_state_dict) is not
+ * ordered before the batch unless the session is told which stream that is.  With enabled != 0 every later submit
+ * records an event on `stream` and makes its slot wait for it on the device (no host synchronisation). */
+int trs_session_set_producer_stream(trs_session* session, void* stream, int enabled);
+/* Generic form: the batch is fed to ANY fused indices -> logits entry point of this library (the five callers of
+ * torecsys/models/sequential.py:31-44: trs_fm_model_forward, trs_deepfm_forward*, trs_dcn_forward,
+ * trs_xdeepfm_forward, trs_ffm_model_forward*, and the 8f-3 models).  `fn` is called once per slice, synchronously
+ * inside the submit call, and must enqueue exactly one forward over `batch` samples starting at `idx_dev` on `stream`:
+ *     fn(ctx, lane, idx_dev, idx_bits, batch, logits_dev, status_dev, stream) -> TRS_OK or an error code.
+ * lane < trs_session_lanes() identifies the (slot, stream) pair: slices with different lanes may run concurrently (give
+ * each its own scratch), slices of one lane are stream-ordered.
+ * `rows` (rows of the largest table, 0 = unknown) only gates the optional host-side index narrowing. */
+typedef int (*trs_forward_fn)(void* ctx, int lane, const void* idx_dev, int idx_bits, int64_t batch, float* logits_dev,
+                              int32_t* status_dev, void* stream);
+int trs_session_submit_fn(trs_session* session, const void* idx_host, int idx_bits, int64_t batch, int fields,
+                          trs_forward_fn fn, void* ctx, int64_t rows, float* logits_host, int64_t* ticket);
+int trs_session_lanes(void);
+/* The other four callers of torecsys/models/sequential.py:31-44 with host buffers; arguments as in the device entry
+ * points (trs_fm_model_forward[_packed], trs_dcn_forward, trs_xdeepfm_forward, trs_ffm_model_forward[_interleaved]).
+ * fm / ffm: `packed` != NULL selects the packed / interleaved shadow table, else the registered tables are used.
+ * xdeepfm: `workspace` is cut into trs_session_lanes() equal parts, each of which must hold
+ * trs_xdeepfm_workspace_bytes(slice batch = ceil(batch / chunks) rounded up to 16, ...). */
+int trs_session_submit_fm(trs_session* session, const void* idx_host, int idx_bits, const int64_t* offsets,
+                          int64_t batch, int fields, const float* w_feat, const float* w_emb, const float* packed,
+                          int64_t rows, int embed, const float* bias, float* logits_host, int64_t* ticket);
+int trs_session_submit_dcn(trs_session* session, const void* idx_host, int idx_bits, const int64_t* offsets,
+                           int64_t batch, int fields, const float* w_emb, int64_t rows, int embed,
+                           const float* cross_w, const float* cross_b, int cross_layers,
+                           const int* mlp_dims, int mlp_layers, const float* const* mlp_w, const float* const* mlp_b,
+                           int activation, const float* fc_w, const float* fc_b, float* logits_host, int64_t* ticket);
+int trs_session_submit_xdeepfm(trs_session* session, const void* idx_host, int idx_bits, const int64_t* offsets,
+                               int64_t batch, int fields, const float* w_feat, const float* w_emb, int64_t rows,
+                               int embed, const float* const* cin_w, const float* const* cin_scale,
+                               const float* const* cin_shift, const int* cin_layer_sizes, int cin_layers,
+                               int cin_is_direct, int cin_activation, const float* cin_fc_w, const float* cin_fc_b,
+                               const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                               const float* const* mlp_b, int mlp_activation, const float* bias, void* workspace,
+                               int64_t workspace_bytes, float* logits_host, int64_t* ticket);
+int trs_session_submit_ffm(trs_session* session, const void* idx_host, int idx_bits, const int64_t* offsets,
+                           int64_t batch, int fields, const float* w_feat, const float* const* tables,
+                           const float* packed, int64_t rows, int embed, const float* bias, float* logits_host,
+                           int64_t* ticket);
+/* DeepFM on the packed table through the tcgen05 kernel (trs_deepfm_forward_tc; workspace from trs_deepfm_tc_prepare) */
+int trs_session_submit_deepfm_tc(trs_session* session, const void* idx_host, int idx_bits,
+                                 const int64_t* offsets, int64_t batch, int fields,
+                                 const float* packed, int64_t rows,
+                                 const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                                 const float* const* mlp_b, int activation, const float* workspace, int variant,
+                                 float* logits_host, int64_t* ticket);
 int trs_session_submit_deepfm(trs_session* session, const void* idx_host, int idx_bits,
                               const int64_t* offsets, int64_t batch, int fields,
                               const float* w_feat, const float* w_emb, int64_t rows, int embed,

@@ -175,10 +175,17 @@ def test_deepfm_fast_path_matches_generic_and_oracle(ops, monkeypatch):
             assert normwise_err(got, want64) <= max(4 * normwise_err(want, want64), 2e-6), batch
 
 
+# the three kernels behind ops.deepfm_packed: round-1 mma.sync (deepfm_packed.cu) and the two pipeline shapes of the
+# tcgen05 kernel (deepfm_tc5.cu: one CTA of 19 warps per SM / two CTAs of 13 warps per SM)
+PACKED_KERNELS = [('mma', 0), ('tc5', 0), ('tc5', 1)]
+
+
+@pytest.mark.parametrize('kernel,variant', PACKED_KERNELS)
 @pytest.mark.parametrize('n', [1, 7, 8, 9, 16, 17, 24, 26, 32, 39, 40])
-def test_deepfm_packed_table_path(ops, n):
-    """deepfm_packed.cu: 128-byte shadow rows + cp.async ring + field-split warps.  Must equal the oracle (and hence
-    the split-table path) for every fields-per-warp instantiation, ragged batches, int32/int64 indices."""
+def test_deepfm_packed_table_path(ops, n, kernel, variant):
+    """deepfm_packed.cu / deepfm_tc5.cu on the 128-byte shadow rows.  Must equal the oracle (and hence the split-table
+    path) for every field count (fields-per-warp instantiations of the mma kernel, padded field groups of the tcgen05
+    one), ragged batches around the 16- / 128-sample tiles, several tiles per CTA, int32/int64 indices."""
     from oracle import restated as R
     from torecsys_b200 import synth
     e = 16
@@ -196,19 +203,22 @@ def test_deepfm_packed_table_path(ops, n):
     assert packed.shape == (rows, 32)
     assert torch.equal(packed[:, :16].cpu(), w_emb) and torch.equal(packed[:, 16].cpu(), w_feat[:, 0])
     assert not packed[:, 17:].any()
-    for batch in (1, 16, 33, 2500, 16 * 148 * 5 + 3):
+    batches = (1, 16, 33, 2500, 16 * 148 * 5 + 3) + ((148 * 128 * 2 + 77, 148 * 300 + 1) if n in (7, 39) else ())
+    for batch in batches:
         idx = torch.from_numpy(synth.integers((batch, n), f'pk{n}/idx{batch}', np.asarray(fs)[None, :]))
         want = R.deepfm_from_indices(idx, off, w_feat, w_emb, ws, bs).numpy()
         want64 = R.deepfm_from_indices(idx, off, w_feat.double(), w_emb.double(), [w.double() for w in ws],
                                        [b.double() for b in bs]).numpy()
         for dt in (torch.int64, torch.int32):
-            got = ops.deepfm_packed(idx.cuda().to(dt), off.cuda(), packed, pack).cpu().numpy()
+            got = ops.deepfm_packed(idx.cuda().to(dt), off.cuda(), packed, pack, kernel=kernel,
+                                    variant=variant).cpu().numpy()
             assert normwise_err(got, want) <= TOL, (n, batch)
             assert normwise_err(got, want64) <= max(4 * normwise_err(want, want64), 2e-6), (n, batch)
 
 
-@pytest.mark.parametrize('batch', [1, 17, 16 * 148 * 3 + 5])
-def test_deepfm_packed_overlapped_launches(ops, batch):
+@pytest.mark.parametrize('kernel,variant', PACKED_KERNELS)
+@pytest.mark.parametrize('batch', [1, 17, 16 * 148 * 3 + 5, 148 * 128 + 1000])
+def test_deepfm_packed_overlapped_launches(ops, batch, kernel, variant):
     """TRS_LAUNCH_OVERLAP_PREVIOUS (programmatic dependent launch): a train of back-to-back launches, each reading
     its own index batch, must give the same logits as ordered launches -- both into separate outputs and into ONE
     reused output buffer (the last launch must win: writes stay ordered behind the previous grid)."""
@@ -229,7 +239,9 @@ def test_deepfm_packed_overlapped_launches(ops, batch):
     trains = 12
     idx = [torch.from_numpy(synth.integers((batch, n), f'pdl/idx{k}', np.asarray(fs)[None, :])).cuda()
            for k in range(trains)]
-    ordered = [ops.deepfm_packed(ix, off.cuda(), packed, pack) for ix in idx]
+    import functools
+    run = functools.partial(ops.deepfm_packed, kernel=kernel, variant=variant)
+    ordered = [run(ix, off.cuda(), packed, pack) for ix in idx]
     want_last = R.deepfm_from_indices(idx[-1].cpu(), off, w_feat, w_emb, ws, bs).numpy()
     assert normwise_err(ordered[-1].cpu().numpy(), want_last) <= TOL
     off_d = off.cuda()
@@ -240,9 +252,9 @@ def test_deepfm_packed_overlapped_launches(ops, batch):
             shared = torch.empty(batch, 1, device='cuda')
             torch.cuda.synchronize()
             for k, ix in enumerate(idx):
-                ops.deepfm_packed(ix, off_d, packed, pack, out=outs[k], overlap_previous=True)
+                run(ix, off_d, packed, pack, out=outs[k], overlap_previous=True)
             for ix in idx:
-                ops.deepfm_packed(ix, off_d, packed, pack, out=shared, overlap_previous=True)
+                run(ix, off_d, packed, pack, out=shared, overlap_previous=True)
             torch.cuda.synchronize()
             for k in range(trains):
                 assert torch.equal(outs[k], ordered[k]), k
@@ -254,7 +266,7 @@ def test_deepfm_packed_overlapped_launches(ops, batch):
     bad = idx[0].clone()
     bad[min(7, batch - 1), 3] = 10 ** 9
     with pytest.raises(IndexError):
-        ops.deepfm_packed(bad, off.cuda(), packed, pack, overlap_previous=True)
+        run(bad, off.cuda(), packed, pack, overlap_previous=True)
 
 
 @pytest.mark.parametrize('n,e,cross_layers,deep,od', [(39, 32, 6, [32, 16, 8], 4), (7, 32, 1, [32], 1),
@@ -417,7 +429,8 @@ def test_fm_model_on_packed_table(ops, n):
         assert normwise_err(got0, want - bias.numpy()) <= TOL, (n, batch)
 
 
-def test_deepfm_packed_out_of_range(ops):
+@pytest.mark.parametrize('kernel,variant', PACKED_KERNELS)
+def test_deepfm_packed_out_of_range(ops, kernel, variant):
     from torecsys_b200 import synth
     n, rows = 39, 39 * 16
     packed = ops.fm_pack_table(torch.randn(rows, 16, device='cuda'), torch.randn(rows, 1, device='cuda'))
@@ -428,7 +441,15 @@ def test_deepfm_packed_out_of_range(ops):
     idx = torch.zeros(20, n, dtype=torch.long, device='cuda')
     idx[7, 38] = 16   # one past the last row of the table
     with pytest.raises(IndexError):
-        ops.deepfm_packed(idx, off, packed, pack)
+        ops.deepfm_packed(idx, off, packed, pack, kernel=kernel, variant=variant)
+    # ... and in a later tile of a CTA (the tcgen05 kernel converts those in its index warp), negative this time
+    big = torch.zeros(148 * 128 * 2 + 5, n, dtype=torch.long, device='cuda')
+    big[-3, 0] = -1
+    with pytest.raises(IndexError):
+        ops.deepfm_packed(big, off, packed, pack, kernel=kernel, variant=variant)
+    big[-3, 0] = 0
+    ops.deepfm_packed(big, off, packed, pack, kernel=kernel, variant=variant)
+    ops.check_index_errors()
 
 
 def test_out_of_range_index_raises(ops):

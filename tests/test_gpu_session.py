@@ -255,3 +255,66 @@ def test_index_column_concatenation_kernel(setup, idx_dtype):
         assert torch.equal(seq(batch_dict), seq1({'idx': idx}))
         embedded = seq._inputs(batch_dict)
         assert torch.equal(embedded['emb_inputs'].rename(None), seq1._inputs({'idx': idx})['emb_inputs'].rename(None))
+
+
+@pytest.mark.parametrize('kind', ['fm_model', 'deepfm_model', 'dcn_model', 'xdeepfm_model', 'ffm_model'])
+@pytest.mark.parametrize('idx_dtype', [torch.int64, torch.int32])
+def test_session_feeds_every_fused_model_from_host_buffers(kind, idx_dtype):
+    """HostSession.submit_model (trs_session_submit_fm / _deepfm* / _dcn / _xdeepfm / _ffm): the five callers of
+    torecsys/models/sequential.py:31-44 fed from host memory, pipelined -- bit-identical to the module's own fused
+    forward on device-resident indices, out-of-range lookups raise at wait()."""
+    import torecsys_b200 as trs
+    from tests.test_gpu_modules import build_sequential
+    from torecsys_b200.host import HostSession
+    from torecsys_b200 import ops
+    ops.set_index_check('sync')
+    b, n, e = 700, 39, 16
+    seq, idx_dev = build_sequential(trs, kind, b, n, e)
+    idx = idx_dev.cpu().to(idx_dtype)
+    with torch.no_grad():
+        want = seq({'idx': idx.cuda()}).cpu()
+    sess = HostSession(1024, n, chunks=3)
+    try:
+        outs = [torch.empty(b, 1).pin_memory() for _ in range(sess.depth)]
+        src = idx.pin_memory()
+        tickets = [sess.submit_model(seq, src, o) for o in outs]     # `depth` batches in flight
+        # the CIN tensor-core kernel starts its K walk at a CTA-dependent point (L2 hot-spot avoidance), so slicing the
+        # batch changes the summation order of xDeepFM: equal within fp32 rounding there, bit-identical elsewhere
+        same = (lambda a, w: normwise_err(a.numpy(), w.numpy()) <= 2e-6) if kind == 'xdeepfm_model' else torch.equal
+        for t, o in zip(tickets, outs):
+            sess.wait(t)
+            assert same(o, want), kind
+        pageable = torch.empty(b, 1)
+        sess.forward_model(seq, idx.clone(), pageable)
+        assert same(pageable, want)
+        bad = idx.clone()
+        bad[b - 1, n - 1] = 10 ** 6
+        with pytest.raises(IndexError):
+            sess.forward_model(seq, bad, pageable)
+        with pytest.raises(ValueError):
+            sess.forward_model(seq, idx[:, :5], pageable)           # non-contiguous / wrong shape host buffer
+    finally:
+        sess.close()
+
+
+def test_session_is_ordered_after_the_callers_stream(setup):
+    """Work enqueued on torch's current stream right before submit (here: rebuilding the packed table from modified
+    weights) is seen by the session's private streams (trs_session_set_producer_stream)."""
+    from torecsys_b200.host import HostSession
+    s = setup
+    ops = s['ops']
+    idx = _idx(s, 4096, 'ord')
+    sess = HostSession(4096, s['n'], chunks=2)
+    try:
+        out = torch.empty(4096, 1).pin_memory()
+        for k in range(4):
+            w_emb = s['w_emb_d'] * (1.0 + 0.25 * k)
+            big = torch.empty(64 << 20, device='cuda').normal_()     # keeps the stream busy ahead of the pack kernel
+            packed = ops.fm_pack_table(w_emb, s['w_feat_d'])          # enqueued, not synchronised
+            t = sess.submit(idx.pin_memory(), s['off_d'], s['pack'], out, packed=packed)
+            sess.wait(t)
+            want = ops.deepfm_packed(idx.cuda(), s['off_d'], packed, s['pack']).cpu()
+            assert torch.equal(out, want), k
+            del big
+    finally:
+        sess.close()

@@ -25,6 +25,10 @@ _P = c_void_p            # device / host data pointer
 _PP = POINTER(c_void_p)  # host array of device pointers
 _IP = POINTER(c_int)     # host int array
 
+# trs_forward_fn: int fn(void* ctx, int lane, const void* idx_dev, int idx_bits, int64_t batch, float* logits_dev,
+#                         int32_t* status_dev, void* stream)
+FORWARD_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p)
+
 # name -> (restype, argtypes): exactly the declarations of include/torecsys_b200.h
 PROTOTYPES = {
     'trs_version': (c_char_p, []),
@@ -67,6 +71,12 @@ PROTOTYPES = {
                                           _P, _P, _P]),
     'trs_deepfm_forward_packed_ex': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, _IP, c_int, _PP, _PP, c_int,
                                              _P, _P, ctypes.c_uint, _P]),
+    'trs_deepfm_tc_workspace_bytes': (c_int64, [c_int, c_int]),
+    'trs_deepfm_tc_supported': (c_int, [c_int, c_int, _IP, c_int, c_int, c_int64, c_int]),
+    'trs_debug_tc5_trace': (c_int, [_P]),
+    'trs_deepfm_tc_prepare': (c_int, [c_int, _P, c_int, _P, _P]),
+    'trs_deepfm_forward_tc': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, _IP, c_int, _PP, _PP, c_int, _P, c_int,
+                                      _P, _P, ctypes.c_uint, _P]),
     'trs_dcn_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, c_int, _P, _P, c_int, _IP, c_int, _PP,
                                 _PP, c_int, _P, _P, _P, _P, _P]),
     'trs_xdeepfm_workspace_bytes': (c_int64, [c_int64, c_int, c_int, _IP, c_int, c_int]),
@@ -92,6 +102,21 @@ PROTOTYPES = {
                                           c_int, _PP, _PP, c_int, _P, POINTER(c_int64)]),
     'trs_session_submit_deepfm_packed': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, c_int64, _IP,
                                                  c_int, _PP, _PP, c_int, _P, POINTER(c_int64)]),
+    'trs_session_set_producer_stream': (c_int, [c_void_p, _P, c_int]),
+    'trs_session_lanes': (c_int, []),
+    'trs_session_submit_fn': (c_int, [c_void_p, _P, c_int, c_int64, c_int, FORWARD_FN, c_void_p, c_int64, _P,
+                                      POINTER(c_int64)]),
+    'trs_session_submit_deepfm_tc': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, c_int64, _IP, c_int, _PP, _PP,
+                                             c_int, _P, c_int, _P, POINTER(c_int64)]),
+    'trs_session_submit_fm': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, _P, _P, c_int64, c_int, _P, _P,
+                                      POINTER(c_int64)]),
+    'trs_session_submit_dcn': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, c_int64, c_int, _P, _P, c_int, _IP,
+                                       c_int, _PP, _PP, c_int, _P, _P, _P, POINTER(c_int64)]),
+    'trs_session_submit_xdeepfm': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _PP, _PP, _PP,
+                                           _IP, c_int, c_int, c_int, _P, _P, _IP, c_int, _PP, _PP, c_int, _P, _P, c_int64,
+                                           _P, POINTER(c_int64)]),
+    'trs_session_submit_ffm': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, _P, _P, c_int64, c_int, _P, _P,
+                                       POINTER(c_int64)]),
     'trs_session_wait': (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
     'trs_session_deepfm_forward_host': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _IP,
                                                 c_int, _PP, _PP, c_int, _P, POINTER(c_int64)]),

@@ -48,14 +48,17 @@ cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t s);
     }                                                                                          \
   } while (0)
 
-// opt a kernel in to the full 227 KB of dynamic shared memory, once per process (one process per GPU)
+// opt a kernel in to the full 227 KB of dynamic shared memory, once per process AND device (the attribute is
+// per device: a second GPU driven from the same process needs its own call)
 constexpr int kMaxDynSmem = 227 * 1024;
 #define TRS_SMEM_OPT_IN(kernel)                                                                          \
   do {                                                                                                   \
-    static bool _done = false;                                                                           \
-    if (!_done) {                                                                                        \
+    static unsigned long long _done = 0;                                                                 \
+    int _dev = 0;                                                                                        \
+    TRS_CUDA(cudaGetDevice(&_dev));                                                                      \
+    if (!((_done >> (_dev & 63)) & 1ull)) {                                                              \
       TRS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ::trs::kMaxDynSmem)); \
-      _done = true;                                                                                      \
+      _done |= 1ull << (_dev & 63);                                                                      \
     }                                                                                                    \
   } while (0)
 

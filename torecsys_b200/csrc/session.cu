@@ -181,6 +181,9 @@ struct trs_session {
   int chunks;
   int64_t next_ticket;
   NarrowPool* narrow;   // null: int64 indices cross the link as they are
+  cudaStream_t producer;   // stream on which the caller prepares tables / parameters (ordering, see submit)
+  int has_producer;
+  cudaEvent_t producer_ready;
   Slot slots[kSlots];
 };
 
@@ -220,6 +223,7 @@ extern "C" int trs_session_create(int64_t max_batch, int fields, int chunks, trs
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.joined, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
   }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->producer_ready, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     set_error("trs_session_create: %s", cudaGetErrorString(e));
     trs_session_destroy(s);
@@ -232,6 +236,7 @@ extern "C" int trs_session_create(int64_t max_batch, int fields, int chunks, trs
 extern "C" int trs_session_destroy(trs_session* s) {
   if (!s) return TRS_OK;
   delete s->narrow;
+  if (s->producer_ready) cudaEventDestroy(s->producer_ready);
   for (int k = 0; k < kSlots; ++k) {
     Slot& sl = s->slots[k];
     for (int i = 0; i < 2; ++i)
@@ -274,13 +279,126 @@ extern "C" int trs_session_set_index_narrowing(trs_session* s, int threads) {
   return threads;
 }
 
+namespace {
+// what a slice of a batch runs: any fused indices -> logits entry point of this library, bound to its parameters
+struct DeepFmCall {
+  const int64_t* offsets;
+  int fields;
+  const float *w_feat, *w_emb, *packed, *workspace;
+  int64_t rows;
+  int embed, variant;
+  const int* mlp_dims;
+  int mlp_layers;
+  const float* const* mlp_w;
+  const float* const* mlp_b;
+  int activation;
+};
+int deepfm_call(void* ctx, int /*lane*/, const void* idx_dev, int idx_bits, int64_t nb, float* logits_dev,
+                int32_t* status_dev, void* stream) {
+  const DeepFmCall& c = *static_cast<const DeepFmCall*>(ctx);
+  if (c.workspace != nullptr)
+    return trs_deepfm_forward_tc(idx_dev, idx_bits, c.offsets, nb, c.fields, c.packed, c.rows, c.mlp_dims, c.mlp_layers,
+                                 c.mlp_w, c.mlp_b, c.activation, c.workspace, c.variant, logits_dev, status_dev, 0u,
+                                 stream);
+  if (c.packed != nullptr)
+    return trs_deepfm_forward_packed(idx_dev, idx_bits, c.offsets, nb, c.fields, c.packed, c.rows, c.mlp_dims,
+                                     c.mlp_layers, c.mlp_w, c.mlp_b, c.activation, logits_dev, status_dev, stream);
+  return trs_deepfm_forward(idx_dev, idx_bits, c.offsets, nb, c.fields, c.w_feat, c.w_emb, c.rows, c.embed, c.mlp_dims,
+                            c.mlp_layers, c.mlp_w, c.mlp_b, c.activation, logits_dev, status_dev, stream);
+}
+struct FmCall {
+  const int64_t* offsets;
+  int fields;
+  const float *w_feat, *w_emb, *packed, *bias;
+  int64_t rows;
+  int embed;
+};
+int fm_call(void* ctx, int, const void* idx_dev, int idx_bits, int64_t nb, float* logits_dev, int32_t* status_dev,
+            void* stream) {
+  const FmCall& c = *static_cast<const FmCall*>(ctx);
+  if (c.packed != nullptr)
+    return trs_fm_model_forward_packed(idx_dev, idx_bits, c.offsets, nb, c.fields, c.packed, c.rows, c.bias, logits_dev,
+                                       status_dev, stream);
+  return trs_fm_model_forward(idx_dev, idx_bits, c.offsets, nb, c.fields, c.w_feat, c.w_emb, c.rows, c.embed, c.bias,
+                              logits_dev, status_dev, stream);
+}
+struct DcnCall {
+  const int64_t* offsets;
+  int fields;
+  const float* w_emb;
+  int64_t rows;
+  int embed;
+  const float *cross_w, *cross_b;
+  int cross_layers;
+  const int* mlp_dims;
+  int mlp_layers;
+  const float* const* mlp_w;
+  const float* const* mlp_b;
+  int activation;
+  const float *fc_w, *fc_b;
+};
+int dcn_call(void* ctx, int, const void* idx_dev, int idx_bits, int64_t nb, float* logits_dev, int32_t* status_dev,
+             void* stream) {
+  const DcnCall& c = *static_cast<const DcnCall*>(ctx);
+  return trs_dcn_forward(idx_dev, idx_bits, c.offsets, nb, c.fields, c.w_emb, c.rows, c.embed, c.cross_w, c.cross_b,
+                         c.cross_layers, c.mlp_dims, c.mlp_layers, c.mlp_w, c.mlp_b, c.activation, c.fc_w, c.fc_b,
+                         logits_dev, status_dev, stream);
+}
+struct XdfmCall {
+  const int64_t* offsets;
+  int fields;
+  const float *w_feat, *w_emb;
+  int64_t rows;
+  int embed;
+  const float* const* cin_w;
+  const float* const* cin_scale;
+  const float* const* cin_shift;
+  const int* cin_sizes;
+  int cin_layers, cin_is_direct, cin_act;
+  const float *cin_fc_w, *cin_fc_b;
+  const int* mlp_dims;
+  int mlp_layers;
+  const float* const* mlp_w;
+  const float* const* mlp_b;
+  int mlp_act;
+  const float* bias;
+  char* workspace;
+  int64_t lane_bytes;
+};
+int xdeepfm_call(void* ctx, int lane, const void* idx_dev, int idx_bits, int64_t nb, float* logits_dev,
+                 int32_t* status_dev, void* stream) {
+  const XdfmCall& c = *static_cast<const XdfmCall*>(ctx);
+  return trs_xdeepfm_forward(idx_dev, idx_bits, c.offsets, nb, c.fields, c.w_feat, c.w_emb, c.rows, c.embed, c.cin_w,
+                             c.cin_scale, c.cin_shift, c.cin_sizes, c.cin_layers, c.cin_is_direct, c.cin_act, c.cin_fc_w,
+                             c.cin_fc_b, c.mlp_dims, c.mlp_layers, c.mlp_w, c.mlp_b, c.mlp_act, c.bias, logits_dev,
+                             c.workspace + (size_t)lane * c.lane_bytes, c.lane_bytes, status_dev, stream);
+}
+struct FfmCall {
+  const int64_t* offsets;
+  int fields;
+  const float* w_feat;
+  const float* const* tables;
+  const float* packed;
+  int64_t rows;
+  int embed;
+  const float* bias;
+};
+int ffm_call(void* ctx, int, const void* idx_dev, int idx_bits, int64_t nb, float* logits_dev, int32_t* status_dev,
+             void* stream) {
+  const FfmCall& c = *static_cast<const FfmCall*>(ctx);
+  if (c.packed != nullptr)
+    return trs_ffm_model_forward_interleaved(idx_dev, idx_bits, c.offsets, nb, c.fields, c.packed, c.rows, c.embed, c.bias,
+                                             logits_dev, status_dev, stream);
+  return trs_ffm_model_forward(idx_dev, idx_bits, c.offsets, nb, c.fields, c.w_feat, c.tables, c.rows, c.embed, c.bias,
+                               logits_dev, status_dev, stream);
+}
+}  // namespace
+
 // Enqueues one batch on a free slot.  On any failure after the first enqueue the slot's streams are drained so that
-// the slot is reusable.
-static int session_submit(trs_session* s, const void* idx_host, int idx_bits, const int64_t* offsets, int64_t batch,
-                          int fields, const float* w_feat, const float* w_emb, const float* packed, int64_t rows,
-                          int embed, const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
-                          const float* const* mlp_b, int activation, float* logits_host, int64_t* ticket) {
-  TRS_REQUIRE(s && idx_host && logits_host && ticket, "trs_session_submit: null pointer");
+// the slot is reusable.  `rows` < 2^31 (or 0 = unknown) gates the host-side int64 -> int32 narrowing.
+static int session_submit(trs_session* s, const void* idx_host, int idx_bits, int64_t batch, int fields,
+                          trs_forward_fn fn, void* ctx, int64_t rows, float* logits_host, int64_t* ticket) {
+  TRS_REQUIRE(s && idx_host && logits_host && ticket && fn, "trs_session_submit: null pointer");
   TRS_REQUIRE(idx_bits == 32 || idx_bits == 64, "trs_session_submit: idx_bits must be 32 or 64");
   TRS_REQUIRE(batch >= 0 && batch <= s->max_batch && fields == s->fields,
               "trs_session_submit: batch/fields exceed the session (%lld x %d)", (long long)s->max_batch, s->fields);
@@ -300,7 +418,7 @@ static int session_submit(trs_session* s, const void* idx_host, int idx_bits, co
     return TRS_OK;
   }
   // int64 indices of a non-trivial batch are narrowed on the host when the session has a narrowing pool
-  const bool narrow = idx_bits == 64 && s->narrow != nullptr && s->chunks <= NarrowPool::kMaxChunks &&
+  const bool narrow = idx_bits == 64 && s->narrow != nullptr && s->chunks <= NarrowPool::kMaxChunks && rows > 0 &&
                       rows < (int64_t(1) << 31) && batch * fields >= 4096;
   if (narrow) idx_bits = 32;
   const size_t isz = idx_bits / 8;
@@ -308,7 +426,14 @@ static int session_submit(trs_session* s, const void* idx_host, int idx_bits, co
   const bool dst_pinned = is_pinned(logits_host);
   if (!dst_pinned) sl.user_logits = logits_host;
   int rc = TRS_OK;
-  cudaError_t e = cudaMemsetAsync(sl.status_dev, 0, TRS_STATUS_WORDS * sizeof(int32_t), sl.streams[0]);
+  cudaError_t e = cudaSuccess;
+  // the slot's private streams are not ordered against the caller's own stream: whatever it enqueued there before
+  // this call (packing the table, uploading offsets, an optimizer step, load_state_dict) is waited for on the device
+  if (s->has_producer) {
+    e = cudaEventRecord(s->producer_ready, s->producer);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(sl.streams[0], s->producer_ready, 0);
+  }
+  if (e == cudaSuccess) e = cudaMemsetAsync(sl.status_dev, 0, TRS_STATUS_WORDS * sizeof(int32_t), sl.streams[0]);
   if (e == cudaSuccess) e = cudaEventRecord(sl.forked, sl.streams[0]);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(sl.streams[1], sl.forked, 0);
   const int chunks = (int)(batch < s->chunks ? batch : s->chunks);
@@ -332,14 +457,8 @@ static int session_submit(trs_session* s, const void* idx_host, int idx_bits, co
     }
     e = cudaMemcpyAsync(static_cast<char*>(sl.idx_dev) + off, src, bytes, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) break;
-    if (packed != nullptr)
-      rc = trs_deepfm_forward_packed(static_cast<char*>(sl.idx_dev) + off, idx_bits, offsets, nb, fields, packed, rows,
-                                     mlp_dims, mlp_layers, mlp_w, mlp_b, activation, sl.logits_dev + b0,
-                                     sl.status_dev, st);
-    else
-      rc = trs_deepfm_forward(static_cast<char*>(sl.idx_dev) + off, idx_bits, offsets, nb, fields, w_feat, w_emb,
-                              rows, embed, mlp_dims, mlp_layers, mlp_w, mlp_b, activation, sl.logits_dev + b0,
-                              sl.status_dev, st);
+    rc = fn(ctx, static_cast<int>(slp - s->slots) * 2 + (c & 1), static_cast<char*>(sl.idx_dev) + off, idx_bits, nb,
+            sl.logits_dev + b0, sl.status_dev, st);
     if (rc != TRS_OK) break;
     float* dst = dst_pinned ? logits_host + b0 : sl.logits_pinned + b0;
     e = cudaMemcpyAsync(dst, sl.logits_dev + b0, (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, st);
@@ -362,6 +481,74 @@ static int session_submit(trs_session* s, const void* idx_host, int idx_bits, co
     return TRS_ERR_CUDA;
   }
   return TRS_OK;
+}
+
+extern "C" int trs_session_set_producer_stream(trs_session* s, void* stream, int enabled) {
+  TRS_REQUIRE(s, "trs_session_set_producer_stream: null session");
+  s->producer = static_cast<cudaStream_t>(stream);
+  s->has_producer = enabled != 0;
+  return TRS_OK;
+}
+
+extern "C" int trs_session_lanes(void) { return 2 * kSlots; }
+
+extern "C" int trs_session_submit_fm(trs_session* s, const void* idx_host, int idx_bits, const int64_t* offsets,
+                                     int64_t batch, int fields, const float* w_feat, const float* w_emb,
+                                     const float* packed, int64_t rows, int embed, const float* bias,
+                                     float* logits_host, int64_t* ticket) {
+  TRS_REQUIRE(packed || (w_feat && w_emb), "trs_session_submit_fm: need the packed table or both tables");
+  FmCall c{offsets, fields, w_feat, w_emb, packed, bias, rows, embed};
+  return session_submit(s, idx_host, idx_bits, batch, fields, fm_call, &c, rows, logits_host, ticket);
+}
+
+extern "C" int trs_session_submit_dcn(trs_session* s, const void* idx_host, int idx_bits, const int64_t* offsets,
+                                      int64_t batch, int fields, const float* w_emb, int64_t rows, int embed,
+                                      const float* cross_w, const float* cross_b, int cross_layers,
+                                      const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                                      const float* const* mlp_b, int activation, const float* fc_w, const float* fc_b,
+                                      float* logits_host, int64_t* ticket) {
+  DcnCall c{offsets, fields, w_emb, rows, embed, cross_w, cross_b, cross_layers, mlp_dims, mlp_layers, mlp_w, mlp_b,
+            activation, fc_w, fc_b};
+  return session_submit(s, idx_host, idx_bits, batch, fields, dcn_call, &c, rows, logits_host, ticket);
+}
+
+extern "C" int trs_session_submit_xdeepfm(trs_session* s, const void* idx_host, int idx_bits, const int64_t* offsets,
+                                          int64_t batch, int fields, const float* w_feat, const float* w_emb,
+                                          int64_t rows, int embed, const float* const* cin_w,
+                                          const float* const* cin_scale, const float* const* cin_shift,
+                                          const int* cin_layer_sizes, int cin_layers, int cin_is_direct,
+                                          int cin_activation, const float* cin_fc_w, const float* cin_fc_b,
+                                          const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                                          const float* const* mlp_b, int mlp_activation, const float* bias,
+                                          void* workspace, int64_t workspace_bytes, float* logits_host,
+                                          int64_t* ticket) {
+  TRS_REQUIRE(s && workspace, "trs_session_submit_xdeepfm: null session / workspace");
+  // one workspace slice per lane: slices on different lanes run concurrently
+  const int64_t lane_bytes = (workspace_bytes / (2 * kSlots)) & ~int64_t(255);
+  const int64_t chunks = batch < s->chunks ? (batch > 0 ? batch : 1) : s->chunks;
+  const int64_t per = (((batch + chunks - 1) / chunks + 15) / 16) * 16;
+  const int64_t need = trs_xdeepfm_workspace_bytes(per, fields, embed, cin_layer_sizes, cin_layers, cin_is_direct);
+  TRS_REQUIRE(need >= 0 && lane_bytes >= need,
+              "trs_session_submit_xdeepfm: workspace too small: %lld bytes per lane x %d lanes needed, %lld given",
+              (long long)need, 2 * kSlots, (long long)workspace_bytes);
+  XdfmCall c{offsets, fields, w_feat, w_emb, rows, embed, cin_w, cin_scale, cin_shift, cin_layer_sizes, cin_layers,
+             cin_is_direct, cin_activation, cin_fc_w, cin_fc_b, mlp_dims, mlp_layers, mlp_w, mlp_b, mlp_activation, bias,
+             static_cast<char*>(workspace), lane_bytes};
+  return session_submit(s, idx_host, idx_bits, batch, fields, xdeepfm_call, &c, rows, logits_host, ticket);
+}
+
+extern "C" int trs_session_submit_ffm(trs_session* s, const void* idx_host, int idx_bits, const int64_t* offsets,
+                                      int64_t batch, int fields, const float* w_feat, const float* const* tables,
+                                      const float* packed, int64_t rows, int embed, const float* bias,
+                                      float* logits_host, int64_t* ticket) {
+  TRS_REQUIRE(packed || (w_feat && tables), "trs_session_submit_ffm: need the interleaved shadow or the tables");
+  FfmCall c{offsets, fields, w_feat, tables, packed, rows, embed, bias};
+  return session_submit(s, idx_host, idx_bits, batch, fields, ffm_call, &c, rows, logits_host, ticket);
+}
+
+extern "C" int trs_session_submit_fn(trs_session* s, const void* idx_host, int idx_bits, int64_t batch, int fields,
+                                     trs_forward_fn fn, void* ctx, int64_t rows, float* logits_host, int64_t* ticket) {
+  return session_submit(s, idx_host, idx_bits, batch, fields, fn, ctx, rows, logits_host, ticket);
 }
 
 extern "C" int trs_session_wait(trs_session* s, int64_t ticket, int64_t* oob_count) {
@@ -388,8 +575,8 @@ extern "C" int trs_session_submit_deepfm(trs_session* s, const void* idx_host, i
                                          int64_t rows, int embed, const int* mlp_dims, int mlp_layers,
                                          const float* const* mlp_w, const float* const* mlp_b, int activation,
                                          float* logits_host, int64_t* ticket) {
-  return session_submit(s, idx_host, idx_bits, offsets, batch, fields, w_feat, w_emb, nullptr, rows, embed, mlp_dims,
-                        mlp_layers, mlp_w, mlp_b, activation, logits_host, ticket);
+  DeepFmCall c{offsets, fields, w_feat, w_emb, nullptr, nullptr, rows, embed, 0, mlp_dims, mlp_layers, mlp_w, mlp_b, activation};
+  return session_submit(s, idx_host, idx_bits, batch, fields, deepfm_call, &c, rows, logits_host, ticket);
 }
 
 extern "C" int trs_session_submit_deepfm_packed(trs_session* s, const void* idx_host, int idx_bits,
@@ -399,8 +586,18 @@ extern "C" int trs_session_submit_deepfm_packed(trs_session* s, const void* idx_
                                                 const float* const* mlp_b, int activation, float* logits_host,
                                                 int64_t* ticket) {
   TRS_REQUIRE(packed, "trs_session_submit_deepfm_packed: null packed table");
-  return session_submit(s, idx_host, idx_bits, offsets, batch, fields, nullptr, nullptr, packed, rows, 16, mlp_dims,
-                        mlp_layers, mlp_w, mlp_b, activation, logits_host, ticket);
+  DeepFmCall c{offsets, fields, nullptr, nullptr, packed, nullptr, rows, 16, 0, mlp_dims, mlp_layers, mlp_w, mlp_b, activation};
+  return session_submit(s, idx_host, idx_bits, batch, fields, deepfm_call, &c, rows, logits_host, ticket);
+}
+
+extern "C" int trs_session_submit_deepfm_tc(trs_session* s, const void* idx_host, int idx_bits, const int64_t* offsets,
+                                            int64_t batch, int fields, const float* packed, int64_t rows,
+                                            const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                                            const float* const* mlp_b, int activation, const float* workspace,
+                                            int variant, float* logits_host, int64_t* ticket) {
+  TRS_REQUIRE(packed && workspace, "trs_session_submit_deepfm_tc: null packed table / workspace");
+  DeepFmCall c{offsets, fields, nullptr, nullptr, packed, workspace, rows, 16, variant, mlp_dims, mlp_layers, mlp_w, mlp_b, activation};
+  return session_submit(s, idx_host, idx_bits, batch, fields, deepfm_call, &c, rows, logits_host, ticket);
 }
 
 extern "C" int trs_session_deepfm_forward_host(trs_session* s, const void* idx_host, int idx_bits,
@@ -410,8 +607,8 @@ extern "C" int trs_session_deepfm_forward_host(trs_session* s, const void* idx_h
                                                const float* const* mlp_b, int activation, float* logits_host,
                                                int64_t* oob_count) {
   int64_t ticket = 0;
-  int rc = session_submit(s, idx_host, idx_bits, offsets, batch, fields, w_feat, w_emb, nullptr, rows, embed, mlp_dims,
-                          mlp_layers, mlp_w, mlp_b, activation, logits_host, &ticket);
+  int rc = trs_session_submit_deepfm(s, idx_host, idx_bits, offsets, batch, fields, w_feat, w_emb, rows, embed, mlp_dims,
+                                     mlp_layers, mlp_w, mlp_b, activation, logits_host, &ticket);
   if (rc != TRS_OK) return rc;
   return trs_session_wait(s, ticket, oob_count);
 }
@@ -422,10 +619,9 @@ extern "C" int trs_session_deepfm_forward_host_packed(trs_session* s, const void
                                                       int mlp_layers, const float* const* mlp_w,
                                                       const float* const* mlp_b, int activation,
                                                       float* logits_host, int64_t* oob_count) {
-  TRS_REQUIRE(packed, "trs_session_deepfm_forward_host_packed: null packed table");
   int64_t ticket = 0;
-  int rc = session_submit(s, idx_host, idx_bits, offsets, batch, fields, nullptr, nullptr, packed, rows, 16, mlp_dims,
-                          mlp_layers, mlp_w, mlp_b, activation, logits_host, &ticket);
+  int rc = trs_session_submit_deepfm_packed(s, idx_host, idx_bits, offsets, batch, fields, packed, rows, mlp_dims,
+                                            mlp_layers, mlp_w, mlp_b, activation, logits_host, &ticket);
   if (rc != TRS_OK) return rc;
   return trs_session_wait(s, ticket, oob_count);
 }

@@ -146,16 +146,20 @@ class DeepFactorizationMachineModel(CtrBaseModel):
             return None
         return _packed_table(self, feat, emb)
 
+    @staticmethod
+    def _packable(pack, fields: int, w: torch.Tensor) -> bool:
+        """Shapes the packed-table kernels (csrc/deepfm_tc5.cu, deepfm_packed.cu) take."""
+        dims = pack.dims_list
+        return (w.shape[1] == 16 and all(d == 16 for d in dims[1:-1]) and 3 <= len(dims) <= 7
+                and pack.act == ops.activation_id('relu') and fields <= 40 and w.shape[0] < 2 ** 31)
+
     def fused_forward(self, inputs_module, batch) -> torch.Tensor:
         feat, emb = inputs_module.schema['feat_inputs'], inputs_module.schema['emb_inputs']
         idx = _index_batch(inputs_module, 'emb_inputs', batch)
         w = emb.embedding.weight
         off = emb._offsets_on(w.device)
         pack = self.deep.mlp_pack()
-        dims = pack.dims_list
-        packable = (w.shape[1] == 16 and all(d == 16 for d in dims[1:-1]) and len(dims) >= 3 and len(dims) <= 7
-                    and pack.act == ops.activation_id('relu') and idx.shape[1] <= 40 and w.shape[0] < 2 ** 31)
-        packed = self.packed_table(feat, emb) if packable else None
+        packed = self.packed_table(feat, emb) if self._packable(pack, idx.shape[1], w) else None
         if packed is not None:
             return ops.deepfm_packed(idx, off, packed, pack)
         return ops.deepfm(idx, off, feat.embedding.weight, w, pack)

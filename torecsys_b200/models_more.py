@@ -79,15 +79,13 @@ class ProductNeuralNetworkModel(CtrBaseModel):
         """One kernel indices -> logits (trs_pnn_inner_forward) for the inner-product variant with one output."""
         lin = self.deep.linears()
         return (isinstance(self.pnn, InnerProductNetworkLayer) and lin[-1].out_features == 1
+                and bool(self.use_bias)     # the kernel's MLP input carries the bias column; without it: L1 route
                 and _feat_emb_pair(inputs_module)
                 and not (self.training and any(isinstance(m, nn.Dropout) and m.p > 0 for m in self.deep.model)))
 
     def fused_forward(self, inputs_module, batch) -> torch.Tensor:
         idx, off, w_feat, w_emb = _fused_args(inputs_module, batch)
-        bias = self.bias.rename(None) if self.use_bias else None
-        if not self.use_bias:
-            raise NotImplementedError('fused PNN needs use_bias=True (the MLP input has the bias column)')
-        return ops.pnn_inner(idx, off, w_feat, w_emb, self.deep.mlp_pack(), bias)
+        return ops.pnn_inner(idx, off, w_feat, w_emb, self.deep.mlp_pack(), self.bias.rename(None))
 
 
 class FeatureImportanceAndBilinearFeatureInteractionNetwork(CtrBaseModel):

@@ -3,6 +3,8 @@
 PyTorch is plumbing here (device memory, current stream); every function below launches hand-written sm_100a
 kernels from libtorecsys_b200.so through ctypes.  CPU tensors are rejected loudly -- there is no fallback.
 """
+import functools
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -548,6 +550,26 @@ class MlpPack:
         self.w = ptr_array([w.data_ptr() for w in weights])
         self.b = ptr_array([b.data_ptr() for b in biases])
         self.act = act_id
+        self._tc = {}      # variant -> (key, workspace): W1 pre-split for the tcgen05 DeepFM kernel
+
+    def tc_workspace(self, fields: int, variant: int) -> torch.Tensor:
+        """W1 in the tensor-core operand layout of csrc/deepfm_tc5.cu (trs_deepfm_tc_prepare), rebuilt when W1 was
+        modified in place (`_version`) or moved; `invalidate()` forces it after writes through `.data`."""
+        w1 = self.keep[0][0]
+        key = (w1.data_ptr(), w1._version, fields)
+        hit = self._tc.get(variant)
+        if hit is None or hit[0] != key:
+            lib = _cabi.load()
+            nbytes = lib.trs_deepfm_tc_workspace_bytes(fields, variant)
+            ws = torch.empty(nbytes // 4, dtype=torch.float32, device=w1.device)
+            check(lib.trs_deepfm_tc_prepare(fields, _ptr(w1.detach()), variant, _ptr(ws), _stream()),
+                  'trs_deepfm_tc_prepare')
+            hit = (key, ws)
+            self._tc[variant] = hit
+        return hit[1]
+
+    def invalidate(self):
+        self._tc.clear()
 
 
 def mlp(x: torch.Tensor, pack: MlpPack) -> torch.Tensor:
@@ -663,23 +685,50 @@ def fm_model_packed(idx, offsets, packed: torch.Tensor, bias: Optional[torch.Ten
     return out
 
 
+DEEPFM_KERNEL = os.environ.get('TRS_DEEPFM_KERNEL', 'auto')            # 'auto' | 'tc5' | 'mma'
+DEEPFM_TC_VARIANT = int(os.environ.get('TRS_DEEPFM_TC5_VARIANT', '1'))  # 0: one CTA per SM, 1: two CTAs per SM
+
+
+def deepfm_tc_supported(fields: int, pack: MlpPack, rows: int, variant: Optional[int] = None) -> bool:
+    variant = DEEPFM_TC_VARIANT if variant is None else variant
+    return bool(_cabi.load().trs_deepfm_tc_supported(fields, 16, pack.dims, pack.layers, pack.act, rows, variant))
+
+
 def deepfm_packed(idx, offsets, packed: torch.Tensor, pack: MlpPack, out: Optional[torch.Tensor] = None,
-                  overlap_previous: bool = False):
+                  overlap_previous: bool = False, kernel: Optional[str] = None, variant: Optional[int] = None):
     """DeepFM forward on the packed table.  `overlap_previous=True` = TRS_LAUNCH_OVERLAP_PREVIOUS (programmatic
     dependent launch): the caller promises that no kernel still running on the current stream writes this call's
-    inputs, so the kernel may read them while the previous kernel drains (outputs are still ordered)."""
+    inputs, so the kernel may read them while the previous kernel drains (outputs are still ordered).
+    kernel: 'tc5' = csrc/deepfm_tc5.cu (layer 1 on tcgen05, the default where supported), 'mma' = csrc/deepfm_packed.cu
+    (mma.sync, round 1), None/'auto' = tc5 if supported else mma."""
     ix, bits, off = _fused_common('deepfm_packed', idx, offsets, packed)
     if packed.dtype != torch.float32 or packed.dim() != 2 or packed.shape[1] != 32 or not packed.is_contiguous():
         raise ValueError('deepfm_packed: packed table must be a contiguous (rows, 32) float32 tensor')
     b, n = ix.shape
-    if ix.data_ptr() % 16:   # a view into a larger tensor: the kernel copies index tiles with 16-byte cp.async
+    if ix.data_ptr() % 16:   # a view into a larger tensor: the kernels copy index tiles with 16-byte transfers
         ix = ix.clone()
     out = out if out is not None else torch.empty((b, 1), dtype=torch.float32, device=packed.device)
     st = _status_tensor(packed.device)
     flags = _cabi.TRS_LAUNCH_OVERLAP_PREVIOUS if overlap_previous else 0
-    check(_cabi.load().trs_deepfm_forward_packed_ex(_ptr(ix), bits, _ptr(off), b, n, _ptr(packed), packed.shape[0],
-                                                    pack.dims, pack.layers, pack.w, pack.b, pack.act, _ptr(out),
-                                                    _ptr(st), flags, _stream()), 'trs_deepfm_forward_packed')
+    kernel = kernel or DEEPFM_KERNEL
+    variant = DEEPFM_TC_VARIANT if variant is None else variant
+    lib = _cabi.load()
+    if kernel not in ('auto', 'tc5', 'mma'):
+        raise ValueError(f"deepfm_packed: kernel must be 'auto', 'tc5' or 'mma', got {kernel!r}")
+    use_tc = kernel != 'mma' and bool(lib.trs_deepfm_tc_supported(n, 16, pack.dims, pack.layers, pack.act,
+                                                                  packed.shape[0], variant))
+    if kernel == 'tc5' and not use_tc:
+        raise NotImplementedError('deepfm_packed: the tcgen05 kernel needs embed 16, hidden widths 16, ReLU and a field '
+                                  'count whose staging fits shared memory')
+    if use_tc:
+        ws = pack.tc_workspace(n, variant)
+        check(lib.trs_deepfm_forward_tc(_ptr(ix), bits, _ptr(off), b, n, _ptr(packed), packed.shape[0], pack.dims,
+                                        pack.layers, pack.w, pack.b, pack.act, _ptr(ws), variant, _ptr(out), _ptr(st),
+                                        flags, _stream()), 'trs_deepfm_forward_tc')
+    else:
+        check(lib.trs_deepfm_forward_packed_ex(_ptr(ix), bits, _ptr(off), b, n, _ptr(packed), packed.shape[0],
+                                               pack.dims, pack.layers, pack.w, pack.b, pack.act, _ptr(out),
+                                               _ptr(st), flags, _stream()), 'trs_deepfm_forward_packed')
     _after_lookup(packed.device)
     return out
 
@@ -847,3 +896,51 @@ def ffm_model(idx, offsets, w_feat, tables: Sequence[torch.Tensor], bias, table_
                                              _ptr(out), _ptr(st), _stream()), 'trs_ffm_model_forward')
     _after_lookup(ws[0].device)
     return out
+
+
+# ------------------------------------------------------------------------------------------------- device guard
+# Every op launches on "the current stream of the current device".  A model that lives on cuda:1 while the current
+# device is cuda:0 must still run on cuda:1 (torch's own ops switch devices per call): each public op finds the device
+# of its first CUDA tensor argument and, if it is not the current one, runs under torch.cuda.device(...), so that
+# _stream() hands the C ABI a stream of the right GPU and the kernels launch there.
+def _first_cuda_device(values):
+    for v in values:
+        if isinstance(v, torch.Tensor):
+            if v.is_cuda:
+                return v.device
+        elif isinstance(v, (list, tuple)):
+            d = _first_cuda_device(v)
+            if d is not None:
+                return d
+        elif isinstance(v, (MlpPack, CinPack)):
+            d = _first_cuda_device(getattr(v, 'keep', ()))
+            if d is not None:
+                return d
+    return None
+
+
+def _device_guard(fn):
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = _first_cuda_device(args) or _first_cuda_device(kwargs.values())
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
+def _install_device_guards():
+    skip = {'activation_id', 'set_index_check', 'check_index_errors', 'index_check_mode', 'status_tensor',
+            'ffm_interleaved_supported', 'cross_backward_supported', 'bilinear_backward_supported',
+            'afm_backward_supported', 'deepfm_tc_supported'}
+    g = globals()
+    for name, obj in list(g.items()):
+        if name.startswith('_') or name in skip or not callable(obj) or isinstance(obj, type):
+            continue
+        if getattr(obj, '__module__', None) != __name__:
+            continue
+        g[name] = _device_guard(obj)
+
+
+_install_device_guards()
