@@ -14,7 +14,21 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get('TORECSYS_REFERENCE', '/root/reference')
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _pick_root() -> str:
+    """TORECSYS_REFERENCE, else the source tree of the build container, else the UNMODIFIED reference installed by
+    `pip install --no-deps --target baseline/_ref` (git-ignored; it travels to the GPU box, where bench.py's
+    reference arm and cpu_baseline use it -- the tests never do)."""
+    cands = [os.environ.get('TORECSYS_REFERENCE'), '/root/reference', os.path.join(_REPO, 'baseline', '_ref')]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, 'torecsys', 'layers')):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:

@@ -284,3 +284,134 @@ def test_ffm_model_keeps_an_interleaved_shadow(trs):
         d = seq({'idx': idx})
         assert normwise_err(c.cpu().numpy(), d.cpu().numpy()) <= TOL
         assert normwise_err(c.cpu().numpy(), a.cpu().numpy()) > 1e-3               # the update is visible
+
+
+def _deepfm_sequential(trs, n=39, e=16, rows_scale=1):
+    from torecsys_b200 import synth
+    fs = [16 * rows_scale * (2 + i % 5) for i in range(n)]
+    feat, emb = trs.MultiIndicesEmbedding(1, fs), trs.MultiIndicesEmbedding(e, fs)
+    feat.set_schema(['idx'])
+    emb.set_schema(['idx'])
+    model = trs.DeepFactorizationMachineModel(e, n, [16, 16, 16], fm_dropout_p=0.0)
+    seq = trs.Sequential(trs.Inputs({'feat_inputs': feat, 'emb_inputs': emb}), model).cuda().eval()
+    idx = torch.from_numpy(synth.integers((1500, n), 'fastpath/idx', np.asarray(fs)[None, :])).cuda()
+    return seq, model, feat, emb, idx, fs
+
+
+def test_deepfm_module_fast_path_tracks_every_invalidation(trs):
+    """Sequential(Inputs, DeepFM) caches a bound call of the tcgen05 kernel (models.py `_build_fast`): the cached call
+    must give what the generic route gives, and be dropped when anything it was derived from changes -- in-place
+    updates, load_state_dict, `.data` writes followed by invalidate_shadows(), the packed-table switch, the index
+    check mode; out-of-range lookups are still reported in deferred mode."""
+    from torecsys_b200 import ops
+    seq, model, feat, emb, idx, fs = _deepfm_sequential(trs)
+    off = emb._offsets_on(idx.device).rename(None).reshape(-1)
+
+    def generic():
+        return ops.deepfm_packed(idx, off, ops.fm_pack_table(emb.embedding.weight.detach(), feat.embedding.weight.detach()),
+                                 model.deep.mlp_pack())
+    ops.set_index_check('deferred')
+    try:
+        with torch.no_grad():
+            a = seq({'idx': idx})
+            assert model.__dict__.get('_fast') is not None            # bound on the first call ...
+            b = seq({'idx': idx})                                      # ... used on the second
+            assert torch.equal(a, b) and torch.equal(a, generic())
+            assert torch.equal(seq({'idx': idx.to(torch.int32)}), a)
+            emb.embedding.weight.mul_(0.5)                             # _version bump
+            c = seq({'idx': idx})
+            assert torch.equal(c, generic()) and not torch.equal(c, a)
+            model.deep.linears()[0].weight.add_(0.01)                  # pre-split W1 must follow
+            d = seq({'idx': idx})
+            assert torch.equal(d, generic()) and not torch.equal(d, c)
+            feat.embedding.weight.data.copy_(feat.embedding.weight.data * 3.0)   # invisible to _version ...
+            stale = seq({'idx': idx})
+            assert torch.equal(stale, d)                                          # ... documented: stale until told
+            seq.invalidate_shadows()
+            e_ = seq({'idx': idx})
+            assert torch.equal(e_, generic()) and not torch.equal(e_, d)
+            sd = {k: v.clone() * 0.5 if 'emb_inputs' in k else v.clone() for k, v in seq.state_dict().items()}
+            seq.load_state_dict(sd)
+            f = seq({'idx': idx})
+            assert torch.equal(f, generic()) and not torch.equal(f, e_)
+            model.use_packed_table = False
+            g = seq({'idx': idx})
+            assert normwise_err(g.cpu().numpy(), f.cpu().numpy()) <= TOL
+            model.use_packed_table = True
+            bad = idx.clone()
+            bad[3, 5] = 10 ** 7
+            seq({'idx': bad})
+            with pytest.raises(IndexError):
+                ops.check_index_errors()
+        ops.set_index_check('sync')
+        with torch.no_grad(), pytest.raises(IndexError):               # sync mode: raised by the call itself
+            seq({'idx': bad})
+    finally:
+        ops.set_index_check('sync')
+
+
+def test_deepfm_adopted_shadow_and_resident_inputs(trs):
+    """adopt_packed_table: a shadow built by the caller is used as is; Sequential.inputs_resident: back-to-back batches
+    launched with TRS_LAUNCH_OVERLAP_PREVIOUS give the logits of ordered launches."""
+    from torecsys_b200 import ops
+    seq, model, feat, emb, idx, fs = _deepfm_sequential(trs, rows_scale=50)
+    packed = ops.fm_pack_table(emb.embedding.weight.detach(), feat.embedding.weight.detach())
+    model.adopt_packed_table(feat, emb, packed)
+    ops.set_index_check('deferred')
+    try:
+        with torch.no_grad():
+            want = [seq({'idx': idx.roll(k, 0)}) for k in range(6)]
+            assert model.__dict__['_packed'] is packed
+            torch.cuda.synchronize()
+            seq.inputs_resident = True
+            batches = [idx.roll(k, 0).contiguous() for k in range(6)]
+            torch.cuda.synchronize()
+            got = [seq({'idx': b}) for b in batches]
+            torch.cuda.synchronize()
+            for g, w in zip(got, want):
+                assert torch.equal(g, w)
+        with pytest.raises(ValueError):
+            model.adopt_packed_table(feat, emb, packed[:-1])
+        ops.check_index_errors()
+    finally:
+        seq.inputs_resident = False
+        ops.set_index_check('sync')
+
+
+def test_reference_composite_inputs_keep_working_with_drop_in_children(trs):
+    """the reference's ConcatInput / StackedInput are dispatched on their class NAME by
+    Inputs.forward (torecsys/inputs/inputs.py:70-72) and must keep working when their children are drop-in embeddings.
+    Needs the reference (baseline/_ref or TORECSYS_REFERENCE); skipped where it is absent."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip('reference not installed (baseline/_ref)')
+    ref_shim.load_reference()
+    from torecsys.inputs.base import ConcatInput, StackedInput
+    from torecsys_b200 import synth
+    b = 64
+    a = trs.SingleIndexEmbedding(8, 50)
+    c = trs.MultiIndicesEmbedding(8, [16, 32, 48], flatten=True)
+    a.set_schema(['user'])
+    c.set_schema(['f0', 'f1', 'f2'])
+    concat = ConcatInput([a, c])
+    x = trs.SingleIndexEmbedding(8, 50)
+    y = trs.SingleIndexEmbedding(8, 70)
+    x.set_schema(['user'])
+    y.set_schema(['item'])
+    stacked = StackedInput([x, y])
+    inputs = trs.Inputs({'concat': concat, 'stack': stacked}).cuda()
+    batch = {'user': torch.from_numpy(synth.integers((b,), 'comp/u', 50)).cuda(),
+             'item': torch.from_numpy(synth.integers((b,), 'comp/i', 70)).cuda(),
+             'f0': torch.from_numpy(synth.integers((b,), 'comp/f0', 16)).cuda(),
+             'f1': torch.from_numpy(synth.integers((b,), 'comp/f1', 32)).cuda(),
+             'f2': torch.from_numpy(synth.integers((b,), 'comp/f2', 48)).cuda()}
+    out = inputs(batch)
+    assert out['concat'].shape == (b, 1, 8 + 24) and out['stack'].shape == (b, 2, 8)
+    # same numbers as plain torch indexing of the registered parameters
+    got = out['concat'].rename(None)
+    wa, wc = a.embedding.weight, c.embedding.weight
+    assert torch.equal(got[:, 0, :8], wa[batch['user']])
+    rows = torch.stack([batch['f0'], batch['f1'] + 16, batch['f2'] + 48], 1)
+    assert torch.equal(got[:, 0, 8:], wc[rows].reshape(b, -1))
+    st = out['stack'].rename(None)
+    assert torch.equal(st[:, 0], x.embedding.weight[batch['user']]) and torch.equal(st[:, 1], y.embedding.weight[batch['item']])
