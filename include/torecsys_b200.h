@@ -316,6 +316,19 @@ int64_t trs_deepfm_tc_workspace_bytes(int fields, int variant);
 int trs_deepfm_tc_supported(int fields, int embed, const int* mlp_dims, int mlp_layers, int activation, int64_t rows,
                             int variant);
 int trs_deepfm_tc_prepare(int fields, const float* w1, int variant, float* workspace, void* stream);
+/* The same forward on a ROW-SHARDED packed table (BASELINE.json north_star: "row-sharding the large embedding tables
+ * ... only when a table exceeds one GPU's HBM"; the reference keeps ONE shared table nn.Embedding(sum(field_sizes), E),
+ * torecsys/inputs/base/multi_indices_emb.py:45-57).  Row g of the packed table lives on rank g % world, at local row
+ * g / world of shards[g % world]; `shards` is a HOST array of `world` device addresses as mapped in THIS process: the
+ * rank's own shard in its HBM, the others peer-mapped over NVLink (CUDA IPC / symmetric memory).  The exchange of
+ * looked-up vectors happens inside the kernel: the row copies (cp.async, one 80-byte request per row) read remote
+ * shards directly while the tensor core works on the rows that have landed -- no staging buffer, no second kernel.
+ * Bit-identical to trs_deepfm_forward_tc on the unsharded table.  world <= 8, rows / world < 2^28. */
+int trs_deepfm_forward_tc_sharded(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                                  const float* const* shards, int world, int64_t rows,
+                                  const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                                  const float* const* mlp_b, int activation, const float* workspace, int variant,
+                                  float* logits, int32_t* status, unsigned flags, void* stream);
 /* debug: event clocks of CTA 0's warp roles into a device buffer of 7 x 512 x 4 int64 (NULL switches it off) */
 int trs_debug_tc5_trace(long long* device_buf);
 int trs_deepfm_forward_tc(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,

@@ -55,6 +55,25 @@ def main():
         covered = sum(hi - lo for lo, hi in sl)
         assert covered == batch and sl[0][0] == 0 and sl[-1][1] == batch
         assert all(sl[i][1] == sl[i + 1][0] for i in range(world - 1))
+    # row-wise plan of ONE oversized table: every global row owned exactly once, local rows dense, the gather of a
+    # random index batch through (owner, local row) reproduces the unsharded lookup exactly
+    from torecsys_b200.sharded import RowShardPlan
+    rows = 10007
+    rp = RowShardPlan(rows, world)
+    counts = [None] * world
+    dist.all_gather_object(counts, rp.rows_of(rank))
+    assert sum(counts) == rows and max(counts) == rp.max_rows() and max(counts) - min(counts) <= 1
+    assert list(rp.global_rows(rank))[:3] == [rank, rank + world, rank + 2 * world]
+    gen = torch.Generator().manual_seed(7)
+    full = torch.randn(rows, 4, generator=gen)                 # same on every rank
+    mine_rows = full[rank::world].clone()
+    assert mine_rows.shape[0] == rp.rows_of(rank)
+    shards = [None] * world
+    dist.all_gather_object(shards, mine_rows)
+    look = torch.randint(0, rows, (500,), generator=gen)
+    got = torch.stack([shards[rp.owner(int(g))][rp.local_row(int(g))] for g in look])
+    assert torch.equal(got, full[look])
+    assert abs(rp.remote_fraction() - (1 - 1 / world)) < 1e-12
     # reduced scalar agrees (the only "collective" bench.py uses: max over ranks of a time)
     t = torch.tensor([float(rank + 1)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

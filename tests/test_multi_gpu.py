@@ -47,3 +47,24 @@ def test_sharded_ffm_over_peer_memory():
     res = _torchrun('tests/multi/sharded_ffm_worker.py', 2, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert 'SHARDED_FFM_OK' in res.stdout
+
+
+@pytest.mark.gpu
+def test_row_sharded_deepfm_matches_single_gpu_bit_for_bit():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs >= 2 GPUs (run with gpurun --gpus 2)')
+    res = _torchrun('tests/multi/sharded_deepfm_worker.py', 2, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert 'SHARDED_DEEPFM_OK' in res.stdout
+
+
+def test_row_shard_plan_single_process():
+    from torecsys_b200.sharded import RowShardPlan
+    p = RowShardPlan(199_999_488, 8)
+    assert p.owner(17) == 1 and p.local_row(17) == 2 and p.rows_of(0) == 24_999_936 and p.max_rows() == 24_999_936
+    assert sum(p.rows_of(r) for r in range(8)) == 199_999_488
+    q = RowShardPlan(10, 4)
+    assert [q.rows_of(r) for r in range(4)] == [3, 3, 2, 2] and list(q.global_rows(3)) == [3, 7]
+    with pytest.raises(ValueError):
+        RowShardPlan(0, 2)

@@ -105,6 +105,10 @@ struct Tc5Args {
   const void* idx;
   const int64_t* offsets;
   const float* packed;          // (rows, 32): v[16], w, pad
+  // row-sharded table (world > 1): row g lives on rank g % world at local row g / world of shard[g % world] --
+  // local HBM for this rank's own shard, peer-mapped memory (NVLink) for the others
+  const float* shard[8];
+  int world;
   const float* w1p;             // prepared W1: [group][12 chunk planes][32 rows: hi 0..15, lo 16..31][4]
   const float* b1;
   const float* wh[kMaxHidden];  // (16, 16)
@@ -138,14 +142,14 @@ __host__ __device__ inline Layout make_layout(int fields, int idx_bytes) {
   l.hid = p;    p += kMaxHidden * 256 * 4;
   l.bias = p;   p += ((1 + kMaxHidden) * 16 + 16 + 4) * 4;
   l.side = p;   p += 2 * 2 * kTileM * 4;
-  l.off = p;    p += ((fields * 8 + 15) & ~15) + 16;
+  l.off = p;    p += ((fields * 8 + 15) & ~15) + 64;   // + the 8 shard base addresses
   l.bars = p;   p += (4 * C::STAGES + 8) * 8;
   l.tmem_slot = p; p += 16;
   l.total = p;
   return l;
 }
 
-template <int IdxBits, class C>
+template <int IdxBits, class C, bool kSharded>
 __global__ void __launch_bounds__(C::kThreads, C::CTAS) deepfm_tc5_kernel(Tc5Args a) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int kIdxBytes = IdxBits / 8;
@@ -158,6 +162,7 @@ __global__ void __launch_bounds__(C::kThreads, C::CTAS) deepfm_tc5_kernel(Tc5Arg
   float* bias_s = reinterpret_cast<float*>(smem + L.bias);
   float* side_s = reinterpret_cast<float*>(smem + L.side);
   long long* off_s = reinterpret_cast<long long*>(smem + L.off);
+  unsigned long long* shard_s = reinterpret_cast<unsigned long long*>(smem + L.off + ((a.fields * 8 + 15) & ~15));
   const uint32_t bar0 = smem_u32(smem + L.bars);
   auto v_full = [&](int s) { return bar0 + 8u * s; };
   auto slot_free = [&](int s) { return bar0 + 8u * (S + s); };
@@ -197,6 +202,8 @@ __global__ void __launch_bounds__(C::kThreads, C::CTAS) deepfm_tc5_kernel(Tc5Arg
   }
   if (warp >= C::PW) {   // (the producers start requesting indices at once; they read the offsets after the barrier)
     for (int i = threadIdx.x - C::PW * 32; i < n_fields; i += blockDim.x - C::PW * 32) off_s[i] = __ldg(a.offsets + i);
+    if (kSharded && threadIdx.x - C::PW * 32 < 8)
+      shard_s[threadIdx.x - C::PW * 32] = reinterpret_cast<unsigned long long>(a.shard[threadIdx.x - C::PW * 32]);
     for (int i = threadIdx.x - C::PW * 32; i < a.hidden_layers * 256; i += blockDim.x - C::PW * 32)
       hid_s[i] = __ldg(a.wh[i >> 8] + (i & 255));
     if (warp == C::kWarpEpilogue0 && lane < 16) {
@@ -269,8 +276,14 @@ __global__ void __launch_bounds__(C::kThreads, C::CTAS) deepfm_tc5_kernel(Tc5Arg
             const int64_t ix = IdxBits == 64 ? *reinterpret_cast<const long long*>(slot_p)
                                              : static_cast<int64_t>(*reinterpret_cast<const int*>(slot_p));
             const int64_t row = ix + off_s[f];
-            if (row >= 0 && row < a.rows) rid[k] = static_cast<int>(row);
-            else {
+            if (row >= 0 && row < a.rows) {
+              if (kSharded) {   // (owner rank, row within its shard) in one word: owner above bit 27
+                const int g = static_cast<int>(row);
+                rid[k] = ((g % a.world) << 28) | (g / a.world);
+              } else {
+                rid[k] = static_cast<int>(row);
+              }
+            } else {
               if (!waited) { pdl_wait(); waited = true; }   // status may still be written by the work this launch overlaps
               report_oob(a.status, (cta_begin + (int64_t)t * kTileM + SPW * warp + sm) * n_fields + f);
             }
@@ -286,7 +299,12 @@ __global__ void __launch_bounds__(C::kThreads, C::CTAS) deepfm_tc5_kernel(Tc5Arg
           for (int i = 0; i < SPW / 4; ++i) {
             const int r = __shfl_sync(0xffffffffu, rid[(fl * SPW + 4 * i) / 32], (4 * i + rsel) & 31);
             unsigned long long src;
-            asm("mad.wide.u32 %0, %1, 128, %2;" : "=l"(src) : "r"(static_cast<unsigned>(max(r, 0))), "l"(src_lane));
+            if (kSharded) {
+              const unsigned long long base = shard_s[max(r, 0) >> 28] + 16ull * sub;
+              asm("mad.wide.u32 %0, %1, 128, %2;" : "=l"(src) : "r"(static_cast<unsigned>(max(r, 0)) & 0x0fffffffu), "l"(base));
+            } else {
+              asm("mad.wide.u32 %0, %1, 128, %2;" : "=l"(src) : "r"(static_cast<unsigned>(max(r, 0))), "l"(src_lane));
+            }
             // row groups beyond a partial tile and the three idle lanes of every row issue nothing
             cp_async16_zfill_if(dst0 + fl * kPlanesPerField * kPlane + 4 * i * 16, reinterpret_cast<const void*>(src),
                                 r >= 0 ? 16 : 0, lane_on && 4 * i < valid_s);
@@ -549,13 +567,19 @@ int launch_tc5(Tc5Args a, int idx_bits, unsigned flags, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = (flags & TRS_LAUNCH_OVERLAP_PREVIOUS) ? 1 : 0;
   cudaError_t e;
-  if (idx_bits == 64) {
-    TRS_SMEM_OPT_IN((deepfm_tc5_kernel<64, C>));
-    e = cudaLaunchKernelEx(&cfg, deepfm_tc5_kernel<64, C>, a);
+#define TRS_TC5_LAUNCH(BITS, SH)                                         \
+  do {                                                                   \
+    TRS_SMEM_OPT_IN((deepfm_tc5_kernel<BITS, C, SH>));                   \
+    e = cudaLaunchKernelEx(&cfg, deepfm_tc5_kernel<BITS, C, SH>, a);     \
+  } while (0)
+  if (a.world > 1) {
+    if (idx_bits == 64) TRS_TC5_LAUNCH(64, true);
+    else TRS_TC5_LAUNCH(32, true);
   } else {
-    TRS_SMEM_OPT_IN((deepfm_tc5_kernel<32, C>));
-    e = cudaLaunchKernelEx(&cfg, deepfm_tc5_kernel<32, C>, a);
+    if (idx_bits == 64) TRS_TC5_LAUNCH(64, false);
+    else TRS_TC5_LAUNCH(32, false);
   }
+#undef TRS_TC5_LAUNCH
   if (e != cudaSuccess) {
     set_error("launch of deepfm_tc5_kernel failed: %s", cudaGetErrorString(e));
     cudaGetLastError();
@@ -614,11 +638,42 @@ extern "C" int trs_deepfm_tc_prepare(int fields, const float* w1, int variant, f
   return check_launch("deepfm_tc5_prep_kernel");
 }
 
+static int forward_tc_common(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                             const float* packed, const float* const* shards, int world, int64_t rows,
+                             const int* mlp_dims, int mlp_layers, const float* const* mlp_w, const float* const* mlp_b,
+                             int activation, const float* workspace, int variant, float* logits, int32_t* status,
+                             unsigned flags, void* stream);
+
+extern "C" int trs_deepfm_forward_tc_sharded(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch,
+                                             int fields, const float* const* shards, int world, int64_t rows,
+                                             const int* mlp_dims, int mlp_layers, const float* const* mlp_w,
+                                             const float* const* mlp_b, int activation, const float* workspace,
+                                             int variant, float* logits, int32_t* status, unsigned flags,
+                                             void* stream) {
+  TRS_REQUIRE(shards && world >= 1 && world <= 8, "trs_deepfm_forward_tc_sharded: 1..8 shards expected");
+  for (int r = 0; r < world; ++r)
+    TRS_REQUIRE(shards[r] && (reinterpret_cast<uintptr_t>(shards[r]) & 127u) == 0,
+                "trs_deepfm_forward_tc_sharded: shard %d is null or not 128-byte aligned", r);
+  TRS_UNSUPPORTED(world > 1 && (rows + world - 1) / world >= (int64_t(1) << 28),
+                  "trs_deepfm_forward_tc_sharded: at most 2^28 rows per shard");
+  return forward_tc_common(idx, idx_bits, offsets, batch, fields, shards[0], shards, world, rows, mlp_dims, mlp_layers,
+                           mlp_w, mlp_b, activation, workspace, variant, logits, status, flags, stream);
+}
+
 extern "C" int trs_deepfm_forward_tc(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
                                      const float* packed, int64_t rows, const int* mlp_dims, int mlp_layers,
                                      const float* const* mlp_w, const float* const* mlp_b, int activation,
                                      const float* workspace, int variant, float* logits, int32_t* status,
                                      unsigned flags, void* stream) {
+  return forward_tc_common(idx, idx_bits, offsets, batch, fields, packed, nullptr, 1, rows, mlp_dims, mlp_layers, mlp_w,
+                           mlp_b, activation, workspace, variant, logits, status, flags, stream);
+}
+
+static int forward_tc_common(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                             const float* packed, const float* const* shards, int world, int64_t rows,
+                             const int* mlp_dims, int mlp_layers, const float* const* mlp_w, const float* const* mlp_b,
+                             int activation, const float* workspace, int variant, float* logits, int32_t* status,
+                             unsigned flags, void* stream) {
   TRS_REQUIRE((flags & ~TRS_LAUNCH_OVERLAP_PREVIOUS) == 0, "trs_deepfm_forward_tc: unknown flags 0x%x", flags);
   TRS_REQUIRE(idx && offsets && packed && logits && mlp_dims && mlp_w && mlp_b && workspace,
               "trs_deepfm_forward_tc: null pointer");
@@ -633,6 +688,8 @@ extern "C" int trs_deepfm_forward_tc(const void* idx, int idx_bits, const int64_
   Tc5Args a{};
   a.idx = idx; a.offsets = offsets; a.packed = packed; a.w1p = workspace; a.logits = logits; a.status = status;
   a.batch = batch; a.rows = rows; a.fields = fields;
+  a.world = world;
+  for (int r = 0; r < 8; ++r) a.shard[r] = (shards != nullptr && r < world) ? shards[r] : packed;
   a.hidden_layers = mlp_layers - 2;
   for (int l = 0; l < mlp_layers; ++l) TRS_REQUIRE(mlp_w[l] && mlp_b[l], "trs_deepfm_forward_tc: null MLP parameter");
   a.b1 = mlp_b[0];

@@ -733,6 +733,33 @@ def deepfm_packed(idx, offsets, packed: torch.Tensor, pack: MlpPack, out: Option
     return out
 
 
+def deepfm_packed_sharded(idx, offsets, shard_ptrs: Sequence[int], rows: int, pack: MlpPack,
+                          out: Optional[torch.Tensor] = None, overlap_previous: bool = False,
+                          variant: Optional[int] = None):
+    """DeepFM forward on a ROW-SHARDED packed table (trs_deepfm_forward_tc_sharded): global row g lives on rank
+    g % world at local row g // world; `shard_ptrs[r]` = address of rank r's (rows_r, 32) packed shard as mapped in this
+    process (own HBM or NVLink peer memory, torecsys_b200.sharded.RowShardedPackedTable).  `rows` = global row count.
+    Bit-identical to deepfm_packed(kernel='tc5') on the unsharded table."""
+    ix, bits, off = _fused_common('deepfm_packed_sharded', idx, offsets)
+    b, n = ix.shape
+    if ix.data_ptr() % 16:
+        ix = ix.clone()
+    world = len(shard_ptrs)
+    variant = DEEPFM_TC_VARIANT if variant is None else variant
+    lib = _cabi.load()
+    if not lib.trs_deepfm_tc_supported(n, 16, pack.dims, pack.layers, pack.act, rows, variant):
+        raise NotImplementedError('deepfm_packed_sharded: needs embed 16, hidden widths 16, ReLU (the tcgen05 kernel)')
+    out = out if out is not None else torch.empty((b, 1), dtype=torch.float32, device=ix.device)
+    st = _status_tensor(ix.device)
+    ws = pack.tc_workspace(n, variant)
+    flags = _cabi.TRS_LAUNCH_OVERLAP_PREVIOUS if overlap_previous else 0
+    check(lib.trs_deepfm_forward_tc_sharded(_ptr(ix), bits, _ptr(off), b, n, ptr_array(list(shard_ptrs)), world, rows,
+                                            pack.dims, pack.layers, pack.w, pack.b, pack.act, _ptr(ws), variant,
+                                            _ptr(out), _ptr(st), flags, _stream()), 'trs_deepfm_forward_tc_sharded')
+    _after_lookup(ix.device)
+    return out
+
+
 def dcn(idx, offsets, w_emb, cross_w, cross_b, pack: MlpPack, fc_w, fc_b, out: Optional[torch.Tensor] = None):
     ix, bits, off = _fused_common('dcn', idx, offsets, w_emb, cross_w, cross_b, fc_w, fc_b)
     we = _f32('dcn', w_emb)

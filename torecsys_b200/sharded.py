@@ -25,6 +25,89 @@ from . import ops
 from .inputs import _reference_offsets
 
 
+class RowShardPlan:
+    """Row-wise partition of ONE table over the ranks (BASELINE.json north_star: "row-sharding the large embedding
+    tables ... only when a table exceeds one GPU's HBM"): global row g lives on rank g % world at local row g // world.
+    The reference keeps the whole nn.Embedding(sum(field_sizes), E) on one device (multi_indices_emb.py:45-57); round-
+    robin rows keep every rank's share of the lookups equal whatever the field sizes and index distribution are."""
+
+    def __init__(self, rows: int, world_size: int):
+        if rows <= 0 or world_size <= 0:
+            raise ValueError('rows and world_size must be positive')
+        self.rows, self.world_size = int(rows), int(world_size)
+
+    def owner(self, row: int) -> int:
+        return row % self.world_size
+
+    def local_row(self, row: int) -> int:
+        return row // self.world_size
+
+    def rows_of(self, rank: int) -> int:
+        """Number of rows rank `rank` holds."""
+        return (self.rows - rank + self.world_size - 1) // self.world_size
+
+    def max_rows(self) -> int:
+        return self.rows_of(0)
+
+    def global_rows(self, rank: int) -> range:
+        return range(rank, self.rows, self.world_size)
+
+    def remote_fraction(self) -> float:
+        return 1.0 - 1.0 / self.world_size
+
+
+class RowShardedPackedTable:
+    """The packed [v|w] table of a (first-order, embedding) pair (ops.fm_pack_table layout, 128-byte rows) split
+    row-wise over the ranks of `group`, every shard peer-mapped in every process (torch symmetric memory)."""
+
+    def __init__(self, rows: int, group: Optional[dist.ProcessGroup] = None, device: Optional[torch.device] = None):
+        import torch.distributed._symmetric_memory as symm_mem
+        if not dist.is_initialized():
+            raise RuntimeError('RowShardedPackedTable needs torch.distributed (NCCL) to be initialised')
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        if self.world > 8:
+            raise NotImplementedError('row sharding is written for the GPUs of one NVSwitch box (world <= 8)')
+        self.device = device if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.plan = RowShardPlan(rows, self.world)
+        self.rows = int(rows)
+        # symmetric allocation: every rank allocates max_rows rows (the last ranks may use one row less)
+        self.local = symm_mem.empty((self.plan.max_rows(), 32), dtype=torch.float32, device=self.device)
+        self._handle = symm_mem.rendezvous(self.local, self.group)
+        self.shard_ptrs = [int(p) for p in self._handle.buffer_ptrs]
+
+    def fill_from(self, w_emb_local: torch.Tensor, w_feat_local: torch.Tensor):
+        """Packs this rank's rows: w_emb_local (rows_of(rank), 16) and w_feat_local (rows_of(rank), 1) are the rows
+        rank, rank + world, ... of the full tables.  Collective (ends with a barrier)."""
+        n = self.plan.rows_of(self.rank)
+        if w_emb_local.shape != (n, 16) or w_feat_local.numel() != n:
+            raise ValueError(f'rank {self.rank} holds {n} rows of the table')
+        packed = ops.fm_pack_table(w_emb_local.to(self.device), w_feat_local.to(self.device))
+        self.local[:n].copy_(packed)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+        return self
+
+
+class ShardedDeepFM:
+    """DeepFactorizationMachineModel.forward (deep_fm.py:55-110) behind Sequential (sequential.py:31-44) on a row-
+    sharded packed table: every rank keeps its slice of the batch and runs the SAME fused tcgen05 kernel as on one GPU;
+    the row copies of the kernel read the other ranks' shards over NVLink (csrc/deepfm_tc5.cu, kSharded).  No
+    collective on the data path; logits are bit-identical to the single-GPU kernel on the unsharded table."""
+
+    def __init__(self, table: RowShardedPackedTable, offsets: torch.Tensor, pack: 'ops.MlpPack'):
+        self.table, self.pack = table, pack
+        self.offsets = offsets.rename(None).reshape(-1).to(device=table.device, dtype=torch.int64).contiguous()
+
+    def forward(self, idx_local: torch.Tensor, out: Optional[torch.Tensor] = None, overlap_previous: bool = False):
+        t = self.table
+        return ops.deepfm_packed_sharded(idx_local, self.offsets, t.shard_ptrs, t.rows, self.pack, out=out,
+                                         overlap_previous=overlap_previous)
+
+    __call__ = forward
+
+
 class TableShardPlan:
     """Which rank owns which table, and where it sits in the owner's buffer."""
 
