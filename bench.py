@@ -225,7 +225,7 @@ def run_reference(args):
     if rank != 0:
         return
     sps, ms, done, info = cpu_reference_run(args.steps, args.warmup, args.batch, args.rows_per_field)
-    print(json.dumps({
+    args.emit(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': sps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': done,
         'warmup': max(1, min(args.warmup, 3)), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -410,7 +410,100 @@ def bench_other_configs(torch, timer, device, rank, peak, args):
     return out
 
 
+def bench_sharded(torch, dist, timer, device, rank, world, args):
+    """The exchange paths (world > 1): configs[4] at FULL size with the field-aware tables sharded over
+    the N GPUs (global batch 262 144, strong in the table, the batch split over the ranks), and configs[1] with its one
+    200 M-row table row-sharded (65 536 samples per rank).  Values are whole-job samples/s, max over ranks."""
+    from torecsys_b200 import ops, sharded as sh
+    out = {}
+    igen = torch.Generator().manual_seed(977 + rank)
+
+    def note(msg):
+        if rank == 0:
+            print(f'[bench] sharded: {msg}', file=sys.stderr, flush=True)
+    # ---- configs[4]: 39 tables x 25 641 408 rows x 16 (64 GB) over `world` GPUs, block exchange ----------------------
+    try:
+        note('configs[4] tables')
+        e, rpf4, b_all = 16, 657_472, 262_144
+        fs = [rpf4] * NUM_FIELDS
+        rows4 = NUM_FIELDS * rpf4
+        b_loc = b_all // world
+        tables = sh.ShardedInterleavedTables(e, fs)
+        bound = (6.0 / (rows4 + e)) ** 0.5
+        tables.init_(lambda local: local.uniform_(-bound, bound))
+        w_feat = torch.empty(rows4, 1, device=device).normal_()
+        bias = torch.zeros(1, device=device)
+        model = sh.ShardedFFMBlocks(tables, w_feat, bias)
+        idx = [torch.randint(0, rpf4, (b_loc, NUM_FIELDS), generator=igen, dtype=torch.int64).to(device) for _ in range(4)]
+        note('configs[4] timing')
+        r = timer.run(lambda i: model(idx[i % 4]), steps=10, repeats=7)
+        ops.check_index_errors()
+        note(f"configs[4] {r['ms_per_step']:.3f} ms per step")
+        plan = tables.block_plan
+        remote = (plan.remote_bytes(0) + plan.remote_bytes(1)) / 2 * b_all          # bytes over NVLink into this rank
+        t = torch.tensor([remote], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # the reduction kernel alone (row ids already gathered): what the chunk fetches sustain
+        rows_loc, first, rows_all, partial = next(iter(model._buf.values()))
+        k = timer.run(lambda i: ops.ffm_shard_blocks(rows_all, plan, tables.shard_ptrs, first,
+                                                     (rank * b_loc, (rank + 1) * b_loc), out=partial), steps=10, repeats=7)
+        r.update({'workload': f'configs[4]: FieldAwareFactorizationMachine {NUM_FIELDS} tables x {rows4} rows (1.0 B rows, '
+                              f'{rows4 * NUM_FIELDS * e * 4 / 1e9:.0f} GB) sharded over {world} GPUs '
+                              f'({rows4 * plan.pitch_bytes / 1e9:.1f} GB each), embed 16, global batch {b_all}',
+                  'value': b_all / (r['ms_per_step'] * 1e-3), 'unit': UNIT,
+                  'scheme': 'tables interleaved per row id on their owner (rank t % world); block (k, m) reduced on k or m by '
+                            'sample parity: one vector of every dot product crosses NVLink, in whole chunks of '
+                            f'{plan.pitch_bytes} B, one cp.async.bulk each (ffm_blocks_kernel); NCCL all-gather of int32 '
+                            'row ids before, NCCL reduce-scatter of the partial logits after',
+                  'nvlink_bytes_in_per_gpu_per_step': float(t.item()),
+                  'nvlink_gbs_per_gpu': float(t.item()) / (r['ms_per_step'] * 1e-3) / 1e9,
+                  'kernel_only': {'ms_per_step': k['ms_per_step'], 'value': b_all / (k['ms_per_step'] * 1e-3),
+                                  'nvlink_gbs_per_gpu': float(t.item()) / (k['ms_per_step'] * 1e-3) / 1e9,
+                                  'kernel': 'ffm_blocks_kernel'},
+                  'bound': {'half_volume_nvlink_900': 900e9 / (float(t.item()) / b_all),
+                            'note': 'samples/s if the inbound NVLink of the busiest rank ran at 900 GB/s; bulk copies of '
+                                    'random 320-byte peer chunks sustain 685 GB/s (profiles/r02_peer_probe.log)'}})
+        out['ffm'] = r
+        del model, tables, w_feat, idx, rows_loc, first, rows_all, partial
+    except Exception as ex:
+        out['ffm'] = {'error': f'{type(ex).__name__}: {ex}'}
+    torch.cuda.empty_cache()
+    # ---- configs[1] with the ONE shared table row-sharded (row g on rank g % world) -----------------------------------
+    try:
+        note('row-sharded DeepFM table')
+        rpf, b = args.rows_per_field, args.batch
+        rows = NUM_FIELDS * rpf
+        table = sh.RowShardedPackedTable(rows)
+        table.local.uniform_(-0.01, 0.01)
+        torch.cuda.synchronize()
+        dist.barrier()
+        mlp_w, mlp_b = make_mlp_params(torch, torch.Generator().manual_seed(0), device)
+        pack = ops.MlpPack(mlp_w, mlp_b, ops.activation_id('relu'))
+        offsets = (torch.arange(NUM_FIELDS, dtype=torch.int64) * rpf).to(device)
+        model = sh.ShardedDeepFM(table, offsets, pack)
+        idx = [torch.randint(0, rpf, (b, NUM_FIELDS), generator=igen, dtype=torch.int64).to(device) for _ in range(8)]
+        o = torch.empty(b, 1, device=device)
+        ops.set_index_check('deferred')
+        r = timer.run(lambda i: model(idx[i % 8], out=o, overlap_previous=True), steps=20, repeats=7)
+        ops.check_index_errors()
+        remote_rows = b * NUM_FIELDS * (1 - 1 / world)
+        r.update({'workload': f'configs[1] with its table row-sharded: DeepFM {NUM_FIELDS} fields, ONE table of {rows} rows '
+                              f'split by row % {world} ({rows * 128 / world / 1e9:.1f} GB of packed rows per GPU), batch {b} per GPU',
+                  'value': world * b / (r['ms_per_step'] * 1e-3), 'unit': UNIT,
+                  'scheme': 'the fused tcgen05 kernel of the single-GPU path; its row copies read the other ranks\' shards '
+                            'over NVLink peer mappings (80 B per row), no collective, logits bit-identical to one GPU',
+                  'nvlink_rows_in_per_gpu_per_s': remote_rows / (r['ms_per_step'] * 1e-3),
+                  'nvlink_gbs_per_gpu': remote_rows * 80 / (r['ms_per_step'] * 1e-3) / 1e9})
+        out['deepfm_row_sharded'] = r
+        del model, table, idx, o
+    except Exception as ex:
+        out['deepfm_row_sharded'] = {'error': f'{type(ex).__name__}: {ex}'}
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # stdout carries the one JSON line only
     import torch
     import torch.distributed as dist
     import torch.nn as nn
@@ -644,8 +737,7 @@ def run_ours(args):
     sharded = None
     if world > 1 and not args.no_configs:
         try:
-            from torecsys_b200 import sharded as sh
-            sharded = sh.bench_sharded(timer, device, rank, world, peak)
+            sharded = bench_sharded(torch, dist, timer, device, rank, world, args)
         except Exception as ex:
             sharded = {'error': f'{type(ex).__name__}: {ex}'}
 
@@ -668,7 +760,7 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             _, _, _, cpu = cpu_reference_run(600, 2, batch, rpf, budget_s=12.0)   # ~12 s of CPU work, bounded
-        print(json.dumps({
+        args.emit(json.dumps({
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'ms_per_step_min': head['ms_min'],
             'ms_per_step_max': head['ms_max'], 'repeats': head['repeats'], 'higher_is_better': True, 'scaling': 'weak',
@@ -721,6 +813,18 @@ def main():
         args.warmup = 3
     if args.repeats < 1:
         args.repeats = 1
+    # stdout carries the ONE JSON line: anything a library prints there meanwhile (NCCL's version banner ...) goes to
+    # stderr -- file descriptor 1 is pointed at stderr until the line is ready
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+    args.emit = emit
     if args.impl == 'reference':
         run_reference(args)
     else:

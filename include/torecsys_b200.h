@@ -396,6 +396,44 @@ int trs_ffm_model_forward_pairs(const void* idx, int idx_bits, const int64_t* of
                                 int64_t first_begin, int64_t first_end,
                                 float* logits, int32_t* status, void* stream);
 
+/* ---- configs[4]: the field-aware tables SHARDED over the GPUs of one NVSwitch box, exchange at chunk granularity ------
+ * (BASELINE.json north_star: "row-sharding the large embedding tables with an ... exchange of looked-up vectors over
+ * NVLink only when a table exceeds one GPU's HBM"; the reference holds N full tables on one device,
+ * torecsys/inputs/base/multi_indices_field_aware_emb.py:49-54, and reads T_t[r_f] for every (t, f), :90-111.)
+ * Rank m owns the tables {t : t % world == m} and stores them interleaved per row id,
+ *     shard_m[r] = [ T_m[r] | T_{m+world}[r] | ... ]   pitch = ceil(fields / world) * embed floats,
+ * so what one rank holds of one row id is ONE contiguous chunk (320 B at 39 fields / 8 ranks / embed 16), fetched by
+ * one bulk copy -- from local HBM or, through a peer mapping, over NVLink.  The pairs between the tables of ranks k and
+ * m ("block (k, m)") are reduced on k for the samples of one parity and on m for the others: every dot product moves
+ * exactly one of its two vectors, all bytes of every fetched chunk are used (csrc/ffm_blocks.cu).
+ *   trs_ffm_shard_plan     HOST: the copy list and the dot-product item list of `rank`, for sample parity 0 and 1.
+ *                          copy_tab int32 [2][copy_capacity][2] = {src rank | field << 8 | (bytes/16) << 16, dst byte
+ *                          offset in the sample's stage}; item_tab uint32 [2][item_capacity] = 16-byte piece index of
+ *                          one operand | the other << 16.  Pass NULL tables to query n_copies[2], n_items[2],
+ *                          tx_bytes[2] (bytes fetched per sample) and *stage_bytes only.  No GPU needed.
+ *   trs_ffm_shard_pack     shard[r][slot][:] = tables[slot][r][:] for the `slots` owned tables (DEVICE array of DEVICE
+ *                          pointers, like trs_ffm_pack_tables), slots_pitch = ceil(fields / world); unused slots are zero-filled.
+ *   trs_ffm_shard_resolve  rows_out[b][f] = idx[b][f] + offsets[f] as int32 (bounds-checked, status as everywhere) and
+ *                          first_out[b] = bias[0] + sum_f w_feat[rows_out[b][f]] (either may be NULL): the part of
+ *                          FieldAwareFactorizationMachineModel.forward (field_aware_factorization_machine.py:62-81)
+ *                          that needs no exchange.
+ *   trs_ffm_shard_blocks   partial[s] = the blocks `rank` reduces for sample s, for ALL batch_all samples (rows_all =
+ *                          the all-gathered row ids), + first[s - own_lo] for own_lo <= s < own_hi.  shards = HOST array
+ *                          of `world` device addresses as mapped in THIS process.  copy_tab / item_tab: DEVICE copies
+ *                          of the plan tables.  Summing `partial` over the ranks (reduce-scatter) gives the logits. */
+int trs_ffm_shard_plan(int fields, int world, int rank, int embed, int32_t* copy_tab, int copy_capacity,
+                       uint32_t* item_tab, int item_capacity, int* n_copies, int* n_items, int* tx_bytes,
+                       int* stage_bytes);
+int trs_ffm_shard_pack(const float* const* tables, int slots, int slots_pitch, int64_t rows, int embed, float* shard,
+                       void* stream);
+int trs_ffm_shard_resolve(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                          int64_t rows, const float* w_feat, const float* bias, int32_t* rows_out, float* first_out,
+                          int32_t* status, void* stream);
+int trs_ffm_shard_blocks(const int32_t* rows_all, int64_t batch_all, int fields, int embed,
+                         const float* const* shards, int world, int rank, const int32_t* copy_tab, int copy_capacity,
+                         const uint32_t* item_tab, int item_capacity, const float* first, int64_t own_lo,
+                         int64_t own_hi, float* partial, void* stream);
+
 /* ---- 8f-3: fused indices -> logits forwards of three more models (Sequential.forward = Inputs.forward + model) --------
  * Arguments as in trs_deepfm_forward; the MLP (HOST arrays of DEVICE pointers) must end in ONE output.
  *   trs_nfm_forward        NeuralFactorizationMachineModel.forward (neural_factorization_machine.py:66-96):

@@ -90,6 +90,11 @@ PROTOTYPES = {
     'trs_ffm_model_forward_interleaved': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, c_int, _P, _P, _P, _P]),
     'trs_ffm_model_forward_pairs': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _P, _P, c_int,
                                             c_int64, c_int64, _P, _P, _P]),
+    'trs_ffm_shard_plan': (c_int, [c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _IP, _IP, _IP, _IP]),
+    'trs_ffm_shard_pack': (c_int, [_P, c_int, c_int, c_int64, c_int, _P, _P]),
+    'trs_ffm_shard_resolve': (c_int, [_P, c_int, _P, c_int64, c_int, c_int64, _P, _P, _P, _P, _P, _P]),
+    'trs_ffm_shard_blocks': (c_int, [_P, c_int64, c_int, c_int, _PP, c_int, c_int, _P, c_int, _P, c_int, _P, c_int64,
+                                     c_int64, _P, _P]),
     'trs_nfm_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _IP, c_int, _PP, _PP, c_int, _P,
                                 _P, _P, _P]),
     'trs_fnn_forward': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _IP, c_int, _PP, _PP, c_int, _P,

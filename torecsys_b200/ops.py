@@ -853,6 +853,98 @@ def ffm_model_pairs(idx, offsets, w_feat, table_ptrs: torch.Tensor, rows: int, e
     return out
 
 
+class FfmShardPlan:
+    """Host tables of trs_ffm_shard_plan for one rank: the chunk copies and dot-product items of a sample of parity 0 / 1
+    (csrc/ffm_blocks.cu).  Pure host logic (numpy); `.device_tables(device)` uploads them once."""
+
+    def __init__(self, fields: int, world: int, rank: int, embed: int):
+        import numpy as np
+        lib = _cabi.load()
+        self.fields, self.world, self.rank, self.embed = fields, world, rank, embed
+        nc, ni, tx, sb = int_array([0, 0]), int_array([0, 0]), int_array([0, 0]), int_array([0])
+        check(lib.trs_ffm_shard_plan(fields, world, rank, embed, None, 0, None, 0, nc, ni, tx, sb), 'trs_ffm_shard_plan')
+        self.n_copies, self.n_items, self.tx_bytes = [nc[0], nc[1]], [ni[0], ni[1]], [tx[0], tx[1]]
+        self.stage_bytes = sb[0]
+        self.copy_capacity, self.item_capacity = max(self.n_copies + [1]), max(self.n_items + [1])
+        self.copy_tab = np.zeros((2, self.copy_capacity, 2), dtype=np.int32)
+        self.item_tab = np.zeros((2, self.item_capacity), dtype=np.uint32)
+        check(lib.trs_ffm_shard_plan(fields, world, rank, embed, self.copy_tab.ctypes.data, self.copy_capacity,
+                                     self.item_tab.ctypes.data, self.item_capacity, nc, ni, tx, sb),
+              'trs_ffm_shard_plan')
+        self.slots = (fields + world - 1) // world
+        self.pitch_bytes = self.slots * embed * 4
+        self._dev = {}
+
+    def copies(self, parity: int):
+        """[(src rank, field, bytes, dst byte offset)] of a sample of this parity."""
+        t = self.copy_tab[parity, :self.n_copies[parity]]
+        return [(int(x) & 0xff, (int(x) >> 8) & 0xff, (int(x) >> 16) * 16, int(y)) for x, y in t]
+
+    def items(self, parity: int):
+        """[(byte offset of piece A, byte offset of piece B)] of a sample of this parity (16-byte pieces)."""
+        t = self.item_tab[parity, :self.n_items[parity]]
+        return [((int(v) & 0xffff) * 16, (int(v) >> 16) * 16) for v in t]
+
+    def remote_bytes(self, parity: int) -> int:
+        return sum(b for src, _, b, _ in self.copies(parity) if src != self.rank)
+
+    def device_tables(self, device):
+        key = (device.type, device.index)
+        if key not in self._dev:
+            self._dev[key] = (torch.from_numpy(self.copy_tab).to(device),
+                              torch.from_numpy(self.item_tab.view('int32')).to(device))
+        return self._dev[key]
+
+
+def ffm_shard_pack(tables: Sequence[torch.Tensor], slots_pitch: int, out: torch.Tensor):
+    """trs_ffm_shard_pack: out (rows, slots_pitch, embed) <- the owned tables [(rows, embed)] interleaved per row id."""
+    _need_cuda('ffm_shard_pack', out, *tables)
+    ts = [_f32('ffm_shard_pack', t) for t in tables]
+    rows, embed = (ts[0].shape if ts else (out.shape[0], out.shape[-1]))
+    if out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != rows * slots_pitch * embed:
+        raise ValueError('ffm_shard_pack: out must be a contiguous float32 (rows, slots_pitch, embed) buffer')
+    tp = torch.tensor([t.data_ptr() for t in ts] or [0], dtype=torch.int64).to(out.device)
+    check(_cabi.load().trs_ffm_shard_pack(_ptr(tp), len(ts), slots_pitch, rows, embed, _ptr(out), _stream()),
+          'trs_ffm_shard_pack')
+    return out
+
+
+def ffm_shard_resolve(idx, offsets, rows: int, w_feat=None, bias=None, rows_out=None, first_out=None,
+                      check_now: bool = True):
+    """trs_ffm_shard_resolve: (int32 global row ids (B, N), bias + first-order term (B,)) of this rank's samples."""
+    ix, bits, off = _fused_common('ffm_shard_resolve', idx, offsets, w_feat, bias)
+    wf = _f32('ffm_shard_resolve', w_feat) if w_feat is not None else None
+    bs = _f32('ffm_shard_resolve', bias).reshape(-1) if bias is not None else None
+    b, n = ix.shape
+    rows_out = rows_out if rows_out is not None else torch.empty((b, n), dtype=torch.int32, device=ix.device)
+    first_out = first_out if first_out is not None else torch.empty((b,), dtype=torch.float32, device=ix.device)
+    st = _status_tensor(ix.device)
+    check(_cabi.load().trs_ffm_shard_resolve(_ptr(ix), bits, _ptr(off), b, n, rows, _ptr(wf), _ptr(bs), _ptr(rows_out),
+                                             _ptr(first_out), _ptr(st), _stream()), 'trs_ffm_shard_resolve')
+    if check_now:
+        _after_lookup(ix.device)
+    return rows_out, first_out
+
+
+def ffm_shard_blocks(rows_all: torch.Tensor, plan: FfmShardPlan, shard_ptrs: Sequence[int], first=None,
+                     own_range=(0, 0), out: Optional[torch.Tensor] = None):
+    """trs_ffm_shard_blocks: this rank's partial logits (B_all,) of ALL samples; `shard_ptrs[r]` = address of rank r's
+    interleaved shard as mapped in this process (own HBM or NVLink peer memory)."""
+    _need_cuda('ffm_shard_blocks', rows_all, first)
+    if rows_all.dtype != torch.int32 or not rows_all.is_contiguous() or rows_all.dim() != 2:
+        raise ValueError('ffm_shard_blocks: rows_all must be a contiguous int32 (B_all, N) tensor')
+    b, n = rows_all.shape
+    if n != plan.fields or len(shard_ptrs) != plan.world:
+        raise ValueError('ffm_shard_blocks: the plan was built for another shape')
+    out = out if out is not None else torch.empty((b,), dtype=torch.float32, device=rows_all.device)
+    ct, it = plan.device_tables(rows_all.device)
+    check(_cabi.load().trs_ffm_shard_blocks(_ptr(rows_all), b, n, plan.embed, ptr_array(list(shard_ptrs)), plan.world,
+                                            plan.rank, _ptr(ct), plan.copy_capacity, _ptr(it), plan.item_capacity,
+                                            _ptr(first), int(own_range[0]), int(own_range[1]), _ptr(out), _stream()),
+          'trs_ffm_shard_blocks')
+    return out
+
+
 def ffm_interleaved_supported(fields: int, embed: int) -> bool:
     """Shapes trs_ffm_model_forward_interleaved takes (power-of-two embed, two samples' chunks in shared memory)."""
     if fields < 2 or fields > 64 or embed < 4 or embed > 128 or embed & (embed - 1):

@@ -250,3 +250,93 @@ class ShardedFFM:
         return out
 
     __call__ = forward
+
+
+class ShardedInterleavedTables:
+    """The N field-aware tables spread over the ranks of `group` (rank t % world owns table t), each rank's tables
+    INTERLEAVED per row id: local[r] = [T_rank[r] | T_{rank+world}[r] | ...] -- what a rank holds of one row id is one
+    contiguous chunk, fetched with one bulk copy (csrc/ffm_blocks.cu).  Peer-mapped everywhere (symmetric memory)."""
+
+    def __init__(self, embed_size: int, field_sizes: Sequence[int], group: Optional[dist.ProcessGroup] = None,
+                 device: Optional[torch.device] = None):
+        import torch.distributed._symmetric_memory as symm_mem
+        if not dist.is_initialized():
+            raise RuntimeError('ShardedInterleavedTables needs torch.distributed (NCCL) to be initialised')
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        if self.world > 8:
+            raise NotImplementedError('the block exchange is written for the GPUs of one NVSwitch box (world <= 8)')
+        self.device = device if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.num_fields = len(field_sizes)
+        self.rows = int(sum(field_sizes))
+        self.embed_size = embed_size
+        self.plan = TableShardPlan(self.num_fields, self.world)
+        self.block_plan = ops.FfmShardPlan(self.num_fields, self.world, self.rank, embed_size)
+        self.offsets = _reference_offsets(field_sizes).rename(None).reshape(-1).to(self.device)
+        self.local = symm_mem.empty((self.rows, self.plan.slots_per_rank, embed_size), dtype=torch.float32,
+                                    device=self.device)
+        self._handle = symm_mem.rendezvous(self.local, self.group)
+        self.shard_ptrs = [int(p) for p in self._handle.buffer_ptrs]
+
+    def fill_from(self, owned_tables: Sequence[torch.Tensor]):
+        """owned_tables = the (rows, embed) tables plan.tables_of(rank), in that order.  Collective (barrier)."""
+        if len(owned_tables) != len(self.plan.tables_of(self.rank)):
+            raise ValueError(f'rank {self.rank} owns the tables {self.plan.tables_of(self.rank)}')
+        ops.ffm_shard_pack([t.to(self.device) for t in owned_tables], self.plan.slots_per_rank, self.local)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+        return self
+
+    def init_(self, fn):
+        """fn(local) initialises the whole interleaved shard in place (synthetic tables); collective (barrier)."""
+        fn(self.local)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+        return self
+
+
+class ShardedFFMBlocks:
+    """FieldAwareFactorizationMachineModel.forward (field_aware_factorization_machine.py:39-81) on interleaved sharded
+    tables, exchange at chunk granularity and half volume (csrc/ffm_blocks.cu):
+      1. resolve: idx + offsets -> int32 row ids, bias + first-order term of the rank's own samples (no exchange);
+      2. all-gather of the row ids (NCCL; 4 B per lookup = 156 B per sample);
+      3. every rank reduces ITS blocks for ALL samples: local chunks from HBM, the partner's chunks over NVLink, one
+         bulk copy per chunk, fetch overlapped with the reduction of earlier samples;
+      4. reduce-scatter (sum) of the (B,) partial logits (NCCL): each rank receives the logits of its samples.
+    All ranks must pass slices of the same length."""
+
+    def __init__(self, tables: ShardedInterleavedTables, w_feat: torch.Tensor, bias: torch.Tensor):
+        self.tables = tables
+        self.w_feat = w_feat      # (rows, 1), replicated: 4 B per row
+        self.bias = bias
+        self._buf = {}
+
+    def forward(self, idx_local: torch.Tensor) -> torch.Tensor:
+        t = self.tables
+        world, rank = t.world, t.rank
+        b_local, n = idx_local.shape
+        key = (b_local, n)
+        if key not in self._buf:
+            self._buf = {key: (torch.empty((b_local, n), dtype=torch.int32, device=t.device),
+                               torch.empty((b_local,), dtype=torch.float32, device=t.device),
+                               torch.empty((world * b_local, n), dtype=torch.int32, device=t.device),
+                               torch.empty((world * b_local,), dtype=torch.float32, device=t.device))}
+        rows_loc, first, rows_all, partial = self._buf[key]
+        ops.ffm_shard_resolve(idx_local, t.offsets, t.rows, self.w_feat, self.bias, rows_loc, first, check_now=False)
+        dist.all_gather_into_tensor(rows_all, rows_loc, group=t.group)
+        ops.ffm_shard_blocks(rows_all, t.block_plan, t.shard_ptrs, first, (rank * b_local, (rank + 1) * b_local),
+                             out=partial)
+        out = torch.empty((b_local, 1), dtype=torch.float32, device=t.device)
+        dist.reduce_scatter_tensor(out.view(-1), partial, op=dist.ReduceOp.SUM, group=t.group)
+        if ops.index_check_mode() == 'sync':
+            # an out-of-range lookup is counted by the rank that owns the sample; every rank must raise together
+            st = ops.status_tensor(t.device)
+            seen = st[:1].clone()
+            dist.all_reduce(seen, op=dist.ReduceOp.SUM, group=t.group)
+            if int(seen.item()) != 0:
+                st.zero_()
+                raise IndexError(f'index out of range in self ({int(seen.item())} lookups across the ranks)')
+        return out
+
+    __call__ = forward
