@@ -525,6 +525,14 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     timer = Timer(torch, dist, world, device, args.steps, args.warmup, args.repeats)
 
+    if args.only_sharded:   # development aid: the exchange paths alone (not the driver's line)
+        res = bench_sharded(torch, dist, timer, device, rank, world, args) if world > 1 else None
+        if rank == 0:
+            args.emit(json.dumps({'only_sharded': True, 'n_gpus': world, 'sharded': res}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     batch, rpf = args.batch, args.rows_per_field
     rows = NUM_FIELDS * rpf
     gen = torch.Generator().manual_seed(0)
@@ -798,6 +806,7 @@ def main():
     ap.add_argument('--e2e-chunks', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-configs', action='store_true', help='skip layout C, configs[2..4] and the sharded runs')
+    ap.add_argument('--only-sharded', action='store_true', help='development: run the sharded (exchange) paths only')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer (e2e) measurements')
     ap.add_argument('--no-overlap', dest='overlap', action='store_false',
                     help='launch the timed kernels fully ordered (no programmatic dependent launch)')

@@ -38,10 +38,20 @@ using tc5::mbar_init;
 using tc5::mbar_wait;
 using tc5::smem_u32;
 
+constexpr int kProducers = 4;     // a warp-wide bulk copy is issued lane by lane (~60 cycles each): the chunk copies
+                                  // of a sample are spread over several warps (measured: 1 warp 2.9 ms)
 constexpr int kConsumers = 6;
-constexpr int kThreads = (1 + kConsumers) * 32;
+constexpr int kThreads = (kProducers + kConsumers) * 32;
 constexpr int kMaxWorld = 8;
 constexpr int kMaxStages = 16;
+constexpr int kRowRing = 8;      // samples whose row ids are in flight / in shared memory
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct BlockArgs {
   const int32_t* rows_all;   // (batch_all, fields) global row ids
@@ -67,7 +77,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffm_blocks_kernel(const BlockArgs
   int2* copy_s = reinterpret_cast<int2*>(p);            p += (size_t)2 * a.max_copies * sizeof(int2);
   uint32_t* item_s = reinterpret_cast<uint32_t*>(p);    p += (size_t)2 * a.max_items * sizeof(uint32_t);
   p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
-  int* rows_s = reinterpret_cast<int*>(p);              p += 64 * sizeof(int);
+  int* rows_s = reinterpret_cast<int*>(p);              p += kProducers * kRowRing * 64 * sizeof(int);
   unsigned long long* shard_s = reinterpret_cast<unsigned long long*>(p);  p += kMaxWorld * 8;
   uint64_t* bars = reinterpret_cast<uint64_t*>(p);      // full[stages], empty[stages]
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + a.stages);
@@ -78,7 +88,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffm_blocks_kernel(const BlockArgs
   if (threadIdx.x < kMaxWorld) shard_s[threadIdx.x] = reinterpret_cast<unsigned long long>(a.shard[threadIdx.x]);
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) {
-      mbar_init(full0 + 8 * s, 1);
+      mbar_init(full0 + 8 * s, kProducers);
       mbar_init(empty0 + 8 * s, kConsumers);
     }
     tc5::fence_barrier_init();
@@ -86,73 +96,106 @@ __global__ void __launch_bounds__(kThreads, 1) ffm_blocks_kernel(const BlockArgs
   __syncthreads();
 
   // sample of this CTA's n-th turn: row n of a (turns x grid) tiling, rotated by n so that the parities -- and with them
-  // the 3-or-4-partner workloads -- alternate within every CTA (grid is even: a plain stride would pin one parity)
-  const int64_t grid = gridDim.x;
-  const int64_t mine = (a.batch_all + grid - 1) / grid;
-  auto sample_of = [&](int64_t n) -> int64_t { return n * grid + (blockIdx.x + n) % grid; };   // >= batch_all: only in the last row
+  // the 3-or-4-partner workloads -- alternate within every CTA (grid is even: a plain stride would pin one parity).
+  // Only the last row can run past batch_all.  Walked incrementally (no division in the loops).
+  const int grid = static_cast<int>(gridDim.x);
+  const int turns = static_cast<int>((a.batch_all + grid - 1) / grid);
+  struct Walk {
+    int n, rot, grid;
+    __device__ Walk(int n0, int cta, int g) : n(n0), rot((cta + n0) % g), grid(g) {}
+    __device__ int64_t sample() const { return static_cast<int64_t>(n) * grid + rot; }
+    __device__ void next() { ++n; if (++rot == grid) rot = 0; }
+  };
   const int fields = a.fields;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ producer
-    auto fetch_rows = [&](int64_t n, int f) -> int {
-      if (n >= mine || f >= fields || sample_of(n) >= a.batch_all) return 0;
-      return __ldg(a.rows_all + sample_of(n) * fields + f);
+  if (warp < kProducers) {
+    // ------------------------------------------------------------------ producers: warp j issues the copies c = j, j + P, ..
+    // (lane l: copy l * P + j) of every sample, with its own ring of row ids and its own share of the stage's byte count
+    int* my_rows = rows_s + warp * kRowRing * 64;
+    int2 mine[2];          // this lane's copy of a sample of parity 0 / 1 (.x = 0: none)
+    uint32_t my_tx[2];     // bytes this warp fetches per sample of parity 0 / 1
+#pragma unroll
+    for (int par = 0; par < 2; ++par) {
+      const int c = lane * kProducers + warp;
+      mine[par] = c < a.n_copies[par] ? copy_s[par * a.max_copies + c] : make_int2(0, 0);
+      uint32_t b = static_cast<uint32_t>(mine[par].x >> 16) << 4;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+      my_tx[par] = b;
+    }
+    // row ids: a ring of kRowRing samples in shared memory, requested kRowRing - 1 samples ahead with 4-byte cp.async
+    Walk ahead(0, blockIdx.x, grid);
+    auto request_rows = [&]() {
+      if (ahead.n < turns) {
+        const int64_t s = ahead.sample();
+        if (s < a.batch_all) {
+          const uint32_t dst = smem_u32(my_rows + (ahead.n % kRowRing) * 64);
+          const int32_t* src = a.rows_all + s * fields;
+          if (lane < fields) cp_async4(dst + lane * 4, src + lane);
+          if (lane + 32 < fields) cp_async4(dst + (lane + 32) * 4, src + lane + 32);
+        }
+      }
+      cp_async_commit();
+      ahead.next();
     };
     // the consumers have left their kConsumers partial sums of the sample in this stage: one value, fixed order
-    auto finish = [&](int64_t n, int stage, uint32_t wrap) {
+    auto finish = [&](int64_t s, int stage, uint32_t wrap) {
       mbar_wait(empty0 + 8 * stage, wrap & 1);
-      if (lane == 0) {
-        const int64_t s = sample_of(n);
-        float v = (a.first != nullptr && s >= a.own_lo && s < a.own_hi) ? __ldg(a.first + (s - a.own_lo)) : 0.f;
+      if (warp == 0 && lane == 0) {
+        float v = part[stage * kConsumers];
 #pragma unroll
-        for (int w = 0; w < kConsumers; ++w) v += part[stage * kConsumers + w];
+        for (int w = 1; w < kConsumers; ++w) v += part[stage * kConsumers + w];
         a.partial[s] = v;
       }
       __syncwarp();
     };
-    int ra = fetch_rows(0, lane), rb = fetch_rows(0, lane + 32);
+#pragma unroll 1
+    for (int i = 0; i < kRowRing - 1; ++i) request_rows();
+    Walk cur(0, blockIdx.x, grid), done(0, blockIdx.x, grid);
     int stage = 0;
     uint32_t wrap = 0;   // how many times the ring has been filled
-    int64_t issued = 0;
-    for (int64_t n = 0; n < mine; ++n) {
-      const int64_t s = sample_of(n);
+#pragma unroll 1
+    for (; cur.n < turns; cur.next()) {
+      const int64_t s = cur.sample();
       if (s >= a.batch_all) break;
       const int par = static_cast<int>(s & 1);
+      request_rows();
+      cp_async_wait<kRowRing - 1>();   // the row ids of sample cur.n have landed
       __syncwarp();
-      rows_s[lane] = ra;
-      rows_s[lane + 32] = rb;
-      __syncwarp();
-      ra = fetch_rows(n + 1, lane);
-      rb = fetch_rows(n + 1, lane + 32);
-      if (wrap > 0) finish(n - a.stages, stage, wrap - 1);
+      if (wrap > 0) {
+        finish(done.sample(), stage, wrap - 1);
+        done.next();
+      }
       const uint32_t bar = full0 + 8 * stage;
-      if (lane == 0) mbar_expect_tx(bar, static_cast<uint32_t>(a.tx_bytes[par]));
+      if (lane == 0) mbar_expect_tx(bar, my_tx[par]);
       __syncwarp();
-      const uint32_t dst0 = smem_u32(stage0 + (size_t)stage * a.stage_bytes);
-      const int2* tab = copy_s + par * a.max_copies;
-      const int nc = a.n_copies[par];
-      for (int c = lane; c < nc; c += 32) {
-        const int2 e = tab[c];
+      const int2 e = mine[par];
+      if (e.x != 0) {
         const int src = e.x & 0xff, f = (e.x >> 8) & 0xff;
         const uint32_t bytes = static_cast<uint32_t>(e.x >> 16) << 4;
-        const unsigned long long g = shard_s[src] + static_cast<unsigned long long>(rows_s[f]) * a.pitch_bytes;
-        bulk_g2s(dst0 + e.y, reinterpret_cast<const void*>(g), bytes, bar);
+        const unsigned long long g = shard_s[src] +
+            static_cast<unsigned long long>(my_rows[(cur.n % kRowRing) * 64 + f]) * a.pitch_bytes;
+        bulk_g2s(smem_u32(stage0 + (size_t)stage * a.stage_bytes) + e.y, reinterpret_cast<const void*>(g), bytes, bar);
       }
-      issued = n + 1;
       if (++stage == a.stages) { stage = 0; ++wrap; }
     }
-    for (int64_t n = issued > a.stages ? issued - a.stages : 0; n < issued; ++n)
-      finish(n, static_cast<int>(n % a.stages), static_cast<uint32_t>(n / a.stages));
+    cp_async_wait<0>();
+    for (; done.n < cur.n; done.next())
+      finish(done.sample(), done.n % a.stages, static_cast<uint32_t>(done.n / a.stages));
   } else {
     // ------------------------------------------------------------------ consumers: every warp takes a slice of the
     // sample's items; all of them walk the stages in order, so a parity wait always refers to the fill it means
-    const int c = warp - 1;
+    const int c = warp - kProducers;
     int stage = 0;
     uint32_t wrap = 0;
-    for (int64_t n = 0; n < mine; ++n) {
-      const int64_t s = sample_of(n);
+#pragma unroll 1
+    for (Walk cur(0, blockIdx.x, grid); cur.n < turns; cur.next()) {
+      const int64_t s = cur.sample();
       if (s >= a.batch_all) break;
       const int par = static_cast<int>(s & 1);
+      // the part of the logit that needed no exchange joins warp 0's slice (requested before the wait)
+      float own = 0.f;
+      if (c == 0 && lane == 0 && a.first != nullptr && s >= a.own_lo && s < a.own_hi) own = __ldg(a.first + (s - a.own_lo));
       mbar_wait(full0 + 8 * stage, wrap & 1);
       const float4* A = reinterpret_cast<const float4*>(stage0 + (size_t)stage * a.stage_bytes);
       const uint32_t* items = item_s + par * a.max_items;
@@ -175,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffm_blocks_kernel(const BlockArgs
         acc0 = fmaf(x0.z, y0.z, acc0); acc0 = fmaf(x0.w, y0.w, acc0);
       }
       const float acc = warp_sum(acc0 + acc1);
-      if (lane == 0) part[stage * kConsumers + c] = acc;
+      if (lane == 0) part[stage * kConsumers + c] = acc + own;
       __syncwarp();                                     // every lane has read its pieces
       if (lane == 0) mbar_arrive(empty0 + 8 * stage);   // (release: the partial sum is visible to the producer)
       if (++stage == a.stages) { stage = 0; ++wrap; }
@@ -387,12 +430,13 @@ extern "C" int trs_ffm_shard_blocks(const int32_t* rows_all, int64_t batch_all, 
     a.n_copies[par] = static_cast<int>(pl.copies[par].size());
     a.n_items[par] = static_cast<int>(pl.items[par].size());
     a.tx_bytes[par] = pl.tx_bytes[par];
+    TRS_UNSUPPORTED(a.n_copies[par] > 32 * kProducers, "trs_ffm_shard_blocks: more than %d chunks per sample", 32 * kProducers);
     TRS_REQUIRE(a.n_copies[par] <= copy_capacity && a.n_items[par] <= item_capacity,
                 "trs_ffm_shard_blocks: table capacities smaller than the plan");
   }
   a.max_copies = copy_capacity; a.max_items = item_capacity;
   a.stage_bytes = pl.stage_bytes;
-  const size_t fixed = (size_t)2 * copy_capacity * 8 + (size_t)2 * item_capacity * 4 + 16 + 64 * 4 + kMaxWorld * 8 +
+  const size_t fixed = (size_t)2 * copy_capacity * 8 + (size_t)2 * item_capacity * 4 + 16 + kProducers * kRowRing * 64 * 4 + kMaxWorld * 8 +
                        2 * kMaxStages * 8 + kMaxStages * kConsumers * 4;
   TRS_UNSUPPORTED(fixed + 2 * (size_t)pl.stage_bytes > (size_t)kMaxDynSmem,
                   "trs_ffm_shard_blocks: two samples of %d fields x %d over %d ranks do not fit shared memory", fields,
