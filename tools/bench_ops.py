@@ -290,6 +290,9 @@ def main():
             x = ops.embedding_gather(w32, ring[0][:32768].contiguous(), off)
             t = timeit(lambda i: ops.cross(x, cw, cb), reps=5)
             report('cross layer (a7, E=32, L=6)', 32768, t, 2 * N * 128, 6 * N * (2 * 32 * 32 + 3 * 32))
+            t = timeit(lambda i: ops.cross(x, cw, cb, tc5=True), reps=5)
+            report('cross layer on tcgen05 (experimental chain in tensor memory)', 32768, t, 2 * N * 128,
+                   6 * N * (2 * 32 * 32 + 3 * 32))
             del x
         if want('dcn'):
             pack = mlp_pack([32, 32, 16, 8, 4], dev)

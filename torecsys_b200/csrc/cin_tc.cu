@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
         mbar_wait(full_a(sa), pa);
         mbar_wait(full_b(sb), pb);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint64_t ad = a_desc0 + sa * a_stage_u;
           const uint64_t bd = b_desc0 + sb * b_stage_u;
           const uint32_t acc0 = q > 0 ? 1u : 0u;

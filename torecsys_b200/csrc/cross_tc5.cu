@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kSlots * 128 + 32, 1) cross_tc5_kernel(CrossTc
           ++n_ready[s];
         }
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint64_t b_hi0 = w_desc0 + (uint64_t)(2 * l) * kPlaneU, b_lo0 = b_hi0 + kPlaneU;
 #pragma unroll
           for (int ks = 0; ks < E / 8; ++ks) {

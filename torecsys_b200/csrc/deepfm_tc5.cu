@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(C::kThreads, C::CTAS) deepfm_tc5_kernel(Tc5Arg
         mbar_wait(lo_full(slot), (pq / S) & 1);
         trace_ev(a, 2, pq, 0);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t d = tmem_base + (t_lo & 1) * kAccCols + 32;
           const uint64_t bd = b_desc0 + ((slot * C::kSlabBytes) >> 4);
 #pragma unroll
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(C::kThreads, C::CTAS) deepfm_tc5_kernel(Tc5Arg
         trace_ev(a, 2, q, 1);
         fence_proxy_async();   // the rows were written by cp.async (generic proxy); the tensor core reads via the async proxy
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t d = tmem_base + (t_hi & 1) * kAccCols;
           const uint64_t ad = a_desc0 + ((slot * C::kStageBytes) >> 4), bd = b_desc0 + ((slot * C::kSlabBytes) >> 4);
 #pragma unroll

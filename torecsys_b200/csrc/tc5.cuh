@@ -34,6 +34,20 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// One lane of a CONVERGED warp (elect.sync).  Guard tcgen05.mma / tcgen05.commit / bulk-copy issue with this, not with
+// `lane == 0`: ptxas then knows a single thread runs the block, keeps the descriptor arithmetic in uniform registers
+// and emits the UTCHMMAs back to back.  Under a lane-id branch it wraps EVERY MMA in an ELECT / BRA.U.ANY loop with
+// R2UR moves -- measured ~80 cycles of issue per MMA in cin_tc_layer_kernel against 64 cycles of math (N = 128).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
