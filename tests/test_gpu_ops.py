@@ -300,6 +300,42 @@ def test_dcn_tensor_core_path(ops, n, e, cross_layers, deep, od):
             assert normwise_err(got, want) <= TOL, (n, e, batch)
 
 
+@pytest.mark.parametrize('n,e,cross_layers,deep,od', [(39, 32, 6, [32, 16, 8], 4), (50, 32, 2, [16], 2), (128, 16, 1, [8], 1),
+                                                      (3, 32, 8, [32, 32, 32, 16], 16), (64, 16, 4, [], 5)])
+def test_dcn_tcgen05_path(ops, n, e, cross_layers, deep, od):
+    """dcn_tc5.cu (the chains of a 128-row tile in tensor memory, polled slots): tiles of 1..42 whole samples, a last
+    partial tile, more tiles than slots x CTAs, an MLP that is one output layer only, out-of-range lookups reported."""
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    tag = f'dcn5_{n}_{e}'
+    fs = [16 * (2 + i % 5) for i in range(n)]
+    rows = sum(fs)
+    off = R.field_offsets(fs)
+    w_emb = torch.from_numpy(synth.uniform((rows, e), f'{tag}/we'))
+    dims = [e] + deep + [od]
+    ws = [torch.from_numpy(synth.uniform((dims[i + 1], dims[i]), f'{tag}/w{i}', -dims[i] ** -0.5, dims[i] ** -0.5))
+          for i in range(len(dims) - 1)]
+    bs = [torch.from_numpy(synth.uniform((dims[i + 1],), f'{tag}/b{i}', -0.5, 0.5)) for i in range(len(dims) - 1)]
+    cw = [torch.from_numpy(synth.uniform((e, e), f'{tag}/cw{l}', -e ** -0.5, e ** -0.5)) for l in range(cross_layers)]
+    cb = [torch.from_numpy(synth.uniform((e,), f'{tag}/cb{l}', -0.5, 0.5)) for l in range(cross_layers)]
+    fc_w = torch.from_numpy(synth.uniform((1, n * (e + od)), f'{tag}/fcw', -0.1, 0.1))
+    fc_b = torch.from_numpy(synth.uniform((1,), f'{tag}/fcb'))
+    pack = ops.MlpPack([w.cuda() for w in ws], [b.cuda() for b in bs], ops.activation_id('relu'))
+    args = (off.cuda(), w_emb.cuda(), torch.stack(cw).cuda(), torch.stack(cb).cuda(), pack, fc_w.cuda(), fc_b.cuda())
+    spt = 128 // n
+    for batch in (max(spt * 4, -(-512 // n)), spt * 4 * 148 * 2 + 3, 5000):
+        idx = torch.from_numpy(synth.integers((batch, n), f'{tag}/idx{batch}', np.asarray(fs)[None, :]))
+        want = R.dcn_from_indices(idx, off, w_emb, cw, cb, ws, bs, fc_w, fc_b).numpy()
+        for dt in (torch.int64, torch.int32):
+            got = ops.dcn(idx.cuda().to(dt), *args)
+            assert normwise_err(got.cpu().numpy(), want) <= TOL, (n, e, batch)
+            assert torch.equal(got, ops.dcn(idx.cuda().to(dt), *args))       # fixed summation order
+    bad = idx.clone()
+    bad[batch - 1, n - 1] = fs[-1]
+    with pytest.raises(IndexError):
+        ops.dcn(bad.cuda(), *args)
+
+
 @pytest.mark.parametrize('n,e,sizes,direct', [(7, 16, [128, 40], False), (39, 16, [64, 64], False),
                                               (5, 8, [200, 12], True), (9, 32, [24, 128, 8], False)])
 def test_cin_tensor_core_wide_layers(ops, n, e, sizes, direct):

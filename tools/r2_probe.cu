@@ -316,7 +316,8 @@ __global__ void __launch_bounds__(128, 1) mma_stream(int n, int n2, int swz, int
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if (threadIdx.x == 0) {
+  // (elect.sync, not `threadIdx.x == 0`: under a lane-id branch ptxas wraps every MMA in an ELECT loop, ~45 cycles each)
+  if (warp == 0 && elect_one()) {
     uint64_t ad, bd, bd2;
     if (swz) {   // K-major SWIZZLE_128B: rows of 128 B, 8-row atoms 1024 B apart (SBO), LBO unused (1)
       const uint64_t sw = static_cast<uint64_t>(2) << 61;

@@ -55,8 +55,10 @@ __device__ __forceinline__ void write_operand(uint32_t taddr_hi, const float (&h
     uint32_t hi[16], lo[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      hi[j] = (__float_as_uint(h[c + j]) + 0x1000u) & 0xffffe000u;
-      lo[j] = (__float_as_uint(h[c + j] - __uint_as_float(hi[j])) + 0x1000u) & 0xffffe000u;
+      // tcgen05.mma kind::tf32 TRUNCATES its fp32 operands (profiles/r02_gather_ceiling.md): the raw value is a valid
+      // hi operand, and lo = h - trunc(h) is exact (its own truncation costs 2^-21 relative, one-sided)
+      hi[j] = __float_as_uint(h[c + j]);
+      lo[j] = __float_as_uint(h[c + j] - __uint_as_float(hi[j] & 0xffffe000u));
     }
     tmem_st16(taddr_hi + c, hi);
     tmem_st16(taddr_hi + E + c, lo);

@@ -29,6 +29,13 @@ int dcn_tc_launch(const void* idx, int idx_bits, const int64_t* offsets, int64_t
                   int cross_layers, const MlpParams& mp, const float* fc_w, const float* fc_b, float* logits,
                   int32_t* status, cudaStream_t s);
 
+int dcn_tc5_supported(int embed, int fields, int cross_layers, const int* mlp_dims, int mlp_layers, int activation,
+                      int64_t rows);
+int dcn_tc5_launch(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
+                   const float* w_emb, int64_t rows, int embed, const float* cross_w, const float* cross_b,
+                   int cross_layers, const MlpParams& mp, const float* fc_w, const float* fc_b, float* logits,
+                   int32_t* status, cudaStream_t s);
+
 namespace {
 
 struct FmFamilyArgs {
@@ -398,7 +405,11 @@ extern "C" int trs_dcn_forward(const void* idx, int idx_bits, const int64_t* off
               "trs_dcn_forward: bad MLP description (at most %d layers)", MlpParams::kMaxLayers);
   TRS_REQUIRE(mlp_dims[0] == embed, "trs_dcn_forward: the per-field MLP input size must be embed");
   if (batch == 0) return TRS_OK;
-  // the per-row dense chains on the tensor pipe (3xTF32 mma.sync, dcn_tc.cu) whenever the shape allows
+  // the per-row dense chains in tensor memory on tcgen05 (dcn_tc5.cu) where the shape allows and the batch fills the SMs,
+  // else on 3xTF32 mma.sync (dcn_tc.cu)
+  if (batch * fields >= 128 * 4 && dcn_tc5_supported(embed, fields, cross_layers, mlp_dims, mlp_layers, activation, rows))
+    return dcn_tc5_launch(idx, idx_bits, offsets, batch, fields, w_emb, rows, embed, cross_w, cross_b, cross_layers,
+                          a.mp, fc_w, fc_b, logits, status, static_cast<cudaStream_t>(stream));
   if (dcn_tc_supported(embed, cross_layers, mlp_dims, mlp_layers, activation) && (fields * 16) % 16 == 0)
     return dcn_tc_launch(idx, idx_bits, offsets, batch, fields, w_emb, rows, embed, cross_w, cross_b, cross_layers,
                          a.mp, fc_w, fc_b, logits, status, static_cast<cudaStream_t>(stream));
