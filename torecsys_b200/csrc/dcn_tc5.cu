@@ -15,9 +15,10 @@
 //     {16, 32}, A from TMEM, W pre-split in shared memory;
 //   * a layer's epilogue (thread = row): tcgen05.ld D -> FP32 update -> raw value as the hi operand (the tensor core
 //     truncates to TF32 itself), lo = v - trunc(v) -> tcgen05.st as the next layer's A.  No shared-memory round trip;
-//   * kSlots tiles are in flight per CTA.  The MMA warp POLLS the slots (mbarrier.test_wait) and serves whichever is
-//     ready, so the slots drift apart and the tensor pipe, the TMEM path and the FP32 pipe overlap (a round-robin of
-//     blocking waits locks the slots in phase: measured 33 % tensor-pipe activity in cross_tc5.cu);
+//   * kSlots tiles are in flight per CTA, each with its OWN MMA-issuing warp blocked on that slot's operand barrier, so
+//     the slots drift apart and the tensor pipe, the TMEM path and the FP32 pipe overlap (one issuer serving the slots
+//     round-robin with blocking waits locks them in phase: 33 % tensor-pipe activity in cross_tc5.cu; one issuer
+//     polling them burns a quarter of the SM's issue slots: measured here, 1.06 ms);
 //   * rows are gathered by each epilogue warp for ITS 32 rows of the slot's next tile: indices two tiles ahead in a
 //     register, the 128-byte rows one tile ahead by cp.async into a staging buffer (8 lanes per row: one coalesced
 //     request per row); x0 then lives in registers for the whole chain;
@@ -36,7 +37,7 @@ using namespace tc5;
 
 constexpr int kSlots = 4;
 constexpr int kMaxSteps = 16;
-constexpr int kThreads = kSlots * 128 + 32;
+constexpr int kThreads = kSlots * 128 + kSlots * 32;   // 4 epilogue warps + 1 MMA-issuing warp per slot
 
 enum StepKind { kCross = 0, kCrossLast = 1, kDeepHidden = 2, kDeepOut = 3 };
 
@@ -65,16 +66,6 @@ struct DcnTc5Args {
   MlpParams mp;
 };
 
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t"
-      "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
 __device__ __forceinline__ void named_barrier(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -168,8 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc5_kernel(const DcnTc5Args a
       if (t >= tiles || r >= tile_rows) return -1;
       const int64_t m = t * tile_rows + r;
       if (m >= total_rows) return -1;
-      const int f = static_cast<int>(m % n_fields);
-      const int64_t row = load_index<IdxBits>(a.idx, m) + off_s[f];
+      const int64_t row = load_index<IdxBits>(a.idx, m) + off_s[r % n_fields];
       if (row < 0 || row >= a.rows) {
         report_oob(a.status, m);
         return -1;
@@ -188,6 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc5_kernel(const DcnTc5Args a
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    const float* fcw = fcw_s + (r < tile_rows ? r % n_fields : 0) * cat;   // a tile starts at a sample: field = r % fields
     const int64_t tile0 = (int64_t)blockIdx.x * kSlots + slot;
     gather(resolve(tile0));
     int rid_next = resolve(tile0 + stride);
@@ -221,9 +212,6 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc5_kernel(const DcnTc5Args a
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready(slot));
-      const int64_t m = tile * tile_rows + r;
-      const int f = (r < tile_rows && m < total_rows) ? static_cast<int>(m % n_fields) : 0;
-      const float* fcw = fcw_s + f * cat;
       float partial = 0.f;
       for (int t = 0; t < a.n_steps; ++t) {
         const Step st = a.steps[t];
@@ -295,35 +283,26 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc5_kernel(const DcnTc5Args a
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else {
-    // =========================== MMA issuer: polls the slots, serves whichever has its operand ready =================
-    int64_t tile[kSlots];
-    int step[kSlots];
-    uint32_t n_ready[kSlots];
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) {
-      tile[s] = (int64_t)blockIdx.x * kSlots + s;
-      step[s] = 0;
-      n_ready[s] = 0;
-    }
+    // =========================== MMA issuers: one warp per slot, blocked on ITS slot's operand ========================
+    // (one warp polling all slots burned a quarter of the SM's issue slots on mbarrier tests -- and starved the
+    //  epilogue warps of its scheduler, which every slot waits for; a round-robin of blocking waits locks the slots in
+    //  phase.  Per-slot issuers sleep in mbarrier.try_wait and the slots drift apart freely.)
+    const int s = warp - kSlots * 4;
     const uint32_t w_base = smem_u32(w_s);
-    for (;;) {
-      bool any = false, served = false;
-#pragma unroll
-      for (int s = 0; s < kSlots; ++s) {
-        if (tile[s] >= tiles) continue;
-        any = true;
-        if (!mbar_test(a_ready(s), n_ready[s] & 1)) continue;
-        served = true;
-        ++n_ready[s];
+    const uint32_t d = tmem_base + s * 96;
+    uint32_t n_ready = 0;
+    for (int64_t tile = (int64_t)blockIdx.x * kSlots + s; tile < tiles; tile += stride) {
+      for (int t = 0; t < a.n_steps; ++t) {
+        const Step st = a.steps[t];
+        mbar_wait(a_ready(s), n_ready & 1);
+        ++n_ready;
         tc_fence_after();
-        const Step st = a.steps[step[s]];
         if (elect_one()) {
           const uint32_t idesc = umma_idesc_tf32(st.npad);
           const uint32_t lbo = st.npad * 16;                                   // bytes between 16-byte K chunks
           const uint64_t b_hi0 = umma_desc(w_base + st.w_off * 4, lbo, 128);
           const uint64_t b_lo0 = b_hi0 + ((st.k * st.npad * 4) >> 4);
           const uint32_t step_u = (2 * lbo) >> 4;                              // one k-step = two chunks
-          const uint32_t d = tmem_base + s * 96;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             if (ks * 8 < st.k) {
@@ -337,13 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc5_kernel(const DcnTc5Args a
           umma_commit(d_full(s));
         }
         __syncwarp();
-        if (++step[s] == a.n_steps) {
-          step[s] = 0;
-          tile[s] += stride;
-        }
       }
-      if (!any) break;
-      if (!served) __nanosleep(32);   // leave the issue slots of this scheduler to its epilogue warps
     }
   }
   tc_fence_before();
