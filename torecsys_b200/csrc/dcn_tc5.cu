@@ -13,6 +13,9 @@
 //     not come from shared memory (SS form: ~40 cycles whatever N).  So: rows on M (128 per tile = floor(128 / fields)
 //     whole samples), every layer = 3 * K/8 MMAs (3xTF32: A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, fp32 accumulate) of N in
 //     {16, 32}, A from TMEM, W pre-split in shared memory;
+//   * the bias rides in the GEMM: every layer has one more k-step whose A columns are the constant [1, 0, .., 0] (written
+//     once per kernel into the slot's TMEM) and whose W rows hold [b_hi | b_lo]: two extra N/2-cycle MMAs replace an LDS +
+//     FADD per element in the epilogue, which is the issue-bound side;
 //   * a layer's epilogue (thread = row): tcgen05.ld D -> FP32 update -> raw value as the hi operand (the tensor core
 //     truncates to TF32 itself), lo = v - trunc(v) -> tcgen05.st as the next layer's A.  No shared-memory round trip;
 //   * kSlots tiles are in flight per CTA, each with its OWN MMA-issuing warp blocked on that slot's operand barrier, so
@@ -37,14 +40,15 @@ using namespace tc5;
 
 constexpr int kSlots = 4;
 constexpr int kMaxSteps = 16;
+constexpr int kSlotCols = 104;
 constexpr int kThreads = kSlots * 128 + kSlots * 32;   // 4 epilogue warps + 1 MMA-issuing warp per slot
 
 enum StepKind { kCross = 0, kCrossLast = 1, kDeepHidden = 2, kDeepOut = 3 };
 
 struct Step {
-  int w_off;      // float offset of the step's hi plane in the weight store ([hi|lo][K/4][npad][4])
-  int b_off;      // float offset of its (zero-padded) bias
-  int k, npad;    // K (multiple of 8) and N (16 or 32) of the MMAs
+  int w_off;      // float offset of the step's hi plane in the weight store ([hi|lo][(K + 8)/4][npad][4])
+  int b_off;      // (unused: the bias is row K of the weights)
+  int k, npad;    // K of the activations (multiple of 8; the weights have K + 8 rows) and N (16 or 32) of the MMAs
   int kind;
   int n_valid;    // outputs that exist (kDeepOut: the MLP's output width)
 };
@@ -110,17 +114,21 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc5_kernel(const DcnTc5Args a
     const float* w = cross ? a.cross_w + (size_t)layer * E * E : a.mp.w[layer];
     const float* b = cross ? a.cross_b + (size_t)layer * E : a.mp.b[layer];
     const int k_in = cross ? E : a.mp.dims[layer], n_out = cross ? E : a.mp.dims[layer + 1];
-    const int plane = st.k * st.npad;
+    const int kk = st.k + 8;                 // + the bias k-step: row K = bias, rows K+1 .. K+7 = 0
+    const int plane = kk * st.npad;
     for (int i = threadIdx.x; i < plane; i += blockDim.x) {
-      const int n = i / st.k, k = i - n * st.k;
-      const float v = (n < n_out && k < k_in) ? __ldg(w + (size_t)n * k_in + k) : 0.f;
+      const int n = i / kk, k = i - n * kk;
+      float v = 0.f;
+      if (n < n_out) {
+        if (k < k_in) v = __ldg(w + (size_t)n * k_in + k);
+        else if (k == st.k && b != nullptr) v = __ldg(b + n);
+      }
       const uint32_t hi = tf32_rna(v);
       const uint32_t lo = tf32_rna(v - __uint_as_float(hi));
       const int pos = ((k >> 2) * st.npad + n) * 4 + (k & 3);
       w_s[st.w_off + pos] = __uint_as_float(hi);
       w_s[st.w_off + plane + pos] = __uint_as_float(lo);
     }
-    for (int i = threadIdx.x; i < st.npad; i += blockDim.x) b_s[st.b_off + i] = (i < n_out && b != nullptr) ? __ldg(b + i) : 0.f;
   }
   for (int i = threadIdx.x; i < n_fields * cat; i += blockDim.x) fcw_s[i] = __ldg(a.fc_w + i);
   for (int i = threadIdx.x; i < n_fields; i += blockDim.x) off_s[i] = __ldg(a.offsets + i);
@@ -148,9 +156,9 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc5_kernel(const DcnTc5Args a
     // =========================== epilogue warps: slot = warp / 4, TMEM lane quarter = warp % 4 ====================
     const int slot = warp >> 2, q = warp & 3;
     const int r = q * 32 + lane;                                  // row of the tile = TMEM lane
-    // 96 columns per slot whatever E is: D [0, 32) | A hi [32, 64) | A lo [64, 96)  (a deep layer may be wider than E)
-    const uint32_t t_d = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + slot * 96;
-    const uint32_t t_hi = t_d + 32, t_lo = t_d + 64;
+    // kSlotCols columns per slot whatever E is: D [0, 32) | A hi [32, 64) | constant [64, 72) | A lo [72, 104)
+    const uint32_t t_d = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + slot * kSlotCols;
+    const uint32_t t_hi = t_d + 32, t_lo = t_d + 72;
     float* stage_w = stage_s + (size_t)warp * 32 * kRowPitch;
     const uint32_t stage_w_s = smem_u32(stage_w);
     constexpr int kChunks = E / 4;                                // 16-byte chunks per row
@@ -179,6 +187,13 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc5_kernel(const DcnTc5Args a
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     const float* fcw = fcw_s + (r < tile_rows ? r % n_fields : 0) * cat;   // a tile starts at a sample: field = r % fields
+    {   // the constant k-step of every layer: A columns [64, 72) = [1, 0, .., 0]  (the 8 columns behind are A lo, rewritten per layer)
+      uint32_t one[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) one[j] = j == 0 ? __float_as_uint(1.0f) : 0u;
+      tmem_st16(t_d + 64, one);
+      tmem_st_wait();
+    }
     const int64_t tile0 = (int64_t)blockIdx.x * kSlots + slot;
     gather(resolve(tile0));
     int rid_next = resolve(tile0 + stride);
@@ -215,7 +230,6 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc5_kernel(const DcnTc5Args a
       float partial = 0.f;
       for (int t = 0; t < a.n_steps; ++t) {
         const Step st = a.steps[t];
-        const float* bias = b_s + st.b_off;
         mbar_wait(d_full(slot), n_full & 1);
         ++n_full;
         tc_fence_after();
@@ -227,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc5_kernel(const DcnTc5Args a
             tmem_ld16(t_d + c, raw);
             float h[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) h[j] = fmaf(x0[c + j], __uint_as_float(raw[j]) + bias[c + j], x0[c + j]);
+            for (int j = 0; j < 16; ++j) h[j] = fmaf(x0[c + j], __uint_as_float(raw[j]), x0[c + j]);
             if (st.kind == kCross) {
               write_operand16(t_hi + c, t_lo + c, h);
             } else {
@@ -246,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc5_kernel(const DcnTc5Args a
               tmem_ld16(t_d + c, raw);
               float v[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + bias[c + j];
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
               if (st.kind == kDeepHidden) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -289,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc5_kernel(const DcnTc5Args a
     //  phase.  Per-slot issuers sleep in mbarrier.try_wait and the slots drift apart freely.)
     const int s = warp - kSlots * 4;
     const uint32_t w_base = smem_u32(w_s);
-    const uint32_t d = tmem_base + s * 96;
+    const uint32_t d = tmem_base + s * kSlotCols;
     uint32_t n_ready = 0;
     for (int64_t tile = (int64_t)blockIdx.x * kSlots + s; tile < tiles; tile += stride) {
       for (int t = 0; t < a.n_steps; ++t) {
@@ -301,18 +315,21 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc5_kernel(const DcnTc5Args a
           const uint32_t idesc = umma_idesc_tf32(st.npad);
           const uint32_t lbo = st.npad * 16;                                   // bytes between 16-byte K chunks
           const uint64_t b_hi0 = umma_desc(w_base + st.w_off * 4, lbo, 128);
-          const uint64_t b_lo0 = b_hi0 + ((st.k * st.npad * 4) >> 4);
+          const uint64_t b_lo0 = b_hi0 + (((st.k + 8) * st.npad * 4) >> 4);
           const uint32_t step_u = (2 * lbo) >> 4;                              // one k-step = two chunks
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             if (ks * 8 < st.k) {
 #pragma unroll
               for (int term = 0; term < 3; ++term) {   // 0: A_lo*B_hi, 1: A_hi*B_lo, 2: A_hi*B_hi
-                const uint32_t a_op = d + (term == 0 ? 64 : 32) + 8 * ks;
+                const uint32_t a_op = d + (term == 0 ? 72 : 32) + 8 * ks;
                 umma_tf32_ts(d, a_op, (term == 1 ? b_lo0 : b_hi0) + ks * step_u, idesc, (ks > 0 || term > 0) ? 1u : 0u);
               }
             }
           }
+          const uint32_t kb = (st.k >> 3) * step_u;    // the bias k-step: A = [1, 0, ..] (its lo plane is zero)
+          umma_tf32_ts(d, d + 64, b_lo0 + kb, idesc, 1u);
+          umma_tf32_ts(d, d + 64, b_hi0 + kb, idesc, 1u);
           umma_commit(d_full(s));
         }
         __syncwarp();
@@ -335,7 +352,7 @@ bool make_plan(int embed, int fields, int cross_layers, const MlpParams& mp, Pla
   int w = 0, b = 0, n = 0;
   for (int l = 0; l < cross_layers; ++l) {
     a.steps[n++] = Step{w, b, embed, embed, l + 1 < cross_layers ? kCross : kCrossLast, embed};
-    w += 2 * embed * embed;
+    w += 2 * (embed + 8) * embed;
     b += embed;
   }
   int k = embed;   // K of the next deep layer = padded width of the previous one
@@ -343,7 +360,7 @@ bool make_plan(int embed, int fields, int cross_layers, const MlpParams& mp, Pla
     const int out = mp.dims[l + 1], npad = out <= 16 ? 16 : 32;
     if (out < 1 || out > 32 || mp.dims[l] > k) return false;
     a.steps[n++] = Step{w, b, k, npad, l + 1 < mp.layers ? kDeepHidden : kDeepOut, out};
-    w += 2 * k * npad;
+    w += 2 * (k + 8) * npad;
     b += npad;
     k = npad;
   }
