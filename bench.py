@@ -317,11 +317,17 @@ def bench_other_configs(torch, timer, device, rank, peak, args):
         r.update({'workload': f'configs[2]: DeepAndCrossNetwork {NUM_FIELDS} fields x {rpf} rows, embed 32, 6 cross layers, '
                               f'MLP [32,16,8]->4, batch {b}',
                   'value': timer.world * b / (r['ms_per_step'] * 1e-3), 'unit': UNIT,
-                  'roofline': hbm_roofline(5308 * b, r['ms_per_step'], peak, 'dcn_tc_kernel<32,64>',
+                  'roofline': hbm_roofline(5308 * b, r['ms_per_step'], peak, 'dcn_tc5_kernel<32, 64>',
                                            recorded_traffic('dcn'),
                                            {'algorithmic_tflops': flops / (r['ms_per_step'] * 1e-3) / 1e12,
-                                            'note': 'compute bound (120 FLOP/B, FP32-exact 3xTF32): the HBM fraction is '
-                                                    'reported for completeness, the tensor pipe is the limiter'})})
+                                            'tensor': {'achieved': flops / (r['ms_per_step'] * 1e-3) / 1e12, 'peak': 1096.0,
+                                                       'unit': 'TFLOP/s', 'frac': flops / (r['ms_per_step'] * 1e-3) / 1e12 / 1096.0,
+                                                       'issued_frac': 3 * flops / (r['ms_per_step'] * 1e-3) / 1e12 / 1096.0},
+                                            'note': 'compute bound (120 FLOP/B, FP32-exact 3xTF32 on tcgen05 with the A '
+                                                    'operand in tensor memory, N = 32 / 16 per MMA): the HBM fraction is '
+                                                    'reported for completeness; `tensor` is measured against the dense '
+                                                    'kind::tf32 rate (tools/r2_probe.cu), the 3x split issues three times '
+                                                    'the algorithmic flops'})})
         out['dcn'] = r
         del w_emb, idx, o
     except Exception as ex:   # a failing secondary config must not take the headline line down

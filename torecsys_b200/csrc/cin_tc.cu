@@ -49,8 +49,10 @@ __global__ void __launch_bounds__(256) cin_tc_transpose_kernel(const float* __re
 }
 
 // W (C, N*H) -> wp[q = yc*N + x][hi|lo][kc 0..3][n 0..npad-1][4 floats]  with k' = q*16 + kc*4 + j,  y = yc*16 + kc*4 + j
+// fold != 0 (layer 0, where h = x0 and z[x, y] = z[y, x]): the pair (x, y) is kept only for y >= x, with the weight
+// W[c, x, y] + W[c, y, x] (W[c, x, x] on the diagonal); the kernel then skips the chunks that lie below the diagonal.
 __global__ void __launch_bounds__(256) cin_tc_prep_weights_kernel(const float* __restrict__ w, int c_begin, int c_eff, int fields,
-                                                                  int h_prev, int hp, int npad,
+                                                                  int h_prev, int hp, int npad, int fold,
                                                                   float* __restrict__ wp) {
   const int chunks = (hp / 16) * fields;
   const int64_t items = (int64_t)chunks * 4 * npad * 4;
@@ -62,7 +64,12 @@ __global__ void __launch_bounds__(256) cin_tc_prep_weights_kernel(const float* _
     const int yc = q / fields, xf = q - yc * fields;
     const int y = yc * 16 + kc * 4 + j;
     float v = 0.f;
-    if (n < c_eff && y < h_prev) v = __ldg(w + (int64_t)(c_begin + n) * fields * h_prev + xf * h_prev + y);
+    if (n < c_eff && y < h_prev) {
+      const float* wc = w + (int64_t)(c_begin + n) * fields * h_prev;
+      if (!fold) v = __ldg(wc + xf * h_prev + y);
+      else if (y > xf) v = __ldg(wc + xf * h_prev + y) + __ldg(wc + y * h_prev + xf);
+      else if (y == xf) v = __ldg(wc + xf * h_prev + y);
+    }
     const uint32_t hi = tf32_rna(v);
     const uint32_t lo = tf32_rna(v - __uint_as_float(hi));
     const int64_t base = (int64_t)q * (2 * 4 * npad * 4);
@@ -85,6 +92,7 @@ struct CinTcArgs {
   int n_direct, hid_begin, hid_count, hp_next;
   int pool_off, pooled_width, act, b_stages;
   int h_pitch, k_valid;    // row pitch of h in floats and its valid columns (loads beyond read as zero); CIN: both = hp
+  int fold;                // layer 0 of a CIN (h == x0): only the chunks with some y >= x are walked (see the weight prep)
   int c_total;             // gridDim.y > 1: channel blocks of `c_block` over c_total channels, one block per blockIdx.y
   int c_block;
   int64_t wp_pass_stride;  // floats between the prepared weights of consecutive channel blocks
@@ -149,7 +157,10 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
 
   const int64_t tiles = (a.m_rows + kTileM - 1) / kTileM;
   const int ychunks = a.hp / 16;
-  const int chunks = ychunks * a.fields;   // K' / 16
+  // fields walked with y-chunk yc: all of them, or (folded layer 0) those with x <= the chunk's last y
+  auto x_count = [&](int yc) { return a.fold ? (16 * yc + 16 < a.fields ? 16 * yc + 16 : a.fields) : a.fields; };
+  int chunks = 0;                          // K' / 16
+  for (int yc = 0; yc < ychunks; ++yc) chunks += x_count(yc);
   // Every CTA walks the K loop from its own starting point (the sum is order independent): otherwise all 148 CTAs
   // stream the SAME weight chunk from L2 at the same moment and hot-spot a few L2 slices.
   const int yc_rot = blockIdx.x % ychunks, x_rot = (blockIdx.x * 5) % a.fields;
@@ -188,8 +199,10 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
 #pragma unroll
         for (int j = 0; j < 16; ++j) hreg[j] = hbuf[p][j];
         load_h(hbuf[p], y0 + p + kPF);
-        for (int xi = 0; xi < a.fields; ++xi) {
-          const int xf = xi + x_rot < a.fields ? xi + x_rot : xi + x_rot - a.fields;
+        const int yc_now = y0 + p + yc_rot < ychunks ? y0 + p + yc_rot : y0 + p + yc_rot - ychunks;
+        const int xn = x_count(yc_now), xr = x_rot % xn;
+        for (int xi = 0; xi < xn; ++xi) {
+          const int xf = xi + xr < xn ? xi + xr : xi + xr - xn;
           mbar_wait(empty_a(sa), pa ^ 1);   // stage free (first pass: passes immediately)
           const float xv = x0_s[xf * kTileM + r];
           if (kATmem) {
@@ -338,10 +351,11 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
     int sb = 0;
     uint32_t pb = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      for (int i = 0; i < chunks; ++i) {
-        const int yci = i / a.fields, xi = i - yci * a.fields;   // same walk as the producers
+      for (int yci = 0; yci < ychunks; ++yci) {               // same walk as the producers
         const int yc = yci + yc_rot < ychunks ? yci + yc_rot : yci + yc_rot - ychunks;
-        const int xf = xi + x_rot < a.fields ? xi + x_rot : xi + x_rot - a.fields;
+        const int xn = x_count(yc), xr = x_rot % xn;
+        for (int xi = 0; xi < xn; ++xi) {
+        const int xf = xi + xr < xn ? xi + xr : xi + xr - xn;
         const int q = yc * a.fields + xf;
         mbar_wait(empty_b(sb), pb ^ 1);
         if (lane == 0) {
@@ -352,6 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
         }
         __syncwarp();
         if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
+        }
       }
     }
   }
@@ -441,8 +456,12 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
     const int c_eff = (is_direct || last) ? hl : 2 * hl;
     const int npad = round_up(c_eff, 32);
     const int64_t w_items = (int64_t)(hp / 16) * fields * 2 * 4 * npad * 4;
+    // layer 0 contracts x0 with itself: z[x, y] = z[y, x], so only y >= x is walked with the two weights added
+    // (K 39 x 48 -> 87 of 117 chunks at 39 fields).  TRS_CIN_NO_FOLD=1 switches it off (A/B measurements).
+    static const bool no_fold = getenv("TRS_CIN_NO_FOLD") != nullptr;
+    const int fold = (l == 0 && !no_fold) ? 1 : 0;
     cin_tc_prep_weights_kernel<<<grid_for(w_items / 2, 256, 8), 256, 0, s>>>(conv_w[l], 0, c_eff, fields, h_prev, hp,
-                                                                             npad, wp);
+                                                                             npad, fold, wp);
     rc = check_launch("cin_tc_prep_weights_kernel");
     if (rc != TRS_OK) return rc;
     CinTcArgs a{};
@@ -455,7 +474,7 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
     a.hid_count = last ? 0 : hl;
     a.hp_next = round_up(hl, 16);
     a.pool_off = pool_off; a.pooled_width = p.pooled_width; a.act = activation;
-    a.h_pitch = hp; a.k_valid = hp;
+    a.h_pitch = hp; a.k_valid = hp; a.fold = fold;
     const bool a_tmem = npad <= 128;   // accumulators leave 256 TMEM columns free: A operand goes to tensor memory
     const size_t a_stage = 2 * 4 * kTileM * 16, b_stage = (size_t)2 * 4 * npad * 16;
     const size_t fixed = (a_tmem ? 0 : kAStages * a_stage) + (size_t)fields * kTileM * 4 + 2 * npad * 4 +
@@ -508,7 +527,7 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
     const int c_cnt = c_dim - c0 < block ? c_dim - c0 : block;
     const int npad = round_up(c_cnt, 32);
     const int64_t w_items = (int64_t)(kp / 16) * 2 * 4 * npad * 4;
-    cin_tc_prep_weights_kernel<<<grid_for(w_items / 2, 256, 8), 256, 0, s>>>(w, c0, c_cnt, 1, k_dim, kp, npad,
+    cin_tc_prep_weights_kernel<<<grid_for(w_items / 2, 256, 8), 256, 0, s>>>(w, c0, c_cnt, 1, k_dim, kp, npad, 0,
                                                                              wp + (size_t)pass * w_floats);
     rc = check_launch("cin_tc_prep_weights_kernel");
   }

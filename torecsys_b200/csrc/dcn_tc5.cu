@@ -307,16 +307,17 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc5_kernel(const DcnTc5Args a
     uint32_t n_ready = 0;
     for (int64_t tile = (int64_t)blockIdx.x * kSlots + s; tile < tiles; tile += stride) {
       for (int t = 0; t < a.n_steps; ++t) {
+        // everything the MMAs need is computed BEFORE the wait: after the wake-up only the issue remains
         const Step st = a.steps[t];
+        const uint32_t idesc = umma_idesc_tf32(st.npad);
+        const uint32_t lbo = st.npad * 16;                                   // bytes between 16-byte K chunks
+        const uint64_t b_hi0 = umma_desc(w_base + st.w_off * 4, lbo, 128);
+        const uint64_t b_lo0 = b_hi0 + (((st.k + 8) * st.npad * 4) >> 4);
+        const uint32_t step_u = (2 * lbo) >> 4;                              // one k-step = two chunks
         mbar_wait(a_ready(s), n_ready & 1);
         ++n_ready;
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t idesc = umma_idesc_tf32(st.npad);
-          const uint32_t lbo = st.npad * 16;                                   // bytes between 16-byte K chunks
-          const uint64_t b_hi0 = umma_desc(w_base + st.w_off * 4, lbo, 128);
-          const uint64_t b_lo0 = b_hi0 + (((st.k + 8) * st.npad * 4) >> 4);
-          const uint32_t step_u = (2 * lbo) >> 4;                              // one k-step = two chunks
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             if (ks * 8 < st.k) {
