@@ -25,5 +25,8 @@ from .models_more import (AttentionalFactorizationMachineModel,  # noqa: F401
                           ProductNeuralNetworkModel)
 from .ops import check_index_errors, set_index_check  # noqa: F401
 from .patch import convert, patch_torecsys, unpatch_torecsys  # noqa: F401
+from . import dispatch  # noqa: F401,E402
+
+dispatch.register()   # torch.ops.torecsys_b200.* (torch.library.custom_op: visible to torch.compile / export)
 
 __version__ = '0.1.0'
