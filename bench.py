@@ -474,6 +474,36 @@ def bench_sharded(torch, dist, timer, device, rank, world, args):
     except Exception as ex:
         out['ffm'] = {'error': f'{type(ex).__name__}: {ex}'}
     torch.cuda.empty_cache()
+    # ---- configs[4] again, sharded along the EMBEDDING dimension: no looked-up vector crosses NVLink ------------------
+    try:
+        note('configs[4] embed-sharded tables')
+        e, rpf4, b_all = 16, 657_472, 262_144
+        rows4 = NUM_FIELDS * rpf4
+        model = sh.EmbedShardedFFM(e, [rpf4] * NUM_FIELDS)
+        bound = (6.0 / (rows4 + e)) ** 0.5
+        model.packed.uniform_(-bound, bound)
+        idx = [torch.randint(0, rpf4, (b_all // world, NUM_FIELDS), generator=igen, dtype=torch.int64).to(device)
+               for _ in range(4)]
+        r = timer.run(lambda i: model(idx[i % 4]), steps=10, repeats=7)
+        ops.check_index_errors()
+        plan = model.plan
+        lo, hi = plan.part_slice(rank, b_all)
+        r.update({'workload': f'configs[4]: FieldAwareFactorizationMachine {NUM_FIELDS} tables x {rows4} rows (1.0 B rows) '
+                              f'sharded over {world} GPUs along the embedding dimension: {plan.cols} of 16 columns of every '
+                              f'table per GPU ({model.packed.numel() * 4 / 1e9:.1f} GB each), global batch {b_all}',
+                  'value': b_all / (r['ms_per_step'] * 1e-3), 'unit': UNIT,
+                  'scheme': f'<a, b> = sum over column groups: {plan.groups} column groups x {plan.parts} batch parts; '
+                            'every rank runs the single-GPU interleaved kernel (ffm_interleaved_kernel) on its columns; '
+                            'NCCL all-gather of the indices before, NCCL reduce-scatter of the partial logits after; no '
+                            'looked-up vector crosses NVLink',
+                  'nvlink_gbs_per_gpu': ((world - 1) * (b_all // world) * NUM_FIELDS * 8 + b_all * 4) /
+                                        (r['ms_per_step'] * 1e-3) / 1e9,
+                  'hbm_gbs_per_gpu': (hi - lo) * NUM_FIELDS * (NUM_FIELDS * plan.cols * 4 + 4) / (r['ms_per_step'] * 1e-3) / 1e9})
+        out['ffm_embed_sharded'] = r
+        del model, idx
+    except Exception as ex:
+        out['ffm_embed_sharded'] = {'error': f'{type(ex).__name__}: {ex}'}
+    torch.cuda.empty_cache()
     # ---- configs[1] with the ONE shared table row-sharded (row g on rank g % world) -----------------------------------
     try:
         note('row-sharded DeepFM table')

@@ -15,8 +15,8 @@ def main():
     from oracle import restated as R
     from tests.oracle_run import normwise_err
     from torecsys_b200 import ops, synth
-    from torecsys_b200.sharded import (ShardedFFM, ShardedFFMBlocks, ShardedFieldAwareTables, ShardedInterleavedTables,
-                                       shard_batch)
+    from torecsys_b200.sharded import (EmbedShardedFFM, ShardedFFM, ShardedFFMBlocks, ShardedFieldAwareTables,
+                                       ShardedInterleavedTables, shard_batch)
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -71,6 +71,20 @@ def main():
     flag = torch.tensor([1 if raised else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     assert int(flag.item()) == 1, 'block exchange: out-of-range lookup was not reported on every rank'
+    ops.check_index_errors()
+    # embedding-dimension sharding: every rank holds its columns of ALL tables, no vector crosses NVLink
+    cols = EmbedShardedFFM(e, fs).fill_from([torch.from_numpy(t) for t in full], w_feat, bias)
+    for dt in (torch.int64, torch.int32):
+        got4 = cols(idx[sl].to(dev).to(dt))
+        err = max(err, normwise_err(got4.cpu().numpy(), want2))
+    try:
+        cols(bad.to(dev))
+        raised = False
+    except IndexError:
+        raised = True
+    flag = torch.tensor([1 if raised else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    assert int(flag.item()) == 1, 'embed-sharded FFM: out-of-range lookup was not reported on every rank'
     ops.check_index_errors()
     remote = sum(1 for t in range(n) if tables.plan.owner(t) != rank)
     ok = torch.tensor([1 if err <= 1e-5 else 0], device=dev)

@@ -68,3 +68,24 @@ def test_row_shard_plan_single_process():
     assert [q.rows_of(r) for r in range(4)] == [3, 3, 2, 2] and list(q.global_rows(3)) == [3, 7]
     with pytest.raises(ValueError):
         RowShardPlan(0, 2)
+
+
+def test_embed_shard_plan_single_process():
+    from torecsys_b200.sharded import EmbedShardPlan
+    p = EmbedShardPlan(16, 8)
+    assert (p.groups, p.cols, p.parts) == (4, 4, 2) and p.memory_fraction() == 0.25
+    # every (column, sample) of the batch is covered by exactly one rank
+    seen = {}
+    for r in range(8):
+        lo, hi = p.part_slice(r, 1001)
+        for c in range(*p.columns(r).indices(16)):
+            for s in (lo, hi - 1):
+                seen[(c, s)] = seen.get((c, s), 0) + 1
+        assert p.columns(r) == slice(4 * (r % 4), 4 * (r % 4) + 4)
+    assert set(seen.values()) == {1}
+    assert sum(hi - lo for lo, hi in (p.part_slice(r, 1001) for r in (0, 4))) == 1001
+    q = EmbedShardPlan(32, 8)
+    assert (q.groups, q.cols, q.parts) == (8, 4, 1)
+    assert EmbedShardPlan(16, 2).cols == 8 and EmbedShardPlan(4, 8).parts == 8
+    with pytest.raises(ValueError):
+        EmbedShardPlan(16, 0)

@@ -10,9 +10,12 @@
 // A sample then needs N contiguous chunks of N*E*4 + 4 bytes (2.5 KB at N = 39, E = 16) instead of N*(N-1) scattered
 // rows, and each chunk is ONE bulk copy of the TMA unit (cp.async.bulk global -> shared, completion on an mbarrier).
 //
-// Kernel: persistent CTA per SM, two sample-sized stages in shared memory.  Warp 8 is the producer: it resolves the
-// row ids of the next sample, waits for the stage to be released, writes the finished sample's logit (fixed-order sum
-// of the eight consumer partials + bias) and issues the N bulk copies.  Warps 0-7 consume: with A_f = the chunk of
+// Kernel: persistent CTA per SM, a ring of sample-sized stages in shared memory (2 at 39 x 16, up to 8 for narrower
+// rows).  Warps 8-11 are producers: each resolves the row ids of ITS fields (f = warp, warp + 4, ..) of the next sample,
+// waits for the stage to be released and issues its bulk copies -- a warp-wide cp.async.bulk is issued lane by lane
+// (~60 cycles each), so one producer warp bounds narrow rows at ~4 000 cycles per sample (measured: 4 columns per table
+// 1.82 ms per 131 072 samples); producer 0 also writes the finished sample's logit (fixed-order sum of the eight
+// consumer partials + bias).  Warps 0-7 consume: with A_f = the chunk of
 // field f, logit = sum_{i<j} <A_j[i], A_i[j]> + sum_f A_f[N*E]; work item = (pair, 16-byte piece), both operands
 // read from shared memory with 128-bit loads (chunk pitch = 64 mod 128 bytes: conflict-free across the pairs of a warp).
 #include "tc5.cuh"
@@ -28,12 +31,15 @@ using tc5::mbar_wait;
 using tc5::smem_u32;
 
 constexpr int kConsumers = 8;
-constexpr int kThreads = (kConsumers + 1) * 32;
+constexpr int kProducers = 4;
+constexpr int kMaxStages = 8;
+constexpr int kThreads = (kConsumers + kProducers) * 32;
 
 struct Layout {
   int pitch_floats;   // row-id pitch of the packed table (multiple of 32 floats)
   int copy_bytes;     // bytes one bulk copy moves: the N rows + the first-order weight, rounded up to 16
   int stage_pitch;    // floats between two chunks in shared memory (bytes = 64 mod 128)
+  int stages;         // samples in flight
   size_t smem_bytes;
 };
 
@@ -46,7 +52,12 @@ inline Layout layout_for(int fields, int embed) {
   if (sp - 128 >= l.copy_bytes) sp -= 128;
   l.stage_pitch = sp / 4;
   const int pairs = fields * (fields - 1) / 2;
-  l.smem_bytes = (size_t)2 * fields * sp + (size_t)((pairs + 1) / 2 * 2) * sizeof(uint16_t) * 2 + 128;
+  const size_t fixed = (size_t)((pairs + 1) / 2 * 2) * sizeof(uint16_t) * 2 + 8 + 2 * kMaxStages * 8 +
+                       kMaxStages * kConsumers * 4 + 64;
+  const size_t stage = (size_t)fields * sp;
+  int st = static_cast<int>(((size_t)kMaxDynSmem - fixed) / stage);
+  l.stages = st > kMaxStages ? kMaxStages : st;
+  l.smem_bytes = (size_t)(l.stages > 0 ? l.stages : 2) * stage + fixed;
   return l;
 }
 
@@ -77,21 +88,21 @@ __global__ void __launch_bounds__(kThreads, 1) ffm_interleaved_kernel(const void
                                                                       int64_t batch, int fields, int embed,
                                                                       const float* __restrict__ packed, int64_t rows,
                                                                       int pitch_floats, int copy_bytes, int stage_pitch,
-                                                                      const float* __restrict__ bias,
+                                                                      int stages, const float* __restrict__ bias,
                                                                       float* __restrict__ logits, int32_t* status) {
   extern __shared__ __align__(128) unsigned char fi_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pairs = fields * (fields - 1) / 2;
   float* stage0 = reinterpret_cast<float*>(fi_smem);
   const size_t stage_floats = (size_t)fields * stage_pitch;
-  unsigned char* tail = fi_smem + 2 * stage_floats * sizeof(float);
+  unsigned char* tail = fi_smem + (size_t)stages * stage_floats * sizeof(float);
   uint16_t* pair_i = reinterpret_cast<uint16_t*>(tail);
   uint16_t* pair_j = pair_i + (pairs + 1) / 2 * 2;
   unsigned char* ctl = reinterpret_cast<unsigned char*>(pair_j + (pairs + 1) / 2 * 2);
   ctl = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ctl) + 7) & ~uintptr_t(7));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ctl);            // full[2], empty[2]
-  float* part = reinterpret_cast<float*>(bars + 4);             // [2][kConsumers]
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ctl);            // full[kMaxStages], empty[kMaxStages]
+  float* part = reinterpret_cast<float*>(bars + 2 * kMaxStages);   // [kMaxStages][kConsumers]
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
 
   for (int p = threadIdx.x; p < pairs; p += kThreads) {
     int i, j;
@@ -100,10 +111,10 @@ __global__ void __launch_bounds__(kThreads, 1) ffm_interleaved_kernel(const void
     pair_j[p] = static_cast<uint16_t>(j);
   }
   if (threadIdx.x == 0) {
-    mbar_init(full0, 1);
-    mbar_init(full0 + 8, 1);
-    mbar_init(empty0, kConsumers);
-    mbar_init(empty0 + 8, kConsumers);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full0 + 8 * s, kProducers);
+      mbar_init(empty0 + 8 * s, kConsumers);
+    }
     tc5::fence_barrier_init();
   }
   __syncthreads();
@@ -111,10 +122,13 @@ __global__ void __launch_bounds__(kThreads, 1) ffm_interleaved_kernel(const void
   const int64_t first = blockIdx.x, step = gridDim.x;
   const int64_t mine = first < batch ? (batch - first + step - 1) / step : 0;   // samples of this CTA
 
-  if (warp == kConsumers) {
-    // ------------------------------------------------------------------ producer
+  if (warp >= kConsumers) {
+    // ------------------------------------------------------------------ producers: warp j takes the fields j, j + P, ..
+    const int pw = warp - kConsumers;
+    const int f = pw + lane * kProducers;                    // this lane's field (lanes beyond the fields idle)
+    const int my_fields = pw < fields ? (fields - pw + kProducers - 1) / kProducers : 0;
     const float bias_v = bias != nullptr ? __ldg(bias) : 0.f;
-    auto resolve = [&](int64_t k, int f) -> int64_t {
+    auto resolve = [&](int64_t k) -> int64_t {
       if (k >= mine || f >= fields) return 0;
       const int64_t pos = (first + k * step) * fields + f;
       int64_t r = load_index<IdxBits>(idx, pos) + __ldg(offsets + f);
@@ -124,10 +138,9 @@ __global__ void __launch_bounds__(kThreads, 1) ffm_interleaved_kernel(const void
       }
       return r;
     };
-    auto finish = [&](int64_t k) {   // sample k's partial sums are complete: one logit, fixed summation order
-      const int s = static_cast<int>(k & 1);
-      mbar_wait(empty0 + 8 * s, static_cast<uint32_t>((k >> 1) & 1));
-      if (lane == 0) {
+    auto finish = [&](int64_t k, int s, uint32_t wrap) {   // sample k's partial sums are complete (stage s)
+      mbar_wait(empty0 + 8 * s, wrap & 1);
+      if (pw == 0 && lane == 0) {                          // one logit, fixed summation order
         float v = bias_v;
 #pragma unroll
         for (int w = 0; w < kConsumers; ++w) v += part[s * kConsumers + w];
@@ -135,32 +148,31 @@ __global__ void __launch_bounds__(kThreads, 1) ffm_interleaved_kernel(const void
       }
       __syncwarp();
     };
-    int64_t ra = resolve(0, lane), rb = resolve(0, lane + 32);
+    int64_t r = resolve(0);
+    int s = 0;
+    uint32_t wrap = 0;
     for (int64_t k = 0; k < mine; ++k) {
-      const int s = static_cast<int>(k & 1);
-      if (k >= 2) finish(k - 2);
+      if (wrap > 0) finish(k - stages, s, wrap - 1);
       const uint32_t bar = full0 + 8 * s;
-      if (lane == 0) mbar_expect_tx(bar, static_cast<uint32_t>(fields) * copy_bytes);
+      if (lane == 0) mbar_expect_tx(bar, static_cast<uint32_t>(my_fields) * copy_bytes);
       __syncwarp();
-      const uint32_t dst = smem_u32(stage0 + s * stage_floats);
-      if (lane < fields)
-        bulk_g2s(dst + lane * stage_pitch * 4, packed + ra * pitch_floats, copy_bytes, bar);
-      if (lane + 32 < fields)
-        bulk_g2s(dst + (lane + 32) * stage_pitch * 4, packed + rb * pitch_floats, copy_bytes, bar);
-      ra = resolve(k + 1, lane);
-      rb = resolve(k + 1, lane + 32);
+      if (f < fields)
+        bulk_g2s(smem_u32(stage0 + s * stage_floats) + f * stage_pitch * 4, packed + r * pitch_floats, copy_bytes, bar);
+      r = resolve(k + 1);
+      if (++s == stages) { s = 0; ++wrap; }
     }
-    if (mine >= 2) finish(mine - 2);
-    if (mine >= 1) finish(mine - 1);
+    for (int64_t k = mine > stages ? mine - stages : 0; k < mine; ++k)
+      finish(k, static_cast<int>(k % stages), static_cast<uint32_t>(k / stages));
   } else {
     // ------------------------------------------------------------------ consumers
     const int lpp = embed >> 2;                 // lanes per pair: one 16-byte piece each (power of two)
     const int lpp_shift = 31 - __clz(lpp);
     const int items = pairs << lpp_shift;
     const int first_at = fields * embed;
+    int s = 0;
+    uint32_t wrap = 0;
     for (int64_t k = 0; k < mine; ++k) {
-      const int s = static_cast<int>(k & 1);
-      mbar_wait(full0 + 8 * s, static_cast<uint32_t>((k >> 1) & 1));
+      mbar_wait(full0 + 8 * s, wrap & 1);
       const float* A = stage0 + s * stage_floats;
       float acc = 0.f;
       for (int item = warp * 32 + lane; item < items; item += kConsumers * 32) {
@@ -179,6 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffm_interleaved_kernel(const void
       if (lane == 0) part[s * kConsumers + warp] = acc;
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + 8 * s);
+      if (++s == stages) { s = 0; ++wrap; }
     }
   }
 }
@@ -215,7 +228,7 @@ extern "C" int trs_ffm_model_forward_interleaved(const void* idx, int idx_bits, 
                   "trs_ffm_model_forward_interleaved: embed must be a power of two in [4, 128] (got %d)", embed);
   TRS_UNSUPPORTED(!aligned16(packed), "trs_ffm_model_forward_interleaved: packed table must be 16-byte aligned");
   const Layout l = layout_for(fields, embed);
-  TRS_UNSUPPORTED(l.smem_bytes > (size_t)kMaxDynSmem,
+  TRS_UNSUPPORTED(l.stages < 2,
                   "trs_ffm_model_forward_interleaved: two samples of %d x %d do not fit shared memory", fields, embed);
   if (batch == 0) return TRS_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -223,13 +236,13 @@ extern "C" int trs_ffm_model_forward_interleaved(const void* idx, int idx_bits, 
   if (idx_bits == 64) {
     TRS_SMEM_OPT_IN(ffm_interleaved_kernel<64>);
     ffm_interleaved_kernel<64><<<grid, kThreads, l.smem_bytes, s>>>(idx, offsets, batch, fields, embed, packed, rows,
-                                                                   l.pitch_floats, l.copy_bytes, l.stage_pitch, bias,
-                                                                   logits, status);
+                                                                   l.pitch_floats, l.copy_bytes, l.stage_pitch, l.stages,
+                                                                   bias, logits, status);
   } else {
     TRS_SMEM_OPT_IN(ffm_interleaved_kernel<32>);
     ffm_interleaved_kernel<32><<<grid, kThreads, l.smem_bytes, s>>>(idx, offsets, batch, fields, embed, packed, rows,
-                                                                   l.pitch_floats, l.copy_bytes, l.stage_pitch, bias,
-                                                                   logits, status);
+                                                                   l.pitch_floats, l.copy_bytes, l.stage_pitch, l.stages,
+                                                                   bias, logits, status);
   }
   return check_launch("ffm_interleaved_kernel");
 }

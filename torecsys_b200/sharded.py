@@ -340,3 +340,112 @@ class ShardedFFMBlocks:
         return out
 
     __call__ = forward
+
+
+class EmbedShardPlan:
+    """Partition of the EMBEDDING DIMENSION of field-aware tables over the ranks: <a, b> = sum over column groups of
+    <a[cols], b[cols]>, so when every rank holds the same columns of ALL tables, a dot-product model needs no exchange
+    of looked-up vectors at all -- only the row ids in and the partial logits out.  `groups` column groups of
+    embed / groups >= 4 columns (one 16-byte piece, what trs_ffm_model_forward_interleaved takes); when the world is
+    larger than that, world / groups ranks share a column group and split the batch between them."""
+
+    def __init__(self, embed_size: int, world_size: int):
+        if embed_size <= 0 or world_size <= 0:
+            raise ValueError('embed_size and world_size must be positive')
+        groups = 1
+        for g in range(1, world_size + 1):
+            if world_size % g == 0 and embed_size % g == 0 and (embed_size // g) % 4 == 0:
+                groups = g
+        self.embed_size, self.world_size = embed_size, world_size
+        self.groups = groups
+        self.cols = embed_size // groups          # columns per rank
+        self.parts = world_size // groups         # ranks sharing a column group = batch parts
+
+    def group_of(self, rank: int) -> int:
+        return rank % self.groups
+
+    def part_of(self, rank: int) -> int:
+        return rank // self.groups
+
+    def columns(self, rank: int) -> slice:
+        g = self.group_of(rank)
+        return slice(g * self.cols, (g + 1) * self.cols)
+
+    def part_slice(self, rank: int, batch_all: int):
+        """Samples (of the all-gathered batch) whose partial logits `rank` computes."""
+        per = (batch_all + self.parts - 1) // self.parts
+        lo = min(self.part_of(rank) * per, batch_all)
+        return lo, min(lo + per, batch_all)
+
+    def memory_fraction(self) -> float:
+        """Share of the tables' bytes one rank holds."""
+        return 1.0 / self.groups
+
+
+class EmbedShardedFFM:
+    """FieldAwareFactorizationMachineModel.forward (field_aware_factorization_machine.py:39-81) with the tables sharded
+    along the embedding dimension (EmbedShardPlan): rank r keeps columns plan.columns(r) of every table as the
+    interleaved shadow of the single-GPU kernel (csrc/ffm_interleaved.cu, one bulk copy per row id) and runs THAT
+    kernel; no looked-up vector crosses NVLink.
+      1. all-gather of the (B / W, N) index slices (NCCL);
+      2. the single-GPU interleaved kernel on the rank's columns for the rank's part of the samples;
+      3. reduce-scatter (sum) of the (B,) partial logits (NCCL).
+    The first-order weights and the bias ride with column group 0.  All ranks must pass slices of the same length."""
+
+    def __init__(self, embed_size: int, field_sizes: Sequence[int], group: Optional[dist.ProcessGroup] = None,
+                 device: Optional[torch.device] = None):
+        if not dist.is_initialized():
+            raise RuntimeError('EmbedShardedFFM needs torch.distributed (NCCL) to be initialised')
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.device = device if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.num_fields = len(field_sizes)
+        self.rows = int(sum(field_sizes))
+        self.plan = EmbedShardPlan(embed_size, self.world)
+        if not ops.ffm_interleaved_supported(self.num_fields, self.plan.cols):
+            raise NotImplementedError(f'{self.num_fields} fields x {self.plan.cols} columns: not a shape of the '
+                                      'interleaved FFM kernel')
+        self.offsets = _reference_offsets(field_sizes).rename(None).reshape(-1).to(self.device)
+        pitch = int(ops._cabi.load().trs_ffm_interleaved_pitch(self.num_fields, self.plan.cols))
+        self.packed = torch.zeros((self.rows, pitch), dtype=torch.float32, device=self.device)
+        self.bias = torch.zeros(1, device=self.device)
+        self._buf = {}
+
+    def fill_from(self, tables: Sequence[torch.Tensor], w_feat: torch.Tensor, bias: torch.Tensor):
+        """tables: the N full (rows, embed) tables (any device); this rank keeps its columns.  Collective (barrier)."""
+        cols = self.plan.columns(self.rank)
+        mine = [t[:, cols].contiguous().to(self.device) for t in tables]
+        first = self.plan.group_of(self.rank) == 0
+        self.packed = ops.ffm_pack_tables(mine, w_feat.to(self.device) if first else None)
+        self.bias = bias.to(self.device).reshape(-1).clone() if first else torch.zeros(1, device=self.device)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+        return self
+
+    def forward(self, idx_local: torch.Tensor) -> torch.Tensor:
+        b_local, n = idx_local.shape
+        b_all = b_local * self.world
+        key = (b_local, n, idx_local.dtype)
+        if key not in self._buf:
+            self._buf = {key: (torch.empty((b_all, n), dtype=idx_local.dtype, device=self.device),
+                               torch.zeros((b_all,), dtype=torch.float32, device=self.device))}
+        idx_all, partial = self._buf[key]
+        dist.all_gather_into_tensor(idx_all, idx_local.contiguous(), group=self.group)
+        lo, hi = self.plan.part_slice(self.rank, b_all)
+        failed = None
+        try:
+            ops.ffm_model_interleaved(idx_all[lo:hi], self.offsets, self.packed, n, self.plan.cols, self.bias,
+                                      out=partial[lo:hi].view(-1, 1))
+        except IndexError as ex:      # sync index checks: every rank must raise together (see below)
+            failed = ex
+        out = torch.empty((b_local, 1), dtype=torch.float32, device=self.device)
+        dist.reduce_scatter_tensor(out.view(-1), partial, op=dist.ReduceOp.SUM, group=self.group)
+        if ops.index_check_mode() == 'sync':
+            seen = torch.tensor([1 if failed is not None else 0], device=self.device)
+            dist.all_reduce(seen, op=dist.ReduceOp.SUM, group=self.group)
+            if int(seen.item()) != 0:
+                raise IndexError(str(failed) if failed is not None else 'index out of range in self (on another rank)')
+        return out
+
+    __call__ = forward
