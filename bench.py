@@ -494,9 +494,9 @@ def bench_sharded(torch, dist, timer, device, rank, world, args):
                   'value': b_all / (r['ms_per_step'] * 1e-3), 'unit': UNIT,
                   'scheme': f'<a, b> = sum over column groups: {plan.groups} column groups x {plan.parts} batch parts; '
                             'every rank runs the single-GPU interleaved kernel (ffm_interleaved_kernel) on its columns; '
-                            'NCCL all-gather of the indices before, NCCL reduce-scatter of the partial logits after; no '
+                            'NCCL all-gather of int32 row ids before, NCCL reduce-scatter of the partial logits after; no '
                             'looked-up vector crosses NVLink',
-                  'nvlink_gbs_per_gpu': ((world - 1) * (b_all // world) * NUM_FIELDS * 8 + b_all * 4) /
+                  'nvlink_gbs_per_gpu': ((world - 1) * (b_all // world) * NUM_FIELDS * 4 + b_all * 4) /
                                         (r['ms_per_step'] * 1e-3) / 1e9,
                   'hbm_gbs_per_gpu': (hi - lo) * NUM_FIELDS * (NUM_FIELDS * plan.cols * 4 + 4) / (r['ms_per_step'] * 1e-3) / 1e9})
         out['ffm_embed_sharded'] = r

@@ -110,3 +110,68 @@ def test_virtual_ranks_match_oracle(n, e, world, batch, idx_dtype):
     bad[0, n - 1] = fs[-1]
     with pytest.raises(IndexError):
         ops.ffm_shard_resolve(bad.cuda(), off.cuda(), rows, w_feat.cuda(), bias.cuda())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('world', [2, 3, 8])
+def test_row_sharded_deepfm_virtual_ranks_bit_exact(world):
+    """trs_deepfm_forward_tc_sharded with every shard of the row-sharded packed table on ONE GPU (row g on shard
+    g % world at local row g // world): logits must equal the unsharded tcgen05 kernel bit for bit and the oracle within
+    1e-5.  The NVLink run of the same entry point is tests/test_multi_gpu.py (torchrun x 2)."""
+    from oracle import restated as R
+    from torecsys_b200 import ops, synth
+    ops.set_index_check('sync')
+    n, e, batch = 39, 16, 148 * 128 + 777
+    fs = [16 * (3 + i % 5) for i in range(n)]
+    rows = sum(fs)
+    off = R.field_offsets(fs)
+    w_feat = torch.from_numpy(synth.uniform((rows, 1), 'vrs/wf'))
+    w_emb = torch.from_numpy(synth.uniform((rows, e), 'vrs/we'))
+    dims = [n * e, 16, 16, 16, 1]
+    ws = [torch.from_numpy(synth.uniform((dims[i + 1], dims[i]), f'vrs/w{i}', -dims[i] ** -0.5, dims[i] ** -0.5)) for i in range(4)]
+    bs = [torch.from_numpy(synth.uniform((dims[i + 1],), f'vrs/b{i}', -0.5, 0.5)) for i in range(4)]
+    pack = ops.MlpPack([w.cuda() for w in ws], [b.cuda() for b in bs], ops.activation_id('relu'))
+    idx = torch.from_numpy(synth.integers((batch, n), 'vrs/idx', np.asarray(fs)[None, :]))
+    full = ops.fm_pack_table(w_emb.cuda(), w_feat.cuda())
+    shards = [full[r::world].contiguous() for r in range(world)]
+    want = ops.deepfm_packed(idx.cuda(), off.cuda(), full, pack, kernel='tc5')
+    for dt in (torch.int64, torch.int32):
+        got = ops.deepfm_packed_sharded(idx.cuda().to(dt), off.cuda(), [s.data_ptr() for s in shards], rows, pack)
+        assert torch.equal(got, want)
+    ref = R.deepfm_from_indices(idx, off, w_feat, w_emb, ws, bs).numpy()
+    assert normwise_err(got.cpu().numpy(), ref) <= TOL
+    bad = idx.clone()
+    bad[5, n - 1] = fs[-1]                      # one past the end of the shared table
+    with pytest.raises(IndexError):
+        ops.deepfm_packed_sharded(bad.cuda(), off.cuda(), [s.data_ptr() for s in shards], rows, pack)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('e,world', [(16, 8), (16, 2), (32, 8), (8, 4)])
+def test_embed_sharded_ffm_virtual_ranks(e, world):
+    """EmbedShardPlan on one GPU: the interleaved kernel on each column group's slice of all tables, partial logits
+    summed over the groups in rank order = the oracle (field_aware_factorization_machine.py:39-81) within 1e-5."""
+    from oracle import restated as R
+    from torecsys_b200 import ops, synth
+    from torecsys_b200.sharded import EmbedShardPlan
+    ops.set_index_check('sync')
+    n, batch = 13, 777
+    fs = [16 * (2 + i % 4) for i in range(n)]
+    rows = sum(fs)
+    off = R.field_offsets(fs)
+    full = [torch.from_numpy(synth.uniform((rows, e), f'ecs/t{t}', -0.5, 0.5)) for t in range(n)]
+    w_feat = torch.from_numpy(synth.uniform((rows, 1), 'ecs/wf'))
+    bias = torch.from_numpy(synth.uniform((1,), 'ecs/b'))
+    idx = torch.from_numpy(synth.integers((batch, n), 'ecs/idx', np.asarray(fs)[None, :]))
+    want = R.ffm_from_indices(idx, off, w_feat, full, bias).numpy()
+    plan = EmbedShardPlan(e, world)
+    assert plan.groups * plan.cols == e and plan.groups * plan.parts == world
+    total = torch.zeros(batch, 1, device='cuda')
+    for r in range(world):
+        lo, hi = plan.part_slice(r, batch)
+        first = plan.group_of(r) == 0
+        packed = ops.ffm_pack_tables([t[:, plan.columns(r)].contiguous().cuda() for t in full],
+                                     w_feat.cuda() if first else None)
+        total[lo:hi] += ops.ffm_model_interleaved(idx[lo:hi].cuda(), off.cuda(), packed, n, plan.cols,
+                                                  bias.cuda() if first else torch.zeros(1, device='cuda'))
+    assert normwise_err(total.cpu().numpy(), want) <= TOL

@@ -387,7 +387,7 @@ class EmbedShardedFFM:
     along the embedding dimension (EmbedShardPlan): rank r keeps columns plan.columns(r) of every table as the
     interleaved shadow of the single-GPU kernel (csrc/ffm_interleaved.cu, one bulk copy per row id) and runs THAT
     kernel; no looked-up vector crosses NVLink.
-      1. all-gather of the (B / W, N) index slices (NCCL);
+      1. idx + offsets -> int32 row ids (bounds-checked), all-gather of the (B / W, N) row-id slices (NCCL);
       2. the single-GPU interleaved kernel on the rank's columns for the rank's part of the samples;
       3. reduce-scatter (sum) of the (B,) partial logits (NCCL).
     The first-order weights and the bias ride with column group 0.  All ranks must pass slices of the same length."""
@@ -426,19 +426,23 @@ class EmbedShardedFFM:
     def forward(self, idx_local: torch.Tensor) -> torch.Tensor:
         b_local, n = idx_local.shape
         b_all = b_local * self.world
-        key = (b_local, n, idx_local.dtype)
+        key = (b_local, n)
         if key not in self._buf:
-            self._buf = {key: (torch.empty((b_all, n), dtype=idx_local.dtype, device=self.device),
-                               torch.zeros((b_all,), dtype=torch.float32, device=self.device))}
-        idx_all, partial = self._buf[key]
-        dist.all_gather_into_tensor(idx_all, idx_local.contiguous(), group=self.group)
-        lo, hi = self.plan.part_slice(self.rank, b_all)
+            self._buf = {key: (torch.empty((b_local, n), dtype=torch.int32, device=self.device),
+                               torch.empty((b_local,), dtype=torch.float32, device=self.device),
+                               torch.empty((b_all, n), dtype=torch.int32, device=self.device),
+                               torch.zeros((b_all,), dtype=torch.float32, device=self.device),
+                               torch.zeros(n, dtype=torch.int64, device=self.device))}
+        rows_loc, scratch, rows_all, partial, zero_off = self._buf[key]
         failed = None
-        try:
-            ops.ffm_model_interleaved(idx_all[lo:hi], self.offsets, self.packed, n, self.plan.cols, self.bias,
-                                      out=partial[lo:hi].view(-1, 1))
+        try:   # idx + offsets -> int32 row ids, bounds-checked where the sample lives: 4 bytes per lookup travel
+            ops.ffm_shard_resolve(idx_local, self.offsets, self.rows, None, None, rows_loc, scratch)
         except IndexError as ex:      # sync index checks: every rank must raise together (see below)
             failed = ex
+        dist.all_gather_into_tensor(rows_all, rows_loc, group=self.group)
+        lo, hi = self.plan.part_slice(self.rank, b_all)
+        ops.ffm_model_interleaved(rows_all[lo:hi], zero_off, self.packed, n, self.plan.cols, self.bias,
+                                  out=partial[lo:hi].view(-1, 1))
         out = torch.empty((b_local, 1), dtype=torch.float32, device=self.device)
         dist.reduce_scatter_tensor(out.view(-1), partial, op=dist.ReduceOp.SUM, group=self.group)
         if ops.index_check_mode() == 'sync':
