@@ -72,7 +72,6 @@ class GatherFieldAwareFn(torch.autograd.Function):
     def backward(ctx, grad):
         idx, offsets = ctx.saved_tensors
         b, n = idx.shape
-        flat = (idx.long() + offsets.view(1, -1)).reshape(-1)
         g = grad.reshape(b, n, n, -1)                      # (B, table t, field f, E)
         grads = [ops.embedding_grad(g[:, t].contiguous(), idx, offsets, ctx.rows) for t in range(n)]
         return (None, None, None) + tuple(grads)
@@ -231,10 +230,13 @@ class CrossFn(torch.autograd.Function):
     def backward(ctx, grad):
         x, w, b = ctx.saved_tensors
         if ops.cross_backward_supported(x.shape[-1]):
-            gx, gw, gb = ops.cross_backward(x, w, b, grad.contiguous())   # trs_cross_backward (csrc/backward.cu)
-            need = ctx.needs_input_grad
-            return (gx if need[0] else None, gw if need[1] else None, gb if need[2] else None)
-        return _grad_of(_cross, [x, w, b], grad)   # other widths: recompute through torch CUDA ops
+            try:
+                gx, gw, gb = ops.cross_backward(x, w, b, grad.contiguous())   # trs_cross_backward (csrc/backward.cu)
+                need = ctx.needs_input_grad
+                return (gx if need[0] else None, gw if need[1] else None, gb if need[2] else None)
+            except NotImplementedError:   # more layers than the kernel's shared memory holds (TRS_ERR_UNSUPPORTED)
+                pass
+        return _grad_of(_cross, [x, w, b], grad)   # other shapes: recompute through torch CUDA ops
 
 
 class CinFn(torch.autograd.Function):

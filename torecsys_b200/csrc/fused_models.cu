@@ -339,7 +339,10 @@ int launch_fm_family(const void* idx, int idx_bits, const int64_t* offsets, int6
     smem = ((size_t)ts * a.pitch + 2 * (size_t)ts * a.hpitch + ts) * sizeof(float);
     if (smem <= 100 * 1024 || ts == 1) break;  // two CTAs per SM when possible
   }
-  TRS_UNSUPPORTED(smem > (size_t)kMaxDynSmem, "%s: fields*embed / MLP widths do not fit shared memory", who);
+  if (smem > (size_t)kMaxDynSmem) {
+    if (x_scratch) cudaFreeAsync(x_scratch, s);
+    TRS_UNSUPPORTED(true, "%s: fields*embed / MLP widths do not fit shared memory", who);
+  }
   a.ts = ts;
   const int64_t tiles = (batch + ts - 1) / ts;
   const int grid = static_cast<int>(tiles < kNumSMs * 2 ? tiles : kNumSMs * 2);

@@ -260,8 +260,15 @@ def embedding_grad_sparse(grad_out: torch.Tensor, idx: torch.Tensor, offsets: Op
                                  _ptr(off) if off is not None else None, b, n, _ptr(flat), _stream()),
           'trs_embedding_rows')
     vals = g.reshape(b * n, e)
+    # an out-of-range lookup (never validated in 'deferred' index-check mode) must not become an out-of-bounds row
+    # of the COO tensor a sparse optimizer scatters into: such rows are dropped here, like lookups of padding_idx
+    # ('sync' mode validated every lookup in the forward: nothing to drop, no extra pass)
+    keep = None
+    if _index_check != 'sync':
+        keep = (flat >= 0) & (flat < rows)
     if padding_idx is not None:
-        keep = flat != int(padding_idx)
+        keep = flat != int(padding_idx) if keep is None else keep & (flat != int(padding_idx))
+    if keep is not None:
         flat, vals = flat[keep], vals[keep].contiguous()
     if not coalesce:
         return _coo(flat, vals, (rows, e), False)
