@@ -395,6 +395,86 @@ static void mma_suite() {
   cudaFree(cyc);
 }
 
+// ------------------------------------------------------------------------------------- tensor memory: ld / st rate
+// One CTA per SM, `warps` warps (4 per TMEM lane quarter group); every warp issues `iters` rounds of U tcgen05.st.x16
+// (MODE 0), tcgen05.ld.x16 (MODE 1), or a ld + two st per round like the epilogue of dcn_tc5.cu (MODE 2), one wait per
+// round.  Reports bytes per cycle and SM.
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1) tmem_rate(int iters, long long* __restrict__ cycles, float* __restrict__ sink) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc(smem_u32(&slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = slot + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + (warp >> 2) * 64;
+  uint32_t v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = threadIdx.x + j;
+  float acc = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    if (MODE == 0) {
+      tmem_st16(base, v);
+      tmem_st16(base + 16, v);
+      tmem_st16(base + 32, v);
+      tmem_st16(base + 48, v);
+      tmem_st_wait();
+    } else if (MODE == 1) {
+      uint32_t r[16];
+      tmem_ld16(base, r);
+      acc += __uint_as_float(r[3]);
+      tmem_ld16(base + 16, r);
+      acc += __uint_as_float(r[5]);
+      tmem_ld16(base + 32, r);
+      acc += __uint_as_float(r[7]);
+      tmem_ld16(base + 48, r);
+      acc += __uint_as_float(r[9]);
+    } else {
+      uint32_t r[16];
+      tmem_ld16(base, r);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = r[j] + 1;
+      tmem_st16(base + 16, v);
+      tmem_st16(base + 32, v);
+      tmem_st_wait();
+    }
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0 && cycles) cycles[blockIdx.x] = t1 - t0;
+  if (acc == 12345.f) sink[threadIdx.x] = acc + v[0];
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(slot, 512);
+}
+
+static void tmem_suite() {
+  long long* cyc;
+  float* sink;
+  CK(cudaMalloc(&cyc, 148 * sizeof(long long)));
+  CK(cudaMalloc(&sink, 4096));
+  const int iters = 2000;
+  for (int mode = 0; mode < 3; ++mode)
+    for (int warps : {4, 8, 16, 32}) {
+      if (warps > 8 && false) continue;
+      if (mode == 0) tmem_rate<0><<<148, warps * 32>>>(iters, cyc, sink);
+      else if (mode == 1) tmem_rate<1><<<148, warps * 32>>>(iters, cyc, sink);
+      else tmem_rate<2><<<148, warps * 32>>>(iters, cyc, sink);
+      CK(cudaDeviceSynchronize());
+      long long h[148];
+      CK(cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost));
+      double mean = 0;
+      for (int i = 0; i < 148; ++i) mean += h[i];
+      mean /= 148;
+      const double bytes = (mode == 2 ? 3.0 : 4.0) * 2048 * warps * iters;   // 32 lanes x 16 columns x 4 B per x16 op
+      printf("tmem %s  warps %2d | %8.1f cycles per round | %7.1f B/cycle/SM\n",
+             mode == 0 ? "st x4 + wait   " : mode == 1 ? "ld x4 (+waits) " : "ld, st x2, wait", warps, mean / iters,
+             bytes / mean);
+    }
+  fflush(stdout);
+}
+
 int main(int argc, char** argv) {
   const char* what = argc > 1 ? argv[1] : "all";
   cudaDeviceProp p;
@@ -402,6 +482,7 @@ int main(int argc, char** argv) {
   printf("device: %s, %d SMs, clock %d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
   if (!strcmp(what, "trunc") || !strcmp(what, "all")) trunc_suite();
   if (!strcmp(what, "mma") || !strcmp(what, "all")) mma_suite();
+  if (!strcmp(what, "tmem") || !strcmp(what, "all")) tmem_suite();
   if (!strcmp(what, "gather") || !strcmp(what, "all")) gather_suite(0);
   if (!strcmp(what, "gatherq")) gather_suite(1);
   return 0;
