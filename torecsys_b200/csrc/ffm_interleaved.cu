@@ -11,7 +11,7 @@
 // rows, and each chunk is ONE bulk copy of the TMA unit (cp.async.bulk global -> shared, completion on an mbarrier).
 //
 // Kernel: persistent CTA per SM, a ring of sample-sized stages in shared memory (2 at 39 x 16, up to 8 for narrower
-// rows).  Warps 8-11 are producers: each resolves the row ids of ITS fields (f = warp, warp + 4, ..) of the next sample,
+// rows).  Warps 8-15 are producers: each resolves the row ids of ITS fields (f = warp, warp + 8, ..) two samples ahead,
 // waits for the stage to be released and issues its bulk copies -- a warp-wide cp.async.bulk is issued lane by lane
 // (~60 cycles each), so one producer warp bounds narrow rows at ~4 000 cycles per sample (measured: 4 columns per table
 // 1.82 ms per 131 072 samples); producer 0 also writes the finished sample's logit (fixed-order sum of the eight
@@ -31,7 +31,7 @@ using tc5::mbar_wait;
 using tc5::smem_u32;
 
 constexpr int kConsumers = 8;
-constexpr int kProducers = 4;
+constexpr int kProducers = 8;
 constexpr int kMaxStages = 8;
 constexpr int kThreads = (kConsumers + kProducers) * 32;
 
@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(kThreads, 1) ffm_interleaved_kernel(const void
       }
       __syncwarp();
     };
-    int64_t r = resolve(0);
-    int s = 0;
+    int64_t r = resolve(0), r_next = resolve(1);   // row ids two samples ahead: a narrow shard's sample lasts less
+    int s = 0;                                     // than an index load
     uint32_t wrap = 0;
     for (int64_t k = 0; k < mine; ++k) {
       if (wrap > 0) finish(k - stages, s, wrap - 1);
@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(kThreads, 1) ffm_interleaved_kernel(const void
       __syncwarp();
       if (f < fields)
         bulk_g2s(smem_u32(stage0 + s * stage_floats) + f * stage_pitch * 4, packed + r * pitch_floats, copy_bytes, bar);
-      r = resolve(k + 1);
+      r = r_next;
+      r_next = resolve(k + 2);
       if (++s == stages) { s = 0; ++wrap; }
     }
     for (int64_t k = mine > stages ? mine - stages : 0; k < mine; ++k)
