@@ -218,6 +218,67 @@ def test_ffm_configs4_one_gpu_full_tables(ops):
     torch.cuda.empty_cache()
 
 
+def test_ffm_configs4_sharded_paths_full_size_virtual_ranks(ops):
+    """configs[4] at FULL size through the sharded paths, on ONE GPU with virtual ranks: the 8 interleaved table shards
+    of the block exchange (8 x 8.2 GB, csrc/ffm_blocks.cu) and the 4 column groups of the embedding-dimension sharding
+    (4 x 16.4 GB) hold the same 39 x 25.6 M x 16 tables; their summed partial logits must agree with each other and with
+    the CPU oracle on a random subset of the batch (compact copy of exactly the rows it touches).  Addresses beyond
+    2^32 bytes in every shard, all copy lists / item lists of all 8 ranks."""
+    from oracle import restated as R
+    from torecsys_b200.sharded import EmbedShardPlan
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 150 * (1 << 30):
+        pytest.skip(f'needs 150 GB of free HBM, have {free >> 30} GB')
+    rng = np.random.default_rng(15)
+    gen = torch.Generator().manual_seed(15)
+    dgen = torch.Generator(device='cuda').manual_seed(15)
+    rpf, e, world, b = 657_472, 16, 8, 4096
+    rows = N * rpf
+    slots = (N + world - 1) // world
+    shards = [torch.empty(rows, slots, e, device='cuda').uniform_(-0.3, 0.3, generator=dgen) for _ in range(world)]
+    w_feat = torch.randn(rows, 1, device='cuda', generator=dgen)
+    bias = torch.rand(1, generator=gen).cuda()
+    off_d = (torch.arange(N, dtype=torch.int64) * rpf).cuda()
+    idx = torch.randint(0, rpf, (b, N), generator=gen).cuda()
+    idx[0, :] = rpf - 1                                      # the last row of every field: the far end of every shard
+    # ---- block exchange: every virtual rank reduces its blocks for all samples
+    rows_all, first = ops.ffm_shard_resolve(idx, off_d, rows, w_feat, bias)
+    ptrs = [s.data_ptr() for s in shards]
+    per = b // world
+    blocks = torch.zeros(b, device='cuda')
+    for k in range(world):
+        plan = ops.FfmShardPlan(N, world, k, e)
+        blocks += ops.ffm_shard_blocks(rows_all, plan, ptrs, first[k * per:(k + 1) * per].contiguous(),
+                                       (k * per, (k + 1) * per))
+    # ---- oracle on a subset
+    sel = torch.from_numpy(rng.choice(b, 96, replace=False)).cuda()
+    sel[0] = 0
+    rows_sel = idx[sel] + off_d
+    uniq, inv = torch.unique(rows_sel.reshape(-1), return_inverse=True)
+    tabs_c = [shards[t % world][:, t // world, :].index_select(0, uniq).cpu() for t in range(N)]
+    want = R.ffm_from_indices(inv.reshape(rows_sel.shape).cpu(), torch.zeros(N, dtype=torch.int64),
+                              w_feat.index_select(0, uniq).cpu(), tabs_c, bias.cpu()).numpy()
+    assert normwise_err(blocks[sel].cpu().numpy().reshape(-1, 1), want) <= TOL
+    # ---- embedding-dimension sharding: one column group at a time (16.4 GB each), same tables
+    plan = EmbedShardPlan(e, world)
+    pitch = int(ops._cabi.load().trs_ffm_interleaved_pitch(N, plan.cols))
+    cols_sum = torch.zeros(b, 1, device='cuda')
+    for g in range(plan.groups):
+        packed = torch.zeros(rows, pitch, device='cuda')
+        for t in range(N):
+            packed[:, t * plan.cols:(t + 1) * plan.cols] = shards[t % world][:, t // world, g * plan.cols:(g + 1) * plan.cols]
+        if g == 0:
+            packed[:, N * plan.cols] = w_feat[:, 0]
+        cols_sum += ops.ffm_model_interleaved(idx, off_d, packed, N, plan.cols, bias if g == 0 else torch.zeros(1, device='cuda'))
+        del packed
+    assert normwise_err(cols_sum[sel].cpu().numpy(), want) <= TOL
+    assert normwise_err(cols_sum.cpu().numpy(), blocks.cpu().numpy().reshape(-1, 1)) <= TOL
+    ops.check_index_errors()
+    del shards, w_feat
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize('each', [False, True])
 def test_bilinear_backward_full_batch_properties(ops, each):
     """trs_bilinear_backward at the BASELINE batch (65 536 x 39 x 16; grad_out 3.1 GB): grad_x of a batch split at a
