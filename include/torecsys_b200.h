@@ -251,6 +251,18 @@ int trs_mlp_forward(const float* x, int64_t rows, const int* dims, int layers,
                     const float* const* weights, const float* const* biases, int activation,
                     float* out, void* stream);
 
+/* Backward of trs_mlp_forward for the NARROW MLPs of the CTR models on this path (DeepFM / xDeepFM / NFM / FNN deep
+ * branches, DCN's per-field MLP): dims[0] % 4 == 0 and every other width <= 32 (trs_mlp_backward_supported; the input
+ * tile and grad_W_1 must fit shared memory).  One kernel (csrc/mlp_bwd.cu): forward recomputed per 32-row tile,
+ * layers walked backwards in FP32, parameter gradients accumulated in shared memory and added to global memory once per
+ * CTA.  grad_weights[l] (dims[l+1], dims[l]) and grad_biases[l] (dims[l+1]) are OVERWRITTEN (zeroed on the stream first);
+ * grad_x (rows, dims[0]) may be NULL; grad_biases may be NULL or hold NULL entries.  HOST arrays of DEVICE pointers. */
+int trs_mlp_backward_supported(const int* dims, int layers);
+int trs_mlp_backward(const float* x, int64_t rows, const int* dims, int layers,
+                     const float* const* weights, const float* const* biases, int activation,
+                     const float* grad_out, float* grad_x, float* const* grad_weights, float* const* grad_biases,
+                     void* stream);
+
 /* ---- a12: fused model forwards, indices -> logits (the L2 boundary: Sequential.forward,
  *      torecsys/models/sequential.py:31-44 = Inputs.forward (torecsys/inputs/inputs.py:56-89) + model.forward) -------
  * Common arguments: idx (batch, fields); offsets (fields) int64; w_feat (rows, 1) = the first-order

@@ -334,6 +334,61 @@ def test_cross_backward_kernel(rows, e, layers):
         assert err <= 2e-5, (what, float(err))
 
 
+@pytest.mark.parametrize('shape,dims,act', [((1000, 624), [624, 16, 16, 16, 1], 'relu'), ((33, 39, 32), [32, 32, 16, 8, 4], 'relu'),
+                                            ((1, 20), [20, 8, 1], 'sigmoid'), ((148 * 32 * 2 + 5, 64), [64, 32, 3], 'tanh'),
+                                            ((77, 64), [64, 5], 'relu'), ((64, 12), [12, 7, 7, 7, 7, 7, 7, 7, 2], 'relu')])
+def test_mlp_backward_kernel(shape, dims, act):
+    """trs_mlp_backward (csrc/mlp_bwd.cu: forward recomputed per 32-row tile, layers walked backwards, parameter gradients
+    accumulated in shared memory) against float64 autograd on the upstream formula (multilayer_perceptron.py:63-84):
+    x and every weight / bias, ragged tiles, 3-D inputs (DCN's per-field MLP), the single-Linear and 8-Linear cases."""
+    from torecsys_b200 import ops, synth
+    tag = f'mlpb{dims[0]}_{len(dims)}'
+    x = torch.from_numpy(synth.uniform(shape, f'{tag}/x', -1.0, 1.0))
+    ws = [torch.from_numpy(synth.uniform((dims[i + 1], dims[i]), f'{tag}/w{i}', -dims[i] ** -0.5, dims[i] ** -0.5))
+          for i in range(len(dims) - 1)]
+    bs = [torch.from_numpy(synth.uniform((dims[i + 1],), f'{tag}/b{i}', -0.5, 0.5)) for i in range(len(dims) - 1)]
+    g = torch.from_numpy(synth.uniform(shape[:-1] + (dims[-1],), f'{tag}/g', -1.0, 1.0))
+    assert ops.mlp_backward_supported(dims)
+    pack = ops.MlpPack([w.cuda() for w in ws], [b.cuda() for b in bs], ops.activation_id(act))
+    gx, gws, gbs = ops.mlp_backward(x.cuda(), pack, g.cuda())
+    fn = {'relu': torch.relu, 'sigmoid': torch.sigmoid, 'tanh': torch.tanh}[act]
+    xd = x.double().requires_grad_(True)
+    wd = [w.double().requires_grad_(True) for w in ws]
+    bd = [b.double().requires_grad_(True) for b in bs]
+    h = xd
+    for i, (w, b) in enumerate(zip(wd, bd)):
+        h = torch.nn.functional.linear(h, w, b)
+        if i < len(wd) - 1:
+            h = fn(h)
+    h.backward(g.double())
+    _check(gx, xd.grad.float(), 'grad x')
+    for i in range(len(ws)):
+        _check(gws[i], wd[i].grad.float(), f'grad W{i}')
+        _check(gbs[i], bd[i].grad.float(), f'grad b{i}')
+    again = ops.mlp_backward(x.cuda(), pack, g.cuda())
+    assert torch.equal(again[0], gx)                      # grad_x has one owner per element: bit-reproducible
+    assert not ops.mlp_backward_supported([624, 400, 400, 1]) and not ops.mlp_backward_supported([30, 8, 1])
+
+
+def test_mlp_function_backward_routes(trs):
+    """DNNLayer in grad mode: narrow stacks differentiate through trs_mlp_backward, wide ones through the torch recompute;
+    both agree with autograd on the registered torch modules."""
+    for sizes in ([16, 16, 16], [400, 16]):
+        torch.manual_seed(3)
+        layer = trs.DNNLayer(inputs_size=64, output_size=1, layer_sizes=sizes, dropout_p=[0.0] * len(sizes)).cuda()
+        x = torch.randn(50, 64, device='cuda', requires_grad=True)
+        out = layer(x.refine_names('B', 'O'))
+        out.rename(None).sum().backward()
+        got = [x.grad.clone()] + [p.grad.clone() for p in layer.parameters()]
+        x2 = x.detach().clone().requires_grad_(True)
+        for p in layer.parameters():
+            p.grad = None
+        layer.model(x2).sum().backward()
+        want = [x2.grad] + [p.grad for p in layer.parameters()]
+        for u, v in zip(got, want):
+            assert normwise_err(u.cpu().numpy(), v.cpu().numpy()) <= GTOL
+
+
 @pytest.mark.parametrize('each', [False, True])
 @pytest.mark.parametrize('b,n,e', [(1, 2, 8), (37, 39, 16), (200, 12, 32), (65, 5, 8), (16 * 148 * 2 + 5, 4, 16),
                                    (64 * 7 + 1, 3, 32)])

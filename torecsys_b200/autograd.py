@@ -295,6 +295,16 @@ class MlpFn(torch.autograd.Function):
     def backward(ctx, grad):
         act = next((m for k, m in ctx.layer.model._modules.items() if k.startswith('Activation')), None)
         x, params = ctx.saved_tensors[0], list(ctx.saved_tensors[1:])
+        pack = ctx.layer.mlp_pack()
+        # narrow MLPs (every width behind the first Linear <= 32): trs_mlp_backward (csrc/mlp_bwd.cu); the pack's
+        # parameter order is the saved one (weight, bias per Linear)
+        if (len(params) == 2 * pack.layers and ops.mlp_backward_supported(pack.dims_list)
+                and x.data_ptr() % 16 == 0 and x.is_contiguous()):
+            gx, gws, gbs = ops.mlp_backward(x, pack, grad.contiguous(), need_x=ctx.needs_input_grad[0])
+            out = []
+            for gw, gb in zip(gws, gbs):
+                out += [gw, gb]
+            return (gx, None) + tuple(out)
 
         def fn(xx, *ps):
             h = xx

@@ -593,6 +593,29 @@ def mlp(x: torch.Tensor, pack: MlpPack) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------- fused models
+def mlp_backward_supported(dims: Sequence[int]) -> bool:
+    """Shapes trs_mlp_backward takes: in % 4 == 0, every other width <= 32, tile + grad_W_1 within shared memory."""
+    return bool(_cabi.load().trs_mlp_backward_supported(int_array(list(dims)), len(dims) - 1))
+
+
+def mlp_backward(x: torch.Tensor, pack: MlpPack, grad_out: torch.Tensor, need_x: bool = True):
+    """(d x, [d W_l], [d b_l]) of mlp(): csrc/mlp_bwd.cu (multilayer_perceptron.py:63-84 differentiated, eval mode)."""
+    _need_cuda('mlp_backward', x, grad_out)
+    x, g = _f32('mlp_backward', x), _f32('mlp_backward', grad_out)
+    k, c = pack.dims_list[0], pack.dims_list[-1]
+    rows = x.numel() // k
+    if x.shape[-1] != k or g.numel() != rows * c:
+        raise ValueError(f'mlp_backward: x {tuple(x.shape)} / grad_out {tuple(g.shape)} do not match the MLP {pack.dims_list}')
+    ws, bs = pack.keep
+    gx = torch.empty_like(x) if need_x else None
+    gws = [torch.empty_like(w, dtype=torch.float32) for w in ws]
+    gbs = [torch.empty_like(b, dtype=torch.float32) for b in bs]
+    check(_cabi.load().trs_mlp_backward(_ptr(x), rows, pack.dims, pack.layers, pack.w, pack.b, pack.act, _ptr(g),
+                                        _ptr(gx), ptr_array([t.data_ptr() for t in gws]),
+                                        ptr_array([t.data_ptr() for t in gbs]), _stream()), 'trs_mlp_backward')
+    return gx, gws, gbs
+
+
 def _fused_common(name, idx, offsets, *tensors):
     _need_cuda(name, idx, offsets, *tensors)
     ix, bits = _index(name, idx)
