@@ -467,8 +467,13 @@ def bench_sharded(torch, dist, timer, device, rank, world, args):
                                   'nvlink_gbs_per_gpu': float(t.item()) / (k['ms_per_step'] * 1e-3) / 1e9,
                                   'kernel': 'ffm_blocks_kernel'},
                   'bound': {'half_volume_nvlink_900': 900e9 / (float(t.item()) / b_all),
-                            'note': 'samples/s if the inbound NVLink of the busiest rank ran at 900 GB/s; bulk copies of '
-                                    'random 320-byte peer chunks sustain 685 GB/s (profiles/r02_peer_probe.log)'}})
+                            'nvlink_ceiling_gbs': {320: 630.5, 640: 672.7, 1280: 672.9}.get(plan.pitch_bytes),
+                            'kernel_frac_of_ceiling': (float(t.item()) / (k['ms_per_step'] * 1e-3) / 1e9) /
+                                                      {320: 630.5, 640: 672.7, 1280: 672.9}.get(plan.pitch_bytes, 672.0),
+                            'note': 'half_volume_nvlink_900 = samples/s if the inbound NVLink of the busiest rank ran at the '
+                                    'nominal 900 GB/s; nvlink_ceiling_gbs = what random bulk copies of this chunk size '
+                                    'sustain INTO a GPU with both directions busy (tools/peer_probe.cu, '
+                                    'profiles/r02_peer_probe.log: 630 GB/s for 320-byte chunks, 672 GB/s for whole lines)'}})
         out['ffm'] = r
         del model, tables, w_feat, idx, rows_loc, first, rows_all, partial
     except Exception as ex:

@@ -225,5 +225,48 @@ int main(int argc, char** argv) {
       printf("ld.global.cg.v4 x8 per lane, chunk %4d: %8.1f GB/s\n", chunk, 296.0 * 8 * units * 4096 / (ms * 1e-3) / 1e9);
     }
   }
+  // ---- both directions at once: GPU 0 pulls from GPU 1 while GPU 1 pulls from GPU 0 (what an all-to-all exchange sees:
+  // read requests of one flow share the link direction with the response data of the other)
+  if (tables[1]) {
+    CK(cudaSetDevice(1));
+    CK(cudaDeviceEnablePeerAccess(0, 0));
+    float* out1;
+    CK(cudaMalloc(&out1, 4096));
+    CK(cudaFuncSetAttribute(peer_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaSetDevice(0));
+    printf("== both directions at once (bulk copies, 8 warps): GB/s of useful bytes INTO each GPU\n");
+    struct Cfg { int chunk, pitch, group, stages; };
+    const Cfg cfgs[] = {{64, 64, 16, 4}, {128, 128, 16, 4}, {256, 256, 8, 4}, {320, 320, 10, 4}, {384, 384, 5, 8},
+                        {640, 640, 5, 4}, {1280, 1280, 4, 4}};
+    for (const Cfg& c : cfgs) {
+      const int warps = 8, ctas = 148;
+      const uint32_t rows = (uint32_t)(table_bytes / c.pitch);
+      const int units = (int)(total / ((int64_t)ctas * warps * c.group * c.chunk));
+      const size_t smem = (size_t)warps * ((size_t)c.stages * c.group * c.chunk + 128);
+      cudaEvent_t a0, b0, a1, b1;
+      CK(cudaSetDevice(0)); cudaEventCreate(&a0); cudaEventCreate(&b0);
+      CK(cudaSetDevice(1)); cudaEventCreate(&a1); cudaEventCreate(&b1);
+      for (int rep = 0; rep < 2; ++rep) {   // first round warms up
+        CK(cudaSetDevice(0));
+        cudaEventRecord(a0);
+        for (int i = 0; i < 3; ++i) peer_gather<<<ctas, warps * 32, smem>>>(tables[1], rows, c.pitch, c.chunk, c.group, c.stages, 1, units, out);
+        cudaEventRecord(b0);
+        CK(cudaSetDevice(1));
+        cudaEventRecord(a1);
+        for (int i = 0; i < 3; ++i) peer_gather<<<ctas, warps * 32, smem>>>(tables[0], rows, c.pitch, c.chunk, c.group, c.stages, 1, units, out1);
+        cudaEventRecord(b1);
+        CK(cudaSetDevice(0)); CK(cudaDeviceSynchronize());
+        CK(cudaSetDevice(1)); CK(cudaDeviceSynchronize());
+      }
+      float ms0, ms1;
+      cudaEventElapsedTime(&ms0, a0, b0);
+      cudaEventElapsedTime(&ms1, a1, b1);
+      const double bytes = (double)ctas * warps * units * c.group * c.chunk * 3;
+      printf("chunk %5d pitch %5d | into GPU 0 %7.1f GB/s | into GPU 1 %7.1f GB/s\n", c.chunk, c.pitch,
+             bytes / (ms0 * 1e-3) / 1e9, bytes / (ms1 * 1e-3) / 1e9);
+      fflush(stdout);
+    }
+    CK(cudaSetDevice(0));
+  }
   return 0;
 }
