@@ -263,6 +263,15 @@ int trs_mlp_backward(const float* x, int64_t rows, const int* dims, int layers,
                      const float* grad_out, float* grad_x, float* const* grad_weights, float* const* grad_biases,
                      void* stream);
 
+/* Backward of trs_senet_forward (compose_excitation_network.py:72-109) for x, w1, b1, w2, b2: one warp per sample,
+ * rows_per_sample <= 64 and reduced <= 32 (trs_senet_backward_supported: FiBiNET's SENET; the N^2-row CEN of FAT-DeepFFM
+ * is not covered).  The four parameter gradients are OVERWRITTEN (zeroed on the stream, accumulated per CTA in shared
+ * memory, one float atomic per element and CTA). */
+int trs_senet_backward_supported(int rows_per_sample, int reduced);
+int trs_senet_backward(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                       int activation, const float* grad_out, int64_t batch, int rows_per_sample, int embed, int reduced,
+                       float* grad_x, float* grad_w1, float* grad_b1, float* grad_w2, float* grad_b2, void* stream);
+
 /* ---- a12: fused model forwards, indices -> logits (the L2 boundary: Sequential.forward,
  *      torecsys/models/sequential.py:31-44 = Inputs.forward (torecsys/inputs/inputs.py:56-89) + model.forward) -------
  * Common arguments: idx (batch, fields); offsets (fields) int64; w_feat (rows, 1) = the first-order

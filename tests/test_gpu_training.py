@@ -370,6 +370,50 @@ def test_mlp_backward_kernel(shape, dims, act):
     assert not ops.mlp_backward_supported([624, 400, 400, 1]) and not ops.mlp_backward_supported([30, 8, 1])
 
 
+@pytest.mark.parametrize('b,m,e,r,act', [(37, 39, 16, 13, 'relu'), (5, 64, 8, 32, 'sigmoid'), (300, 10, 4, 3, 'tanh'),
+                                         (8 * 296 + 3, 39, 16, 7, 'relu'), (1, 1, 1, 1, 'relu')])
+def test_senet_backward_kernel(b, m, e, r, act):
+    """trs_senet_backward (csrc/mlp_bwd.cu, one warp per sample) against float64 autograd on the upstream formula
+    (compose_excitation_network.py:72-109): x, ReductionLinear and AdditionLinear weights and biases."""
+    from torecsys_b200 import ops, synth
+    tag = f'seb{m}_{e}_{r}'
+    x = torch.from_numpy(synth.uniform((b, m, e), f'{tag}/x', -1.0, 1.0))
+    w1 = torch.from_numpy(synth.uniform((r, m), f'{tag}/w1', -m ** -0.5, m ** -0.5))
+    b1 = torch.from_numpy(synth.uniform((r,), f'{tag}/b1', -0.3, 0.3))
+    w2 = torch.from_numpy(synth.uniform((m, r), f'{tag}/w2', -r ** -0.5, r ** -0.5))
+    b2 = torch.from_numpy(synth.uniform((m,), f'{tag}/b2', -0.3, 0.3))
+    g = torch.from_numpy(synth.uniform((b, m, e), f'{tag}/g', -1.0, 1.0))
+    assert ops.senet_backward_supported(m, r) and not ops.senet_backward_supported(1521, 100)
+    got = ops.senet_backward(x.cuda(), w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), ops.activation_id(act), g.cuda())
+    fn = {'relu': torch.relu, 'sigmoid': torch.sigmoid, 'tanh': torch.tanh}[act]
+    leaves = [t.double().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    xd, w1d, b1d, w2d, b2d = leaves
+    a = fn(torch.nn.functional.linear(fn(torch.nn.functional.linear(xd.mean(-1), w1d, b1d)), w2d, b2d))
+    (xd * a.unsqueeze(-1)).backward(g.double())
+    for u, v, what in zip(got, leaves, ('x', 'w1', 'b1', 'w2', 'b2')):
+        _check(u, v.grad.float(), f'grad {what}')
+
+
+@pytest.mark.parametrize('kernel_type', ['mat', 'vec', 'num'])
+@pytest.mark.parametrize('b,n,e', [(33, 39, 16), (70, 5, 8), (4, 12, 32)])
+def test_opn_backward_through_the_bilinear_kernel(trs, kernel_type, b, n, e):
+    """OpnFn.backward: the outer-product layer is the field-each bilinear layer summed over its output columns, so its
+    gradients come from trs_bilinear_backward; compared with float64 autograd on outer_product_network.py:80-131."""
+    from torecsys_b200 import synth
+    from torecsys_b200.autograd import OpnFn, _opn
+    pairs = n * (n - 1) // 2
+    shape = {'mat': (e, pairs, e), 'vec': (1, pairs, e), 'num': (1, pairs, 1)}[kernel_type]
+    x = torch.from_numpy(synth.uniform((b, n, e), f'opnb/{kernel_type}/{n}/{e}/x', -1.0, 1.0))
+    k = torch.from_numpy(synth.uniform(shape, f'opnb/{kernel_type}/{n}/{e}/k', -0.5, 0.5))
+    g = torch.from_numpy(synth.uniform((b, pairs), f'opnb/{kernel_type}/{n}/{e}/g', -1.0, 1.0))
+    xc, kc = x.cuda().requires_grad_(True), k.cuda().requires_grad_(True)
+    OpnFn.apply(xc, kc, kernel_type).backward(g.cuda())
+    xd, kd = x.double().requires_grad_(True), k.double().requires_grad_(True)
+    _opn(xd, kd, kernel_type).backward(g.double())
+    _check(xc.grad, xd.grad.float(), 'grad x')
+    _check(kc.grad, kd.grad.float(), 'grad kernel')
+
+
 def test_mlp_function_backward_routes(trs):
     """DNNLayer in grad mode: narrow stacks differentiate through trs_mlp_backward, wide ones through the torch recompute;
     both agree with autograd on the registered torch modules."""

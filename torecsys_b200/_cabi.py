@@ -90,6 +90,8 @@ PROTOTYPES = {
     'trs_ffm_model_forward_interleaved': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, c_int, _P, _P, _P, _P]),
     'trs_ffm_model_forward_pairs': (c_int, [_P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _P, _P, c_int,
                                             c_int64, c_int64, _P, _P, _P]),
+    'trs_senet_backward_supported': (c_int, [c_int, c_int]),
+    'trs_senet_backward': (c_int, [_P, _P, _P, _P, _P, c_int, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     'trs_mlp_backward_supported': (c_int, [_IP, c_int]),
     'trs_mlp_backward': (c_int, [_P, c_int64, _IP, c_int, _PP, _PP, c_int, _P, _P, _PP, _PP, _P]),
     'trs_ffm_shard_plan': (c_int, [c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _IP, _IP, _IP, _IP]),

@@ -204,6 +204,28 @@ class OpnFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad):
+        x, kernel = ctx.saved_tensors
+        n, e = x.shape[-2], x.shape[-1]
+        if ops.bilinear_backward_supported(n, e):
+            # out[b,p] = sum_h ((x_i W_p) * x_j)[h] with W_p[e][h] = kernel[h,p,e] ('mat'), diag(kernel[0,p,:]) ('vec') or
+            # kernel[0,p,0] * I ('num'): the field-each bilinear layer summed over its output columns, so its backward
+            # kernel (trs_bilinear_backward, csrc/bilinear_bwd.cu) with grad_out broadcast over h gives grad_x and grad_W_p
+            pairs = n * (n - 1) // 2
+            if ctx.kernel_type == 'mat':
+                w = kernel.permute(1, 2, 0).contiguous()                        # (P, E_e, E_h)
+            elif ctx.kernel_type == 'vec':
+                w = torch.diag_embed(kernel[0])                                 # (P, E, E)
+            else:
+                w = kernel[0, :, 0].view(pairs, 1, 1) * torch.eye(e, device=x.device).unsqueeze(0)
+            g = grad.reshape(-1, pairs, 1).expand(-1, pairs, e).contiguous()
+            gx, gw, _ = ops.bilinear_backward(x, w, g, True, with_bias=False)
+            if ctx.kernel_type == 'mat':
+                gk = gw.permute(2, 0, 1)                                        # (E_h, P, E_e)
+            elif ctx.kernel_type == 'vec':
+                gk = torch.diagonal(gw, dim1=1, dim2=2).unsqueeze(0)            # (1, P, E)
+            else:
+                gk = torch.diagonal(gw, dim1=1, dim2=2).sum(-1).view(1, pairs, 1)
+            return gx.view_as(x), gk.contiguous().view_as(kernel), None
         return _grad_of(lambda a, k: _opn(a, k, ctx.kernel_type), list(ctx.saved_tensors), grad) + (None,)
 
 
@@ -216,6 +238,14 @@ class SenetFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad):
+        x, w1, b1, w2, b2 = ctx.saved_tensors
+        try:
+            act_id = ops.activation_id(ctx.activation)
+        except Exception:
+            act_id = None
+        if act_id is not None and x.dim() == 3 and ops.senet_backward_supported(x.shape[1], w1.shape[0]):
+            # trs_senet_backward (csrc/mlp_bwd.cu): FiBiNET-size SENET; the N^2-row CEN keeps the torch recompute
+            return ops.senet_backward(x, w1, b1, w2, b2, act_id, grad.contiguous()) + (None,)
         act = ctx.activation if ctx.activation is not None else (lambda t: t)
         return _grad_of(lambda *a: _senet(*a, act), list(ctx.saved_tensors), grad) + (None,)
 

@@ -267,3 +267,165 @@ extern "C" int trs_mlp_backward(const float* x, int64_t rows, const int* dims, i
   mlp_backward_kernel<<<grid, kThreads, smem, s>>>(a);
   return check_launch("mlp_backward_kernel");
 }
+
+// ---- backward of ComposeExcitationNetworkLayer.forward (compose_excitation_network.py:72-109), SENET of FiBiNET ---------
+//     p[m] = mean_e x[m,e];  u = act(W1 p + b1) (R);  s = act(W2 u + b2) (M);  out[m,e] = x[m,e] * s[m]
+//     ds[m] = sum_e g[m,e] x[m,e];  dz2 = ds * act'(s);  du = W2^T dz2;  dz1 = du * act'(u);  dp = W1^T dz1
+//     grad_x[m,e] = g[m,e] * s[m] + dp[m] / E;  grad_W2 += dz2 u^T, grad_b2 += dz2, grad_W1 += dz1 p^T, grad_b1 += dz1
+// One warp per sample (M <= 64 fields, R <= 32): lane = field (two per lane), the small vectors through shuffles /
+// shared memory; the CTA accumulates the parameter gradients of its samples in shared memory (one owner thread per
+// element, fixed order over the CTA's warps) and adds them to global memory once.
+namespace trs {
+namespace {
+
+constexpr int kSeWarps = 8, kSeMaxM = 64, kSeMaxR = 32;
+
+__global__ void __launch_bounds__(kSeWarps * 32) senet_backward_kernel(
+    const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ b1,
+    const float* __restrict__ w2, const float* __restrict__ b2, int act, const float* __restrict__ g, int64_t batch,
+    int m_dim, int embed, int r_dim, float* __restrict__ gx, float* __restrict__ gw1, float* __restrict__ gb1,
+    float* __restrict__ gw2, float* __restrict__ gb2) {
+  __shared__ float w1_s[kSeMaxR][kSeMaxM + 1], w2_s[kSeMaxM][kSeMaxR + 1], b1_s[kSeMaxR], b2_s[kSeMaxM];
+  __shared__ float gw1_s[kSeMaxR][kSeMaxM + 1], gw2_s[kSeMaxM][kSeMaxR + 1], gb1_s[kSeMaxR], gb2_s[kSeMaxM];
+  __shared__ float p_s[kSeWarps][kSeMaxM], u_s[kSeWarps][kSeMaxR], dz1_s[kSeWarps][kSeMaxR], dz2_s[kSeWarps][kSeMaxM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  for (int i = tid; i < kSeMaxR * (kSeMaxM + 1); i += blockDim.x) {
+    const int r = i / (kSeMaxM + 1), m = i - r * (kSeMaxM + 1);
+    w1_s[r][m] = (r < r_dim && m < m_dim) ? __ldg(w1 + r * m_dim + m) : 0.f;
+    gw1_s[r][m] = 0.f;
+  }
+  for (int i = tid; i < kSeMaxM * (kSeMaxR + 1); i += blockDim.x) {
+    const int m = i / (kSeMaxR + 1), r = i - m * (kSeMaxR + 1);
+    w2_s[m][r] = (m < m_dim && r < r_dim) ? __ldg(w2 + m * r_dim + r) : 0.f;
+    gw2_s[m][r] = 0.f;
+  }
+  for (int i = tid; i < kSeMaxR; i += blockDim.x) { b1_s[i] = i < r_dim ? __ldg(b1 + i) : 0.f; gb1_s[i] = 0.f; }
+  for (int i = tid; i < kSeMaxM; i += blockDim.x) { b2_s[i] = i < m_dim ? __ldg(b2 + i) : 0.f; gb2_s[i] = 0.f; }
+  __syncthreads();
+  const float inv_e = 1.f / static_cast<float>(embed);
+  const int64_t rounds = (batch + (int64_t)gridDim.x * kSeWarps - 1) / ((int64_t)gridDim.x * kSeWarps);
+  for (int64_t it = 0; it < rounds; ++it) {
+    const int64_t b = (it * gridDim.x + blockIdx.x) * kSeWarps + warp;
+    const bool live = b < batch;
+    // p, ds per field (lane owns fields lane and lane + 32)
+    float pm[2] = {0.f, 0.f}, ds[2] = {0.f, 0.f};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = lane + 32 * h;
+      if (live && m < m_dim) {
+        const float* xr = x + (b * m_dim + m) * embed;
+        const float* gr = g + (b * m_dim + m) * embed;
+        float sx = 0.f, sg = 0.f;
+        for (int e = 0; e < embed; ++e) {
+          const float xv = __ldg(xr + e);
+          sx += xv;
+          sg = fmaf(__ldg(gr + e), xv, sg);
+        }
+        pm[h] = sx * inv_e;
+        ds[h] = sg;
+      }
+      p_s[warp][m] = pm[h];
+    }
+    __syncwarp();
+    // u[r] (lane = r)
+    float z1 = b1_s[lane];
+    for (int m = 0; m < m_dim; ++m) z1 = fmaf(w1_s[lane][m], p_s[warp][m], z1);
+    const float u = lane < r_dim ? apply_act(z1, act) : 0.f;
+    u_s[warp][lane] = u;
+    __syncwarp();
+    // s[m], dz2[m]
+    float sv[2], dz2[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = lane + 32 * h;
+      float z2 = b2_s[m];
+      for (int r = 0; r < r_dim; ++r) z2 = fmaf(w2_s[m][r], u_s[warp][r], z2);
+      sv[h] = m < m_dim ? apply_act(z2, act) : 0.f;
+      dz2[h] = (live && m < m_dim) ? ds[h] * act_grad(sv[h], z2, act) : 0.f;
+      dz2_s[warp][m] = dz2[h];
+    }
+    __syncwarp();
+    // du[r], dz1[r]
+    float du = 0.f;
+    for (int m = 0; m < m_dim; ++m) du = fmaf(w2_s[m][lane], dz2_s[warp][m], du);
+    const float dz1 = lane < r_dim ? du * act_grad(u, z1, act) : 0.f;
+    dz1_s[warp][lane] = dz1;
+    __syncwarp();
+    // dp[m], grad_x
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = lane + 32 * h;
+      if (live && m < m_dim) {
+        float dp = 0.f;
+        for (int r = 0; r < r_dim; ++r) dp = fmaf(w1_s[r][m], dz1_s[warp][r], dp);
+        dp *= inv_e;
+        const float* gr = g + (b * m_dim + m) * embed;
+        float* o = gx + (b * m_dim + m) * embed;
+        for (int e = 0; e < embed; ++e) o[e] = fmaf(__ldg(gr + e), sv[h], dp);
+      }
+    }
+    __syncthreads();
+    // parameter gradients of this round's kSeWarps samples: one owner thread per element, warps in fixed order
+    for (int i = tid; i < r_dim * m_dim; i += blockDim.x) {
+      const int r = i / m_dim, m = i - r * m_dim;
+      float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < kSeWarps; ++w) {
+        a1 = fmaf(dz1_s[w][r], p_s[w][m], a1);
+        a2 = fmaf(dz2_s[w][m], u_s[w][r], a2);
+      }
+      gw1_s[r][m] += a1;
+      gw2_s[m][r] += a2;
+    }
+    if (tid < r_dim) {
+      float a1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < kSeWarps; ++w) a1 += dz1_s[w][tid];
+      gb1_s[tid] += a1;
+    }
+    if (tid >= 64 && tid - 64 < m_dim) {
+      float a2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < kSeWarps; ++w) a2 += dz2_s[w][tid - 64];
+      gb2_s[tid - 64] += a2;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < r_dim * m_dim; i += blockDim.x) {
+    const int r = i / m_dim, m = i - r * m_dim;
+    atomicAdd(gw1 + i, gw1_s[r][m]);
+    atomicAdd(gw2 + m * r_dim + r, gw2_s[m][r]);
+  }
+  if (tid < r_dim) atomicAdd(gb1 + tid, gb1_s[tid]);
+  if (tid >= 64 && tid - 64 < m_dim) atomicAdd(gb2 + tid - 64, gb2_s[tid - 64]);
+}
+
+}  // namespace
+}  // namespace trs
+
+extern "C" int trs_senet_backward_supported(int rows_per_sample, int reduced) {
+  return rows_per_sample >= 1 && rows_per_sample <= kSeMaxM && reduced >= 1 && reduced <= kSeMaxR ? 1 : 0;
+}
+
+extern "C" int trs_senet_backward(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                                  int activation, const float* grad_out, int64_t batch, int rows_per_sample, int embed,
+                                  int reduced, float* grad_x, float* grad_w1, float* grad_b1, float* grad_w2,
+                                  float* grad_b2, void* stream) {
+  TRS_REQUIRE(x && w1 && b1 && w2 && b2 && grad_out && grad_x && grad_w1 && grad_b1 && grad_w2 && grad_b2,
+              "trs_senet_backward: null pointer");
+  TRS_REQUIRE(batch >= 0 && embed > 0, "trs_senet_backward: bad sizes");
+  TRS_REQUIRE(activation >= TRS_ACT_NONE && activation <= TRS_ACT_TANH, "trs_senet_backward: unknown activation");
+  TRS_UNSUPPORTED(!trs_senet_backward_supported(rows_per_sample, reduced),
+                  "trs_senet_backward: at most %d rows per sample and %d reduced units", kSeMaxM, kSeMaxR);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  TRS_CUDA(cudaMemsetAsync(grad_w1, 0, (size_t)reduced * rows_per_sample * sizeof(float), s));
+  TRS_CUDA(cudaMemsetAsync(grad_w2, 0, (size_t)reduced * rows_per_sample * sizeof(float), s));
+  TRS_CUDA(cudaMemsetAsync(grad_b1, 0, (size_t)reduced * sizeof(float), s));
+  TRS_CUDA(cudaMemsetAsync(grad_b2, 0, (size_t)rows_per_sample * sizeof(float), s));
+  if (batch == 0) return TRS_OK;
+  const int64_t want = (batch + kSeWarps - 1) / kSeWarps;
+  const int grid = static_cast<int>(want < kNumSMs * 2 ? want : kNumSMs * 2);
+  senet_backward_kernel<<<grid, kSeWarps * 32, 0, s>>>(x, w1, b1, w2, b2, activation, grad_out, batch, rows_per_sample,
+                                                     embed, reduced, grad_x, grad_w1, grad_b1, grad_w2, grad_b2);
+  return check_launch("senet_backward_kernel");
+}

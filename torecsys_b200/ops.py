@@ -593,6 +593,26 @@ def mlp(x: torch.Tensor, pack: MlpPack) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------- fused models
+def senet_backward_supported(rows_per_sample: int, reduced: int) -> bool:
+    return bool(_cabi.load().trs_senet_backward_supported(rows_per_sample, reduced))
+
+
+def senet_backward(x, w1, b1, w2, b2, act: int, grad_out):
+    """(d x, d w1, d b1, d w2, d b2) of senet(): csrc/mlp_bwd.cu (compose_excitation_network.py:72-109 differentiated)."""
+    x, b, m, e = _bne('senet_backward', x)
+    _need_cuda('senet_backward', w1, b1, w2, b2, grad_out)
+    w1, b1, w2, b2, g = (_f32('senet_backward', t) for t in (w1, b1, w2, b2, grad_out))
+    r = w1.shape[0]
+    if tuple(w1.shape) != (r, m) or tuple(w2.shape) != (m, r) or g.numel() != x.numel():
+        raise ValueError(f'senet_backward: parameter / grad_out shapes do not match x {tuple(x.shape)}')
+    gx = torch.empty_like(x)
+    gw1, gb1, gw2, gb2 = (torch.empty_like(t) for t in (w1, b1, w2, b2))
+    check(_cabi.load().trs_senet_backward(_ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), act, _ptr(g), b, m, e, r,
+                                          _ptr(gx), _ptr(gw1), _ptr(gb1), _ptr(gw2), _ptr(gb2), _stream()),
+          'trs_senet_backward')
+    return gx, gw1, gb1, gw2, gb2
+
+
 def mlp_backward_supported(dims: Sequence[int]) -> bool:
     """Shapes trs_mlp_backward takes: in % 4 == 0, every other width <= 32, tile + grad_W_1 within shared memory."""
     return bool(_cabi.load().trs_mlp_backward_supported(int_array(list(dims)), len(dims) - 1))
