@@ -295,7 +295,7 @@ int cross_tc5_dispatch(const CrossTc5Args& a, cudaStream_t s) {
 
 template <int E>
 int cross_tc5_pick(const CrossTc5Args& a, cudaStream_t s) {
-  static const int slots = getenv("TRS_TC5_SLOTS") ? atoi(getenv("TRS_TC5_SLOTS")) : 2;   // 2 measured best
+  static const int slots = getenv("TRS_TC5_SLOTS") ? atoi(getenv("TRS_TC5_SLOTS")) : 3;   // 1: 148 us, 2: 151, 3: 141, 4: 161
   switch (slots) {
     case 1: return cross_tc5_dispatch<E, 1>(a, s);
     case 2: return cross_tc5_dispatch<E, 2>(a, s);

@@ -10,6 +10,8 @@ namespace trs {
 
 int cross_tc_launch(const float* x, const float* w, const float* b, int layers, int64_t rows, int embed, float* out,
                     cudaStream_t s);
+int cross_tc5_launch(const float* x, const float* w, const float* b, int layers, int64_t rows, int embed, float* out,
+                     cudaStream_t s);
 int dense_tc_supported(int k_dim, int c_dim, const void* x, const void* out);
 int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const float* bias, int c_dim, int activation,
                  float* out, cudaStream_t s);
@@ -445,8 +447,14 @@ extern "C" int trs_cross_forward(const float* x, const float* weights, const flo
   TRS_REQUIRE(x && out && (layers == 0 || (weights && biases)), "trs_cross_forward: null pointer");
   TRS_REQUIRE(rows >= 0 && embed > 0 && layers >= 0, "trs_cross_forward: bad sizes");
   if (rows == 0) return TRS_OK;
-  // E in {8,16,32,64}: register-resident 3xTF32 mma.sync chain (dcn_tc.cu); FP32 FFMA tiles otherwise.  (A tcgen05
-  // version with the chain in tensor memory exists -- cross_tc5.cu, trs_cross_forward_tc5 -- and measured slower.)
+  // Large inputs, E in {16, 32}: the chain of a 128-row tile in tensor memory on tcgen05 (cross_tc5.cu: 141-155 us for
+  // 1.28 M rows x 6 layers of width 32 against 241 us for the mma.sync chain, once its MMAs are issued under elect.sync).
+  // Else E in {8,16,32,64}: register-resident 3xTF32 mma.sync chain (dcn_tc.cu); FP32 FFMA tiles otherwise.
+  static const bool no_tc5 = getenv("TRS_DISABLE_TC5") != nullptr || getenv("TRS_DISABLE_TC") != nullptr;
+  if (!no_tc5 && layers >= 1 && rows >= 32768) {
+    const int rc = cross_tc5_launch(x, weights, biases, layers, rows, embed, out, static_cast<cudaStream_t>(stream));
+    if (rc != TRS_ERR_UNSUPPORTED) return rc;
+  }
   {
     const int rc = cross_tc_launch(x, weights, biases, layers, rows, embed, out, static_cast<cudaStream_t>(stream));
     if (rc != TRS_ERR_UNSUPPORTED) return rc;
