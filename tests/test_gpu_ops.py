@@ -336,6 +336,30 @@ def test_dcn_tcgen05_path(ops, n, e, cross_layers, deep, od):
         ops.dcn(bad.cuda(), *args)
 
 
+@pytest.mark.parametrize('b,n,e,a', [(300, 39, 16, 16), (129, 39, 16, 8), (1000, 10, 32, 32), (5000, 5, 16, 20),
+                                     (26 * 148 * 3 + 1, 4, 32, 1), (64, 64, 16, 16)])
+def test_afm_tcgen05_path(ops, b, n, e, a):
+    """afm_tc5.cu: the (sample, pair) rows of the batch in 128-row tiles, pair products as the A operand in tensor
+    memory, raw scores from the accumulators, then the per-sample softmax / weighted-sum kernel: output and attention
+    scores against the oracle (attentional_factorization_machine.py:99-120); ragged last tiles, padded attention
+    widths, tiles that span many samples (few pairs) and samples that span many tiles."""
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    tag = f'afm5/{n}/{e}/{a}'
+    x = torch.from_numpy(synth.uniform((b, n, e), f'{tag}/x{b}', -1.0, 1.0))
+    w1 = torch.from_numpy(synth.uniform((a, e), f'{tag}/w1', -e ** -0.5, e ** -0.5))
+    b1 = torch.from_numpy(synth.uniform((a,), f'{tag}/b1', -0.3, 0.3))
+    w2 = torch.from_numpy(synth.uniform((1, a), f'{tag}/w2', -a ** -0.5, a ** -0.5))
+    b2 = torch.from_numpy(synth.uniform((1,), f'{tag}/b2', -0.3, 0.3))
+    assert b * n * (n - 1) // 2 >= 128 * 148                  # the shape takes the tcgen05 route
+    out, sc = ops.afm(x.cuda(), w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda())
+    want_o, want_s = R.afm_layer(x, w1, b1, w2, b2)
+    assert normwise_err(out.cpu().numpy(), want_o.numpy()) <= TOL
+    assert normwise_err(sc.cpu().numpy(), want_s.numpy()) <= TOL
+    o2, s2 = ops.afm(x.cuda(), w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda())
+    assert torch.equal(o2, out) and torch.equal(s2, sc)
+
+
 @pytest.mark.parametrize('n,e,sizes,direct', [(7, 16, [128, 40], False), (39, 16, [64, 64], False),
                                               (5, 8, [200, 12], True), (9, 32, [24, 128, 8], False)])
 def test_cin_tensor_core_wide_layers(ops, n, e, sizes, direct):

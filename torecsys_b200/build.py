@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(PKG_DIR, 'libtorecsys_b200.so')
 STAMP = os.path.join(ROOT, 'build', 'sources.sha1')
 
 SOURCES = ['api.cu', 'embedding.cu', 'pairwise.cu', 'dense.cu', 'cin.cu', 'cin_tc.cu', 'fused_models.cu',
-           'deepfm_fast.cu', 'deepfm_packed.cu', 'deepfm_tc5.cu', 'dcn_tc.cu', 'dcn_tc5.cu', 'afm_tc.cu', 'ipn_tc.cu', 'bilinear_tc.cu', 'pnn_senet.cu', 'cross_tc5.cu', 'backward.cu', 'mlp_bwd.cu', 'bilinear_bwd.cu', 'afm_bwd.cu', 'fused_more.cu', 'ffm_interleaved.cu', 'ffm_blocks.cu', 'session.cu']
+           'deepfm_fast.cu', 'deepfm_packed.cu', 'deepfm_tc5.cu', 'dcn_tc.cu', 'dcn_tc5.cu', 'afm_tc.cu', 'afm_tc5.cu', 'ipn_tc.cu', 'bilinear_tc.cu', 'pnn_senet.cu', 'cross_tc5.cu', 'backward.cu', 'mlp_bwd.cu', 'bilinear_bwd.cu', 'afm_bwd.cu', 'fused_more.cu', 'ffm_interleaved.cu', 'ffm_blocks.cu', 'session.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

@@ -12,6 +12,8 @@ int bilinear_tc_launch(const float* x, const float* w, const float* bias, int ea
                        int embed, int64_t out_stride, float* out, cudaStream_t s);
 int afm_tc_launch(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, int64_t batch,
                   int fields, int embed, int attn, float* out, float* scores, cudaStream_t s);
+int afm_tc5_launch(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, int64_t batch,
+                   int fields, int embed, int attn, float* out, float* scores, cudaStream_t s);
 
 namespace {
 
@@ -438,6 +440,10 @@ extern "C" int trs_afm_forward(const float* x, const float* w1, const float* b1,
   TRS_REQUIRE(batch >= 0 && fields > 1 && embed > 0 && attn > 0, "trs_afm_forward: bad sizes");
   if (batch == 0) return TRS_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {  // large batches, embed 16 / 32, attn <= 32: tcgen05 with the pair products in tensor memory (afm_tc5.cu)
+    const int rc = afm_tc5_launch(x, w1, b1, w2, b2, batch, fields, embed, attn, out, scores, s);
+    if (rc != TRS_ERR_UNSUPPORTED) return rc;
+  }
   {  // the pair x embed x attn contraction on the tensor pipe (afm_tc.cu) when the shape allows
     const int rc = afm_tc_launch(x, w1, b1, w2, b2, batch, fields, embed, attn, out, scores, s);
     if (rc != TRS_ERR_UNSUPPORTED) return rc;
