@@ -475,23 +475,45 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
     a.hp_next = round_up(hl, 16);
     a.pool_off = pool_off; a.pooled_width = p.pooled_width; a.act = activation;
     a.h_pitch = hp; a.k_valid = hp; a.fold = fold;
-    const bool a_tmem = npad <= 128;   // accumulators leave 256 TMEM columns free: A operand goes to tensor memory
-    const size_t a_stage = 2 * 4 * kTileM * 16, b_stage = (size_t)2 * 4 * npad * 16;
-    const size_t fixed = (a_tmem ? 0 : kAStages * a_stage) + (size_t)fields * kTileM * 4 + 2 * npad * 4 +
-                         (2 * kMaxAStages + 2 * kMaxBStages + 2) * 8 + 16 + 128;
-    int b_stages = kMaxBStages;
-    while (b_stages > 2 && b_stages * b_stage + fixed > (size_t)kMaxDynSmem) --b_stages;
-    const size_t smem = b_stages * b_stage + fixed;
-    TRS_UNSUPPORTED(smem > (size_t)kMaxDynSmem, "cin: tensor-core tile does not fit shared memory");
-    a.b_stages = b_stages;
     if (a.h_next != nullptr && a.hp_next != hl)   // zero the padding columns the next layer will read
       TRS_CUDA(cudaMemsetAsync(a.h_next, 0, (size_t)m_rows * a.hp_next * sizeof(float), s));
     const int64_t tiles = (m_rows + kTileM - 1) / kTileM;
     const int grid = static_cast<int>(tiles < kNumSMs ? tiles : kNumSMs);
-    if (a_tmem) cin_tc_layer_kernel<true><<<grid, kThreads, smem, s>>>(a);
-    else cin_tc_layer_kernel<false><<<grid, kThreads, smem, s>>>(a);
-    rc = check_launch("cin_tc_layer_kernel");
-    if (rc != TRS_OK) return rc;
+    // A layer wider than 128 channels either runs as one pass with the A operand in shared memory (SS form: the shared-
+    // memory port carries A reads + A stores + B reads + the weight stream, ~138 of 128 B/cycle wanted) or -- TRS_CIN_SPLIT=1
+    // -- as two passes of <= 128 channels each with the A operand in tensor memory (the operand is generated twice).
+    // Measured (CIN [128,128], B = 65 536): one pass 9.09 ms, two passes 9.42 ms -- the split stays an experiment.
+    static const bool split_wide = getenv("TRS_CIN_SPLIT") != nullptr;
+    const int passes = (npad > 128 && split_wide) ? 2 : 1;
+    for (int pass = 0; pass < passes; ++pass) {
+      CinTcArgs ap = a;
+      if (passes == 2) {
+        ap.c_begin = pass * 128;
+        ap.c_eff = c_eff - ap.c_begin < 128 ? c_eff - ap.c_begin : 128;
+        ap.npad = round_up(ap.c_eff, 32);
+        const int64_t items = (int64_t)(hp / 16) * fields * 2 * 4 * ap.npad * 4;
+        float* wpp = wp + (pass == 0 ? 0 : (int64_t)(hp / 16) * fields * 2 * 4 * 128 * 4);
+        cin_tc_prep_weights_kernel<<<grid_for(items / 2, 256, 8), 256, 0, s>>>(conv_w[l], ap.c_begin, ap.c_eff, fields,
+                                                                               h_prev, hp, ap.npad, fold, wpp);
+        rc = check_launch("cin_tc_prep_weights_kernel");
+        if (rc != TRS_OK) return rc;
+        ap.wp = wpp;
+      }
+      const int np = ap.npad;
+      const bool a_tmem = np <= 128;   // accumulators leave 256 TMEM columns free: A operand goes to tensor memory
+      const size_t a_stage = 2 * 4 * kTileM * 16, b_stage = (size_t)2 * 4 * np * 16;
+      const size_t fixed = (a_tmem ? 0 : kAStages * a_stage) + (size_t)fields * kTileM * 4 + 2 * np * 4 +
+                           (2 * kMaxAStages + 2 * kMaxBStages + 2) * 8 + 16 + 128;
+      int b_stages = kMaxBStages;
+      while (b_stages > 2 && b_stages * b_stage + fixed > (size_t)kMaxDynSmem) --b_stages;
+      const size_t smem = b_stages * b_stage + fixed;
+      TRS_UNSUPPORTED(smem > (size_t)kMaxDynSmem, "cin: tensor-core tile does not fit shared memory");
+      ap.b_stages = b_stages;
+      if (a_tmem) cin_tc_layer_kernel<true><<<grid, kThreads, smem, s>>>(ap);
+      else cin_tc_layer_kernel<false><<<grid, kThreads, smem, s>>>(ap);
+      rc = check_launch("cin_tc_layer_kernel");
+      if (rc != TRS_OK) return rc;
+    }
     h = a.h_next;
     hp = a.hp_next;
     h_prev = hl;
