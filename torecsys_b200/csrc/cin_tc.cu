@@ -506,9 +506,12 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
                            (2 * kMaxAStages + 2 * kMaxBStages + 2) * 8 + 16 + 128;
       int b_stages = kMaxBStages;
       while (b_stages > 2 && b_stages * b_stage + fixed > (size_t)kMaxDynSmem) --b_stages;
+      static const int cap_b = getenv("TRS_CIN_B_STAGES") ? atoi(getenv("TRS_CIN_B_STAGES")) : 0;   // experiments
+      if (cap_b >= 2 && cap_b < b_stages) b_stages = cap_b;
       const size_t smem = b_stages * b_stage + fixed;
       TRS_UNSUPPORTED(smem > (size_t)kMaxDynSmem, "cin: tensor-core tile does not fit shared memory");
       ap.b_stages = b_stages;
+      if (getenv("TRS_CIN_VERBOSE")) fprintf(stderr, "cin layer %d pass %d: npad %d, a_tmem %d, b_stages %d, smem %zu\n", l, pass, np, (int)a_tmem, b_stages, smem);
       if (a_tmem) cin_tc_layer_kernel<true><<<grid, kThreads, smem, s>>>(ap);
       else cin_tc_layer_kernel<false><<<grid, kThreads, smem, s>>>(ap);
       rc = check_launch("cin_tc_layer_kernel");
