@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) cin_tc_transpose_kernel(const float* __re
 // fold != 0 (layer 0, where h = x0 and z[x, y] = z[y, x]): the pair (x, y) is kept only for y >= x, with the weight
 // W[c, x, y] + W[c, y, x] (W[c, x, x] on the diagonal); the kernel then skips the chunks that lie below the diagonal.
 __global__ void __launch_bounds__(256) cin_tc_prep_weights_kernel(const float* __restrict__ w, int c_begin, int c_eff, int fields,
-                                                                  int h_prev, int hp, int npad, int fold, int pair,
+                                                                  int h_prev, int hp, int npad, int fold,
                                                                   float* __restrict__ wp) {
   const int chunks = (hp / 16) * fields;
   const int64_t items = (int64_t)chunks * 4 * npad * 4;
@@ -73,15 +73,8 @@ __global__ void __launch_bounds__(256) cin_tc_prep_weights_kernel(const float* _
     const uint32_t hi = tf32_rna(v);
     const uint32_t lo = tf32_rna(v - __uint_as_float(hi));
     const int64_t base = (int64_t)q * (2 * 4 * npad * 4);
-    if (pair) {   // CTA pairs: CTA r of the pair streams the columns [r * npad/2, (r + 1) * npad/2) as ONE contiguous half stage
-      const int nh = npad >> 1, r = n / nh, nl = n - r * nh;
-      const int64_t half = base + (int64_t)r * (2 * 4 * nh * 4);
-      wp[half + ((0 * 4 + kc) * nh + nl) * 4 + j] = __uint_as_float(hi);
-      wp[half + ((1 * 4 + kc) * nh + nl) * 4 + j] = __uint_as_float(lo);
-    } else {
-      wp[base + ((0 * 4 + kc) * npad + n) * 4 + j] = __uint_as_float(hi);
-      wp[base + ((1 * 4 + kc) * npad + n) * 4 + j] = __uint_as_float(lo);
-    }
+    wp[base + ((0 * 4 + kc) * npad + n) * 4 + j] = __uint_as_float(hi);
+    wp[base + ((1 * 4 + kc) * npad + n) * 4 + j] = __uint_as_float(lo);
   }
 }
 
@@ -109,14 +102,9 @@ struct CinTcArgs {
 //   per half hi[16] | lo[16]) with tcgen05.st, the accumulators use columns 0..255, and only the weights stream from
 //   shared memory -- the SS form with both operands in shared memory is smem-port bound for N = 128
 //   (profiles/r01_cin_tcgen05_notes.md).  kATmem = false (npad = 256): accumulators need all 512 columns, A in smem.
-// kPair = true: the kernel runs as CTA PAIRS (cluster of 2, tcgen05 cta_group::2): one MMA spans the 128-row halves of both
-//   CTAs (M = 256), each CTA streams only HALF of the weight columns into its shared memory, the leader CTA (rank 0)
-//   issues every MMA and its commits arrive on the barriers of both CTAs; the peer's producers, weight loader (through a
-//   relay in its idle MMA warp) and epilogue warps signal the leader's barriers with cluster-scope arrives.
-template <bool kATmem, bool kPair>
+template <bool kATmem>
 __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   if (gridDim.y > 1) {   // wide dense layer: this CTA column owns one channel block
     a.c_begin = blockIdx.y * a.c_block;
     a.c_eff = a.c_total - a.c_begin < a.c_block ? a.c_total - a.c_begin : a.c_block;
@@ -127,16 +115,14 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
   const int npad = a.npad;
   const int dstride = kATmem ? 128 : npad;                     // TMEM columns between the two accumulator halves
   const uint32_t a_stage_bytes = kATmem ? 0 : 2 * 4 * kTileM * 16;   // hi/lo x 4 chunks x 256 rows x 16 B = 32 KB
-  const int nb = kPair ? npad >> 1 : npad;                     // weight columns in THIS CTA's shared memory
-  const uint32_t b_stage_bytes = 2 * 4 * nb * 16;              // hi/lo x 4 chunks x nb rows x 16 B
+  const uint32_t b_stage_bytes = 2 * 4 * npad * 16;            // hi/lo x 4 chunks x npad rows x 16 B
   unsigned char* a_smem = smem_raw;
   unsigned char* b_smem = a_smem + (size_t)kAS * a_stage_bytes;
   float* x0_s = reinterpret_cast<float*>(b_smem + (size_t)a.b_stages * b_stage_bytes);   // [fields][256]
   float* ss_s = x0_s + (size_t)a.fields * kTileM;                                        // scale[npad], shift[npad]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ss_s + 2 * npad);
-  // barriers: full_a[kMaxAStages], empty_a[kMaxAStages], full_b[kMaxBStages], empty_b[kMaxBStages], acc_full, acc_empty,
-  // peer_b[kMaxBStages] (pairs: "the peer's half of the weight stage has landed", arrived remotely)
-  constexpr int kNumBars = 2 * kMaxAStages + 3 * kMaxBStages + 2;
+  // barriers: full_a[kMaxAStages], empty_a[kMaxAStages], full_b[kMaxBStages], empty_b[kMaxBStages], acc_full, acc_empty
+  constexpr int kNumBars = 2 * kMaxAStages + 2 * kMaxBStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   const uint32_t bar0 = smem_u32(bars);
   auto full_a = [&](int s) { return bar0 + 8u * s; };
@@ -144,46 +130,32 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
   auto full_b = [&](int s) { return bar0 + 8u * (2 * kMaxAStages + s); };
   auto empty_b = [&](int s) { return bar0 + 8u * (2 * kMaxAStages + kMaxBStages + s); };
   const uint32_t acc_full = bar0 + 8u * (2 * kMaxAStages + 2 * kMaxBStages), acc_empty = acc_full + 8u;
-  auto peer_b = [&](int s) { return acc_empty + 8u + 8u * s; };
-  constexpr uint32_t kWarpsPerBar = (kProducerThreads / 32) * (kPair ? 2 : 1);   // both CTAs' warps arrive at the leader
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kAS; ++s) {
-      mbar_init(full_a(s), kWarpsPerBar);   // one arrive per producer warp
+      mbar_init(full_a(s), kProducerThreads / 32);   // one arrive per producer warp
       mbar_init(empty_a(s), 1);
     }
     for (int s = 0; s < a.b_stages; ++s) {
       mbar_init(full_b(s), 1);
       mbar_init(empty_b(s), 1);
-      mbar_init(peer_b(s), 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, kWarpsPerBar);
+    mbar_init(acc_empty, kProducerThreads / 32);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < npad; i += blockDim.x) {
     ss_s[i] = i < a.c_eff ? (a.scale ? __ldg(a.scale + a.c_begin + i) : 1.f) : 0.f;
     ss_s[npad + i] = (i < a.c_eff && a.shift) ? __ldg(a.shift + a.c_begin + i) : 0.f;
   }
-  if (warp == 8) {
-    if (kPair) tmem_alloc_pair(smem_u32(tmem_slot), 512);
-    else tmem_alloc(smem_u32(tmem_slot), 512);
-  }
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
-  if (kPair) cluster_sync_all();   // both CTAs' barriers are initialised before anyone arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int64_t tiles = (a.m_rows + kTileM - 1) / kTileM;
-  // this CTA's i-th tile.  Pairs walk PAIR-tiles of 512 rows (CTA r takes the r-th 256 of them; a tile past the end is
-  // all padding, its CTA still runs the protocol).
-  const int64_t iters = kPair ? ((tiles + 1) / 2 - (blockIdx.x >> 1) + (gridDim.x >> 1) - 1) / (gridDim.x >> 1)
-                              : (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  auto tile_of = [&](int64_t i) -> int64_t {
-    return kPair ? 2 * ((blockIdx.x >> 1) + i * (gridDim.x >> 1)) + rank : blockIdx.x + i * gridDim.x;
-  };
   const int ychunks = a.hp / 16;
   // fields walked with y-chunk yc: all of them, or (folded layer 0) those with x <= the chunk's last y
   auto x_count = [&](int yc) { return a.fold ? (16 * yc + 16 < a.fields ? 16 * yc + 16 : a.fields) : a.fields; };
@@ -191,8 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
   for (int yc = 0; yc < ychunks; ++yc) chunks += x_count(yc);
   // Every CTA walks the K loop from its own starting point (the sum is order independent): otherwise all 148 CTAs
   // stream the SAME weight chunk from L2 at the same moment and hot-spot a few L2 slices.
-  const int rot_id = kPair ? blockIdx.x >> 1 : blockIdx.x;   // both CTAs of a pair walk K in the same order
-  const int yc_rot = rot_id % ychunks, x_rot = (rot_id * 5) % a.fields;
+  const int yc_rot = blockIdx.x % ychunks, x_rot = (blockIdx.x * 5) % a.fields;
 
   if (warp < 8) {
     // =========================== A producers, then epilogue =====================================================
@@ -200,8 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
     int sa = 0;                  // A ring position and phase
     uint32_t pa = 0;
     uint32_t tile_n = 0;
-    for (int64_t it = 0; it < iters; ++it, ++tile_n) {
-      const int64_t tile = tile_of(it);
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_n) {
       const int64_t m = tile * kTileM + r;
       const bool row_ok = m < a.m_rows;
       for (int xf = 0; xf < a.fields; ++xf) x0_s[xf * kTileM + r] = row_ok ? (a.xt ? __ldg(a.xt + m * a.hp0 + xf) : 1.f) : 0.f;   // xt == null: x0 = 1 (plain dense layer)
@@ -268,10 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
           fence_proxy_async();   // make the generic-proxy stores visible to the tensor core (async proxy)
           }
           __syncwarp();
-          if (lane == 0) {
-            if (kPair) mbar_arrive_cluster(full_a(sa), 0);   // the leader's MMA warp waits for both CTAs' operands
-            else mbar_arrive(full_a(sa));
-          }
+          if (lane == 0) mbar_arrive(full_a(sa));
           if (++sa == kAS) { sa = 0; pa ^= 1; }
         }
       }
@@ -320,27 +287,12 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        if (kPair) mbar_arrive_cluster(acc_empty, 0);
-        else mbar_arrive(acc_empty);
-      }
-    }
-  } else if (warp == 8 && kPair && rank != 0) {
-    // =========================== peer CTA: relay "my half of the weight stage has landed" to the leader ===============
-    uint32_t pb = 0;
-    int sb = 0;
-    for (int64_t it = 0; it < iters; ++it) {
-      for (int q = 0; q < chunks; ++q) {
-        mbar_wait(full_b(sb), pb);
-        if (lane == 0) mbar_arrive_cluster(peer_b(sb), 0);
-        __syncwarp();
-        if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
-      }
+      if (lane == 0) mbar_arrive(acc_empty);
     }
   } else if (warp == 8) {
     // =========================== MMA issuer ===============================================================================
-    const uint32_t idesc = umma_idesc_tf32(npad, kPair ? 256 : 128);
-    const uint32_t a_lbo = kTileM * 16, b_lbo = nb * 16;
+    const uint32_t idesc = umma_idesc_tf32(npad);
+    const uint32_t a_lbo = kTileM * 16, b_lbo = npad * 16;
     // descriptors differ only in their 14-bit start-address field (16-byte units, shared memory < 256 KB): build the
     // two base descriptors once and add offsets, so that issuing an MMA costs a few integer adds in the one issuing
     // thread (with N = 128 an MMA lasts only ~64 cycles; descriptor arithmetic was the limiter)
@@ -352,13 +304,12 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
     const uint32_t a_half_u = (128 * 16) >> 4;                                // rows 128..255
     uint32_t tile_n = 0, pa = 0, pb = 0;
     int sa = 0, sb = 0;
-    for (int64_t it = 0; it < iters; ++it, ++tile_n) {
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_n) {
       mbar_wait(acc_empty, (tile_n & 1) ^ 1);   // epilogue of the previous tile has drained TMEM
       tc_fence_after();
       for (int q = 0; q < chunks; ++q) {
         mbar_wait(full_a(sa), pa);
         mbar_wait(full_b(sb), pb);
-        if (kPair) mbar_wait(peer_b(sb), pb);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t ad = a_desc0 + sa * a_stage_u;
@@ -378,25 +329,17 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
                 const uint64_t bsel = term == 1 ? b_lo : b_hi;
                 if (kATmem) {
                   const uint32_t ta_hi = tmem_base + 256 + sa * 64 + half * 32 + 8 * ks;
-                  if (kPair) umma_tf32_ts_pair(d, term == 0 ? ta_hi + 16 : ta_hi, bsel, idesc, accf);
-                  else umma_tf32_ts(d, term == 0 ? ta_hi + 16 : ta_hi, bsel, idesc, accf);
+                  umma_tf32_ts(d, term == 0 ? ta_hi + 16 : ta_hi, bsel, idesc, accf);
                 } else {
                   const uint64_t a_hi = ad + ks * a_ks_u + half * a_half_u;
-                  if (kPair) umma_tf32_pair(d, term == 0 ? a_hi + a_lo_u : a_hi, bsel, idesc, accf);
-                  else umma_tf32(d, term == 0 ? a_hi + a_lo_u : a_hi, bsel, idesc, accf);
+                  umma_tf32(d, term == 0 ? a_hi + a_lo_u : a_hi, bsel, idesc, accf);
                 }
               }
             }
           }
-          if (kPair) {                                  // (multicast: the same barriers in both CTAs)
-            umma_commit_pair(empty_a(sa));
-            umma_commit_pair(empty_b(sb));
-            if (q == chunks - 1) umma_commit_pair(acc_full);
-          } else {
-            umma_commit(empty_a(sa));                     // stages reusable once these MMAs have read them
-            umma_commit(empty_b(sb));
-            if (q == chunks - 1) umma_commit(acc_full);   // accumulators complete -> epilogue
-          }
+          umma_commit(empty_a(sa));                     // stages reusable once these MMAs have read them
+          umma_commit(empty_b(sb));
+          if (q == chunks - 1) umma_commit(acc_full);   // accumulators complete -> epilogue
         }
         __syncwarp();
         if (++sa == kAS) { sa = 0; pa ^= 1; }
@@ -407,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
     // =========================== weight loader (bulk copies L2 -> smem) ======================================================
     int sb = 0;
     uint32_t pb = 0;
-    for (int64_t it = 0; it < iters; ++it) {
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       for (int yci = 0; yci < ychunks; ++yci) {               // same walk as the producers
         const int yc = yci + yc_rot < ychunks ? yci + yc_rot : yci + yc_rot - ychunks;
         const int xn = x_count(yc), xr = x_rot % xn;
@@ -418,8 +361,8 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
         if (lane == 0) {
           mbar_expect_tx(full_b(sb), b_stage_bytes);
           bulk_g2s(smem_u32(b_smem + (size_t)sb * b_stage_bytes),
-                   reinterpret_cast<const unsigned char*>(a.wp) + ((size_t)q * (kPair ? 2 : 1) + rank) * b_stage_bytes,
-                   b_stage_bytes, full_b(sb));
+                   reinterpret_cast<const unsigned char*>(a.wp) + (size_t)q * b_stage_bytes, b_stage_bytes,
+                   full_b(sb));
         }
         __syncwarp();
         if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
@@ -429,11 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
   }
   tc_fence_before();
   __syncthreads();
-  if (kPair) cluster_sync_all();   // the leader's MMAs read the peer's shared / tensor memory: nobody leaves early
-  if (warp == 8) {
-    if (kPair) tmem_dealloc_pair(tmem_base, 512);
-    else tmem_dealloc(tmem_base, 512);
-  }
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace
@@ -505,12 +444,8 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
   cin_tc_transpose_kernel<<<grid_for(m_rows * p.hp0, 256, 8), 256, 0, s>>>(x, batch, fields, embed, p.hp0, xt);
   int rc = check_launch("cin_tc_transpose_kernel");
   if (rc != TRS_OK) return rc;
-  TRS_SMEM_OPT_IN((cin_tc_layer_kernel<true, false>));
-  TRS_SMEM_OPT_IN((cin_tc_layer_kernel<false, false>));
-  TRS_SMEM_OPT_IN((cin_tc_layer_kernel<true, true>));
-  TRS_SMEM_OPT_IN((cin_tc_layer_kernel<false, true>));
-  // TRS_CIN_PAIR=1: CTA pairs (cta_group::2), see the kernel
-  static const bool use_pairs = getenv("TRS_CIN_PAIR") != nullptr;
+  TRS_SMEM_OPT_IN(cin_tc_layer_kernel<true>);
+  TRS_SMEM_OPT_IN(cin_tc_layer_kernel<false>);
 
   const float* h = xt;
   int hp = p.hp0, h_prev = fields, pool_off = 0;
@@ -526,7 +461,7 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
     static const bool no_fold = getenv("TRS_CIN_NO_FOLD") != nullptr;
     const int fold = (l == 0 && !no_fold) ? 1 : 0;
     cin_tc_prep_weights_kernel<<<grid_for(w_items / 2, 256, 8), 256, 0, s>>>(conv_w[l], 0, c_eff, fields, h_prev, hp,
-                                                                             npad, fold, 0, wp);
+                                                                             npad, fold, wp);
     rc = check_launch("cin_tc_prep_weights_kernel");
     if (rc != TRS_OK) return rc;
     CinTcArgs a{};
@@ -559,25 +494,16 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
         const int64_t items = (int64_t)(hp / 16) * fields * 2 * 4 * ap.npad * 4;
         float* wpp = wp + (pass == 0 ? 0 : (int64_t)(hp / 16) * fields * 2 * 4 * 128 * 4);
         cin_tc_prep_weights_kernel<<<grid_for(items / 2, 256, 8), 256, 0, s>>>(conv_w[l], ap.c_begin, ap.c_eff, fields,
-                                                                               h_prev, hp, ap.npad, fold, 0, wpp);
+                                                                               h_prev, hp, ap.npad, fold, wpp);
         rc = check_launch("cin_tc_prep_weights_kernel");
         if (rc != TRS_OK) return rc;
         ap.wp = wpp;
       }
       const int np = ap.npad;
       const bool a_tmem = np <= 128;   // accumulators leave 256 TMEM columns free: A operand goes to tensor memory
-      const bool pair = use_pairs && tiles >= 2 * kNumSMs;
-      if (pair) {   // the weights again, in the pair layout (each CTA's half of the columns contiguous)
-        const int64_t items = (int64_t)(hp / 16) * fields * 2 * 4 * np * 4;
-        cin_tc_prep_weights_kernel<<<grid_for(items / 2, 256, 8), 256, 0, s>>>(conv_w[l], ap.c_begin, ap.c_eff, fields,
-                                                                               h_prev, hp, np, fold, 1,
-                                                                               const_cast<float*>(ap.wp));
-        rc = check_launch("cin_tc_prep_weights_kernel");
-        if (rc != TRS_OK) return rc;
-      }
-      const size_t a_stage = 2 * 4 * kTileM * 16, b_stage = (size_t)2 * 4 * (pair ? np / 2 : np) * 16;
+      const size_t a_stage = 2 * 4 * kTileM * 16, b_stage = (size_t)2 * 4 * np * 16;
       const size_t fixed = (a_tmem ? 0 : kAStages * a_stage) + (size_t)fields * kTileM * 4 + 2 * np * 4 +
-                           (2 * kMaxAStages + 3 * kMaxBStages + 2) * 8 + 16 + 128;
+                           (2 * kMaxAStages + 2 * kMaxBStages + 2) * 8 + 16 + 128;
       int b_stages = kMaxBStages;
       while (b_stages > 2 && b_stages * b_stage + fixed > (size_t)kMaxDynSmem) --b_stages;
       static const int cap_b = getenv("TRS_CIN_B_STAGES") ? atoi(getenv("TRS_CIN_B_STAGES")) : 0;   // experiments
@@ -585,29 +511,9 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
       const size_t smem = b_stages * b_stage + fixed;
       TRS_UNSUPPORTED(smem > (size_t)kMaxDynSmem, "cin: tensor-core tile does not fit shared memory");
       ap.b_stages = b_stages;
-      if (getenv("TRS_CIN_VERBOSE")) fprintf(stderr, "cin layer %d pass %d: npad %d, a_tmem %d, pair %d, b_stages %d, smem %zu\n", l, pass, np, (int)a_tmem, (int)pair, b_stages, smem);
-      if (pair) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(kNumSMs & ~1);
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        const cudaError_t e = a_tmem ? cudaLaunchKernelEx(&cfg, cin_tc_layer_kernel<true, true>, ap)
-                                     : cudaLaunchKernelEx(&cfg, cin_tc_layer_kernel<false, true>, ap);
-        if (e != cudaSuccess) {
-          set_error("launch of cin_tc_layer_kernel (pairs) failed: %s", cudaGetErrorString(e));
-          cudaGetLastError();
-          return TRS_ERR_CUDA;
-        }
-      } else if (a_tmem) cin_tc_layer_kernel<true, false><<<grid, kThreads, smem, s>>>(ap);
-      else cin_tc_layer_kernel<false, false><<<grid, kThreads, smem, s>>>(ap);
+      if (getenv("TRS_CIN_VERBOSE")) fprintf(stderr, "cin layer %d pass %d: npad %d, a_tmem %d, b_stages %d, smem %zu\n", l, pass, np, (int)a_tmem, b_stages, smem);
+      if (a_tmem) cin_tc_layer_kernel<true><<<grid, kThreads, smem, s>>>(ap);
+      else cin_tc_layer_kernel<false><<<grid, kThreads, smem, s>>>(ap);
       rc = check_launch("cin_tc_layer_kernel");
       if (rc != TRS_OK) return rc;
     }
@@ -646,7 +552,7 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
     const int c_cnt = c_dim - c0 < block ? c_dim - c0 : block;
     const int npad = round_up(c_cnt, 32);
     const int64_t w_items = (int64_t)(kp / 16) * 2 * 4 * npad * 4;
-    cin_tc_prep_weights_kernel<<<grid_for(w_items / 2, 256, 8), 256, 0, s>>>(w, c0, c_cnt, 1, k_dim, kp, npad, 0, 0,
+    cin_tc_prep_weights_kernel<<<grid_for(w_items / 2, 256, 8), 256, 0, s>>>(w, c0, c_cnt, 1, k_dim, kp, npad, 0,
                                                                              wp + (size_t)pass * w_floats);
     rc = check_launch("cin_tc_prep_weights_kernel");
   }
@@ -661,7 +567,7 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
     a.pool_off = 0; a.pooled_width = 0; a.act = activation;
     const size_t a_stage = 2 * 4 * kTileM * 16, b_stage = (size_t)2 * 4 * a.npad * 16;
     const size_t fixed = (a_tmem ? 0 : kAStages * a_stage) + (size_t)kTileM * 4 + 2 * a.npad * 4 +
-                         (2 * kMaxAStages + 3 * kMaxBStages + 2) * 8 + 16 + 128;
+                         (2 * kMaxAStages + 2 * kMaxBStages + 2) * 8 + 16 + 128;
     int b_stages = kMaxBStages;
     while (b_stages > 2 && b_stages * b_stage + fixed > (size_t)kMaxDynSmem) --b_stages;
     a.b_stages = b_stages;
@@ -670,11 +576,11 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
     const int per_pass = kNumSMs / passes > 0 ? kNumSMs / passes : 1;
     const dim3 grid(static_cast<unsigned>(tiles < per_pass ? tiles : per_pass), passes);
     if (a_tmem) {
-      TRS_SMEM_OPT_IN((cin_tc_layer_kernel<true, false>));
-      cin_tc_layer_kernel<true, false><<<grid, kThreads, smem, s>>>(a);
+      TRS_SMEM_OPT_IN(cin_tc_layer_kernel<true>);
+      cin_tc_layer_kernel<true><<<grid, kThreads, smem, s>>>(a);
     } else {
-      TRS_SMEM_OPT_IN((cin_tc_layer_kernel<false, false>));
-      cin_tc_layer_kernel<false, false><<<grid, kThreads, smem, s>>>(a);
+      TRS_SMEM_OPT_IN(cin_tc_layer_kernel<false>);
+      cin_tc_layer_kernel<false><<<grid, kThreads, smem, s>>>(a);
     }
     rc = check_launch("cin_tc_layer_kernel(dense)");
   }
