@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include "tc5.cuh"
+#include "tile_ops.cuh"
 
 namespace trs {
 namespace {
@@ -53,7 +54,8 @@ __global__ void __launch_bounds__(256) cin_tc_transpose_kernel(const float* __re
 // W[c, x, y] + W[c, y, x] (W[c, x, x] on the diagonal); the kernel then skips the chunks that lie below the diagonal.
 __global__ void __launch_bounds__(256) cin_tc_prep_weights_kernel(const float* __restrict__ w, int c_begin, int c_eff, int fields,
                                                                   int h_prev, int hp, int npad, int fold,
-                                                                  float* __restrict__ wp) {
+                                                                  float* __restrict__ wp, int c_real = 1 << 30,
+                                                                  int sel_embed = 1) {
   const int chunks = (hp / 16) * fields;
   const int64_t items = (int64_t)chunks * 4 * npad * 4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
@@ -64,7 +66,9 @@ __global__ void __launch_bounds__(256) cin_tc_prep_weights_kernel(const float* _
     const int yc = q / fields, xf = q - yc * fields;
     const int y = yc * 16 + kc * 4 + j;
     float v = 0.f;
-    if (n < c_eff && y < h_prev) {
+    if (n < c_eff && y < h_prev && c_begin + n >= c_real) {
+      v = (y % sel_embed == c_begin + n - c_real) ? 1.f : 0.f;   // selector channel (dense mode: fields == 1, k = y)
+    } else if (n < c_eff && y < h_prev) {
       const float* wc = w + (int64_t)(c_begin + n) * fields * h_prev;
       if (!fold) v = __ldg(wc + xf * h_prev + y);
       else if (y > xf) v = __ldg(wc + xf * h_prev + y) + __ldg(wc + y * h_prev + xf);
@@ -96,19 +100,52 @@ struct CinTcArgs {
   int c_total;             // gridDim.y > 1: channel blocks of `c_block` over c_total channels, one block per blockIdx.y
   int c_block;
   int64_t wp_pass_stride;  // floats between the prepared weights of consecutive channel blocks
+  // ---- dense mode, fused ends (wide deep branch of DeepFM) ---------------------------------------------
+  // gather: row m of the input is sample m's embedding rows, read straight from the table by the A producers
+  // (k = field * g_embed + e), so the (B, fields * embed) matrix never exists in HBM
+  const void* g_idx;        // (m_rows, g_fields) indices, null = plain dense input `h`
+  const int64_t* g_offsets;
+  const float* g_table;     // (g_rows, g_embed)
+  const float* g_wfeat;     // (g_rows,) first-order table or null
+  const float* g_bias;      // scalar added to the row base or null
+  int32_t* g_status;
+  float* row_base;          // (m_rows,) <- first-order + FM (+ bias): written by the CTA that owns the selector channels
+  int64_t g_rows;
+  int g_idx_bits, g_fields, g_embed;
+  // selector channels [c_real, c_real + sel_count): weight 1 where k % g_embed == channel - c_real, so their accumulators
+  // are the FM field sums s[e] = sum_f v[f, e]; the epilogue turns them into 0.5 * (sum_e s[e]^2 - sum v^2)
+  int c_real, sel_count;
+  // dot: the layer feeds a one-output Linear -- instead of storing its activations the epilogue writes
+  // dot_out[blockIdx.y][m] = sum_{c in this block} act[m][c] * dot_w[c]
+  const float* dot_w;
+  float* dot_out;
+  // TRS_DENSE_TRACE=1: per CTA cycle counters of the dense instantiations, 8 per CTA (see dense_tc_run)
+  long long* trace;
+  int coop;   // dense, A operand in shared memory: cooperative producers (always with gather)
 };
 
 // kATmem = true (npad <= 128): the generated A operand goes to TENSOR MEMORY (columns 256..511, four 64-column stages:
 //   per half hi[16] | lo[16]) with tcgen05.st, the accumulators use columns 0..255, and only the weights stream from
 //   shared memory -- the SS form with both operands in shared memory is smem-port bound for N = 128
 //   (profiles/r01_cin_tcgen05_notes.md).  kATmem = false (npad = 256): accumulators need all 512 columns, A in smem.
-template <bool kATmem>
-__global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) {
+//
+// kFused = true: the dense-mode instantiation: channel blocks in multiples of 16 and the fused ends described in CinTcArgs
+//   (rows gathered from the embedding table by the producers, FM / first-order row base, one-output Linear folded into the
+//   epilogue).
+__host__ __device__ inline int ss_pitch(int npad) { return (npad + 31) & ~31; }   // floats per per-channel array in smem
+
+// The dense instantiations run 12 warps: ptxas budgets 168 registers per thread for them, the two idle warps, the MMA warp
+// and the weight loader hand theirs back (setmaxnreg) and the eight producer / epilogue warps grow to 232 -- the
+// cooperative gather keeps 4 chunks x 16 loaded values plus the next chunk's row ids in flight per thread, and a SPILLED
+// in-flight load stalls the warp until the load lands (measured 6 400 cycles per chunk with 300 bytes of spills).
+constexpr int kDenseThreads = 384;
+template <bool kATmem, bool kFused, bool kTrace = false>
+__global__ void __launch_bounds__(kFused ? kDenseThreads : kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (gridDim.y > 1) {   // wide dense layer: this CTA column owns one channel block
     a.c_begin = blockIdx.y * a.c_block;
     a.c_eff = a.c_total - a.c_begin < a.c_block ? a.c_total - a.c_begin : a.c_block;
-    a.npad = (a.c_eff + 31) & ~31;
+    a.npad = (a.c_eff + 15) & ~15;
     a.wp += blockIdx.y * a.wp_pass_stride;
   }
   constexpr int kAS = kATmem ? 4 : kAStages;                   // A ring depth
@@ -119,11 +156,15 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
   unsigned char* a_smem = smem_raw;
   unsigned char* b_smem = a_smem + (size_t)kAS * a_stage_bytes;
   float* x0_s = reinterpret_cast<float*>(b_smem + (size_t)a.b_stages * b_stage_bytes);   // [fields][256]
-  float* ss_s = x0_s + (size_t)a.fields * kTileM;                                        // scale[npad], shift[npad]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ss_s + 2 * npad);
+  float* ss_s = x0_s + (size_t)a.fields * kTileM;                    // scale, shift, dot weight, selector flag: [np32] each
+  const int np32 = ss_pitch(npad);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ss_s + 4 * np32);
   // barriers: full_a[kMaxAStages], empty_a[kMaxAStages], full_b[kMaxBStages], empty_b[kMaxBStages], acc_full, acc_empty
   constexpr int kNumBars = 2 * kMaxAStages + 2 * kMaxBStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  // (dense) per-warp transpose buffers of the epilogue, 8 x 32 rows x 36 floats: over the A ring, which is idle once the
+  // tile's accumulators are complete, or -- A operand in tensor memory -- in their own space behind the barriers
+  float* stage_s = kATmem ? reinterpret_cast<float*>(tmem_slot + 4) : reinterpret_cast<float*>(a_smem);
   const uint32_t bar0 = smem_u32(bars);
   auto full_a = [&](int s) { return bar0 + 8u * s; };
   auto empty_a = [&](int s) { return bar0 + 8u * (kMaxAStages + s); };
@@ -145,10 +186,18 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
     mbar_init(acc_empty, kProducerThreads / 32);
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-    ss_s[i] = i < a.c_eff ? (a.scale ? __ldg(a.scale + a.c_begin + i) : 1.f) : 0.f;
-    ss_s[npad + i] = (i < a.c_eff && a.shift) ? __ldg(a.shift + a.c_begin + i) : 0.f;
+  for (int i = threadIdx.x; i < np32; i += blockDim.x) {
+    const int gc = a.c_begin + i;
+    const bool real = i < a.c_eff && gc < a.c_real;      // (selector channels: scale 1, no bias)
+    ss_s[i] = i < a.c_eff ? ((real && a.scale) ? __ldg(a.scale + gc) : 1.f) : 0.f;
+    ss_s[np32 + i] = (real && a.shift) ? __ldg(a.shift + gc) : 0.f;
+    ss_s[2 * np32 + i] = (kFused && real && a.dot_w) ? __ldg(a.dot_w + gc) : 0.f;
+    ss_s[3 * np32 + i] = (kFused && i < a.c_eff && gc >= a.c_real) ? 1.f : 0.f;
   }
+  // the CTA column that writes the per-row base (first-order + FM): the one whose channel block holds the selectors
+  const bool do_base = kFused && a.row_base != nullptr &&
+                       (a.sel_count > 0 ? (a.c_begin <= a.c_real && a.c_real + a.sel_count <= a.c_begin + a.c_eff)
+                                        : blockIdx.y == 0);
   if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
@@ -165,12 +214,18 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
   // stream the SAME weight chunk from L2 at the same moment and hot-spot a few L2 slices.
   const int yc_rot = blockIdx.x % ychunks, x_rot = (blockIdx.x * 5) % a.fields;
 
+  if (kFused) {
+    if (warp < 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  }
   if (warp < 8) {
     // =========================== A producers, then epilogue =====================================================
     const int r = threadIdx.x;   // row within the tile
     int sa = 0;                  // A ring position and phase
     uint32_t pa = 0;
     uint32_t tile_n = 0;
+    long long tr_wait_a = 0, tr_wait_acc = 0, tr_epi = 0;   // (trace) producer warp 0: cycles blocked / in the epilogue
+    const long long tr_t0 = (kTrace) ? clock64() : 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_n) {
       const int64_t m = tile * kTileM + r;
       const bool row_ok = m < a.m_rows;
@@ -179,6 +234,149 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
       // lasts less than a global-load latency, so the loads run that many chunks ahead of their use
       constexpr int kPF = kATmem ? 3 : 4;   // (register budget: the TMEM form also holds hi[16] / lo[16])
       float hbuf[kPF][16];
+      float first = 0.f, sq = 0.f;        // (fused gather) this row's sum of first-order values / of v^2
+      if (kFused && !kATmem && a.coop) {
+        // ---- dense layer, A operand in shared memory: the warp produces its 32 rows COOPERATIVELY -- lane (g, kq) =
+        // (lane / 4, lane % 4) handles the 16-byte piece kq of rows 8 i + g (i = 0..3), so the four lanes of a group read
+        // the 64 bytes of one row with ONE request (a thread per row issues four 16-byte requests per row: a random
+        // gather is bound by the request rate, ~35 G/s -- measured 745 us for the gathered layer that way), and every
+        // piece goes to the same place in the UMMA layout as before.  Gather (g_idx != null): row m = sample m, chunk yc
+        // = 16 columns of field f = 16 yc / embed (embed % 16 == 0); the lane also owns the first-order lookup of row
+        // 8 kq + g and reports that row's out-of-range indices.
+        const int g = lane >> 2, kq = lane & 3;
+        const bool gather = a.g_idx != nullptr;
+        int64_t mm[4];        // gather: flat position of the row's first index, else the row
+        bool ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          mm[i] = tile * kTileM + warp * 32 + 8 * i + g;
+          ok[i] = mm[i] < a.m_rows;
+          if (gather) mm[i] *= a.g_fields;
+        }
+        float hw[kPF];
+        float sq4[4] = {0.f, 0.f, 0.f, 0.f};
+        // The raw indices (and the field offset) of a chunk are fetched one chunk ahead of the row loads that need them
+        // and NOTHING touches them before that: a warp issues in order, so any instruction that consumes a load (the
+        // offset add, a sign extension, a range check) right behind it stalls the warp for a full memory latency -- five
+        // such stalls per chunk cost 6 400 cycles per chunk where the tile's MMAs need 1 250.  Loads of rows beyond the
+        // batch read position 0 of the index array instead of branching.
+        uint32_t rlo[4], rhi[4];
+        int64_t offn = 0;
+        auto fetch_idx = [&](int yci) {
+          const int yc = yci + yc_rot < ychunks ? yci + yc_rot : yci + yc_rot - ychunks;
+          const int f = yci < ychunks ? (yc * 16) / a.g_embed : 0;
+          offn = __ldg(a.g_offsets + f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int64_t pos = (ok[i] ? mm[i] : 0) + f;
+            if (a.g_idx_bits == 64)
+              asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(rlo[i]), "=r"(rhi[i])
+                           : "l"(reinterpret_cast<const long long*>(a.g_idx) + pos));
+            else
+              asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(rlo[i]) : "l"(reinterpret_cast<const int*>(a.g_idx) + pos));
+          }
+        };
+        if (gather) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rlo[i] = rhi[i] = 0u;
+          fetch_idx(0);
+        }
+        auto load_c = [&](float (&dst)[16], float& wv, int yci) {
+          const int yc = yci + yc_rot < ychunks ? yci + yc_rot : yci + yc_rot - ychunks;
+          const int k = yc * 16 + 4 * kq;
+          wv = 0.f;
+          if (gather) {
+            const int f = (yc * 16) / a.g_embed;
+            const int within = k - f * a.g_embed;
+            const bool starts = yc * 16 == f * a.g_embed;
+            const bool kok = yci < ychunks;
+            // (ONE first-order load per chunk, issued behind the loop: four predicated loads into the same register
+            // wait for each other -- write-after-write on the scoreboard, a memory latency each)
+            int64_t rr_own = -1;
+            bool own_live = false;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              const int64_t iv = a.g_idx_bits == 64
+                                     ? static_cast<int64_t>((static_cast<uint64_t>(rhi[i]) << 32) | rlo[i])
+                                     : static_cast<int64_t>(static_cast<int32_t>(rlo[i]));
+              const int64_t rr = iv + offn;
+              const bool live = ok[i] && kok;
+              if (live && rr >= 0 && rr < a.g_rows)
+                v = ldg_stream_f4(reinterpret_cast<const float4*>(a.g_table + rr * a.g_embed + within));
+              if (i == kq) { rr_own = rr; own_live = live; }
+              dst[4 * i + 0] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+            }
+            if (do_base && starts && own_live) {
+              if (rr_own >= 0 && rr_own < a.g_rows) {
+                if (a.g_wfeat != nullptr) wv = ldg_stream_f1(a.g_wfeat + rr_own);
+              } else {
+                report_oob(a.g_status, (tile * kTileM + warp * 32 + 8 * kq + g) * (int64_t)a.g_fields + f);
+              }
+            }
+            fetch_idx(yci + 1);
+            return;
+          }
+          const bool kok = yci < ychunks && k < a.k_valid;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[i] && kok) v = __ldg(reinterpret_cast<const float4*>(a.h + mm[i] * a.h_pitch + k));
+            dst[4 * i + 0] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+          }
+        };
+#pragma unroll
+        for (int p = 0; p < kPF; ++p) load_c(hbuf[p], hw[p], p);
+        for (int y0 = 0; y0 < ychunks; y0 += kPF) {
+#pragma unroll
+          for (int p = 0; p < kPF; ++p) {
+            if (y0 + p >= ychunks) break;
+            float hreg[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) hreg[j] = hbuf[p][j];
+            if (do_base) {
+              first += hw[p];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) sq4[j >> 2] = fmaf(hreg[j], hreg[j], sq4[j >> 2]);
+            }
+            load_c(hbuf[p], hw[p], y0 + p + kPF);
+            const long long tw0 = (kTrace && threadIdx.x == 0) ? clock64() : 0;
+            mbar_wait(empty_a(sa), pa ^ 1);
+            if (kTrace && threadIdx.x == 0) tr_wait_a += clock64() - tw0;
+            unsigned char* dst = a_smem + (size_t)sa * a_stage_bytes + kq * (kTileM * 16) + (warp * 32 + g) * 16;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float z = hreg[4 * i + j];
+                hi[j] = (__float_as_uint(z) + 0x1000u) & 0xffffe000u;
+                lo[j] = (__float_as_uint(z - __uint_as_float(hi[j])) + 0x1000u) & 0xffffe000u;
+              }
+              *reinterpret_cast<uint4*>(dst + 8 * i * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(dst + 4 * (kTileM * 16) + 8 * i * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_a(sa));
+            if (++sa == kAS) { sa = 0; pa ^= 1; }
+          }
+        }
+        if (do_base) {
+          // hand every row's sums to the thread that runs its epilogue (lane = row within the warp = 8 i + g)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            sq4[i] += __shfl_xor_sync(0xffffffffu, sq4[i], 1);
+            sq4[i] += __shfl_xor_sync(0xffffffffu, sq4[i], 2);
+          }
+          first = __shfl_sync(0xffffffffu, first, 4 * (lane & 7) + (lane >> 3));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float t = __shfl_sync(0xffffffffu, sq4[i], 4 * (lane & 7));
+            if ((lane >> 3) == i) sq = t;
+          }
+        }
+      } else {
       auto load_h = [&](float (&dst)[16], int yci) {
         const int yc = yci + yc_rot < ychunks ? yci + yc_rot : yci + yc_rot - ychunks;
 #pragma unroll
@@ -243,22 +441,102 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
         }
       }
       }
+      }   // (thread-per-row producers)
       // ---- epilogue of this tile: warps 0-3 -> accumulator half 0 (rows 0..127), warps 4-7 -> half 1 ------------
+      const long long te0 = (kTrace && threadIdx.x == 0) ? clock64() : 0;
       mbar_wait(acc_full, tile_n & 1);
       tc_fence_after();
+      const long long te1 = (kTrace && threadIdx.x == 0) ? clock64() : 0;
       const int half = warp >> 2;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + half * dstride;
       const int64_t b = row_ok ? m / a.embed : 0;
       const int e = row_ok ? static_cast<int>(m - b * a.embed) : 0;
+      float dot = 0.f, ssq = 0.f;   // (fused ends) this row's share of the one-output Linear / sum_e s[e]^2
       for (int c0 = 0; c0 < npad; c0 += 32) {
         uint32_t raw[32];
-        tmem_ld32(taddr + c0, raw);
-        float v[32];
+        if (!kFused || c0 + 32 <= npad) {
+          tmem_ld32(taddr + c0, raw);
+        } else {   // 16-column tail of a dense channel block
+          uint32_t r16[16];
+          tmem_ld16(taddr + c0, r16);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          v[j] = apply_act(fmaf(__uint_as_float(raw[j]), ss_s[c0 + j], ss_s[npad + c0 + j]), a.act);
+          for (int j = 0; j < 16; ++j) { raw[j] = r16[j]; raw[16 + j] = 0u; }
+        }
+        float v[32];
+        if (kFused) {
+          // dense layer: no per-channel scale, the bias comes as 128-bit broadcast loads, ReLU without the switch (the
+          // epilogue runs with two warps per scheduler, every dependent shared-memory load is exposed)
+          const float4* sh4 = reinterpret_cast<const float4*>(ss_s + np32 + c0);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = sh4[j4];
+            v[4 * j4 + 0] = __uint_as_float(raw[4 * j4 + 0]) + b4.x;
+            v[4 * j4 + 1] = __uint_as_float(raw[4 * j4 + 1]) + b4.y;
+            v[4 * j4 + 2] = __uint_as_float(raw[4 * j4 + 2]) + b4.z;
+            v[4 * j4 + 3] = __uint_as_float(raw[4 * j4 + 3]) + b4.w;
+          }
+          if (a.act == TRS_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (a.act != TRS_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], a.act);
+          }
+          if (a.dot_out != nullptr) {
+            const float4* dw4 = reinterpret_cast<const float4*>(ss_s + 2 * np32 + c0);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 w4 = dw4[j4];
+              dot = fmaf(v[4 * j4 + 0], w4.x, dot);
+              dot = fmaf(v[4 * j4 + 1], w4.y, dot);
+              dot = fmaf(v[4 * j4 + 2], w4.z, dot);
+              dot = fmaf(v[4 * j4 + 3], w4.w, dot);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = apply_act(fmaf(__uint_as_float(raw[j]), ss_s[c0 + j], ss_s[np32 + c0 + j]), a.act);
+        }
+        if (kFused && do_base && a.sel_count > 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float rv = __uint_as_float(raw[j]);
+            ssq = fmaf(rv * ss_s[3 * np32 + c0 + j], rv, ssq);
+          }
+        }
         // hidden half -> next layer's activations, row-major
-        if (a.h_next != nullptr) {
+        if (kFused && a.h_next != nullptr) {
+          // dense layer: the warp's 32 rows x 32 columns go through a shared-memory transpose so that every store
+          // instruction writes four whole 128-byte lines (a thread per row writes 16 bytes into each of 32 lines: the
+          // epilogue of a 400-wide layer took 44 K cycles per tile that way, more than the tile's MMAs)
+          float* st = stage_s + warp * (32 * 36);
+          __syncwarp();
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<float4*>(st + lane * 36 + 4 * j4) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          __syncwarp();
+          const int cc = lane & 7;
+          const int c = a.c_begin + c0 + 4 * cc;              // global channel of this lane's four columns
+          const int cl = c0 + 4 * cc;                         // ... within the block
+          const bool vec_ok = (a.hp_next & 3) == 0 && ((c - a.hid_begin) & 3) == 0;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int jr = it * 4 + (lane >> 3);
+            const int64_t mr = tile * kTileM + warp * 32 + jr;
+            if (mr >= a.m_rows) continue;
+            const float4 o = *reinterpret_cast<const float4*>(st + jr * 36 + 4 * cc);
+            float* orow = a.h_next + mr * a.hp_next - a.hid_begin;
+            if (vec_ok && c >= a.hid_begin && c + 3 < a.hid_begin + a.hid_count && cl + 3 < a.c_eff) {
+              *reinterpret_cast<float4*>(orow + c) = o;
+            } else {
+              const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (c + j >= a.hid_begin && c + j < a.hid_begin + a.hid_count && cl + j < a.c_eff) orow[c + j] = ov[j];
+            }
+          }
+        } else if (a.h_next != nullptr) {
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const int c = a.c_begin + c0 + 4 * j4;   // global channel
@@ -285,9 +563,24 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
           }
         }
       }
+      if (kFused && row_ok) {
+        if (a.dot_out != nullptr) a.dot_out[(int64_t)blockIdx.y * a.m_rows + m] = dot;
+        if (do_base)
+          a.row_base[m] = first + (a.sel_count > 0 ? 0.5f * (ssq - sq) : 0.f) + (a.g_bias ? __ldg(a.g_bias) : 0.f);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
+      // the transpose buffers lie over the A ring: no warp may start producing the next tile before all have stored
+      if (kFused && !kATmem) asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (kTrace && threadIdx.x == 0) {
+        tr_wait_acc += te1 - te0;
+        tr_epi += clock64() - te1;
+      }
+    }
+    if (kTrace && threadIdx.x == 0) {
+      long long* t = a.trace + 8 * (blockIdx.y * gridDim.x + blockIdx.x);
+      t[0] = clock64() - tr_t0; t[1] = tr_wait_a; t[2] = tr_wait_acc; t[3] = tr_epi;
     }
   } else if (warp == 8) {
     // =========================== MMA issuer ===============================================================================
@@ -304,13 +597,19 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
     const uint32_t a_half_u = (128 * 16) >> 4;                                // rows 128..255
     uint32_t tile_n = 0, pa = 0, pb = 0;
     int sa = 0, sb = 0;
+    long long tr_fa = 0, tr_fb = 0, tr_ae = 0;   // (trace) cycles the MMA warp waits for A, for B, for the epilogue
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_n) {
+      const long long tm0 = (kTrace) ? clock64() : 0;
       mbar_wait(acc_empty, (tile_n & 1) ^ 1);   // epilogue of the previous tile has drained TMEM
       tc_fence_after();
+      if (kTrace) tr_ae += clock64() - tm0;
       for (int q = 0; q < chunks; ++q) {
+        const long long tm1 = (kTrace) ? clock64() : 0;
         mbar_wait(full_a(sa), pa);
+        const long long tm2 = (kTrace) ? clock64() : 0;
         mbar_wait(full_b(sb), pb);
         tc_fence_after();
+        if (kTrace) { tr_fa += tm2 - tm1; tr_fb += clock64() - tm2; }
         if (elect_one()) {
           const uint64_t ad = a_desc0 + sa * a_stage_u;
           const uint64_t bd = b_desc0 + sb * b_stage_u;
@@ -346,7 +645,11 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
         if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
       }
     }
-  } else {
+    if (kTrace && lane == 0) {
+      long long* t = a.trace + 8 * (blockIdx.y * gridDim.x + blockIdx.x);
+      t[4] = tr_fa; t[5] = tr_fb; t[6] = tr_ae;
+    }
+  } else if (warp == 9) {
     // =========================== weight loader (bulk copies L2 -> smem) ======================================================
     int sb = 0;
     uint32_t pb = 0;
@@ -444,8 +747,8 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
   cin_tc_transpose_kernel<<<grid_for(m_rows * p.hp0, 256, 8), 256, 0, s>>>(x, batch, fields, embed, p.hp0, xt);
   int rc = check_launch("cin_tc_transpose_kernel");
   if (rc != TRS_OK) return rc;
-  TRS_SMEM_OPT_IN(cin_tc_layer_kernel<true>);
-  TRS_SMEM_OPT_IN(cin_tc_layer_kernel<false>);
+  TRS_SMEM_OPT_IN((cin_tc_layer_kernel<true, false>));
+  TRS_SMEM_OPT_IN((cin_tc_layer_kernel<false, false>));
 
   const float* h = xt;
   int hp = p.hp0, h_prev = fields, pool_off = 0;
@@ -475,6 +778,7 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
     a.hp_next = round_up(hl, 16);
     a.pool_off = pool_off; a.pooled_width = p.pooled_width; a.act = activation;
     a.h_pitch = hp; a.k_valid = hp; a.fold = fold;
+    a.c_real = 1 << 30;   // (no selector channels: every channel is a real one)
     if (a.h_next != nullptr && a.hp_next != hl)   // zero the padding columns the next layer will read
       TRS_CUDA(cudaMemsetAsync(a.h_next, 0, (size_t)m_rows * a.hp_next * sizeof(float), s));
     const int64_t tiles = (m_rows + kTileM - 1) / kTileM;
@@ -502,7 +806,7 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
       const int np = ap.npad;
       const bool a_tmem = np <= 128;   // accumulators leave 256 TMEM columns free: A operand goes to tensor memory
       const size_t a_stage = 2 * 4 * kTileM * 16, b_stage = (size_t)2 * 4 * np * 16;
-      const size_t fixed = (a_tmem ? 0 : kAStages * a_stage) + (size_t)fields * kTileM * 4 + 2 * np * 4 +
+      const size_t fixed = (a_tmem ? 0 : kAStages * a_stage) + (size_t)fields * kTileM * 4 + 4 * ss_pitch(np) * 4 +
                            (2 * kMaxAStages + 2 * kMaxBStages + 2) * 8 + 16 + 128;
       int b_stages = kMaxBStages;
       while (b_stages > 2 && b_stages * b_stage + fixed > (size_t)kMaxDynSmem) --b_stages;
@@ -512,8 +816,8 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
       TRS_UNSUPPORTED(smem > (size_t)kMaxDynSmem, "cin: tensor-core tile does not fit shared memory");
       ap.b_stages = b_stages;
       if (getenv("TRS_CIN_VERBOSE")) fprintf(stderr, "cin layer %d pass %d: npad %d, a_tmem %d, b_stages %d, smem %zu\n", l, pass, np, (int)a_tmem, b_stages, smem);
-      if (a_tmem) cin_tc_layer_kernel<true><<<grid, kThreads, smem, s>>>(ap);
-      else cin_tc_layer_kernel<false><<<grid, kThreads, smem, s>>>(ap);
+      if (a_tmem) cin_tc_layer_kernel<true, false><<<grid, kThreads, smem, s>>>(ap);
+      else cin_tc_layer_kernel<false, false><<<grid, kThreads, smem, s>>>(ap);
       rc = check_launch("cin_tc_layer_kernel");
       if (rc != TRS_OK) return rc;
     }
@@ -529,45 +833,104 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
 
 // ---- a plain dense layer out = act(x W^T + b) on the same kernel: a CIN layer with ONE field and x0 = 1 ----------------
 // x (rows, K) row-major with K % 4 == 0, W (C, K), out (rows, C).  C <= 128 runs the TMEM-operand form; wider layers are
-// cut into equal channel blocks of at most 256 (one block per blockIdx.y, the SMs divided between the blocks), each CTA
-// streaming only its block of the weights.  Scratch for the pre-split weights comes from the stream-ordered pool.
+// cut into equal channel blocks of at most 256 (multiples of 16; one block per blockIdx.y, the SMs divided between the
+// blocks), each CTA streaming only its block of the weights.  Scratch for the pre-split weights comes from the
+// stream-ordered pool.  TRS_DENSE_BLOCK=n caps the channel block (A/B measurements: <= 128 selects the TMEM-operand form).
+//
+// DenseFuse (tile_ops.cuh) adds the fused ends of the wide deep branch (multilayer_perceptron.py:63-84 fed by
+// multi_indices_emb.py:92-112): `idx` != null -> the input rows are gathered from the embedding table by the producers and
+// the per-row base first-order + FM (+ bias) is written to row_base; `dot_w` != null -> the layer's activations are not
+// stored, dot_out[block][row] receives their product with the one-output Linear that follows.
 int dense_tc_supported(int k_dim, int c_dim, const void* x, const void* out) {
   static const bool disabled = getenv("TRS_DISABLE_TC") != nullptr;
   return !disabled && k_dim % 4 == 0 && k_dim >= 16 && c_dim >= 16 && aligned16(x) && aligned16(out);
 }
 
-int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const float* bias, int c_dim, int activation,
-                 float* out, cudaStream_t s) {
+// channel blocks of a dense layer with c_real outputs (+ sel selector channels, kept inside ONE block); 0 = no split found
+static int dense_plan(int c_real, int sel, int* block_out) {
+  static const int cap_env = getenv("TRS_DENSE_BLOCK") ? atoi(getenv("TRS_DENSE_BLOCK")) : 0;
+  const int cap = (cap_env >= 16 && cap_env <= 256) ? cap_env / 16 * 16 : 256;
+  const int c_total = c_real + sel;
+  const int passes0 = (c_total + cap - 1) / cap;
+  for (int block = round_up((c_total + passes0 - 1) / passes0, 16); block <= 256; block += 16) {
+    if (sel > 0 && c_real / block != (c_real + sel - 1) / block) continue;   // selectors would straddle two blocks
+    *block_out = block;
+    return (c_total + block - 1) / block;
+  }
+  return 0;
+}
+
+int dense_tc_passes(int c_dim, int sel) {
+  int block = 0;
+  return dense_plan(c_dim, sel, &block);
+}
+
+__global__ void __launch_bounds__(256) dense_dot_finish_kernel(const float* __restrict__ dot, int passes, int64_t rows,
+                                                               const float* __restrict__ bias, float* __restrict__ out,
+                                                               int accumulate) {
+  const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  float v = accumulate ? out[m] : 0.f;
+  for (int p = 0; p < passes; ++p) v += __ldg(dot + (int64_t)p * rows + m);   // fixed order: deterministic
+  out[m] = v + (bias ? __ldg(bias) : 0.f);
+}
+
+// out[m] (+)= sum_p dot[p][m] + bias: closes a layer that ran with DenseFuse::dot_w
+int dense_dot_finish(const float* dot, int passes, int64_t rows, const float* bias, float* out, int accumulate,
+                     cudaStream_t s) {
   if (rows == 0) return TRS_OK;
+  dense_dot_finish_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, s>>>(dot, passes, rows, bias, out,
+                                                                                    accumulate);
+  return check_launch("dense_dot_finish_kernel");
+}
+
+int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const float* bias, int c_dim, int activation,
+                 float* out, cudaStream_t s, const DenseFuse* fz) {
+  if (rows == 0) return TRS_OK;
+  const bool gather = fz != nullptr && fz->idx != nullptr;
+  const int sel = (gather && fz->use_fm) ? fz->embed : 0;
+  if (gather) TRS_REQUIRE(fz->embed % 16 == 0 && fz->fields * fz->embed == k_dim, "dense: bad gather description");
   const int kp = round_up(k_dim, 16);
-  const int passes = (c_dim + 255) / 256;
-  const int block = round_up((c_dim + passes - 1) / passes, 32);
-  const bool a_tmem = block <= 128;
-  const size_t w_floats = (size_t)(kp / 16) * 2 * 4 * block * 4;   // upper bound per channel block
+  int block = 0;
+  const int passes = dense_plan(c_dim, sel, &block);
+  TRS_UNSUPPORTED(passes == 0, "dense: no channel split keeps the selector channels in one block");
+  const int c_total = c_dim + sel;
+  const bool a_tmem = block <= 128 && !gather;   // (the gathering producers write the shared-memory operand form)
+  const size_t w_floats = (size_t)(kp / 16) * 2 * 4 * block * 4;   // per channel block
   float* wp = nullptr;
   TRS_CUDA(scratch_alloc(reinterpret_cast<void**>(&wp), w_floats * sizeof(float) * passes, s));
   int rc = TRS_OK;
   for (int pass = 0; pass < passes && rc == TRS_OK; ++pass) {
     const int c0 = pass * block;
-    const int c_cnt = c_dim - c0 < block ? c_dim - c0 : block;
-    const int npad = round_up(c_cnt, 32);
+    const int c_cnt = c_total - c0 < block ? c_total - c0 : block;
+    const int npad = round_up(c_cnt, 16);
     const int64_t w_items = (int64_t)(kp / 16) * 2 * 4 * npad * 4;
     cin_tc_prep_weights_kernel<<<grid_for(w_items / 2, 256, 8), 256, 0, s>>>(w, c0, c_cnt, 1, k_dim, kp, npad, 0,
-                                                                             wp + (size_t)pass * w_floats);
+                                                                             wp + (size_t)pass * w_floats, c_dim,
+                                                                             sel > 0 ? sel : 1);
     rc = check_launch("cin_tc_prep_weights_kernel");
   }
   if (rc == TRS_OK) {
     CinTcArgs a{};
     a.xt = nullptr; a.h = x; a.wp = wp; a.scale = nullptr; a.shift = bias;
-    a.h_next = out; a.pooled = nullptr;
+    a.h_next = (fz != nullptr && fz->dot_w != nullptr) ? nullptr : out; a.pooled = nullptr;
     a.m_rows = rows; a.fields = 1; a.embed = 1; a.hp0 = 0; a.hp = kp; a.h_pitch = k_dim; a.k_valid = k_dim;
-    a.c_begin = 0; a.c_eff = c_dim < block ? c_dim : block; a.npad = round_up(a.c_eff, 32);
-    a.c_total = c_dim; a.c_block = block; a.wp_pass_stride = (int64_t)w_floats;
+    a.c_begin = 0; a.c_eff = c_total < block ? c_total : block; a.npad = round_up(a.c_eff, 16);
+    a.c_total = c_total; a.c_block = block; a.wp_pass_stride = (int64_t)w_floats;
     a.n_direct = 0; a.hid_begin = 0; a.hid_count = c_dim; a.hp_next = c_dim;
     a.pool_off = 0; a.pooled_width = 0; a.act = activation;
+    a.c_real = c_dim; a.sel_count = sel;
+    static const bool coop_env = getenv("TRS_DENSE_COOP") ? atoi(getenv("TRS_DENSE_COOP")) != 0 : true;
+    a.coop = (gather || coop_env) ? 1 : 0;
+    if (fz != nullptr) {
+      a.g_idx = fz->idx; a.g_idx_bits = fz->idx_bits; a.g_offsets = fz->offsets; a.g_table = fz->table;
+      a.g_wfeat = fz->w_feat; a.g_bias = fz->bias; a.g_status = fz->status; a.row_base = gather ? fz->row_base : nullptr;
+      a.g_rows = fz->table_rows; a.g_fields = fz->fields; a.g_embed = fz->embed;
+      a.dot_w = fz->dot_w; a.dot_out = fz->dot_w != nullptr ? fz->dot_out : nullptr;
+    }
     const size_t a_stage = 2 * 4 * kTileM * 16, b_stage = (size_t)2 * 4 * a.npad * 16;
-    const size_t fixed = (a_tmem ? 0 : kAStages * a_stage) + (size_t)kTileM * 4 + 2 * a.npad * 4 +
-                         (2 * kMaxAStages + 2 * kMaxBStages + 2) * 8 + 16 + 128;
+    const size_t fixed = (a_tmem ? (size_t)8 * 32 * 36 * 4 : kAStages * a_stage) + (size_t)kTileM * 4 +
+                         4 * ss_pitch(a.npad) * 4 + (2 * kMaxAStages + 2 * kMaxBStages + 2) * 8 + 16 + 128;
     int b_stages = kMaxBStages;
     while (b_stages > 2 && b_stages * b_stage + fixed > (size_t)kMaxDynSmem) --b_stages;
     a.b_stages = b_stages;
@@ -575,14 +938,42 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
     const int64_t tiles = (rows + kTileM - 1) / kTileM;
     const int per_pass = kNumSMs / passes > 0 ? kNumSMs / passes : 1;
     const dim3 grid(static_cast<unsigned>(tiles < per_pass ? tiles : per_pass), passes);
-    if (a_tmem) {
-      TRS_SMEM_OPT_IN(cin_tc_layer_kernel<true>);
-      cin_tc_layer_kernel<true><<<grid, kThreads, smem, s>>>(a);
+    static const bool trace_on = getenv("TRS_DENSE_TRACE") != nullptr;
+    if (trace_on) {
+      TRS_CUDA(cudaMalloc(reinterpret_cast<void**>(&a.trace), sizeof(long long) * 8 * grid.x * grid.y));
+      TRS_CUDA(cudaMemsetAsync(a.trace, 0, sizeof(long long) * 8 * grid.x * grid.y, s));
+    }
+    // every dense launch takes the kFused instantiation (16-column channel-block tails); <*, false> is the CIN's
+    if (trace_on && a_tmem) {
+      TRS_SMEM_OPT_IN((cin_tc_layer_kernel<true, true, true>));
+      cin_tc_layer_kernel<true, true, true><<<grid, kDenseThreads, smem, s>>>(a);
+    } else if (trace_on) {
+      TRS_SMEM_OPT_IN((cin_tc_layer_kernel<false, true, true>));
+      cin_tc_layer_kernel<false, true, true><<<grid, kDenseThreads, smem, s>>>(a);
+    } else if (a_tmem) {
+      TRS_SMEM_OPT_IN((cin_tc_layer_kernel<true, true>));
+      cin_tc_layer_kernel<true, true><<<grid, kDenseThreads, smem, s>>>(a);
     } else {
-      TRS_SMEM_OPT_IN(cin_tc_layer_kernel<false>);
-      cin_tc_layer_kernel<false><<<grid, kThreads, smem, s>>>(a);
+      TRS_SMEM_OPT_IN((cin_tc_layer_kernel<false, true>));
+      cin_tc_layer_kernel<false, true><<<grid, kDenseThreads, smem, s>>>(a);
     }
     rc = check_launch("cin_tc_layer_kernel(dense)");
+    if (trace_on && rc == TRS_OK) {
+      const int n = grid.x * grid.y;
+      long long* hbuf = static_cast<long long*>(malloc(sizeof(long long) * 8 * n));
+      cudaStreamSynchronize(s);
+      cudaMemcpy(hbuf, a.trace, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost);
+      double sum[8] = {0};
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < 8; ++j) sum[j] += (double)hbuf[8 * i + j] / n;
+      fprintf(stderr,
+              "dense trace K %d C %d(+%d) block %d x%d %s gather %d dot %d tiles/cta %.2f: total %.0f cyc | producer: wait A-free "
+              "%.0f, wait acc %.0f, epilogue %.0f | mma: wait A %.0f, wait B %.0f, wait epilogue %.0f\n",
+              k_dim, c_dim, sel, block, passes, a_tmem ? "TS" : "SS", (int)gather, (int)(a.dot_out != nullptr),
+              (double)tiles / grid.x, sum[0], sum[1], sum[2], sum[3], sum[4], sum[5], sum[6]);
+      free(hbuf);
+      cudaFree(a.trace);
+    }
   }
   cudaFreeAsync(wp, s);
   return rc;

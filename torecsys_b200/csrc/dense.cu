@@ -14,7 +14,10 @@ int cross_tc5_launch(const float* x, const float* w, const float* b, int layers,
                      cudaStream_t s);
 int dense_tc_supported(int k_dim, int c_dim, const void* x, const void* out);
 int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const float* bias, int c_dim, int activation,
-                 float* out, cudaStream_t s);
+                 float* out, cudaStream_t s, const DenseFuse* fz);
+int dense_tc_passes(int c_dim, int sel);
+int dense_dot_finish(const float* dot, int passes, int64_t rows, const float* bias, float* out, int accumulate,
+                     cudaStream_t s);
 
 namespace {
 
@@ -383,22 +386,66 @@ int mlp_chain_supported(const int* dims, int layers, int64_t rows, const void* x
   return wide ? 1 : 0;
 }
 
-int mlp_chain_run(const float* x, int64_t rows, const MlpParams& mp, float* out, int accumulate, cudaStream_t s) {
+// The layer before a one-output Linear runs with that Linear folded into its epilogue (its activations are never stored)
+// when it is a tensor-core layer; TRS_MLP_NO_DOT=1 switches that off (A/B measurements).
+static bool chain_dot_fusable(const MlpParams& mp) {
+  static const bool off = getenv("TRS_MLP_NO_DOT") != nullptr;
+  const int L = mp.layers;
+  return !off && L >= 2 && mp.dims[L] == 1 && chain_layer_on_tc(mp.dims[L - 2], mp.dims[L - 1]);
+}
+
+// Can the chain read its input rows straight from an embedding table (DenseFuse gather, cin_tc.cu)?  The first layer must
+// be a tensor-core layer, the rows whole 16-column chunks, and the FM selector channels must fit one channel block.
+int mlp_chain_gather_supported(const int* dims, int layers, int fields, int embed, int use_fm) {
+  static const bool off = getenv("TRS_MLP_NO_GATHER") != nullptr;
+  if (off || layers < 2 || embed % 16 != 0 || dims[0] != fields * embed || dims[layers] != 1) return 0;
+  if (!chain_layer_on_tc(dims[0], dims[1]) || dims[0] < 16) return 0;
+  if (use_fm && embed > 64) return 0;
+  return dense_tc_passes(dims[1], use_fm ? embed : 0) > 0 ? 1 : 0;
+}
+
+// `gather` != null (mlp_chain_gather_supported): x is ignored, layer 0 gathers its rows itself and writes the row base
+// (first-order + FM + bias) to out, onto which the last layer accumulates.
+int mlp_chain_run(const float* x, int64_t rows, const MlpParams& mp, float* out, int accumulate, cudaStream_t s,
+                  const DenseFuse* gather) {
+  const int L = mp.layers;
   int hmax = 0;
-  for (int l = 1; l < mp.layers; ++l) hmax = mp.dims[l] > hmax ? mp.dims[l] : hmax;
+  for (int l = 1; l < L; ++l) hmax = mp.dims[l] > hmax ? mp.dims[l] : hmax;
+  const bool dot = chain_dot_fusable(mp);
+  const int sel_last = (gather != nullptr && L == 2 && gather->use_fm) ? gather->embed : 0;
+  const int dot_passes = dot ? dense_tc_passes(mp.dims[L - 1], sel_last) : 0;
   const size_t half = ((size_t)rows * hmax + 63) / 64 * 64;
+  const size_t dot_floats = ((size_t)rows * dot_passes + 63) / 64 * 64;
   float* buf = nullptr;
-  if (mp.layers > 1) TRS_CUDA(scratch_alloc(reinterpret_cast<void**>(&buf), 2 * half * sizeof(float), s));
+  if (L > 1) TRS_CUDA(scratch_alloc(reinterpret_cast<void**>(&buf), (2 * half + dot_floats) * sizeof(float), s));
+  float* dot_buf = buf + 2 * half;
+  if (gather != nullptr) accumulate = 1;
   const float* cur = x;
   int rc = TRS_OK;
-  for (int l = 0; l < mp.layers && rc == TRS_OK; ++l) {
-    const bool last = l == mp.layers - 1;
+  for (int l = 0; l < L && rc == TRS_OK; ++l) {
+    const bool last = l == L - 1;
+    if (last && dot) {
+      rc = dense_dot_finish(dot_buf, dot_passes, rows, mp.b[l], out, accumulate, s);
+      break;
+    }
     float* dst = last ? out : buf + (l & 1) * half;
     const int act = last ? TRS_ACT_NONE : mp.act;
     if (chain_layer_tall(mp.dims[l], mp.dims[l + 1]) && !(last && accumulate)) {
       rc = tall_dense_run(cur, rows, mp.dims[l], mp.w[l], mp.b[l], mp.dims[l + 1], act, dst, s);
     } else if (chain_layer_on_tc(mp.dims[l], mp.dims[l + 1])) {
-      rc = dense_tc_run(cur, rows, mp.dims[l], mp.w[l], mp.b[l], mp.dims[l + 1], act, dst, s);
+      DenseFuse fz;
+      bool fused = false;
+      if (l == 0 && gather != nullptr) {
+        fz = *gather;
+        fz.row_base = out;
+        fused = true;
+      }
+      if (dot && l == L - 2) {
+        fz.dot_w = mp.w[L - 1];
+        fz.dot_out = dot_buf;
+        fused = true;
+      }
+      rc = dense_tc_run(cur, rows, mp.dims[l], mp.w[l], mp.b[l], mp.dims[l + 1], act, dst, s, fused ? &fz : nullptr);
     } else {
       narrow_dense_kernel<<<grid_for(rows * 32, 256, 8), 256, 0, s>>>(cur, rows, mp.dims[l], mp.w[l], mp.b[l],
                                                                       mp.dims[l + 1], act, dst,
@@ -425,7 +472,7 @@ extern "C" int trs_mlp_forward(const float* x, int64_t rows, const int* dims, in
               "trs_mlp_forward: bad layer description (at most %d layers)", MlpParams::kMaxLayers);
   if (rows == 0) return TRS_OK;
   if (mlp_chain_supported(dims, layers, rows, x, out, 0))
-    return mlp_chain_run(x, rows, mp, out, 0, static_cast<cudaStream_t>(stream));
+    return mlp_chain_run(x, rows, mp, out, 0, static_cast<cudaStream_t>(stream), nullptr);
   const int in_pitch = tile_pitch(dims[0]);
   const int hpitch = tile_pitch(mlp_max_hidden(dims, layers));
   int ts = 64;

@@ -22,7 +22,9 @@ int deepfm_fast_launch(const void* idx, int idx_bits, const int64_t* offsets, in
                        const float* const* mlp_b, int mlp_layers, float* logits, int32_t* status, cudaStream_t s);
 
 int mlp_chain_supported(const int* dims, int layers, int64_t rows, const void* x, const void* out, int accumulate);
-int mlp_chain_run(const float* x, int64_t rows, const MlpParams& mp, float* out, int accumulate, cudaStream_t s);
+int mlp_chain_run(const float* x, int64_t rows, const MlpParams& mp, float* out, int accumulate, cudaStream_t s,
+                  const DenseFuse* gather);
+int mlp_chain_gather_supported(const int* dims, int layers, int fields, int embed, int use_fm);
 int dcn_tc_supported(int embed, int cross_layers, const int* mlp_dims, int mlp_layers, int activation);
 int dcn_tc_launch(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
                   const float* w_emb, int64_t rows, int embed, const float* cross_w, const float* cross_b,
@@ -323,6 +325,14 @@ int launch_fm_family(const void* idx, int idx_bits, const int64_t* offsets, int6
   float* x_scratch = nullptr;
   bool chained = false;
   if (mlp_layers > 0 && mlp_chain_supported(mlp_dims, mlp_layers, batch, logits, logits, 1)) {
+    // Fully fused form: the first tensor-core layer gathers the rows itself and emits first-order + FM per
+    // sample, the last hidden layer carries the logit Linear in its epilogue -- no gather kernel, no (B, N*E) matrix.
+    if (a.x_out == nullptr && mlp_chain_gather_supported(mlp_dims, mlp_layers, fields, embed, use_fm)) {
+      DenseFuse g;
+      g.idx = idx; g.idx_bits = idx_bits; g.offsets = offsets; g.table = w_emb; g.w_feat = w_feat; g.bias = bias;
+      g.status = status; g.table_rows = rows; g.fields = fields; g.embed = embed; g.use_fm = use_fm;
+      return mlp_chain_run(nullptr, batch, chain, logits, 1, s, &g);
+    }
     chained = true;
     a.mp.layers = 0;
     mlp_layers = 0;
@@ -355,7 +365,7 @@ int launch_fm_family(const void* idx, int idx_bits, const int64_t* offsets, int6
   }
   int rc = check_launch("fm_family_kernel");
   if (chained) {
-    if (rc == TRS_OK) rc = mlp_chain_run(a.x_out, batch, chain, logits, 1, s);
+    if (rc == TRS_OK) rc = mlp_chain_run(a.x_out, batch, chain, logits, 1, s, nullptr);
     if (x_scratch) cudaFreeAsync(x_scratch, s);
   }
   return rc;

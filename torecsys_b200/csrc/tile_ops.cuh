@@ -25,6 +25,26 @@ struct MlpParams {
   int act;
 };
 
+// Fused ends of a tcgen05 dense layer (dense_tc_run, cin_tc.cu) -- the wide deep branch of DeepFM-style models:
+//   idx != null   : the layer's input rows are gathered by the kernel itself (row m = the `fields` embedding rows of sample
+//                   m, k = field * embed + e), and row_base[m] = sum_f w_feat[r_f] + (use_fm ? FM(rows) : 0) + bias
+//   dot_w != null : the layer feeds a one-output Linear; its activations are not stored, dot_out[block][m] receives the
+//                   partial products (dense_tc_passes() blocks, closed by dense_dot_finish)
+struct DenseFuse {
+  const void* idx = nullptr;
+  int idx_bits = 64;
+  const int64_t* offsets = nullptr;
+  const float* table = nullptr;     // (table_rows, embed)
+  const float* w_feat = nullptr;    // (table_rows,) or null
+  const float* bias = nullptr;      // scalar or null
+  int32_t* status = nullptr;
+  float* row_base = nullptr;        // (rows,)
+  int64_t table_rows = 0;
+  int fields = 0, embed = 0, use_fm = 0;
+  const float* dot_w = nullptr;     // (c_dim,)
+  float* dot_out = nullptr;         // (passes, rows)
+};
+
 #ifdef __CUDACC__
 
 // Gathers `ts` samples x `fields` rows of `embed` floats into tile[s * pitch + n * row_pitch + e].
