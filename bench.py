@@ -373,7 +373,34 @@ def bench_other_configs(torch, timer, device, rank, peak, args):
                                               '(profiles/r02_gather_ceiling.md); achieved = ALGORITHMIC flops '
                                               '(32.91 MFLOP/sample), the 3xTF32 split issues three times that'}})
         out['xdeepfm'] = r
-        del w_emb, w_feat, idx, o, ws_buf
+        del idx, o, ws_buf
+        # ---- the same tables under a DeepFM with the paper-size deep branch [400, 400, 400] ---------------
+        try:
+            wide = [NUM_FIELDS * e, 400, 400, 400, 1]
+            ws, bs = make_mlp_params(torch, gen, device, wide)
+            wpack = ops.MlpPack(ws, bs, ops.activation_id('relu'))
+            idx = ring(b, 4, rpf)
+            o = torch.empty(b, 1, device=device)
+            r = timer.run(lambda i: ops.deepfm(idx[i % 4], offsets, w_feat, w_emb, wpack, out=o), steps=5)
+            ops.check_index_errors()
+            flops = 2.0 * sum(wide[i] * wide[i + 1] for i in range(4)) * b
+            tf = flops / (r['ms_per_step'] * 1e-3) / 1e12
+            r.update({'workload': f'SURVEY 8f-1: DeepFM {NUM_FIELDS} fields x {rpf} rows, embed 16, MLP [400, 400, 400] '
+                                  f'(split tables), batch {b}',
+                      'value': timer.world * b / (r['ms_per_step'] * 1e-3), 'unit': UNIT,
+                      'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': 1096.0, 'unit': 'TFLOP/s',
+                                   'frac': tf / 1096.0, 'issued_frac': 3 * tf / 1096.0, 'traffic': None,
+                                   'kernel': 'cin_tc_layer_kernel<dense>',
+                                   'note': 'three launches of the dense form of the tcgen05 kernel: layer 1 gathers its '
+                                           'rows from the table itself and emits first-order + FM per sample, layer 3 '
+                                           'carries the logit Linear in its epilogue; no (B, 624) matrix in HBM; '
+                                           'achieved = ALGORITHMIC flops (1.14 MFLOP/sample), 3xTF32 issues three times '
+                                           'that'}})
+            out['deepfm_wide'] = r
+            del idx, o
+        except Exception as ex:
+            out['deepfm_wide'] = {'error': f'{type(ex).__name__}: {ex}'}
+        del w_emb, w_feat
     except Exception as ex:
         out['xdeepfm'] = {'error': f'{type(ex).__name__}: {ex}'}
     torch.cuda.empty_cache()

@@ -447,10 +447,14 @@ def test_mlp_tensor_core_chain(ops, dims):
         assert normwise_err(got, want64) <= TOL, (dims, rows)
 
 
-@pytest.mark.parametrize('n,e,deep', [(39, 16, [400, 400, 400]), (26, 8, [256, 64]), (10, 10, [96, 96])])
+@pytest.mark.parametrize('n,e,deep', [(39, 16, [400, 400, 400]), (26, 8, [256, 64]), (10, 10, [96, 96]),
+                                      (12, 32, [256, 128]), (5, 64, [144]), (7, 16, [48, 40]), (39, 16, [400])])
 def test_deepfm_wide_mlp(ops, n, e, deep):
-    """DeepFM with a production-size deep branch: gather + first-order + FM in one kernel, the MLP as a chain of
-    tensor-core layers accumulating into the logits.  Also the small-batch route (one-kernel FFMA tile MLP)."""
+    """DeepFM with a production-size deep branch.  embed % 16 == 0: the first tcgen05 layer gathers its rows from the
+    table itself and emits first-order + FM per sample (FM field sums = selector channels of the same GEMM), the last
+    hidden layer carries the logit Linear in its epilogue (csrc/cin_tc.cu dense mode: rows spanning 1 / 2 / 4 chunks,
+    one- to three-layer branches, channel counts around the 16-column block granularity).  Other widths: gather +
+    first-order + FM in one kernel, then the chain.  Also the small-batch route (one-kernel FFMA tile MLP)."""
     from oracle import restated as R
     from torecsys_b200 import synth
     tag = f'dfw{n}_{e}'
@@ -467,6 +471,31 @@ def test_deepfm_wide_mlp(ops, n, e, deep):
         for dt in (torch.int64, torch.int32):
             got = ops.deepfm(idx.cuda().to(dt), off.cuda(), w_feat.cuda(), w_emb.cuda(), pack).cpu().numpy()
             assert normwise_err(got, want) <= TOL, (n, e, batch)
+
+
+def test_deepfm_wide_mlp_out_of_range(ops):
+    """The gathering dense layer reports out-of-range lookups like every other lookup kernel (IndexError), for rows in
+    the first and in a later tile of a CTA, and stays usable afterwards."""
+    n, e = 39, 16
+    rows = n * 16
+    w_emb = torch.randn(rows, e, device='cuda')
+    w_feat = torch.randn(rows, 1, device='cuda')
+    dims = [n * e, 400, 400, 1]
+    pack = ops.MlpPack([torch.randn(dims[i + 1], dims[i], device='cuda') * 0.05 for i in range(3)],
+                       [torch.randn(dims[i + 1], device='cuda') for i in range(3)], ops.activation_id('relu'))
+    off = (torch.arange(n) * 16).cuda()
+    for batch, bad_row, bad_col, bad in ((2000, 7, 38, 16), (148 * 256 + 300, 148 * 256 + 299, 0, -1)):
+        idx = torch.zeros(batch, n, dtype=torch.long, device='cuda')
+        good = ops.deepfm(idx, off, w_feat, w_emb, pack)
+        ops.check_index_errors()
+        idx[bad_row, bad_col] = bad
+        with pytest.raises(IndexError):
+            ops.deepfm(idx, off, w_feat, w_emb, pack)
+            ops.check_index_errors()
+        idx[bad_row, bad_col] = 0
+        again = ops.deepfm(idx, off, w_feat, w_emb, pack)
+        ops.check_index_errors()
+        assert torch.equal(good, again)
 
 
 @pytest.mark.parametrize('n', [3, 39])

@@ -1,0 +1,12 @@
+#!/bin/bash
+# dense layers: producer form x A-ring depth
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_ops.py -x -q -p no:cacheprovider -k "mlp_tensor_core_chain or deepfm_wide_mlp" > gpurun_out/r2_tests_f1.log 2>&1
+echo "tests rc=$? $(tail -1 gpurun_out/r2_tests_f1.log)"
+for cfg in "0 2" "0 3" "1 2" "1 3" "1 4"; do
+  set -- $cfg
+  echo "== TRS_DENSE_COOP=$1 TRS_DENSE_A_STAGES=$2"
+  TRS_DENSE_COOP=$1 TRS_DENSE_A_STAGES=$2 timeout 200 python tools/bench_ops.py --only deepfm_generic_mlp400 2>/dev/null | grep -o '"op": "[^"]*", "batch": [0-9]*, "us": [0-9.]*' | sed 's/"op": "\(.\{12\}\)[^"]*"/\1/'
+done
+echo "== trace, coop 1, 3 stages"
+TRS_DENSE_COOP=1 TRS_DENSE_A_STAGES=3 TRS_DENSE_TRACE=1 timeout 200 python tools/bench_ops.py --only deepfm_generic_mlp400 2>&1 | grep "dense trace" | awk '{k=$4" "$6" "$12" "$14; if (n[k]++ == 3) print}'

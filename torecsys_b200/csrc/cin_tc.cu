@@ -122,6 +122,7 @@ struct CinTcArgs {
   // TRS_DENSE_TRACE=1: per CTA cycle counters of the dense instantiations, 8 per CTA (see dense_tc_run)
   long long* trace;
   int coop;   // dense, A operand in shared memory: cooperative producers (always with gather)
+  int a_stages;   // dense, A operand in shared memory: depth of the A ring (2..kMaxAStages)
 };
 
 // kATmem = true (npad <= 128): the generated A operand goes to TENSOR MEMORY (columns 256..511, four 64-column stages:
@@ -139,7 +140,7 @@ __host__ __device__ inline int ss_pitch(int npad) { return (npad + 31) & ~31; } 
 // cooperative gather keeps 4 chunks x 16 loaded values plus the next chunk's row ids in flight per thread, and a SPILLED
 // in-flight load stalls the warp until the load lands (measured 6 400 cycles per chunk with 300 bytes of spills).
 constexpr int kDenseThreads = 384;
-template <bool kATmem, bool kFused, bool kTrace = false>
+template <bool kATmem, bool kFused, bool kTrace = false, int kGB = 0>   // kGB: gather with 32- / 64-bit indices (0 = none)
 __global__ void __launch_bounds__(kFused ? kDenseThreads : kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (gridDim.y > 1) {   // wide dense layer: this CTA column owns one channel block
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(kFused ? kDenseThreads : kThreads, 1) cin_tc_l
     a.npad = (a.c_eff + 15) & ~15;
     a.wp += blockIdx.y * a.wp_pass_stride;
   }
-  constexpr int kAS = kATmem ? 4 : kAStages;                   // A ring depth
+  const int kAS = kATmem ? 4 : (kFused ? a.a_stages : kAStages);   // A ring depth
   const int npad = a.npad;
   const int dstride = kATmem ? 128 : npad;                     // TMEM columns between the two accumulator halves
   const uint32_t a_stage_bytes = kATmem ? 0 : 2 * 4 * kTileM * 16;   // hi/lo x 4 chunks x 256 rows x 16 B = 32 KB
@@ -198,6 +199,11 @@ __global__ void __launch_bounds__(kFused ? kDenseThreads : kThreads, 1) cin_tc_l
   const bool do_base = kFused && a.row_base != nullptr &&
                        (a.sel_count > 0 ? (a.c_begin <= a.c_real && a.c_real + a.sel_count <= a.c_begin + a.c_eff)
                                         : blockIdx.y == 0);
+  // (gather) the field offsets live in shared memory, in the x0 array a dense layer does not use: a global load of a
+  // warp-uniform value gets an R2UR right behind it, which stalls the warp for the load's latency once per chunk
+  int64_t* off_s = reinterpret_cast<int64_t*>(x0_s);
+  if (kGB != 0)
+    for (int i = threadIdx.x; i < a.g_fields; i += blockDim.x) off_s[i] = __ldg(a.g_offsets + i);
   if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
@@ -229,13 +235,14 @@ __global__ void __launch_bounds__(kFused ? kDenseThreads : kThreads, 1) cin_tc_l
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_n) {
       const int64_t m = tile * kTileM + r;
       const bool row_ok = m < a.m_rows;
+      if (!(kFused && !kATmem && (kGB != 0 || a.coop)))   // (the cooperative dense producers have no x0; gather keeps offsets there)
       for (int xf = 0; xf < a.fields; ++xf) x0_s[xf * kTileM + r] = row_ok ? (a.xt ? __ldg(a.xt + m * a.hp0 + xf) : 1.f) : 0.f;   // xt == null: x0 = 1 (plain dense layer)
       // kPF y-chunks of this row's h are in flight in registers: with few fields (one, for a plain dense layer) a chunk
       // lasts less than a global-load latency, so the loads run that many chunks ahead of their use
       constexpr int kPF = kATmem ? 3 : 4;   // (register budget: the TMEM form also holds hi[16] / lo[16])
       float hbuf[kPF][16];
       float first = 0.f, sq = 0.f;        // (fused gather) this row's sum of first-order values / of v^2
-      if (kFused && !kATmem && a.coop) {
+      if (kFused && !kATmem && (kGB != 0 || a.coop)) {
         // ---- dense layer, A operand in shared memory: the warp produces its 32 rows COOPERATIVELY -- lane (g, kq) =
         // (lane / 4, lane % 4) handles the 16-byte piece kq of rows 8 i + g (i = 0..3), so the four lanes of a group read
         // the 64 bytes of one row with ONE request (a thread per row issues four 16-byte requests per row: a random
@@ -244,102 +251,115 @@ __global__ void __launch_bounds__(kFused ? kDenseThreads : kThreads, 1) cin_tc_l
         // = 16 columns of field f = 16 yc / embed (embed % 16 == 0); the lane also owns the first-order lookup of row
         // 8 kq + g and reports that row's out-of-range indices.
         const int g = lane >> 2, kq = lane & 3;
-        const bool gather = a.g_idx != nullptr;
-        int64_t mm[4];        // gather: flat position of the row's first index, else the row
+        constexpr bool kGather = kGB != 0;
+        const int64_t row0 = tile * kTileM + warp * 32 + g;   // rows of this lane: row0 + 8 i
         bool ok[4];
+        const unsigned char* rp[4];   // gather: address of the row's first index (of row 0 for rows beyond the batch:
+                                      // no branch around the load); else: address of the row's piece kq of chunk 0
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          mm[i] = tile * kTileM + warp * 32 + 8 * i + g;
-          ok[i] = mm[i] < a.m_rows;
-          if (gather) mm[i] *= a.g_fields;
+          ok[i] = row0 + 8 * i < a.m_rows;
+          if (kGather)
+            rp[i] = static_cast<const unsigned char*>(a.g_idx) + (ok[i] ? (row0 + 8 * i) * a.g_fields : 0) * (kGB / 8);
+          else
+            rp[i] = reinterpret_cast<const unsigned char*>(a.h + (ok[i] ? (row0 + 8 * i) : 0) * a.h_pitch + 4 * kq);
         }
-        float hw[kPF];
+        constexpr int kPFc = 5;   // chunks in flight per thread: random DRAM rows under load take several chunk times
+        float hbc[kPFc][16];
+        float hw[kPFc];
         float sq4[4] = {0.f, 0.f, 0.f, 0.f};
-        // The raw indices (and the field offset) of a chunk are fetched one chunk ahead of the row loads that need them
-        // and NOTHING touches them before that: a warp issues in order, so any instruction that consumes a load (the
+        // The producers are bound by their INSTRUCTION count (two warps per scheduler): the walk over the chunks keeps
+        // its field / column counters incrementally (no division), addresses are one IMAD.WIDE each, the range check one
+        // unsigned compare.
+        // Gather: the raw indices (and the field offset) of a chunk are fetched one chunk ahead of the row loads that need
+        // them and NOTHING touches them before that: a warp issues in order, so any instruction that consumes a load (an
         // offset add, a sign extension, a range check) right behind it stalls the warp for a full memory latency -- five
-        // such stalls per chunk cost 6 400 cycles per chunk where the tile's MMAs need 1 250.  Loads of rows beyond the
-        // batch read position 0 of the index array instead of branching.
-        uint32_t rlo[4], rhi[4];
+        // such stalls per chunk cost 6 400 cycles per chunk where the tile's MMAs need 1 250.
+        int cy = yc_rot;                                           // chunk the next fetch / plain load is for
+        int cf = kGather ? (yc_rot * 16) / a.g_embed : 0;          // ... its field
+        int cw = kGather ? yc_rot * 16 - cf * a.g_embed : 0;       // ... its first column within the field's row
+        int lf = 0, lw = 0;                                        // field / column of the chunk whose indices are held
+        const uint32_t row_bytes = kGather ? static_cast<uint32_t>(a.g_embed) * 4u : 0u;
+        uint32_t rlo[4] = {0u, 0u, 0u, 0u}, rhi[4] = {0u, 0u, 0u, 0u};
         int64_t offn = 0;
-        auto fetch_idx = [&](int yci) {
-          const int yc = yci + yc_rot < ychunks ? yci + yc_rot : yci + yc_rot - ychunks;
-          const int f = yci < ychunks ? (yc * 16) / a.g_embed : 0;
-          offn = __ldg(a.g_offsets + f);
+        auto advance = [&]() {
+          cw += 16;
+          if (kGather && cw == a.g_embed) { cw = 0; ++cf; }
+          if (++cy == ychunks) { cy = 0; cf = 0; cw = 0; }
+        };
+        auto fetch_idx = [&](bool live) {   // live (warp-uniform): the chunk exists
+          lf = live ? cf : 0;
+          lw = cw;
+          offn = off_s[lf];
+          const uint32_t fo = static_cast<uint32_t>(lf) * (kGB / 8);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int64_t pos = (ok[i] ? mm[i] : 0) + f;
-            if (a.g_idx_bits == 64)
-              asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(rlo[i]), "=r"(rhi[i])
-                           : "l"(reinterpret_cast<const long long*>(a.g_idx) + pos));
+            if (kGB == 64)
+              asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(rlo[i]), "=r"(rhi[i]) : "l"(rp[i] + fo));
             else
-              asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(rlo[i]) : "l"(reinterpret_cast<const int*>(a.g_idx) + pos));
+              asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(rlo[i]) : "l"(rp[i] + fo));
           }
+          advance();
         };
-        if (gather) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) rlo[i] = rhi[i] = 0u;
-          fetch_idx(0);
-        }
+        if (kGather) fetch_idx(true);
         auto load_c = [&](float (&dst)[16], float& wv, int yci) {
-          const int yc = yci + yc_rot < ychunks ? yci + yc_rot : yci + yc_rot - ychunks;
-          const int k = yc * 16 + 4 * kq;
+          const bool live = yci < ychunks;
           wv = 0.f;
-          if (gather) {
-            const int f = (yc * 16) / a.g_embed;
-            const int within = k - f * a.g_embed;
-            const bool starts = yc * 16 == f * a.g_embed;
-            const bool kok = yci < ychunks;
+          if (kGather) {
+            const unsigned char* tb = reinterpret_cast<const unsigned char*>(a.g_table + lw + 4 * kq);
+            const bool starts = lw == 0;
             // (ONE first-order load per chunk, issued behind the loop: four predicated loads into the same register
             // wait for each other -- write-after-write on the scoreboard, a memory latency each)
-            int64_t rr_own = -1;
-            bool own_live = false;
+            uint32_t rr_own = 0u;
+            bool own_live = false, own_in = false;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-              const int64_t iv = a.g_idx_bits == 64
-                                     ? static_cast<int64_t>((static_cast<uint64_t>(rhi[i]) << 32) | rlo[i])
-                                     : static_cast<int64_t>(static_cast<int32_t>(rlo[i]));
-              const int64_t rr = iv + offn;
-              const bool live = ok[i] && kok;
-              if (live && rr >= 0 && rr < a.g_rows)
-                v = ldg_stream_f4(reinterpret_cast<const float4*>(a.g_table + rr * a.g_embed + within));
-              if (i == kq) { rr_own = rr; own_live = live; }
+              const int64_t rr = (kGB == 64 ? static_cast<int64_t>((static_cast<uint64_t>(rhi[i]) << 32) | rlo[i])
+                                            : static_cast<int64_t>(static_cast<int32_t>(rlo[i]))) + offn;
+              const bool inr = static_cast<uint64_t>(rr) < static_cast<uint64_t>(a.g_rows);   // 0 <= rr < rows
+              const bool lv = ok[i] && live;
+              if (lv && inr)
+                v = ldg_stream_f4(reinterpret_cast<const float4*>(
+                    tb + static_cast<uint64_t>(static_cast<uint32_t>(rr)) * row_bytes));
+              if (i == kq) { rr_own = static_cast<uint32_t>(rr); own_live = lv; own_in = inr; }
               dst[4 * i + 0] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
             }
             if (do_base && starts && own_live) {
-              if (rr_own >= 0 && rr_own < a.g_rows) {
+              if (own_in) {
                 if (a.g_wfeat != nullptr) wv = ldg_stream_f1(a.g_wfeat + rr_own);
               } else {
-                report_oob(a.g_status, (tile * kTileM + warp * 32 + 8 * kq + g) * (int64_t)a.g_fields + f);
+                report_oob(a.g_status, (row0 + 8 * kq) * (int64_t)a.g_fields + lf);
               }
             }
-            fetch_idx(yci + 1);
+            fetch_idx(yci + 1 < ychunks);
             return;
           }
-          const bool kok = yci < ychunks && k < a.k_valid;
+          const bool kok = live && cy * 16 + 4 * kq < a.k_valid;
+          const uint32_t ko = static_cast<uint32_t>(cy) * 64u;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok[i] && kok) v = __ldg(reinterpret_cast<const float4*>(a.h + mm[i] * a.h_pitch + k));
+            if (ok[i] && kok) v = __ldg(reinterpret_cast<const float4*>(rp[i] + ko));
             dst[4 * i + 0] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
           }
+          advance();
         };
 #pragma unroll
-        for (int p = 0; p < kPF; ++p) load_c(hbuf[p], hw[p], p);
-        for (int y0 = 0; y0 < ychunks; y0 += kPF) {
+        for (int p = 0; p < kPFc; ++p) load_c(hbc[p], hw[p], p);
+        for (int y0 = 0; y0 < ychunks; y0 += kPFc) {
 #pragma unroll
-          for (int p = 0; p < kPF; ++p) {
+          for (int p = 0; p < kPFc; ++p) {
             if (y0 + p >= ychunks) break;
             float hreg[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) hreg[j] = hbuf[p][j];
+            for (int j = 0; j < 16; ++j) hreg[j] = hbc[p][j];
             if (do_base) {
               first += hw[p];
 #pragma unroll
               for (int j = 0; j < 16; ++j) sq4[j >> 2] = fmaf(hreg[j], hreg[j], sq4[j >> 2]);
             }
-            load_c(hbuf[p], hw[p], y0 + p + kPF);
+            load_c(hbc[p], hw[p], y0 + p + kPFc);
             const long long tw0 = (kTrace && threadIdx.x == 0) ? clock64() : 0;
             mbar_wait(empty_a(sa), pa ^ 1);
             if (kTrace && threadIdx.x == 0) tr_wait_a += clock64() - tw0;
@@ -889,7 +909,10 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
   if (rows == 0) return TRS_OK;
   const bool gather = fz != nullptr && fz->idx != nullptr;
   const int sel = (gather && fz->use_fm) ? fz->embed : 0;
-  if (gather) TRS_REQUIRE(fz->embed % 16 == 0 && fz->fields * fz->embed == k_dim, "dense: bad gather description");
+  if (gather)
+    TRS_REQUIRE(fz->embed % 16 == 0 && fz->fields * fz->embed == k_dim && fz->fields <= kTileM / 2 &&
+                    fz->table_rows <= (int64_t)1 << 32 && (fz->idx_bits == 32 || fz->idx_bits == 64),
+                "dense: bad gather description");
   const int kp = round_up(k_dim, 16);
   int block = 0;
   const int passes = dense_plan(c_dim, sel, &block);
@@ -920,8 +943,10 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
     a.n_direct = 0; a.hid_begin = 0; a.hid_count = c_dim; a.hp_next = c_dim;
     a.pool_off = 0; a.pooled_width = 0; a.act = activation;
     a.c_real = c_dim; a.sel_count = sel;
-    static const bool coop_env = getenv("TRS_DENSE_COOP") ? atoi(getenv("TRS_DENSE_COOP")) != 0 : true;
+    static const bool coop_env = getenv("TRS_DENSE_COOP") ? atoi(getenv("TRS_DENSE_COOP")) != 0 : false;
     a.coop = (gather || coop_env) ? 1 : 0;
+    static const int a_stages_env = getenv("TRS_DENSE_A_STAGES") ? atoi(getenv("TRS_DENSE_A_STAGES")) : 0;
+    a.a_stages = (a_stages_env >= 2 && a_stages_env <= kMaxAStages) ? a_stages_env : kAStages;
     if (fz != nullptr) {
       a.g_idx = fz->idx; a.g_idx_bits = fz->idx_bits; a.g_offsets = fz->offsets; a.g_table = fz->table;
       a.g_wfeat = fz->w_feat; a.g_bias = fz->bias; a.g_status = fz->status; a.row_base = gather ? fz->row_base : nullptr;
@@ -929,7 +954,7 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
       a.dot_w = fz->dot_w; a.dot_out = fz->dot_w != nullptr ? fz->dot_out : nullptr;
     }
     const size_t a_stage = 2 * 4 * kTileM * 16, b_stage = (size_t)2 * 4 * a.npad * 16;
-    const size_t fixed = (a_tmem ? (size_t)8 * 32 * 36 * 4 : kAStages * a_stage) + (size_t)kTileM * 4 +
+    const size_t fixed = (a_tmem ? (size_t)8 * 32 * 36 * 4 : a.a_stages * a_stage) + (size_t)kTileM * 4 +
                          4 * ss_pitch(a.npad) * 4 + (2 * kMaxAStages + 2 * kMaxBStages + 2) * 8 + 16 + 128;
     int b_stages = kMaxBStages;
     while (b_stages > 2 && b_stages * b_stage + fixed > (size_t)kMaxDynSmem) --b_stages;
@@ -944,19 +969,24 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
       TRS_CUDA(cudaMemsetAsync(a.trace, 0, sizeof(long long) * 8 * grid.x * grid.y, s));
     }
     // every dense launch takes the kFused instantiation (16-column channel-block tails); <*, false> is the CIN's
-    if (trace_on && a_tmem) {
-      TRS_SMEM_OPT_IN((cin_tc_layer_kernel<true, true, true>));
-      cin_tc_layer_kernel<true, true, true><<<grid, kDenseThreads, smem, s>>>(a);
-    } else if (trace_on) {
-      TRS_SMEM_OPT_IN((cin_tc_layer_kernel<false, true, true>));
-      cin_tc_layer_kernel<false, true, true><<<grid, kDenseThreads, smem, s>>>(a);
-    } else if (a_tmem) {
-      TRS_SMEM_OPT_IN((cin_tc_layer_kernel<true, true>));
-      cin_tc_layer_kernel<true, true><<<grid, kDenseThreads, smem, s>>>(a);
+#define TRS_DENSE_LAUNCH(...)                                                    \
+  do {                                                                           \
+    TRS_SMEM_OPT_IN((cin_tc_layer_kernel<__VA_ARGS__>));                         \
+    cin_tc_layer_kernel<__VA_ARGS__><<<grid, kDenseThreads, smem, s>>>(a);       \
+  } while (0)
+    const int gb = gather ? fz->idx_bits : 0;
+    if (trace_on) {
+      if (a_tmem) TRS_DENSE_LAUNCH(true, true, true, 0);
+      else if (gb == 64) TRS_DENSE_LAUNCH(false, true, true, 64);
+      else if (gb == 32) TRS_DENSE_LAUNCH(false, true, true, 32);
+      else TRS_DENSE_LAUNCH(false, true, true, 0);
     } else {
-      TRS_SMEM_OPT_IN((cin_tc_layer_kernel<false, true>));
-      cin_tc_layer_kernel<false, true><<<grid, kDenseThreads, smem, s>>>(a);
+      if (a_tmem) TRS_DENSE_LAUNCH(true, true, false, 0);
+      else if (gb == 64) TRS_DENSE_LAUNCH(false, true, false, 64);
+      else if (gb == 32) TRS_DENSE_LAUNCH(false, true, false, 32);
+      else TRS_DENSE_LAUNCH(false, true, false, 0);
     }
+#undef TRS_DENSE_LAUNCH
     rc = check_launch("cin_tc_layer_kernel(dense)");
     if (trace_on && rc == TRS_OK) {
       const int n = grid.x * grid.y;

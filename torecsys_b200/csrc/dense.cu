@@ -399,7 +399,7 @@ static bool chain_dot_fusable(const MlpParams& mp) {
 int mlp_chain_gather_supported(const int* dims, int layers, int fields, int embed, int use_fm) {
   static const bool off = getenv("TRS_MLP_NO_GATHER") != nullptr;
   if (off || layers < 2 || embed % 16 != 0 || dims[0] != fields * embed || dims[layers] != 1) return 0;
-  if (!chain_layer_on_tc(dims[0], dims[1]) || dims[0] < 16) return 0;
+  if (!chain_layer_on_tc(dims[0], dims[1]) || dims[0] < 16 || fields > 128) return 0;
   if (use_fm && embed > 64) return 0;
   return dense_tc_passes(dims[1], use_fm ? embed : 0) > 0 ? 1 : 0;
 }
