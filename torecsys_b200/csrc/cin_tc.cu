@@ -28,7 +28,7 @@ namespace {
 constexpr int kTileM = 256;          // rows per CTA tile (2 x UMMA_M 128)
 constexpr int kBK = 16;              // K per stage = 4 sixteen-byte chunks = 2 UMMA k-steps
 constexpr int kProducerThreads = 256;
-constexpr int kThreads = kProducerThreads + 64;   // + MMA warp + weight-loader warp
+constexpr int kThreads = kProducerThreads + 128;  // + MMA warp + weight-loader warp + two idle warps (register donors)
 constexpr int kAStages = 2;          // operand-A ring in smem (32 KB per stage; generation is cheap, two stages suffice)
 constexpr int kMaxAStages = 4;       // (four 64-column stages when the A ring lives in tensor memory)
 constexpr int kMaxBStages = 8;       // weight ring: deep, the L2 -> smem stream is latency-bound
@@ -133,15 +133,39 @@ struct CinTcArgs {
 // kFused = true: the dense-mode instantiation: channel blocks in multiples of 16 and the fused ends described in CinTcArgs
 //   (rows gathered from the embedding table by the producers, FM / first-order row base, one-output Linear folded into the
 //   epilogue).
+// Sum of 32 channel values over the E consecutive lanes (rows) of a sample as a butterfly REDUCE-SCATTER: at every step
+// a lane hands half of its channels to its partner and sums the partner's copies of the half it keeps -- 30 shuffles
+// (E = 16) instead of the 128 of an all-reduce per channel, the same pairing and order of additions (bit-identical sums);
+// the lane ends up with the 32 / E channels starting at `chan` and writes them.
+template <int E>
+__device__ __forceinline__ void pool_rows(float (&w)[32], int lane, bool row_ok, float* prow, int lim) {
+  int chan = 0;
+#pragma unroll
+  for (int o = E / 2, half = 16; o >= 1; o >>= 1, half >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send = up ? w[j] : w[j + half];
+      const float keep = up ? w[j + half] : w[j];
+      w[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+    if (up) chan += half;
+  }
+  constexpr int kLeft = 32 / E;
+#pragma unroll
+  for (int j = 0; j < kLeft; ++j)
+    if (row_ok && chan + j < lim) prow[chan + j] = w[j];
+}
+
 __host__ __device__ inline int ss_pitch(int npad) { return (npad + 31) & ~31; }   // floats per per-channel array in smem
 
-// The dense instantiations run 12 warps: ptxas budgets 168 registers per thread for them, the two idle warps, the MMA warp
-// and the weight loader hand theirs back (setmaxnreg) and the eight producer / epilogue warps grow to 232 -- the
-// cooperative gather keeps 4 chunks x 16 loaded values plus the next chunk's row ids in flight per thread, and a SPILLED
-// in-flight load stalls the warp until the load lands (measured 6 400 cycles per chunk with 300 bytes of spills).
-constexpr int kDenseThreads = 384;
+// The kernel runs 12 warps: ptxas budgets 168 registers per thread, the two idle warps, the MMA warp and the weight loader
+// hand theirs back (setmaxnreg) and the eight producer / epilogue warps grow to 232 -- the cooperative gather keeps
+// 5 chunks x 16 loaded values plus the next chunk's indices in flight per thread, and a SPILLED in-flight load stalls the
+// warp until the load lands (measured 6 400 cycles per chunk with 300 bytes of spills).
+constexpr int kDenseThreads = kThreads;
 template <bool kATmem, bool kFused, bool kTrace = false, int kGB = 0>   // kGB: gather with 32- / 64-bit indices (0 = none)
-__global__ void __launch_bounds__(kFused ? kDenseThreads : kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (gridDim.y > 1) {   // wide dense layer: this CTA column owns one channel block
     a.c_begin = blockIdx.y * a.c_block;
@@ -220,10 +244,8 @@ __global__ void __launch_bounds__(kFused ? kDenseThreads : kThreads, 1) cin_tc_l
   // stream the SAME weight chunk from L2 at the same moment and hot-spot a few L2 slices.
   const int yc_rot = blockIdx.x % ychunks, x_rot = (blockIdx.x * 5) % a.fields;
 
-  if (kFused) {
-    if (warp < 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  }
+  if (warp < 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp < 8) {
     // =========================== A producers, then epilogue =====================================================
     const int r = threadIdx.x;   // row within the tile
@@ -421,7 +443,9 @@ __global__ void __launch_bounds__(kFused ? kDenseThreads : kThreads, 1) cin_tc_l
         const int xn = x_count(yc_now), xr = x_rot % xn;
         for (int xi = 0; xi < xn; ++xi) {
           const int xf = xi + xr < xn ? xi + xr : xi + xr - xn;
+          const long long tw0 = (kTrace && threadIdx.x == 0) ? clock64() : 0;
           mbar_wait(empty_a(sa), pa ^ 1);   // stage free (first pass: passes immediately)
+          if (kTrace && threadIdx.x == 0) tr_wait_a += clock64() - tw0;
           const float xv = x0_s[xf * kTileM + r];
           if (kATmem) {
             // 16 z values of this row -> TMEM columns [hi 0..15 | lo 16..31] of this half's slot in stage sa
@@ -470,7 +494,6 @@ __global__ void __launch_bounds__(kFused ? kDenseThreads : kThreads, 1) cin_tc_l
       const int half = warp >> 2;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + half * dstride;
       const int64_t b = row_ok ? m / a.embed : 0;
-      const int e = row_ok ? static_cast<int>(m - b * a.embed) : 0;
       float dot = 0.f, ssq = 0.f;   // (fused ends) this row's share of the one-output Linear / sum_e s[e]^2
       for (int c0 = 0; c0 < npad; c0 += 32) {
         uint32_t raw[32];
@@ -514,9 +537,24 @@ __global__ void __launch_bounds__(kFused ? kDenseThreads : kThreads, 1) cin_tc_l
             }
           }
         } else {
+          // CIN layer: folded Conv-bias + eval-BN as scale / shift (128-bit broadcast loads), ReLU without the switch
+          const float4* sc4 = reinterpret_cast<const float4*>(ss_s + c0);
+          const float4* sh4 = reinterpret_cast<const float4*>(ss_s + np32 + c0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = apply_act(fmaf(__uint_as_float(raw[j]), ss_s[c0 + j], ss_s[np32 + c0 + j]), a.act);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 s4 = sc4[j4], b4 = sh4[j4];
+            v[4 * j4 + 0] = fmaf(__uint_as_float(raw[4 * j4 + 0]), s4.x, b4.x);
+            v[4 * j4 + 1] = fmaf(__uint_as_float(raw[4 * j4 + 1]), s4.y, b4.y);
+            v[4 * j4 + 2] = fmaf(__uint_as_float(raw[4 * j4 + 2]), s4.z, b4.z);
+            v[4 * j4 + 3] = fmaf(__uint_as_float(raw[4 * j4 + 3]), s4.w, b4.w);
+          }
+          if (a.act == TRS_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (a.act != TRS_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], a.act);
+          }
         }
         if (kFused && do_base && a.sel_count > 0) {
 #pragma unroll
@@ -526,10 +564,10 @@ __global__ void __launch_bounds__(kFused ? kDenseThreads : kThreads, 1) cin_tc_l
           }
         }
         // hidden half -> next layer's activations, row-major
-        if (kFused && a.h_next != nullptr) {
-          // dense layer: the warp's 32 rows x 32 columns go through a shared-memory transpose so that every store
-          // instruction writes four whole 128-byte lines (a thread per row writes 16 bytes into each of 32 lines: the
-          // epilogue of a 400-wide layer took 44 K cycles per tile that way, more than the tile's MMAs)
+        if (a.h_next != nullptr && a.c_begin + c0 + 32 > a.hid_begin && a.c_begin + c0 < a.hid_begin + a.hid_count) {
+          // the warp's 32 rows x 32 columns go through a shared-memory transpose so that every store instruction
+          // writes four whole 128-byte lines (a thread per row writes 16 bytes into each of 32 lines: the epilogue
+          // of a 400-wide dense layer took 44 K cycles per tile that way, more than the tile's MMAs)
           float* st = stage_s + warp * (32 * 36);
           __syncwarp();
 #pragma unroll
@@ -556,31 +594,18 @@ __global__ void __launch_bounds__(kFused ? kDenseThreads : kThreads, 1) cin_tc_l
                 if (c + j >= a.hid_begin && c + j < a.hid_begin + a.hid_count && cl + j < a.c_eff) orow[c + j] = ov[j];
             }
           }
-        } else if (a.h_next != nullptr) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const int c = a.c_begin + c0 + 4 * j4;   // global channel
-            if (row_ok && c >= a.hid_begin && c + 3 < a.hid_begin + a.hid_count && c0 + 4 * j4 + 3 < a.c_eff &&
-                (a.hp_next & 3) == 0)
-              *reinterpret_cast<float4*>(a.h_next + m * a.hp_next + (c - a.hid_begin)) =
-                  make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-            else if (row_ok) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (c + j >= a.hid_begin && c + j < a.hid_begin + a.hid_count && c0 + 4 * j4 + j < a.c_eff)
-                  a.h_next[m * a.hp_next + (c + j - a.hid_begin)] = v[4 * j4 + j];
-            }
-          }
         }
         // direct half -> sum over the `embed` rows of each sample (consecutive lanes), one writer per (b, c)
-        if (a.c_begin + c0 < a.n_direct) {
+        if (!kFused && a.c_begin + c0 < a.n_direct) {
+          if (!row_ok) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float sum = row_ok ? v[j] : 0.f;
-            for (int o = a.embed >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (row_ok && e == 0 && a.c_begin + c0 + j < a.n_direct && c0 + j < a.c_eff)
-              a.pooled[b * a.pooled_width + a.pool_off + a.c_begin + c0 + j] = sum;
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
+          float* prow = a.pooled + b * a.pooled_width + a.pool_off + a.c_begin + c0;
+          const int lim = min(a.n_direct - a.c_begin - c0, a.c_eff - c0);   // channels of this group that exist
+          if (a.embed == 16) pool_rows<16>(v, lane, row_ok, prow, lim);
+          else if (a.embed == 32) pool_rows<32>(v, lane, row_ok, prow, lim);
+          else pool_rows<8>(v, lane, row_ok, prow, lim);
         }
       }
       if (kFused && row_ok) {
@@ -592,7 +617,7 @@ __global__ void __launch_bounds__(kFused ? kDenseThreads : kThreads, 1) cin_tc_l
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
       // the transpose buffers lie over the A ring: no warp may start producing the next tile before all have stored
-      if (kFused && !kATmem) asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (!kATmem) asm volatile("bar.sync 1, 256;" ::: "memory");
       if (kTrace && threadIdx.x == 0) {
         tr_wait_acc += te1 - te0;
         tr_epi += clock64() - te1;
@@ -701,6 +726,21 @@ __global__ void __launch_bounds__(kFused ? kDenseThreads : kThreads, 1) cin_tc_l
 }  // namespace
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// TRS_DENSE_TRACE / TRS_CIN_TRACE: averages the per-CTA cycle counters of a traced launch and prints them
+static void trace_report(long long* dev, int n, cudaStream_t s, const char* label) {
+  long long* hbuf = static_cast<long long*>(malloc(sizeof(long long) * 8 * n));
+  cudaStreamSynchronize(s);
+  cudaMemcpy(hbuf, dev, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost);
+  double sum[8] = {0};
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < 8; ++j) sum[j] += (double)hbuf[8 * i + j] / n;
+  fprintf(stderr,
+          "%s: total %.0f cyc | producer: wait A-free %.0f, wait acc %.0f, epilogue %.0f | mma: wait A %.0f, wait B %.0f, "
+          "wait epilogue %.0f\n", label, sum[0], sum[1], sum[2], sum[3], sum[4], sum[5], sum[6]);
+  free(hbuf);
+  cudaFree(dev);
+}
 
 struct CinTcPlan {
   int hp0, hp_max, pooled_width;
@@ -826,7 +866,8 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
       const int np = ap.npad;
       const bool a_tmem = np <= 128;   // accumulators leave 256 TMEM columns free: A operand goes to tensor memory
       const size_t a_stage = 2 * 4 * kTileM * 16, b_stage = (size_t)2 * 4 * np * 16;
-      const size_t fixed = (a_tmem ? 0 : kAStages * a_stage) + (size_t)fields * kTileM * 4 + 4 * ss_pitch(np) * 4 +
+      const size_t fixed = (a_tmem ? (size_t)8 * 32 * 36 * 4 : kAStages * a_stage) + (size_t)fields * kTileM * 4 +
+                           4 * ss_pitch(np) * 4 +
                            (2 * kMaxAStages + 2 * kMaxBStages + 2) * 8 + 16 + 128;
       int b_stages = kMaxBStages;
       while (b_stages > 2 && b_stages * b_stage + fixed > (size_t)kMaxDynSmem) --b_stages;
@@ -836,10 +877,27 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
       TRS_UNSUPPORTED(smem > (size_t)kMaxDynSmem, "cin: tensor-core tile does not fit shared memory");
       ap.b_stages = b_stages;
       if (getenv("TRS_CIN_VERBOSE")) fprintf(stderr, "cin layer %d pass %d: npad %d, a_tmem %d, b_stages %d, smem %zu\n", l, pass, np, (int)a_tmem, b_stages, smem);
-      if (a_tmem) cin_tc_layer_kernel<true, false><<<grid, kThreads, smem, s>>>(ap);
+      static const bool cin_trace = getenv("TRS_CIN_TRACE") != nullptr;
+      if (cin_trace) {
+        TRS_CUDA(cudaMalloc(reinterpret_cast<void**>(&ap.trace), sizeof(long long) * 8 * grid));
+        TRS_CUDA(cudaMemsetAsync(ap.trace, 0, sizeof(long long) * 8 * grid, s));
+        if (a_tmem) {
+          TRS_SMEM_OPT_IN((cin_tc_layer_kernel<true, false, true>));
+          cin_tc_layer_kernel<true, false, true><<<grid, kThreads, smem, s>>>(ap);
+        } else {
+          TRS_SMEM_OPT_IN((cin_tc_layer_kernel<false, false, true>));
+          cin_tc_layer_kernel<false, false, true><<<grid, kThreads, smem, s>>>(ap);
+        }
+      } else if (a_tmem) cin_tc_layer_kernel<true, false><<<grid, kThreads, smem, s>>>(ap);
       else cin_tc_layer_kernel<false, false><<<grid, kThreads, smem, s>>>(ap);
       rc = check_launch("cin_tc_layer_kernel");
       if (rc != TRS_OK) return rc;
+      if (cin_trace) {
+        char label[160];
+        snprintf(label, sizeof label, "cin trace layer %d pass %d npad %d %s chunks/tile fold %d tiles/cta %.2f", l, pass, np,
+                 a_tmem ? "TS" : "SS", fold, (double)tiles / grid);
+        trace_report(ap.trace, grid, s, label);
+      }
     }
     h = a.h_next;
     hp = a.hp_next;
@@ -989,20 +1047,10 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
 #undef TRS_DENSE_LAUNCH
     rc = check_launch("cin_tc_layer_kernel(dense)");
     if (trace_on && rc == TRS_OK) {
-      const int n = grid.x * grid.y;
-      long long* hbuf = static_cast<long long*>(malloc(sizeof(long long) * 8 * n));
-      cudaStreamSynchronize(s);
-      cudaMemcpy(hbuf, a.trace, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost);
-      double sum[8] = {0};
-      for (int i = 0; i < n; ++i)
-        for (int j = 0; j < 8; ++j) sum[j] += (double)hbuf[8 * i + j] / n;
-      fprintf(stderr,
-              "dense trace K %d C %d(+%d) block %d x%d %s gather %d dot %d tiles/cta %.2f: total %.0f cyc | producer: wait A-free "
-              "%.0f, wait acc %.0f, epilogue %.0f | mma: wait A %.0f, wait B %.0f, wait epilogue %.0f\n",
-              k_dim, c_dim, sel, block, passes, a_tmem ? "TS" : "SS", (int)gather, (int)(a.dot_out != nullptr),
-              (double)tiles / grid.x, sum[0], sum[1], sum[2], sum[3], sum[4], sum[5], sum[6]);
-      free(hbuf);
-      cudaFree(a.trace);
+      char label[200];
+      snprintf(label, sizeof label, "dense trace K %d C %d(+%d) block %d x%d %s gather %d dot %d tiles/cta %.2f", k_dim, c_dim,
+               sel, block, passes, a_tmem ? "TS" : "SS", (int)gather, (int)(a.dot_out != nullptr), (double)tiles / grid.x);
+      trace_report(a.trace, grid.x * grid.y, s, label);
     }
   }
   cudaFreeAsync(wp, s);
