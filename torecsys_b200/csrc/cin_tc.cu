@@ -83,8 +83,11 @@ __global__ void __launch_bounds__(256) cin_tc_prep_weights_kernel(const float* _
 }
 
 struct CinTcArgs {
-  const float* xt;       // [(b,e)][hp0]  (x0 operand; also layer-0 h)
-  const float* h;        // [(b,e)][hp]   input activations of this layer
+  const float* xt;       // unused (the x0 operand used to come from a transposed copy [(b,e)][hp0])
+  const float* xb;       // CIN: the layer input x (B, N, E) as the lookup wrote it -- the x0 operand of every layer and,
+                         // with h == null, layer 0's activations; rows (b, e) read it with stride E (the 16 lanes of a
+                         // sample make one 64-byte request per field).  Null = plain dense layer (x0 = 1)
+  const float* h;        // [(b,e)][hp]   input activations of this layer (null: layer 0 of a CIN, see xb)
   const float* wp;       // prepared weights
   const float* scale;    // per channel (indexed c_begin + c), null = 1
   const float* shift;    // per channel, null = 0
@@ -257,8 +260,11 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_n) {
       const int64_t m = tile * kTileM + r;
       const bool row_ok = m < a.m_rows;
+      const int64_t xb_b = (a.xb != nullptr && row_ok) ? m / a.embed : 0;           // sample / embedding column of this row
+      const float* xrow = a.xb != nullptr ? a.xb + xb_b * a.fields * a.embed + (row_ok ? m - xb_b * a.embed : 0) : nullptr;
       if (!(kFused && !kATmem && (kGB != 0 || a.coop)))   // (the cooperative dense producers have no x0; gather keeps offsets there)
-      for (int xf = 0; xf < a.fields; ++xf) x0_s[xf * kTileM + r] = row_ok ? (a.xt ? __ldg(a.xt + m * a.hp0 + xf) : 1.f) : 0.f;   // xt == null: x0 = 1 (plain dense layer)
+      for (int xf = 0; xf < a.fields; ++xf)
+        x0_s[xf * kTileM + r] = row_ok ? (xrow != nullptr ? __ldg(xrow + xf * a.embed) : 1.f) : 0.f;   // dense: x0 = 1
       // kPF y-chunks of this row's h are in flight in registers: with few fields (one, for a plain dense layer) a chunk
       // lasts less than a global-load latency, so the loads run that many chunks ahead of their use
       constexpr int kPF = kATmem ? 3 : 4;   // (register budget: the TMEM form also holds hi[16] / lo[16])
@@ -421,6 +427,14 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
       } else {
       auto load_h = [&](float (&dst)[16], int yci) {
         const int yc = yci + yc_rot < ychunks ? yci + yc_rot : yci + yc_rot - ychunks;
+        if (!kFused && a.h == nullptr) {   // layer 0 of a CIN: h = x0, straight from x (B, N, E)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int y = yc * 16 + j;
+            dst[j] = (row_ok && yci < ychunks && y < a.k_valid) ? __ldg(xrow + y * a.embed) : 0.f;
+          }
+          return;
+        }
 #pragma unroll
         for (int v4 = 0; v4 < 4; ++v4) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -804,13 +818,11 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
   float* wprep = pooled + p.pooled_floats;
   const int64_t m_rows = batch * embed;
 
-  cin_tc_transpose_kernel<<<grid_for(m_rows * p.hp0, 256, 8), 256, 0, s>>>(x, batch, fields, embed, p.hp0, xt);
-  int rc = check_launch("cin_tc_transpose_kernel");
-  if (rc != TRS_OK) return rc;
+  int rc = TRS_OK;   // (no transposed copy of x any more: the layer kernels read x (B, N, E) in place)
   TRS_SMEM_OPT_IN((cin_tc_layer_kernel<true, false>));
   TRS_SMEM_OPT_IN((cin_tc_layer_kernel<false, false>));
 
-  const float* h = xt;
+  const float* h = nullptr;   // layer 0 reads x itself
   int hp = p.hp0, h_prev = fields, pool_off = 0;
   float* wp = wprep;
   for (int l = 0; l < layers; ++l) {
@@ -828,7 +840,7 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
     rc = check_launch("cin_tc_prep_weights_kernel");
     if (rc != TRS_OK) return rc;
     CinTcArgs a{};
-    a.xt = xt; a.h = h; a.wp = wp; a.scale = scale[l]; a.shift = shift[l];
+    a.xt = nullptr; a.xb = x; a.h = h; a.wp = wp; a.scale = scale[l]; a.shift = shift[l];
     a.h_next = last ? nullptr : hbuf[l & 1];
     a.pooled = pooled;
     a.m_rows = m_rows; a.fields = fields; a.embed = embed; a.hp0 = p.hp0; a.hp = hp; a.npad = npad; a.c_eff = c_eff;
@@ -837,7 +849,7 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
     a.hid_count = last ? 0 : hl;
     a.hp_next = round_up(hl, 16);
     a.pool_off = pool_off; a.pooled_width = p.pooled_width; a.act = activation;
-    a.h_pitch = hp; a.k_valid = hp; a.fold = fold;
+    a.h_pitch = hp; a.k_valid = l == 0 ? fields : hp; a.fold = fold;
     a.c_real = 1 << 30;   // (no selector channels: every channel is a real one)
     if (a.h_next != nullptr && a.hp_next != hl)   // zero the padding columns the next layer will read
       TRS_CUDA(cudaMemsetAsync(a.h_next, 0, (size_t)m_rows * a.hp_next * sizeof(float), s));

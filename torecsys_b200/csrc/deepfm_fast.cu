@@ -68,6 +68,9 @@ struct FastArgs {
   int32_t* status;
   int64_t batch, rows;
   int fields, hidden_layers;
+  float* x_out;        // null, or (B, N, 16): the gathered rows, for a consumer behind this kernel (xDeepFM's CIN)
+  const float* bias;   // null, or a scalar added to every logit (xDeepFM's model bias)
+  int use_fm;          // 0: no second-order FM term (xDeepFM: first-order + MLP only)
 };
 
 // shared memory carve-up (bytes): [W1 frags: N*2*2*32 float4][hidden frags: L*2*2*2*32 float2][biases][rid]
@@ -168,6 +171,12 @@ __global__ void __launch_bounds__(kWarps * 32, 2) deepfm_fast_kernel(FastArgs a)
         const int n = n0 + u;
         if (n < n_fields) {
           const float4 va = xa[u], vb = xb[u];
+          if (a.x_out != nullptr) {   // lanes t = 0..3 write the 64 bytes of a row together
+            if (b0 + g < a.batch)
+              *reinterpret_cast<float4*>(a.x_out + ((b0 + g) * n_fields + n) * 16 + 4 * t) = va;
+            if (b0 + g + 8 < a.batch)
+              *reinterpret_cast<float4*>(a.x_out + ((b0 + g + 8) * n_fields + n) * 16 + 4 * t) = vb;
+          }
           sa.x += va.x; sa.y += va.y; sa.z += va.z; sa.w += va.w;
           qa.x = fmaf(va.x, va.x, qa.x); qa.y = fmaf(va.y, va.y, qa.y);
           qa.z = fmaf(va.z, va.z, qa.z); qa.w = fmaf(va.w, va.w, qa.w);
@@ -198,6 +207,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) deepfm_fast_kernel(FastArgs a)
     // ---- FM second order + first order, reduced over the 4 lanes of a row ------------------------------------
     float fm_a = 0.5f * ((sa.x * sa.x - qa.x) + (sa.y * sa.y - qa.y) + (sa.z * sa.z - qa.z) + (sa.w * sa.w - qa.w));
     float fm_b = 0.5f * ((sb.x * sb.x - qb.x) + (sb.y * sb.y - qb.y) + (sb.z * sb.z - qb.z) + (sb.w * sb.w - qb.w));
+    if (!a.use_fm) fm_a = fm_b = 0.f;
     float side_a = fm_a + first_a, side_b = fm_b + first_b;
 
     // ---- layer 1 epilogue: bias + ReLU.  acc[j] = {(g, 8j+2t), (g, 8j+2t+1), (g+8, 8j+2t), (g+8, 8j+2t+1)} ----
@@ -252,7 +262,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) deepfm_fast_kernel(FastArgs a)
     side_a += __shfl_xor_sync(0xffffffffu, side_a, 2);
     side_b += __shfl_xor_sync(0xffffffffu, side_b, 2);
     if (t == 0) {
-      const float bo = wo[16];
+      const float bo = wo[16] + (a.bias != nullptr ? __ldg(a.bias) : 0.f);
       if (b0 + g < a.batch) a.logits[b0 + g] = side_a + bo;
       if (b0 + g + 8 < a.batch) a.logits[b0 + g + 8] = side_b + bo;
     }
@@ -282,12 +292,14 @@ int deepfm_fast_supported(int fields, int embed, const int* mlp_dims, int mlp_la
 
 int deepfm_fast_launch(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
                        const float* w_feat, const float* w_emb, int64_t rows, const float* const* mlp_w,
-                       const float* const* mlp_b, int mlp_layers, float* logits, int32_t* status, cudaStream_t s) {
+                       const float* const* mlp_b, int mlp_layers, float* logits, int32_t* status, cudaStream_t s,
+                       float* x_out, const float* bias, int use_fm) {
   TRS_REQUIRE(idx_bits == 32 || idx_bits == 64, "trs_deepfm_forward: idx_bits must be 32 or 64");
   TRS_REQUIRE(aligned16(w_emb) && aligned16(mlp_w[0]), "trs_deepfm_forward: w_emb / W1 must be 16-byte aligned");
   FastArgs a{};
   a.idx = idx; a.offsets = offsets; a.w_feat = w_feat; a.w_emb = w_emb; a.logits = logits; a.status = status;
   a.batch = batch; a.rows = rows; a.fields = fields;
+  a.x_out = x_out; a.bias = bias; a.use_fm = use_fm;
   a.hidden_layers = mlp_layers - 2;
   a.w1 = mlp_w[0];
   a.b1 = mlp_b[0];

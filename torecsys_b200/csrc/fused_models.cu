@@ -19,7 +19,8 @@ int cin_run(const float* x, const float* const* conv_w, const float* const* scal
 int deepfm_fast_supported(int fields, int embed, const int* mlp_dims, int mlp_layers, int activation, int64_t rows);
 int deepfm_fast_launch(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
                        const float* w_feat, const float* w_emb, int64_t rows, const float* const* mlp_w,
-                       const float* const* mlp_b, int mlp_layers, float* logits, int32_t* status, cudaStream_t s);
+                       const float* const* mlp_b, int mlp_layers, float* logits, int32_t* status, cudaStream_t s,
+                       float* x_out, const float* bias, int use_fm);
 
 int mlp_chain_supported(const int* dims, int layers, int64_t rows, const void* x, const void* out, int accumulate);
 int mlp_chain_run(const float* x, int64_t rows, const MlpParams& mp, float* out, int accumulate, cudaStream_t s,
@@ -316,6 +317,16 @@ int launch_fm_family(const void* idx, int idx_bits, const int64_t* offsets, int6
     a.mp.layers = 0;
   }
   if (batch == 0) return TRS_OK;
+  // Criteo-shaped deep branch (E = 16, hidden widths 16, ReLU): the register-resident mma.sync kernel of deepfm_fast.cu,
+  // with or without the FM term, the rows written out for a consumer behind it (xDeepFM: 446 -> ~200 us per 65 536)
+  if (mlp_layers > 0 && w_feat != nullptr && aligned16(w_emb) && aligned16(mlp_w[0]) && (x_out == nullptr || aligned16(x_out)) &&
+      deepfm_fast_supported(fields, embed, mlp_dims, mlp_layers, activation, rows)) {
+    bool all = true;
+    for (int l = 0; l < mlp_layers; ++l) all = all && mlp_w[l] != nullptr && mlp_b != nullptr && mlp_b[l] != nullptr;
+    if (all)
+      return deepfm_fast_launch(idx, idx_bits, offsets, batch, fields, w_feat, w_emb, rows, mlp_w, mlp_b, mlp_layers,
+                                logits, status, s, x_out, bias, use_fm);
+  }
   a.idx = idx; a.offsets = offsets; a.w_feat = w_feat; a.w_emb = w_emb; a.bias = bias; a.x_out = x_out;
   a.logits = logits; a.status = status; a.batch = batch; a.rows = rows; a.fields = fields; a.embed = embed;
   a.use_fm = use_fm;
@@ -396,7 +407,7 @@ extern "C" int trs_deepfm_forward(const void* idx, int idx_bits, const int64_t* 
   if (idx && offsets && w_emb && logits && mlp_dims && mlp_w && mlp_b && batch > 0 &&
       deepfm_fast_supported(fields, embed, mlp_dims, mlp_layers, activation, rows)) {
     return deepfm_fast_launch(idx, idx_bits, offsets, batch, fields, w_feat, w_emb, rows, mlp_w, mlp_b, mlp_layers,
-                              logits, status, s);
+                              logits, status, s, nullptr, nullptr, 1);
   }
   return launch_fm_family(idx, idx_bits, offsets, batch, fields, w_feat, w_emb, rows, embed, 1, mlp_dims, mlp_layers,
                           mlp_w, mlp_b, activation, nullptr, nullptr, logits, status, s, "trs_deepfm_forward");
