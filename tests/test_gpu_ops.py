@@ -428,7 +428,8 @@ def _wide_mlp(tag, dims):
                                   [128, 1024, 16]])
 def test_mlp_tensor_core_chain(ops, dims):
     """Wide DNNLayer stacks run layer by layer on tcgen05 (cin_tc.cu dense mode: one field, x0 = 1): channel blocks
-    over blockIdx.y (400 -> 2 x 224, 1024 -> 4 x 256), the TMEM-operand form (<= 128 channels), input widths that
+    over blockIdx.y in multiples of 16 (400 -> 4 x 112, 1024 -> 8 x 128; the last hidden layer of [624,400,400,400,1]
+    carries the logit Linear in its epilogue), the TMEM-operand form (<= 128 channels), input widths that
     are not a multiple of 16, narrow layers in between / at the end, ragged row counts around the 256-row tiles."""
     from oracle import restated as R
     from torecsys_b200 import synth

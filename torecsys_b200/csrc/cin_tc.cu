@@ -937,9 +937,12 @@ int dense_tc_supported(int k_dim, int c_dim, const void* x, const void* out) {
 }
 
 // channel blocks of a dense layer with c_real outputs (+ sel selector channels, kept inside ONE block); 0 = no split found
-static int dense_plan(int c_real, int sel, int* block_out) {
+// Plain layers take blocks of at most 128 channels -- the TMEM-operand form, and 7 waves of 37 CTAs instead of 3.46 of
+// 74 for 400 channels at 65 536 rows (measured 558 -> 518 us for the 624-400-400-400-1 chain); a gathering layer keeps two
+// wide blocks, every block's CTA column gathers the rows again.
+static int dense_plan(int c_real, int sel, int gather, int* block_out) {
   static const int cap_env = getenv("TRS_DENSE_BLOCK") ? atoi(getenv("TRS_DENSE_BLOCK")) : 0;
-  const int cap = (cap_env >= 16 && cap_env <= 256) ? cap_env / 16 * 16 : 256;
+  const int cap = (cap_env >= 16 && cap_env <= 256) ? cap_env / 16 * 16 : (gather ? 256 : 128);
   const int c_total = c_real + sel;
   const int passes0 = (c_total + cap - 1) / cap;
   for (int block = round_up((c_total + passes0 - 1) / passes0, 16); block <= 256; block += 16) {
@@ -950,9 +953,9 @@ static int dense_plan(int c_real, int sel, int* block_out) {
   return 0;
 }
 
-int dense_tc_passes(int c_dim, int sel) {
+int dense_tc_passes(int c_dim, int sel, int gather) {
   int block = 0;
-  return dense_plan(c_dim, sel, &block);
+  return dense_plan(c_dim, sel, gather, &block);
 }
 
 __global__ void __launch_bounds__(256) dense_dot_finish_kernel(const float* __restrict__ dot, int passes, int64_t rows,
@@ -985,7 +988,7 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
                 "dense: bad gather description");
   const int kp = round_up(k_dim, 16);
   int block = 0;
-  const int passes = dense_plan(c_dim, sel, &block);
+  const int passes = dense_plan(c_dim, sel, gather ? 1 : 0, &block);
   TRS_UNSUPPORTED(passes == 0, "dense: no channel split keeps the selector channels in one block");
   const int c_total = c_dim + sel;
   const bool a_tmem = block <= 128 && !gather;   // (the gathering producers write the shared-memory operand form)

@@ -15,7 +15,7 @@ int cross_tc5_launch(const float* x, const float* w, const float* b, int layers,
 int dense_tc_supported(int k_dim, int c_dim, const void* x, const void* out);
 int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const float* bias, int c_dim, int activation,
                  float* out, cudaStream_t s, const DenseFuse* fz);
-int dense_tc_passes(int c_dim, int sel);
+int dense_tc_passes(int c_dim, int sel, int gather);
 int dense_dot_finish(const float* dot, int passes, int64_t rows, const float* bias, float* out, int accumulate,
                      cudaStream_t s);
 
@@ -401,7 +401,7 @@ int mlp_chain_gather_supported(const int* dims, int layers, int fields, int embe
   if (off || layers < 2 || embed % 16 != 0 || dims[0] != fields * embed || dims[layers] != 1) return 0;
   if (!chain_layer_on_tc(dims[0], dims[1]) || dims[0] < 16 || fields > 128) return 0;
   if (use_fm && embed > 64) return 0;
-  return dense_tc_passes(dims[1], use_fm ? embed : 0) > 0 ? 1 : 0;
+  return dense_tc_passes(dims[1], use_fm ? embed : 0, 1) > 0 ? 1 : 0;
 }
 
 // `gather` != null (mlp_chain_gather_supported): x is ignored, layer 0 gathers its rows itself and writes the row base
@@ -413,7 +413,7 @@ int mlp_chain_run(const float* x, int64_t rows, const MlpParams& mp, float* out,
   for (int l = 1; l < L; ++l) hmax = mp.dims[l] > hmax ? mp.dims[l] : hmax;
   const bool dot = chain_dot_fusable(mp);
   const int sel_last = (gather != nullptr && L == 2 && gather->use_fm) ? gather->embed : 0;
-  const int dot_passes = dot ? dense_tc_passes(mp.dims[L - 1], sel_last) : 0;
+  const int dot_passes = dot ? dense_tc_passes(mp.dims[L - 1], sel_last, (gather != nullptr && L == 2) ? 1 : 0) : 0;
   const size_t half = ((size_t)rows * hmax + 63) / 64 * 64;
   const size_t dot_floats = ((size_t)rows * dot_passes + 63) / 64 * 64;
   float* buf = nullptr;
