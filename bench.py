@@ -389,7 +389,7 @@ def bench_other_configs(torch, timer, device, rank, peak, args):
                                   f'(split tables), batch {b}',
                       'value': timer.world * b / (r['ms_per_step'] * 1e-3), 'unit': UNIT,
                       'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': 1096.0, 'unit': 'TFLOP/s',
-                                   'frac': tf / 1096.0, 'issued_frac': 3 * tf / 1096.0, 'traffic': None,
+                                   'frac': tf / 1096.0, 'issued_frac': 3 * tf / 1096.0, 'traffic': recorded_traffic('deepfm_wide'),
                                    'kernel': 'cin_tc_layer_kernel<dense>',
                                    'note': 'three launches of the dense form of the tcgen05 kernel: layer 1 gathers its '
                                            'rows from the table itself and emits first-order + FM per sample, layer 3 '
@@ -775,7 +775,25 @@ def run_ours(args):
         sess.close()
         # batches in flight overlap each other, so the pipelined loop does not cut a batch into chunks (fewer API calls)
         sess = HostSession(batch, NUM_FIELDS, chunks=1)
-        e2e_value = time_e2e(sess, True, host_idx)
+        e2e_raw_value = time_e2e(sess, True, host_idx)
+        # the same int64 host batches, narrowed to int32 by the session's host threads (AVX-512 / AVX2, streaming stores
+        # into the pinned staging buffer) before they cross the link: the plugin's own work, inside the timed region
+        e2e_narrow = {}
+        cpus = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+        for threads in sorted({max(2, cpus // (2 * world)), max(2, (cpus - 2) // world), max(2, cpus // world)}):   # per rank: the ranks share the host
+            try:
+                used = sess.set_index_narrowing(threads)
+                e2e_narrow[used] = time_e2e(sess, True, host_idx)
+            except Exception as ex:
+                e2e_narrow[threads] = f'{type(ex).__name__}: {ex}'
+        sess.set_index_narrowing(0)
+        narrow_ok = {k: v for k, v in e2e_narrow.items() if isinstance(v, float)}
+        best_threads = max(narrow_ok, key=narrow_ok.get) if narrow_ok else 0
+        e2e_value = e2e_raw_value
+        if narrow_ok and narrow_ok[best_threads] > e2e_raw_value:
+            e2e_value = narrow_ok[best_threads]
+        else:
+            best_threads = 0
         # same call with the loader handing over int32 indices (the reference accepts them, multi_indices_emb.py:104)
         host_idx32 = [h.to(torch.int32).pin_memory() for h in host_idx]
         e2e_int32_value = time_e2e(sess, True, host_idx32)
@@ -793,13 +811,18 @@ def run_ours(args):
         torch.cuda.synchronize()
         h2d_gbs = 20 * batch * NUM_FIELDS * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
         del scratch
-        e2e = {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': batch * NUM_FIELDS * 8,
+        e2e = {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': batch * NUM_FIELDS * (4 if best_threads else 8),
+               'host_input_bytes_per_step': batch * NUM_FIELDS * 8,
                'd2h_bytes_per_step': batch * 4, 'steps': e2e_steps, 'repeats': 3, 'chunks': 1,
                'sync_call_chunks': args.e2e_chunks,
                'mode': f'pipelined, {sess.depth} batches in flight (trs_session_submit_deepfm_tc / trs_session_wait), '
-                       'int64 host indices, median of 3 regions',
+                       'int64 host indices' + (f', narrowed to int32 by {best_threads} host threads before the copy '
+                                               '(trs_session_set_index_narrowing)' if best_threads else '') +
+                       ', median of 3 regions',
+               'int64_as_is_value': e2e_raw_value, 'narrowed_value_by_threads': e2e_narrow,
                'sync_call_value': e2e_sync_value, 'int32_indices_value': e2e_int32_value,
-               'h2d_gbs_in_e2e': e2e_value / world * NUM_FIELDS * 8 / 1e9, 'h2d_gbs_bare_pinned_copy': h2d_gbs}
+               'h2d_gbs_in_e2e': e2e_value / world * NUM_FIELDS * (4 if best_threads else 8) / 1e9,
+               'h2d_gbs_bare_pinned_copy': h2d_gbs}
 
     footprint = {'registered_parameters_gb': rows * (EMBED + 1) * 4 / 1e9,
                  'packed_shadow_gb': rows * 128 / 1e9 if packed is not None else 0.0,

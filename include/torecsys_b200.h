@@ -501,6 +501,10 @@ int trs_session_depth(void);
  * reported as out-of-range lookups exactly as in the int64 path.  threads = 0 turns it off, -1 picks
  * min(8, usable CPUs / 2).  Returns the thread count in use (>= 0) or a negative TRS_ERR_* code. */
 int trs_session_set_index_narrowing(trs_session* session, int threads);
+/* The conversion those threads run, on plain host arrays (no device involved; the CPU test suite checks every form
+ * against the scalar one): dst[i] = src[i] if it fits int32, else INT32_MIN.  which: 0 = the form the sessions use on
+ * this CPU, 1 = scalar, 2 = AVX2, 3 = AVX-512 (TRS_ERR_UNSUPPORTED when the CPU lacks the instruction set). */
+int trs_host_narrow_indices(const int64_t* src, int32_t* dst, int64_t n, int which);
 /* Ordering against the caller's own work: the slots run on private streams, so device work the caller enqueued on
  * `stream` before a submit (packing the shadow table, uploading offsets, an optimizer step, load_state_dict) is not
  * ordered before the batch unless the session is told which stream that is.  With enabled != 0 every later submit

@@ -46,6 +46,34 @@ def test_library_contains_sm100a_sass_with_tensor_and_async_copy_instructions():
     assert 'LDGSTS' in packed and 'HMMA' in packed
 
 
+def test_host_index_narrowing_forms_agree():
+    """The int64 -> int32 conversion of the host-fed path (csrc/session.cu): the AVX2 / AVX-512 forms (streaming stores,
+    unaligned heads and tails, lengths around the vector widths) equal the scalar one, including values that do not fit
+    int32 (-> INT32_MIN, reported as out-of-range lookups downstream)."""
+    import ctypes
+    import numpy as np
+    lib = _cabi.load()
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 7, 8, 15, 16, 17, 63, 64, 1000, 16384, 100003):
+        src = rng.integers(0, 2 ** 31 - 1, size=n, dtype=np.int64)
+        if n > 5:
+            src[rng.integers(0, n, size=max(1, n // 97))] = rng.integers(2 ** 31, 2 ** 40, size=max(1, n // 97))
+            src[rng.integers(0, n, size=max(1, n // 89))] = -rng.integers(1, 2 ** 35, size=max(1, n // 89))
+            src[n // 2] = -1
+            src[n // 3] = -2 ** 31
+        want = np.where((src >= -2 ** 31) & (src < 2 ** 31), src, -2 ** 31).astype(np.int32)
+        for which in (0, 1, 2, 3):
+            for shift in (0, 1, 3):        # destination alignment: the staging buffer is aligned, slices of it need not be
+                buf = np.full(n + 32, 77, dtype=np.int32)
+                dst = buf[shift:shift + n]
+                rc = lib.trs_host_narrow_indices(ctypes.c_void_p(src.ctypes.data), ctypes.c_void_p(dst.ctypes.data), n, which)
+                if rc == _cabi.TRS_ERR_UNSUPPORTED:
+                    continue
+                assert rc == 0, _cabi.last_error()
+                assert np.array_equal(dst, want), (n, which, shift)
+                assert (buf[:shift] == 77).all() and (buf[shift + n:] == 77).all()
+
+
 def test_argument_errors_are_reported_without_a_gpu():
     lib = _cabi.load()
     rc = lib.trs_fm_forward(None, 4, 3, 8, None, None)
