@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
         // 8 kq + g and reports that row's out-of-range indices.
         const int g = lane >> 2, kq = lane & 3;
         constexpr bool kGather = kGB != 0;
+
         const int64_t row0 = tile * kTileM + warp * 32 + g;   // rows of this lane: row0 + 8 i
         bool ok[4];
         const unsigned char* rp[4];   // gather: address of the row's first index (of row 0 for rows beyond the batch:
