@@ -55,7 +55,14 @@ __global__ void __launch_bounds__(256) cin_tc_transpose_kernel(const float* __re
 __global__ void __launch_bounds__(256) cin_tc_prep_weights_kernel(const float* __restrict__ w, int c_begin, int c_eff, int fields,
                                                                   int h_prev, int hp, int npad, int fold,
                                                                   float* __restrict__ wp, int c_real = 1 << 30,
-                                                                  int sel_embed = 1) {
+                                                                  int sel_embed = 1, int c_block = 0, int c_total = 0,
+                                                                  int64_t pass_stride = 0) {
+  if (c_block > 0) {   // dense layer: one launch prepares every channel block (blockIdx.y), 16-column granularity
+    c_begin = blockIdx.y * c_block;
+    c_eff = c_total - c_begin < c_block ? c_total - c_begin : c_block;
+    npad = (c_eff + 15) & ~15;
+    wp += blockIdx.y * pass_stride;
+  }
   const int chunks = (hp / 16) * fields;
   const int64_t items = (int64_t)chunks * 4 * npad * 4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
@@ -997,14 +1004,11 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
   float* wp = nullptr;
   TRS_CUDA(scratch_alloc(reinterpret_cast<void**>(&wp), w_floats * sizeof(float) * passes, s));
   int rc = TRS_OK;
-  for (int pass = 0; pass < passes && rc == TRS_OK; ++pass) {
-    const int c0 = pass * block;
-    const int c_cnt = c_total - c0 < block ? c_total - c0 : block;
-    const int npad = round_up(c_cnt, 16);
-    const int64_t w_items = (int64_t)(kp / 16) * 2 * 4 * npad * 4;
-    cin_tc_prep_weights_kernel<<<grid_for(w_items / 2, 256, 8), 256, 0, s>>>(w, c0, c_cnt, 1, k_dim, kp, npad, 0,
-                                                                             wp + (size_t)pass * w_floats, c_dim,
-                                                                             sel > 0 ? sel : 1);
+  {
+    const int64_t w_items = (int64_t)(kp / 16) * 2 * 4 * block * 4;   // of the widest block
+    const dim3 pgrid(grid_for(w_items / 2, 256, 2), passes);
+    cin_tc_prep_weights_kernel<<<pgrid, 256, 0, s>>>(w, 0, 0, 1, k_dim, kp, 0, 0, wp, c_dim, sel > 0 ? sel : 1, block,
+                                                     c_total, (int64_t)w_floats);
     rc = check_launch("cin_tc_prep_weights_kernel");
   }
   if (rc == TRS_OK) {
