@@ -103,6 +103,49 @@ def test_deepfm_configs1_full_size(ops):
     torch.cuda.empty_cache()
 
 
+def test_deepfm_wide_branch_full_size(ops):
+    """SURVEY 8f-1 at the configs[1] table size: DeepFM with the paper-size deep branch [400, 400, 400] on 200 M rows,
+    batch 65 536 -- the first tcgen05 layer gathers its rows from the table and emits first-order + FM, the last hidden
+    layer carries the logit Linear.  The K walk of a tile starts at a CTA-dependent chunk (weights and table reads of
+    the CTAs are spread over L2), so moving a sample to another tile changes its rounding: permutation and split hold
+    within the 1e-5 bar, the index width bit for bit; a sampled subset is re-run by the CPU oracle."""
+    from oracle import restated as R
+    rng = np.random.default_rng(14)
+    gen = torch.Generator().manual_seed(14)
+    rows, b = N * ROWS_PER_FIELD, 65536
+    dgen = torch.Generator(device='cuda').manual_seed(14)
+    w_emb = torch.randn(rows, 16, device='cuda', generator=dgen) * 0.5
+    w_feat = torch.randn(rows, 1, device='cuda', generator=dgen)
+    off_d = (torch.arange(N, dtype=torch.int64) * ROWS_PER_FIELD).cuda()
+    ws, bs = _mlp([N * 16, 400, 400, 400, 1], gen)
+    pack = ops.MlpPack([w.cuda() for w in ws], [x.cuda() for x in bs], ops.activation_id('relu'))
+    idx = torch.randint(0, ROWS_PER_FIELD, (b, N), generator=gen).cuda()
+    idx[0, :] = 0
+    idx[1, :] = ROWS_PER_FIELD - 1
+    fwd = lambda ix: ops.deepfm(ix, off_d, w_feat, w_emb, pack)
+    got = fwd(idx)
+    assert torch.isfinite(got).all()
+    assert torch.equal(fwd(idx), got)                                    # run to run: bit for bit
+    assert torch.equal(fwd(idx.to(torch.int32)), got)
+    perm = torch.from_numpy(rng.permutation(b)).cuda()
+    assert normwise_err(fwd(idx[perm].contiguous()).cpu().numpy(), got[perm].cpu().numpy()) <= TOL
+    k = b // 3 + 5
+    parts = torch.cat([fwd(idx[:k].contiguous()), fwd(idx[k:].contiguous())])
+    assert normwise_err(parts.cpu().numpy(), got.cpu().numpy()) <= TOL
+    sel = torch.from_numpy(np.concatenate([[0, 1], rng.choice(b, 382, replace=False)])).cuda()
+    idx_c, (we_c, wf_c) = _compact(idx[sel] + off_d, w_emb, w_feat)
+    zero = torch.zeros(N, dtype=torch.int64)
+    want = R.deepfm_from_indices(idx_c, zero, wf_c, we_c, ws, bs).numpy()
+    want64 = R.deepfm_from_indices(idx_c, zero, wf_c.double(), we_c.double(), [w.double() for w in ws],
+                                   [x.double() for x in bs]).numpy()
+    g = got[sel].cpu().numpy()
+    assert normwise_err(g, want) <= TOL
+    assert normwise_err(g, want64) <= TOL
+    ops.check_index_errors()
+    del w_emb, w_feat
+    torch.cuda.empty_cache()
+
+
 def test_dcn_configs2_full_size(ops):
     """configs[2]: Deep & Cross, 39 fields, 200 M rows, embed 32, 6 cross layers, MLP 32-16-8 -> 4, batch 131 072."""
     from oracle import restated as R
