@@ -396,6 +396,16 @@ def bench_other_configs(torch, timer, device, rank, peak, args):
                                            'carries the logit Linear in its epilogue; no (B, 624) matrix in HBM; '
                                            'achieved = ALGORITHMIC flops (1.14 MFLOP/sample), 3xTF32 issues three times '
                                            'that'}})
+            try:   # the same model on the packed [v | w] shadow table (what the module API builds for E = 16)
+                pk = ops.fm_pack_table(w_emb, w_feat)
+                rp = timer.run(lambda i: ops.deepfm_packed(idx[i % 4], offsets, pk, wpack, out=o, kernel='auto'), steps=5)
+                ops.check_index_errors()
+                r['packed_table'] = {'value': timer.world * b / (rp['ms_per_step'] * 1e-3), 'ms_per_step': rp['ms_per_step'],
+                                     'shadow_gb': pk.numel() * 4 / 1e9,
+                                     'note': 'row and first-order value out of one 128-byte line'}
+                del pk
+            except Exception as ex:
+                r['packed_table'] = {'error': f'{type(ex).__name__}: {ex}'}
             out['deepfm_wide'] = r
             del idx, o
         except Exception as ex:

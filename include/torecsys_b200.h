@@ -318,6 +318,10 @@ int trs_deepfm_forward_packed(const void* idx, int idx_bits, const int64_t* offs
  * parameters of this call (work enqueued as copies/memsets is ordered as usual).  flags = 0 is exactly
  * trs_deepfm_forward_packed. */
 #define TRS_LAUNCH_OVERLAP_PREVIOUS 1u
+/* 1 when trs_deepfm_forward_packed[_ex] runs this deep branch on the packed table through the gathering tcgen05 layer
+ * (deep_fm.py:55-110 with paper-size `deep_layer_sizes`: some layer >= 64 x 64, batch >= 1 024): the row and its
+ * first-order value come out of the same 128-byte line. */
+int trs_deepfm_packed_wide_supported(int fields, const int* mlp_dims, int mlp_layers, int64_t batch);
 int trs_deepfm_forward_packed_ex(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch, int fields,
                                  const float* packed, int64_t rows,
                                  const int* mlp_dims, int mlp_layers, const float* const* mlp_w,

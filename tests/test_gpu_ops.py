@@ -474,6 +474,37 @@ def test_deepfm_wide_mlp(ops, n, e, deep):
             assert normwise_err(got, want) <= TOL, (n, e, batch)
 
 
+@pytest.mark.parametrize('n,deep', [(39, [400, 400, 400]), (12, [256, 128]), (39, [400])])
+def test_deepfm_wide_mlp_on_packed_table(ops, n, deep):
+    """The same fused wide deep branch on the packed [v16 | w | pad] table (trs_deepfm_forward_packed: the gathering layer
+    reads the row and its first-order value out of one 128-byte line); small batches are refused (the packed-table kernels
+    take 16-wide branches only) and the module falls back to the split tables."""
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    tag = f'dfwp{n}'
+    fs = [16 * (3 + i % 5) for i in range(n)]
+    rows = sum(fs)
+    off = R.field_offsets(fs)
+    w_feat = torch.from_numpy(synth.uniform((rows, 1), f'{tag}/wf'))
+    w_emb = torch.from_numpy(synth.uniform((rows, 16), f'{tag}/we'))
+    ws, bs = _wide_mlp(tag, [n * 16] + deep + [1])
+    pack = ops.MlpPack([w.cuda() for w in ws], [b.cuda() for b in bs], ops.activation_id('relu'))
+    packed = ops.fm_pack_table(w_emb.cuda(), w_feat.cuda())
+    assert not ops.deepfm_packed_wide_supported(n, pack, 100)
+    for batch in (1024, 4100):
+        assert ops.deepfm_packed_wide_supported(n, pack, batch)
+        idx = torch.from_numpy(synth.integers((batch, n), f'{tag}/idx{batch}', np.asarray(fs)[None, :]))
+        want = R.deepfm_from_indices(idx, off, w_feat, w_emb, ws, bs).numpy()
+        for dt in (torch.int64, torch.int32):
+            got = ops.deepfm_packed(idx.cuda().to(dt), off.cuda(), packed, pack, kernel='auto').cpu().numpy()
+            assert normwise_err(got, want) <= TOL, (n, batch)
+    bad = torch.zeros(2000, n, dtype=torch.long, device='cuda')
+    bad[1999, n - 1] = fs[-1]
+    with pytest.raises(IndexError):
+        ops.deepfm_packed(bad, off.cuda(), packed, pack, kernel='auto')
+        ops.check_index_errors()
+
+
 def test_deepfm_wide_mlp_out_of_range(ops):
     """The gathering dense layer reports out-of-range lookups like every other lookup kernel (IndexError), for rows in
     the first and in a later tile of a CTA, and stays usable afterwards."""

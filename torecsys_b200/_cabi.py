@@ -71,6 +71,7 @@ PROTOTYPES = {
                                           _P, _P, _P]),
     'trs_deepfm_forward_packed_ex': (c_int, [_P, c_int, _P, c_int64, c_int, _P, c_int64, _IP, c_int, _PP, _PP, c_int,
                                              _P, _P, ctypes.c_uint, _P]),
+    'trs_deepfm_packed_wide_supported': (c_int, [c_int, _IP, c_int, c_int64]),
     'trs_deepfm_tc_workspace_bytes': (c_int64, [c_int, c_int]),
     'trs_deepfm_tc_supported': (c_int, [c_int, c_int, _IP, c_int, c_int, c_int64, c_int]),
     'trs_deepfm_forward_tc_sharded': (c_int, [_P, c_int, _P, c_int64, c_int, _PP, c_int, c_int64, _IP, c_int, _PP, _PP,

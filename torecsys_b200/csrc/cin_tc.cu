@@ -122,6 +122,7 @@ struct CinTcArgs {
   float* row_base;          // (m_rows,) <- first-order + FM (+ bias): written by the CTA that owns the selector channels
   int64_t g_rows;
   int g_idx_bits, g_fields, g_embed;
+  int g_pitch, g_wcol;      // floats between table rows; >= 0: first-order value in that column of the row's line
   // selector channels [c_real, c_real + sel_count): weight 1 where k % g_embed == channel - c_real, so their accumulators
   // are the FM field sums s[e] = sum_f v[f, e]; the epilogue turns them into 0.5 * (sum_e s[e]^2 - sum v^2)
   int c_real, sel_count;
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
         int cf = kGather ? (yc_rot * 16) / a.g_embed : 0;          // ... its field
         int cw = kGather ? yc_rot * 16 - cf * a.g_embed : 0;       // ... its first column within the field's row
         int lf = 0, lw = 0;                                        // field / column of the chunk whose indices are held
-        const uint32_t row_bytes = kGather ? static_cast<uint32_t>(a.g_embed) * 4u : 0u;
+        const uint32_t row_bytes = kGather ? static_cast<uint32_t>(a.g_pitch) * 4u : 0u;
         uint32_t rlo[4] = {0u, 0u, 0u, 0u}, rhi[4] = {0u, 0u, 0u, 0u};
         int64_t offn = 0;
         auto advance = [&]() {
@@ -364,6 +365,8 @@ __global__ void __launch_bounds__(kThreads, 1) cin_tc_layer_kernel(CinTcArgs a) 
             if (do_base && starts && own_live) {
               if (own_in) {
                 if (a.g_wfeat != nullptr) wv = ldg_stream_f1(a.g_wfeat + rr_own);
+                else if (a.g_wcol >= 0)   // packed table: the value lies in the line the row load is fetching anyway
+                  wv = ldg_stream_f1(a.g_table + static_cast<uint64_t>(rr_own) * a.g_pitch + a.g_wcol);
               } else {
                 report_oob(a.g_status, (row0 + 8 * kq) * (int64_t)a.g_fields + lf);
               }
@@ -992,7 +995,8 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
   const int sel = (gather && fz->use_fm) ? fz->embed : 0;
   if (gather)
     TRS_REQUIRE(fz->embed % 16 == 0 && fz->fields * fz->embed == k_dim && fz->fields <= kTileM / 2 &&
-                    fz->table_rows <= (int64_t)1 << 32 && (fz->idx_bits == 32 || fz->idx_bits == 64),
+                    fz->table_rows <= (int64_t)1 << 32 && (fz->idx_bits == 32 || fz->idx_bits == 64) &&
+                    (fz->row_pitch == 0 || (fz->row_pitch % 4 == 0 && fz->row_pitch >= fz->embed)),
                 "dense: bad gather description");
   const int kp = round_up(k_dim, 16);
   int block = 0;
@@ -1029,6 +1033,7 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
       a.g_idx = fz->idx; a.g_idx_bits = fz->idx_bits; a.g_offsets = fz->offsets; a.g_table = fz->table;
       a.g_wfeat = fz->w_feat; a.g_bias = fz->bias; a.g_status = fz->status; a.row_base = gather ? fz->row_base : nullptr;
       a.g_rows = fz->table_rows; a.g_fields = fz->fields; a.g_embed = fz->embed;
+      a.g_pitch = fz->row_pitch > 0 ? fz->row_pitch : fz->embed; a.g_wcol = fz->w_col;
       a.dot_w = fz->dot_w; a.dot_out = fz->dot_w != nullptr ? fz->dot_out : nullptr;
     }
     const size_t a_stage = 2 * 4 * kTileM * 16, b_stage = (size_t)2 * 4 * a.npad * 16;

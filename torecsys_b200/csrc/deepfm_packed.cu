@@ -25,9 +25,13 @@
 // kernel is the HBM request rate, not the tensor pipe.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tile_ops.cuh"
 
 namespace trs {
+int mlp_chain_supported(const int* dims, int layers, int64_t rows, const void* x, const void* out, int accumulate);
+int mlp_chain_gather_supported(const int* dims, int layers, int fields, int embed, int use_fm);
+int mlp_chain_run(const float* x, int64_t rows, const MlpParams& mp, float* out, int accumulate, cudaStream_t s,
+                  const DenseFuse* gather);
 namespace {
 
 constexpr int kWarps = 8;
@@ -535,6 +539,16 @@ extern "C" int trs_deepfm_forward_packed(const void* idx, int idx_bits, const in
                                       mlp_b, activation, logits, status, 0u, stream);
 }
 
+// Does trs_deepfm_forward_packed[_ex] take this deep branch on the packed table through the gathering tcgen05 layer (a wide
+// MLP: some layer >= 64 x 64, one output, batch >= 1 024)?  Narrow 16-wide branches take the packed-table kernels.
+extern "C" int trs_deepfm_packed_wide_supported(int fields, const int* mlp_dims, int mlp_layers, int64_t batch) {
+  if (mlp_dims == nullptr || mlp_layers < 2 || fields < 1) return 0;
+  alignas(16) static const float probe[4] = {0.f, 0.f, 0.f, 0.f};   // (the chain test wants 16-byte aligned x / out)
+  return mlp_chain_supported(mlp_dims, mlp_layers, batch, probe, probe, 1) &&
+                 mlp_chain_gather_supported(mlp_dims, mlp_layers, fields, 16, 1)
+             ? 1 : 0;
+}
+
 extern "C" int trs_deepfm_forward_packed_ex(const void* idx, int idx_bits, const int64_t* offsets, int64_t batch,
                                             int fields, const float* packed, int64_t rows, const int* mlp_dims,
                                             int mlp_layers, const float* const* mlp_w, const float* const* mlp_b,
@@ -545,6 +559,18 @@ extern "C" int trs_deepfm_forward_packed_ex(const void* idx, int idx_bits, const
               "trs_deepfm_forward_packed: null pointer");
   TRS_REQUIRE(idx_bits == 32 || idx_bits == 64, "trs_deepfm_forward_packed: idx_bits must be 32 or 64");
   TRS_REQUIRE(batch >= 0 && fields > 0 && rows > 0 && mlp_layers >= 1, "trs_deepfm_forward_packed: bad sizes");
+  // A paper-size deep branch on the packed table: the gathering tcgen05 layer of cin_tc.cu reads the 64-byte
+  // row AND its first-order value out of the same 128-byte line -- the 4-byte lookups into a separate first-order table
+  // cost as much DRAM traffic as all the rows.
+  if (trs_deepfm_packed_wide_supported(fields, mlp_dims, mlp_layers, batch) && aligned16(logits)) {
+    MlpParams mp;
+    TRS_REQUIRE(fill_mlp_params(mp, mlp_dims, mlp_layers, mlp_w, mlp_b, activation) == 0,
+                "trs_deepfm_forward_packed: bad MLP description");
+    DenseFuse g;
+    g.idx = idx; g.idx_bits = idx_bits; g.offsets = offsets; g.table = packed; g.w_feat = nullptr; g.bias = nullptr;
+    g.status = status; g.table_rows = rows; g.fields = fields; g.embed = 16; g.use_fm = 1; g.row_pitch = 32; g.w_col = 16;
+    return mlp_chain_run(nullptr, batch, mp, logits, 1, static_cast<cudaStream_t>(stream), &g);
+  }
   TRS_UNSUPPORTED(!deepfm_packed_supported(fields, 16, mlp_dims, mlp_layers, activation, rows),
                   "trs_deepfm_forward_packed: needs embed 16, hidden widths 16, ReLU, <= 40 fields, < 2^31 rows");
   TRS_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127u) == 0 && aligned16(mlp_w[0]) && aligned16(idx),

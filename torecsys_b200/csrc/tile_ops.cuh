@@ -41,6 +41,8 @@ struct DenseFuse {
   float* row_base = nullptr;        // (rows,)
   int64_t table_rows = 0;
   int fields = 0, embed = 0, use_fm = 0;
+  int row_pitch = 0;                // floats between consecutive table rows (0: embed)
+  int w_col = -1;                   // >= 0: the first-order value is column w_col of the row's own line (packed [v|w] table)
   const float* dot_w = nullptr;     // (c_dim,)
   float* dot_out = nullptr;         // (passes, rows)
 };

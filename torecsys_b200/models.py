@@ -222,7 +222,14 @@ class DeepFactorizationMachineModel(_ShadowOwner, CtrBaseModel):
         w = emb.embedding.weight
         off = emb._offsets_on(w.device)
         pack = self.deep.mlp_pack()
-        packed = self.packed_table(feat, emb) if self._packable(pack, idx.shape[1], w) else None
+        narrow = self._packable(pack, idx.shape[1], w)
+        # a paper-size deep branch takes the packed table too (the gathering tcgen05 layer reads the row and its
+        # first-order value out of one line), for batches the tensor-core chain takes
+        wide = (not narrow and w.shape[1] == 16 and w.shape[0] < 2 ** 31
+                and ops.deepfm_packed_wide_supported(idx.shape[1], pack, idx.shape[0]))
+        packed = self.packed_table(feat, emb) if (narrow or wide) else None
+        if packed is not None and wide:
+            return ops.deepfm_packed(idx, off, packed, pack, kernel='auto')
         if packed is not None:
             self._build_fast(feat, emb, off, pack, packed, idx.shape[1])
             return ops.deepfm_packed(idx, off, packed, pack, overlap_previous=inputs_resident)

@@ -783,6 +783,11 @@ def deepfm_packed(idx, offsets, packed: torch.Tensor, pack: MlpPack, out: Option
     return out
 
 
+def deepfm_packed_wide_supported(fields: int, pack: MlpPack, batch: int) -> bool:
+    """deepfm_packed() runs this (wide) deep branch through the gathering tcgen05 layer on the packed table."""
+    return bool(_cabi.load().trs_deepfm_packed_wide_supported(fields, pack.dims, pack.layers, batch))
+
+
 def deepfm_packed_sharded(idx, offsets, shard_ptrs: Sequence[int], rows: int, pack: MlpPack,
                           out: Optional[torch.Tensor] = None, overlap_previous: bool = False,
                           variant: Optional[int] = None):
