@@ -216,6 +216,45 @@ def test_deepfm_criteo_shape_uses_packed_table_and_tracks_weight_updates(trs):
     assert normwise_err(out3.cpu().numpy(), out2.cpu().numpy()) <= TOL
 
 
+def test_deepfm_paper_size_branch_through_the_module_api(trs):
+    """Sequential(Inputs, DeepFactorizationMachineModel) with a paper-size deep branch: large batches take
+    the gathering tcgen05 layer on the packed shadow table, small ones the split tables; both match the oracle, follow
+    in-place weight updates, and equal each other and the registered-table route (use_packed_table = False)."""
+    from oracle import restated as R
+    from torecsys_b200 import synth
+    n, e = 12, 16
+    fs = [16 * (2 + i % 5) for i in range(n)]
+    feat, emb = trs.MultiIndicesEmbedding(1, fs), trs.MultiIndicesEmbedding(e, fs)
+    feat.set_schema(['idx'])
+    emb.set_schema(['idx'])
+    model = trs.DeepFactorizationMachineModel(e, n, [256, 128], fm_dropout_p=0.0)
+    seq = trs.Sequential(trs.Inputs({'feat_inputs': feat, 'emb_inputs': emb}), model).cuda().eval()
+
+    def oracle(idx):
+        lin = model.deep.linears()
+        return R.deepfm_from_indices(idx.cpu(), R.field_offsets(fs), feat.embedding.weight.detach().cpu(),
+                                     emb.embedding.weight.detach().cpu(), [l.weight.detach().cpu() for l in lin],
+                                     [l.bias.detach().cpu() for l in lin]).numpy()
+
+    for b in (300, 2500):
+        idx = torch.from_numpy(synth.integers((b, n), f'modw/idx{b}', np.asarray(fs)[None, :])).cuda()
+        model.use_packed_table = True
+        with torch.no_grad():
+            out = seq({'idx': idx})
+        assert out.shape == (b, 1) and normwise_err(out.cpu().numpy(), oracle(idx)) <= TOL
+        if b >= 1024:
+            assert model._packed is not None and model._packed.shape == (sum(fs), 32)
+        with torch.no_grad():                   # in-place update bumps _version -> the shadow table is rebuilt
+            emb.embedding.weight.mul_(0.75)
+            feat.embedding.weight.add_(0.5)
+            out2 = seq({'idx': idx})
+        assert normwise_err(out2.cpu().numpy(), oracle(idx)) <= TOL
+        model.use_packed_table = False
+        with torch.no_grad():
+            out3 = seq({'idx': idx})
+        assert normwise_err(out3.cpu().numpy(), out2.cpu().numpy()) <= TOL
+
+
 def test_embedding_modules_names_offsets_and_errors(trs):
     fs = [16, 32, 48]
     emb = trs.MultiIndicesEmbedding(8, fs).cuda()
