@@ -2,9 +2,9 @@
 // TMEM, FP32-accurate through the 3xTF32 split (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, fp32 accumulate).
 //
 // GEMM view per layer: D[(b,e), c] = sum_{x,y} x0[(b,e), x] * h[(b,e), y] * W[c, x*H + y].
-//   * rows (b,e) are independent, so activations are kept ROW-major between layers: x0T [(b,e)][Hp0] (one transpose of
-//     the (B,N,E) input) and h_l [(b,e)][Hp_l] -- which is exactly the accumulator layout (TMEM lane = row, column =
-//     channel), so the epilogue writes full 128-byte lines and the next layer reads contiguous rows;
+//   * rows (b,e) are independent, so activations are kept ROW-major between layers: h_l [(b,e)][Hp_l] -- which is exactly
+//     the accumulator layout (TMEM lane = row, column = channel); the layer input x (B,N,E) is read in place (x0 of
+//     every layer, h of layer 0: the E lanes of a sample read consecutive floats of one field's row);
 //   * the K index is re-ordered y-chunk-major: k' = (yc*N + x)*16 + (y%16).  A producer thread owns one row, keeps
 //     the 16 h values of the current y-chunk in registers across the N chunks that share it, and per chunk emits
 //     z = x0[x] * h[y] split into TF32 hi/lo straight into the UMMA canonical (K-major, no swizzle) smem layout;
@@ -13,8 +13,12 @@
 //   * CTA tile = 256 rows x Npad channels (two M=128 accumulators = up to 512 TMEM columns), BK = 16 per stage;
 //     per chunk 2 halves x 2 k-steps x 3 split terms = 12 tcgen05.mma; tcgen05.commit frees the stage / signals
 //     the epilogue; roles: warps 0-7 = A producers then epilogue (tcgen05.ld -> folded Conv-bias + eval-BN + act ->
-//     hidden half stored row-major, direct half summed over e with shuffles -> pooled), warp 8 = MMA issuer,
-//     warp 9 = weight loader;
+//     hidden half stored row-major through a shared-memory transpose (whole lines per store), direct half summed over
+//     e by a butterfly reduce-scatter -> pooled), warp 8 = MMA issuer, warp 9 = weight loader, warps 10-11 idle: they
+//     and warps 8-9 hand their registers to the producers (setmaxnreg);
+//   * the same kernel is the DENSE layer of wide MLPs (one field, x0 = 1; kFused instantiations: channel blocks over
+//     blockIdx.y, rows gathered from an embedding table, FM / first-order row base, logit Linear in the epilogue);
+//   * TRS_CIN_TRACE / TRS_DENSE_TRACE: per-role cycle counters (what each role waits for), see trace_report();
 //   * the dead hidden half of the last layer (computed and discarded by the reference) is not computed.
 // Shapes outside (E in {8,16,32}, channels <= 256 per layer) use the FFMA path in cin.cu.
 #include <stdlib.h>
@@ -26,7 +30,7 @@ namespace trs {
 namespace {
 
 constexpr int kTileM = 256;          // rows per CTA tile (2 x UMMA_M 128)
-constexpr int kBK = 16;              // K per stage = 4 sixteen-byte chunks = 2 UMMA k-steps
+// (K per stage = 16 = 4 sixteen-byte chunks = 2 UMMA k-steps)
 constexpr int kProducerThreads = 256;
 constexpr int kThreads = kProducerThreads + 128;  // + MMA warp + weight-loader warp + two idle warps (register donors)
 constexpr int kAStages = 2;          // operand-A ring in smem (32 KB per stage; generation is cheap, two stages suffice)
@@ -36,19 +40,6 @@ constexpr int kMaxBStages = 8;       // weight ring: deep, the L2 -> smem stream
 using namespace tc5;
 
 // ---- preparation kernels ------------------------------------------------------------------------------------------------
-// x (B, N, E) -> xt [(b,e)][hp0] row-major with zero padding (layer-0 "h" and the x0 operand of every layer)
-__global__ void __launch_bounds__(256) cin_tc_transpose_kernel(const float* __restrict__ x, int64_t batch, int fields,
-                                                               int embed, int hp0, float* __restrict__ xt) {
-  const int64_t items = batch * embed * hp0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = i / hp0;
-    const int n = static_cast<int>(i - m * hp0);
-    const int64_t b = m / embed;
-    const int e = static_cast<int>(m - b * embed);
-    xt[i] = n < fields ? __ldg(x + (b * fields + n) * embed + e) : 0.f;
-  }
-}
-
 // W (C, N*H) -> wp[q = yc*N + x][hi|lo][kc 0..3][n 0..npad-1][4 floats]  with k' = q*16 + kc*4 + j,  y = yc*16 + kc*4 + j
 // fold != 0 (layer 0, where h = x0 and z[x, y] = z[y, x]): the pair (x, y) is kept only for y >= x, with the weight
 // W[c, x, y] + W[c, y, x] (W[c, x, x] on the diagonal); the kernel then skips the chunks that lie below the diagonal.
@@ -90,7 +81,6 @@ __global__ void __launch_bounds__(256) cin_tc_prep_weights_kernel(const float* _
 }
 
 struct CinTcArgs {
-  const float* xt;       // unused (the x0 operand used to come from a transposed copy [(b,e)][hp0])
   const float* xb;       // CIN: the layer input x (B, N, E) as the lookup wrote it -- the x0 operand of every layer and,
                          // with h == null, layer 0's activations; rows (b, e) read it with stride E (the 16 lanes of a
                          // sample make one 64-byte request per field).  Null = plain dense layer (x0 = 1)
@@ -823,7 +813,7 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
               "cin: workspace too small for the tensor-core path");
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   ws += (128 - (reinterpret_cast<uintptr_t>(ws) & 127)) & 127;
-  float* xt = reinterpret_cast<float*>(ws);
+  float* xt = reinterpret_cast<float*>(ws);   // (space of the former transposed copy of x: unused, kept in the layout)
   float* hbuf[2] = {xt + p.xt_floats, xt + p.xt_floats + p.h_floats};
   float* pooled = hbuf[1] + p.h_floats;
   float* wprep = pooled + p.pooled_floats;
@@ -851,7 +841,7 @@ int cin_tc_run(const float* x, const float* const* conv_w, const float* const* s
     rc = check_launch("cin_tc_prep_weights_kernel");
     if (rc != TRS_OK) return rc;
     CinTcArgs a{};
-    a.xt = nullptr; a.xb = x; a.h = h; a.wp = wp; a.scale = scale[l]; a.shift = shift[l];
+    a.xb = x; a.h = h; a.wp = wp; a.scale = scale[l]; a.shift = shift[l];
     a.h_next = last ? nullptr : hbuf[l & 1];
     a.pooled = pooled;
     a.m_rows = m_rows; a.fields = fields; a.embed = embed; a.hp0 = p.hp0; a.hp = hp; a.npad = npad; a.c_eff = c_eff;
@@ -1017,7 +1007,7 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
   }
   if (rc == TRS_OK) {
     CinTcArgs a{};
-    a.xt = nullptr; a.h = x; a.wp = wp; a.scale = nullptr; a.shift = bias;
+    a.h = x; a.wp = wp; a.scale = nullptr; a.shift = bias;
     a.h_next = (fz != nullptr && fz->dot_w != nullptr) ? nullptr : out; a.pooled = nullptr;
     a.m_rows = rows; a.fields = 1; a.embed = 1; a.hp0 = 0; a.hp = kp; a.h_pitch = k_dim; a.k_valid = k_dim;
     a.c_begin = 0; a.c_eff = c_total < block ? c_total : block; a.npad = round_up(a.c_eff, 16);
