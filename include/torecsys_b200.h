@@ -509,6 +509,10 @@ int trs_session_set_index_narrowing(trs_session* session, int threads);
  * against the scalar one): dst[i] = src[i] if it fits int32, else INT32_MIN.  which: 0 = the form the sessions use on
  * this CPU, 1 = scalar, 2 = AVX2, 3 = AVX-512 (TRS_ERR_UNSUPPORTED when the CPU lacks the instruction set). */
 int trs_host_narrow_indices(const int64_t* src, int32_t* dst, int64_t n, int which);
+/* The narrowing pool of the sessions on plain host arrays: `threads` host threads (the caller included) convert
+ * src[0, n) -> dst `reps` times; returns the best time of one pass in nanoseconds (how the conversion scales over the
+ * host's cores: tools/r2_narrow_scaling.py), or a negative TRS_ERR_* code. */
+int64_t trs_host_narrow_pool_ns(const int64_t* src, int32_t* dst, int64_t n, int threads, int reps);
 /* Ordering against the caller's own work: the slots run on private streams, so device work the caller enqueued on
  * `stream` before a submit (packing the shadow table, uploading offsets, an optimizer step, load_state_dict) is not
  * ordered before the batch unless the session is told which stream that is.  With enabled != 0 every later submit

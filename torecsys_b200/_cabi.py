@@ -111,6 +111,7 @@ PROTOTYPES = {
     'trs_session_depth': (c_int, []),
     'trs_session_set_index_narrowing': (c_int, [c_void_p, c_int]),
     'trs_host_narrow_indices': (c_int, [_P, _P, c_int64, c_int]),
+    'trs_host_narrow_pool_ns': (c_int64, [_P, _P, c_int64, c_int, c_int]),
     'trs_session_submit_deepfm': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, _P, c_int64, c_int, _IP,
                                           c_int, _PP, _PP, c_int, _P, POINTER(c_int64)]),
     'trs_session_submit_deepfm_packed': (c_int, [c_void_p, _P, c_int, _P, c_int64, c_int, _P, c_int64, _IP,
