@@ -110,3 +110,32 @@ def test_tall_dense_tensor_core_kernel_logic(emulated_tall_dense, args):
     ragged rows / K tails (K a multiple of 4 but not of 16 or 64) / output counts that are not a multiple of 8."""
     res = subprocess.run([emulated_tall_dense] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
+
+
+@pytest.fixture(scope='module')
+def emulated_pool_rows(tmp_path_factory):
+    """pool_rows<E> of csrc/cin_tc.cu (the CIN epilogue's butterfly reduce-scatter over the rows of a sample) on its own."""
+    if shutil.which('g++') is None:
+        pytest.skip('g++ not available')
+    src = open(os.path.join(ROOT, 'torecsys_b200', 'csrc', 'cin_tc.cu')).read()
+    start = 'template <int E>\n__device__ __forceinline__ void pool_rows'
+    body = start + src.split(start, 1)[1].split('__host__ __device__ inline int ss_pitch', 1)[0]
+    out = tmp_path_factory.mktemp('emu')
+    cpp = out / 'pool_rows_emu.cpp'
+    cpp.write_text('#include "cuda_emu.h"\n#include <cstring>\nnamespace trs {\n' + body + '}  // namespace trs\n'
+                   + open(os.path.join(EMU, 'pool_rows_main.inc')).read())
+    exe = out / 'pool_rows_emu'
+    res = subprocess.run(['g++', '-std=c++20', '-O1', '-pthread', '-I', EMU, '-Wno-unknown-pragmas', str(cpp), '-o',
+                          str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return str(exe)
+
+
+# embed, warps, channels that exist in the group, first row beyond the batch (a multiple of embed)
+@pytest.mark.parametrize('args', [(16, 8, 32, 256), (16, 2, 32, 48), (8, 4, 20, 128), (32, 3, 7, 64), (16, 1, 1, 16),
+                                  (8, 1, 32, 0)])
+def test_cin_pool_rows_butterfly_is_bit_identical_to_the_all_reduce(emulated_pool_rows, args):
+    """Every (sample, channel) sum of the reduce-scatter equals the all-reduce it replaced bit for bit, is written by
+    exactly one lane, respects the channel limit of a partial group and skips samples beyond the batch."""
+    res = subprocess.run([emulated_pool_rows] + [str(a) for a in args], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
