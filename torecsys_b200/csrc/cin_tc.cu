@@ -1018,7 +1018,8 @@ int dense_tc_run(const float* x, int64_t rows, int k_dim, const float* w, const 
     static const bool coop_env = getenv("TRS_DENSE_COOP") ? atoi(getenv("TRS_DENSE_COOP")) != 0 : false;
     a.coop = (gather || coop_env) ? 1 : 0;
     static const int a_stages_env = getenv("TRS_DENSE_A_STAGES") ? atoi(getenv("TRS_DENSE_A_STAGES")) : 0;
-    a.a_stages = (a_stages_env >= 2 && a_stages_env <= kMaxAStages) ? a_stages_env : kAStages;
+    // (the gathering producers run a stage further ahead of the MMAs: 798 -> 777 us for DeepFM-[400,400,400])
+    a.a_stages = (a_stages_env >= 2 && a_stages_env <= kMaxAStages) ? a_stages_env : (gather ? 3 : kAStages);
     if (fz != nullptr) {
       a.g_idx = fz->idx; a.g_idx_bits = fz->idx_bits; a.g_offsets = fz->offsets; a.g_table = fz->table;
       a.g_wfeat = fz->w_feat; a.g_bias = fz->bias; a.g_status = fz->status; a.row_base = gather ? fz->row_base : nullptr;
