@@ -74,6 +74,24 @@ def test_host_index_narrowing_forms_agree():
                 assert (buf[:shift] == 77).all() and (buf[shift + n:] == 77).all()
 
 
+def test_host_index_narrowing_pool_splits_a_batch_over_threads():
+    """The sessions' narrowing pool (helper threads + the caller, 16 384-element blocks claimed from an atomic counter):
+    same result as the scalar form for any thread count, including more threads than blocks."""
+    import ctypes
+    import numpy as np
+    lib = _cabi.load()
+    rng = np.random.default_rng(6)
+    for n in (1, 5000, 16384 * 3 + 77, 200_001):
+        src = rng.integers(-5, 2 ** 33, size=n, dtype=np.int64)
+        want = np.where((src >= -2 ** 31) & (src < 2 ** 31), src, -2 ** 31).astype(np.int32)
+        for threads in (1, 2, 5, 32):
+            dst = np.full(n, 77, dtype=np.int32)
+            ns = lib.trs_host_narrow_pool_ns(ctypes.c_void_p(src.ctypes.data), ctypes.c_void_p(dst.ctypes.data), n, threads, 2)
+            assert ns > 0, _cabi.last_error()
+            assert np.array_equal(dst, want), (n, threads)
+    assert lib.trs_host_narrow_pool_ns(None, None, 4, 1, 1) < 0
+
+
 def test_argument_errors_are_reported_without_a_gpu():
     lib = _cabi.load()
     rc = lib.trs_fm_forward(None, 4, 3, 8, None, None)
