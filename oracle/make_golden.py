@@ -345,6 +345,19 @@ def main():
         np.savez_compressed(os.path.join(out_dir, 'model_grads.npz'), **store)
         print('model_grads.npz', len(store), 'arrays', os.path.getsize(os.path.join(out_dir, 'model_grads.npz')) // 1024, 'KiB')
         return
+    if '--baseline' in sys.argv:     # BASELINE.json's own layer shapes (round 2): models_baseline.npz only
+        store = {}
+        for key in cases.BASELINE_SHAPES:
+            kind, b, n, e = key
+            cid = cases.case_id(kind, b, n, e)
+            with cases.baseline_shape(key):
+                for k, v in run_model(trs, kind, b, n, e, torch.float32).items():
+                    store[f'{cid}/{k}'] = v
+                for k, v in run_model(trs, kind, b, n, e, torch.float64).items():
+                    store[f'{cid}/{k}/f64'] = v
+        np.savez_compressed(os.path.join(out_dir, 'models_baseline.npz'), **store)
+        print('models_baseline.npz', len(store), 'arrays', os.path.getsize(os.path.join(out_dir, 'models_baseline.npz')) // 1024, 'KiB')
+        return
     jobs = [] if only_new else [('layers.npz', cases.LAYER_KINDS, run_layer),
                                 ('embeddings.npz', cases.EMB_KINDS, run_emb),
                                 ('models.npz', cases.MODEL_KINDS, run_model)]

@@ -32,6 +32,34 @@ MLP_SIZES = [16, 16, 16]
 DCN_DEEP = ([32, 16, 8], 4)  # reference tests/test_models.py:57-66
 
 
+# BASELINE.json's own shapes at a reduced batch and table size (goldens in models_baseline.npz): configs[2] (embed 32,
+# 6 cross layers, MLP 32-16-8 -> 4), configs[3] (CIN [128, 128], not direct) and the paper-size DeepFM of SURVEY 8f-1
+# (deep branch [400, 400, 400], a batch large enough for the tensor-core chain).  key = (kind, B, N, E).
+BASELINE_SHAPES = {
+    ('dcn_model', 256, 39, 32): dict(CROSS_LAYERS=6, DCN_DEEP=([32, 16, 8], 4)),
+    ('xdeepfm_model', 64, 39, 16): dict(CIN_SIZES=[128, 128], MLP_SIZES=[16, 16, 16]),
+    ('deepfm_model', 1024, 39, 16): dict(MLP_SIZES=[400, 400, 400]),
+}
+
+
+class baseline_shape:
+    """with cases.baseline_shape(key): ... -- the layer-size constants of this module take the BASELINE shape of `key`
+    (model_case, the golden generator and the oracle runners read them at call time)."""
+
+    def __init__(self, key):
+        self.new = BASELINE_SHAPES[key]
+
+    def __enter__(self):
+        g = globals()
+        self.old = {k: g[k] for k in self.new}
+        g.update(self.new)
+        return self
+
+    def __exit__(self, *exc):
+        globals().update(self.old)
+        return False
+
+
 def case_id(kind, b, n, e):
     return f'{kind}_B{b}_N{n}_E{e}'
 

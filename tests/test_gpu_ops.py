@@ -148,6 +148,28 @@ def test_fused_model_parity(ops, golden, kind, b, n, e, idx_dtype):
     assert normwise_err(got, f64) <= max(4 * normwise_err(golden[f'{cid}/out'], f64), floor), cid
 
 
+@pytest.mark.parametrize('key', list(cases.BASELINE_SHAPES), ids=lambda k: cases.case_id(*k))
+def test_fused_model_parity_at_baseline_shapes(ops, key):
+    """The fused indices -> logits kernels at BASELINE.json's own layer shapes against outputs of the REAL reference
+    (tests/golden/models_baseline.npz, oracle/make_golden.py --baseline): configs[2] on dcn_tc5 (embed 32, 6 cross
+    layers, MLP 32-16-8 -> 4), configs[3] with CIN [128, 128] on tcgen05, and the paper-size DeepFM [400, 400, 400]
+    through the gathering dense layer; int64 and int32 indices."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'models_baseline.npz'))
+    kind, b, n, e = key
+    cid = cases.case_id(kind, b, n, e)
+    with cases.baseline_shape(key):
+        want = oracle_model(kind, b, n, e, torch.float32)['out'].numpy()
+        outs = [run_model_cuda(ops, kind, b, n, e, dt).cpu().numpy() for dt in (torch.int64, torch.int32)]
+    ref, f64 = g[f'{cid}/out'], g[f'{cid}/out/f64']
+    for got in outs:
+        assert got.shape == (b, 1)
+        assert normwise_err(got, want) <= TOL, (cid, 'vs oracle')
+        assert normwise_err(got, ref) <= TOL, (cid, 'vs reference golden')
+        assert normwise_err(got, f64) <= TOL, (cid, 'vs the reference in float64')
+    assert np.array_equal(outs[0], outs[1])
+
+
 def test_deepfm_fast_path_matches_generic_and_oracle(ops, monkeypatch):
     """Criteo shape (39 fields, E=16, MLP 16-16-16) goes through deepfm_fast.cu (3xTF32 mma.sync); ragged batch
     sizes exercise the 16-sample warp tiles and the tail masking."""

@@ -52,6 +52,23 @@ def test_model_oracle_matches_reference(golden, kind, b, n, e):
     assert normwise_err(got64, golden[f'{cid}/out/f64']) <= 1e-12, cid
 
 
+@pytest.mark.parametrize('key', list(cases.BASELINE_SHAPES), ids=lambda k: cases.case_id(*k))
+def test_model_oracle_matches_reference_at_baseline_shapes(key):
+    """BASELINE.json's own layer shapes -- configs[2] (embed 32, 6 cross layers), configs[3] (CIN [128, 128]) and the
+    paper-size DeepFM [400, 400, 400] of SURVEY 8f-1 -- through the real reference (oracle/make_golden.py --baseline,
+    tests/golden/models_baseline.npz): the oracle restates them to fp32 round-off / 1e-12 in fp64."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'models_baseline.npz'))
+    kind, b, n, e = key
+    cid = cases.case_id(kind, b, n, e)
+    with cases.baseline_shape(key):
+        got = oracle_model(kind, b, n, e, torch.float32)['out'].numpy()
+        got64 = oracle_model(kind, b, n, e, torch.float64)['out'].numpy()
+    assert got.shape == g[f'{cid}/out'].shape == (b, 1)
+    assert normwise_err(got, g[f'{cid}/out']) <= 5e-6, cid
+    assert normwise_err(got64, g[f'{cid}/out/f64']) <= 1e-12, cid
+
+
 def test_offsets_follow_the_float32_rounding_quirk():
     """multi_indices_emb.py:54 builds offsets through a float32 tensor; restated identically."""
     from oracle.restated import field_offsets
